@@ -1,0 +1,154 @@
+/* magnify_b200 -- C ABI of the B200-native per-marker quantification hot path.
+ *
+ * One shared library (magnify_b200/libmagnify_b200.so, built by __graft_entry__.build() with
+ * nvcc -gencode arch=compute_100a,code=sm_100a).  Every entry point takes plain pointers and
+ * sizes; pointers are DEVICE pointers unless the parameter name starts with `host_`.  All
+ * launches go to the caller's stream (`stream` is a cudaStream_t passed as void*; NULL = the
+ * legacy default stream) and return without synchronising.  Return value: 0 on success,
+ * a negative MGB_E* code for argument errors (nothing launched), or a positive cudaError_t.
+ *
+ * The reference (FordyceLab/magnify v0.12.5) is pure Python; there is no FFI in it to mirror.
+ * Each function below names the reference lines whose arithmetic it replaces; the Python
+ * binding a magnify maintainer would add is in INTEGRATION.md (ctypes) and implemented in
+ * magnify_b200/_lib.py.
+ *
+ * Array layouts (row-major, contiguous):
+ *   tiles  (C, T, R, Cc, H, W)   the reference's canonical tile stack (preprocess.py:24)
+ *   image  (C, T, Him, Wim)      stitched images, Him = R*(H-ov), Wim = Cc*(W-ov) (stitch.py:23-39)
+ *   boxes  (M, T, 2) int32       (top, left) of every marker's ROI at every timepoint
+ *   roi    (M, C, T, L, L)       find.py:533 / find.py:89-92 after the stack at :182
+ *   fg,bg  (M, Tm, L, L) uint8   0/1 masks; Tm = number of distinct mask timesteps
+ *   stats  (M, C, T, 6) float64  n_fg, n_bg, sum_fg, sum_bg, mean_fg, mean_bg
+ */
+#ifndef MAGNIFY_B200_H
+#define MAGNIFY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGB_ABI_VERSION 1
+
+#define MGB_OK 0
+#define MGB_EINVAL (-1)      /* bad argument (null pointer, negative size, bad itemsize ...) */
+#define MGB_EALIGN (-2)      /* pointer / pitch does not meet the alignment a fast path needs */
+#define MGB_EUNSUPPORTED (-3) /* shape or dtype outside what this build implements */
+
+/* dtype codes for the generic (any-dtype) entry points */
+#define MGB_U8 0
+#define MGB_U16 1
+#define MGB_F32 2
+#define MGB_F64 3
+
+int mgb_abi_version(void);
+/* Human-readable text for a return code of this library (cudaGetErrorString for codes > 0). */
+const char* mgb_error_string(int code);
+/* Number of SMs of the current device (grid sizing / reporting). */
+int mgb_sm_count(void);
+/* Kernels launched by this library in this process so far (bench.py's gpu_launches). */
+int64_t mgb_launch_count(void);
+
+/* ---- F2: tile stitching, reference src/magnify/stitch.py:22-39 ----------------------------
+ * image[c,t,y,x] = tiles[c,t, y/h, x/w, clip + y%h, clip + x%w], clip = overlap/2,
+ * h = H-overlap, w = W-overlap.  Pure copy for any itemsize in {1,2,4,8}.  Argument checks
+ * mirror stitch.py:8-9,16-20 (overlap < 0 or >= tile size -> MGB_EINVAL).  Picks a 128-bit
+ * vectorised kernel when W*itemsize and Wim*itemsize are multiples of 16 bytes, else an
+ * element-wise kernel; `used_fast` (host pointer, may be NULL) reports which. */
+int mgb_stitch(const void* tiles, void* image, int64_t C, int64_t T, int64_t R, int64_t Cc,
+               int64_t H, int64_t W, int64_t overlap, int itemsize, int* host_used_fast,
+               void* stream);
+
+/* ---- F1: flat-field correction, reference src/magnify/preprocess.py:83-87 -----------------
+ * out = trunc((((max(float64(x) - dark, 0)) / flat) * M) / M2) with the two GLOBAL maxima
+ * M = max(max(x - dark, 0)), M2 = max(max(x - dark, 0) / flat) over every tile pixel.
+ * flat / dark are float64 tables (K, H, W), K = 1 (shared) or K = C (per channel); scalars
+ * are expanded by the caller.  flat must be finite and > 0.
+ *
+ * Pass 1a: per-position maximum of the raw uint16 pixels over all tiles that share a table.
+ * Exact because x -> max(x-d,0) and t -> t/f (f > 0) are monotone, so both maxima are attained
+ * at the per-position maximum.  tiles is viewed as (C, P, HW) with P = T*R*Cc planes per
+ * channel; `splits` CTAs share each position and write xmax_partial (splits, K, HW). */
+int mgb_flatfield_tilemax_u16(const uint16_t* tiles, int64_t C, int64_t P, int64_t HW, int K,
+                              int splits, uint16_t* xmax_partial, void* stream);
+/* Pass 1b: maxima[0] = max(maxima[0], M), maxima[1] = max(maxima[1], M2) (device float64[2])
+ * from the partial per-position maxima, in exact IEEE float64 (__dsub_rn / __ddiv_rn).  The
+ * caller zero-initialises maxima (all values are >= 0); several calls (time chunks, channels)
+ * accumulate into it with atomic max. */
+int mgb_flatfield_maxima(const uint16_t* xmax_partial, int splits, int K, int64_t HW,
+                         const double* flat, const double* dark, double* maxima, void* stream);
+/* Any-dtype pass 1 (slow, exact): maxima over n elements of a (C, P, HW) stack. maxima must be
+ * zero-initialised by the caller (values are >= 0); results are combined with atomic max so
+ * several calls may accumulate into the same maxima. */
+int mgb_flatfield_maxima_generic(const void* tiles, int dtype, int64_t C, int64_t P, int64_t HW,
+                                 int K, const double* flat, const double* dark, double* maxima,
+                                 void* stream);
+/* Pass 2 preparation: per-position fast-path coefficients gain[k,p], bias[k,p] (float64) from
+ * flat, dark and the (all-reduced) maxima.  The apply kernel evaluates one FMA per pixel,
+ * s = (2^20 + x) * gain + bias, whose mantissa holds floor(v) in its high word and frac(v) in
+ * its low word; pixels within 2^-24 of an integer (or with unusable coefficients, flagged
+ * NaN here) are recomputed with the reference's exact operation order. */
+int mgb_flatfield_tables(const double* flat, const double* dark, int K, int64_t HW,
+                         const double* maxima, double* gain, double* bias, void* stream);
+/* Pass 2: flat-field apply fused with the stitch (read 2 B, write 2*phi B per tile pixel).
+ * With overlap = 0 and R = Cc = 1 this is flat-field alone.  uint16 only; needs W % 8 == 0,
+ * (Cc*(W-overlap)) % 8 == 0 and 16-byte aligned base pointers, else MGB_EALIGN (the caller
+ * then uses mgb_flatfield_apply_generic + mgb_stitch). */
+int mgb_flatfield_stitch_u16(const uint16_t* tiles, uint16_t* image, int64_t C, int64_t T,
+                             int64_t R, int64_t Cc, int64_t H, int64_t W, int64_t overlap, int K,
+                             const double* flat, const double* dark, const double* gain,
+                             const double* bias, const double* maxima, void* stream);
+/* Any-dtype exact flat-field apply in tile layout (no stitch): out[i] = cast(v(x[i])). */
+int mgb_flatfield_apply_generic(const void* tiles, void* out, int dtype, int64_t C, int64_t P,
+                                int64_t HW, int K, const double* flat, const double* dark,
+                                const double* maxima, void* stream);
+
+/* ---- F3: bounding boxes, reference src/magnify/utils.py:55-80 and the callers' round() -----
+ * boxes[i] = (top, left) of bounding_box(round(x[i]), round(y[i]), L, W, H) with Python's
+ * round-half-even (find.py:163-164,328-329,371-372,574-575,595-596).  rel (nullable) receives
+ * (round(y) - top, round(x) - left), the mask centre of find.py:380-381. */
+int mgb_bounding_boxes(const double* x, const double* y, int64_t n, int L, int64_t W, int64_t H,
+                       int32_t* boxes, int32_t* rel, void* stream);
+
+/* ---- F4 (+R): ROI gather, reference find.py:160-169, 324-334, 370-377, 589-602 -------------
+ * roi[m,c,t] = image[c,t, top:top+L, left:left+L] for any itemsize in {1,2,4,8}. */
+int mgb_roi_gather(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
+                   const int32_t* boxes, int64_t M, int L, void* roi, void* stream);
+/* Gather fused with the masked reductions the consumers run (identify.py:76-80,
+ * filter.py:21-22,51, README.md:21-22): uint16 only.  mask_t (T) int32 maps each timepoint to
+ * its mask timestep in fg/bg (M, Tm, L, L) (beads: all 0, find.py:585-586; chip: the source
+ * search timestep, find.py:151,172-173).  roi may be NULL (summaries only).  stats (M,C,T,6)
+ * float64: exact integer sums, mean = sum / count (NaN for an empty mask, like nanmean). */
+int mgb_roi_gather_stats_u16(const uint16_t* image, int64_t C, int64_t T, int64_t H, int64_t W,
+                             const int32_t* boxes, const int32_t* mask_t, int64_t Tm,
+                             const uint8_t* fg, const uint8_t* bg, int64_t M, int L,
+                             uint16_t* roi, double* stats, void* stream);
+/* Exact masked median per (m,c,t) of a uint16 roi (M,C,T,L,L) (identify.py:79, filter.py:21-22):
+ * mean of the two middle values for even counts, NaN for an empty mask, as np.nanmedian. */
+int mgb_roi_median_u16(const uint16_t* roi, int64_t M, int64_t C, int64_t T, int L,
+                       const int32_t* mask_t, int64_t Tm, const uint8_t* mask, double* median,
+                       void* stream);
+
+/* ---- F8: chip masks, reference utils.py:30-52 through find.py:380-400 ----------------------
+ * fg[m] = disc(radius r_fg[m]), bg[m] = annulus(r_inner < d <= r_outer) centred on rel[m] =
+ * (y_rel, x_rel); cv.circle(thickness=-1) == {dx^2 + dy^2 <= r^2}.  counts (M,2) int32
+ * (nullable) receives the fg/bg pixel counts. */
+int mgb_chip_masks(const int32_t* rel, const int32_t* r_fg, int r_inner, int r_outer, int64_t M,
+                   int L, uint8_t* fg, uint8_t* bg, int32_t* counts, void* stream);
+
+/* ---- F5-F7: bead masks, reference utils.py:380-465 and find.py:561-586 ---------------------
+ * HOST helper: hw[0..r] = row half-widths of filled_circle_points(r) (utils.py:398-430). */
+int mgb_disc_halfwidths(int r, int32_t* host_hw);
+/* labels (H, W) int32: -1 none, i sole owner, -2 shared (utils.py:380-395).  beads (M,3) int32
+ * rows (row, col, radius >= 1); hw (rmax+1, rmax+1) int32 table, row r = halfwidths of radius r. */
+int mgb_bead_labels(const int32_t* beads, int64_t M, int64_t H, int64_t W, const int32_t* hw,
+                    int rmax, int32_t* labels, void* stream);
+/* fg[m] = (labels[box m] == m), bg[m] = (labels[box m] == -1)  (find.py:580-584); boxes (M,2). */
+int mgb_bead_masks(const int32_t* labels, int64_t H, int64_t W, const int32_t* boxes, int64_t M,
+                   int L, uint8_t* fg, uint8_t* bg, int32_t* counts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAGNIFY_B200_H */

@@ -1,0 +1,204 @@
+// F5-F8: per-ROI foreground / background masks, hand-written for sm_100a.
+// Reference: src/magnify/utils.py:30-52 (circle, annulus), 380-465 (circle_labels,
+// filled_circle_points, circle_points); call sites find.py:380-400 (chip), 561-586 (beads).
+#include "common.cuh"
+
+namespace mgb {
+
+// ---- F8: chip masks ------------------------------------------------------------------------
+// cv.circle(thickness=-1) with integer centre and radius r is {dx^2 + dy^2 <= r^2} clipped to
+// the canvas (pinned against cv2 4.13.0 by tests/test_oracle_geometry.py and
+// tests/golden/masks_cv.npz); annulus = outer & ~inner.
+__global__ void __launch_bounds__(kThreads)
+chip_masks_kernel(const int32_t* __restrict__ rel, const int32_t* __restrict__ r_fg, int r_inner,
+                  int r_outer, int L, uint8_t* __restrict__ fg, uint8_t* __restrict__ bg,
+                  int32_t* __restrict__ counts) {
+  __shared__ uint32_t red[2][kThreads / 32];
+  const int64_t m = blockIdx.x;
+  const int cy = rel[2 * m], cx = rel[2 * m + 1];
+  const long long rf = r_fg[m];
+  const long long rf2 = rf < 0 ? -1 : rf * rf;
+  const long long ri2 = r_inner < 0 ? -1 : (long long)r_inner * r_inner;
+  const long long ro2 = r_outer < 0 ? -1 : (long long)r_outer * r_outer;
+  uint8_t* f = fg + m * (int64_t)L * L;
+  uint8_t* b = bg + m * (int64_t)L * L;
+  uint32_t nf = 0, nb = 0;
+  const int total = L * L;
+  for (int i = threadIdx.x; i < total; i += kThreads) {
+    const int row = i / L, col = i - row * L;
+    const long long dy = row - cy, dx = col - cx;
+    const long long d2 = dx * dx + dy * dy;
+    const bool isf = d2 <= rf2;
+    const bool isb = (d2 <= ro2) && !(d2 <= ri2);
+    f[i] = isf;
+    b[i] = isb;
+    nf += isf;
+    nb += isb;
+  }
+  if (counts) {
+    nf = __reduce_add_sync(0xffffffffu, nf);
+    nb = __reduce_add_sync(0xffffffffu, nb);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = nf; red[1][threadIdx.x >> 5] = nb; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t a = 0, c = 0;
+      for (int i = 0; i < kThreads / 32; ++i) { a += red[0][i]; c += red[1][i]; }
+      counts[2 * m] = (int32_t)a;
+      counts[2 * m + 1] = (int32_t)c;
+    }
+  }
+}
+
+// ---- F6: bead label raster -----------------------------------------------------------------
+// The first disc to touch a pixel claims it with a CAS on -1; every later touch stores -2.
+// Once a pixel left -1 no CAS can succeed again, so the result is order independent and equals
+// the serial loop of utils.py:384-393.
+__global__ void __launch_bounds__(128)
+bead_labels_kernel(const int32_t* __restrict__ beads, int64_t H, int64_t W,
+                   const int32_t* __restrict__ hw, int rmax, int32_t* __restrict__ labels) {
+  const int64_t i = blockIdx.x;
+  const int cy = beads[3 * i], cx = beads[3 * i + 1], r = beads[3 * i + 2];
+  if (r < 1 || r > rmax) return;
+  const int32_t* hwr = hw + (int64_t)r * (rmax + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int d = -r + warp; d <= r; d += 4) {
+    const long long yy = (long long)cy + d;
+    if (yy < 0 || yy >= H) continue;
+    const int half = hwr[d < 0 ? -d : d];
+    for (int e = -half + lane; e <= half; e += 32) {
+      const long long xx = (long long)cx + e;
+      if (xx < 0 || xx >= W) continue;
+      int32_t* cell = labels + yy * W + xx;
+      const int old = atomicCAS(cell, -1, (int)i);
+      if (old != -1) atomicExch(cell, -2);
+    }
+  }
+}
+
+// ---- F7: bead masks ------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+bead_masks_kernel(const int32_t* __restrict__ labels, int64_t W, const int32_t* __restrict__ boxes,
+                  int L, uint8_t* __restrict__ fg, uint8_t* __restrict__ bg,
+                  int32_t* __restrict__ counts) {
+  __shared__ uint32_t red[2][kThreads / 32];
+  const int64_t m = blockIdx.x;
+  const int top = boxes[2 * m], left = boxes[2 * m + 1];
+  const int32_t* src = labels + (int64_t)top * W + left;
+  uint8_t* f = fg + m * (int64_t)L * L;
+  uint8_t* b = bg + m * (int64_t)L * L;
+  uint32_t nf = 0, nb = 0;
+  const int total = L * L;
+  for (int i = threadIdx.x; i < total; i += kThreads) {
+    const int row = i / L, col = i - row * L;
+    const int lab = __ldg(src + (int64_t)row * W + col);
+    const bool isf = lab == (int)m;   // find.py:582
+    const bool isb = lab == -1;       // find.py:584
+    f[i] = isf;
+    b[i] = isb;
+    nf += isf;
+    nb += isb;
+  }
+  if (counts) {
+    nf = __reduce_add_sync(0xffffffffu, nf);
+    nb = __reduce_add_sync(0xffffffffu, nb);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = nf; red[1][threadIdx.x >> 5] = nb; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t a = 0, c = 0;
+      for (int i = 0; i < kThreads / 32; ++i) { a += red[0][i]; c += red[1][i]; }
+      counts[2 * m] = (int32_t)a;
+      counts[2 * m + 1] = (int32_t)c;
+    }
+  }
+}
+
+}  // namespace mgb
+
+using namespace mgb;
+
+extern "C" {
+
+int mgb_chip_masks(const int32_t* rel, const int32_t* r_fg, int r_inner, int r_outer, int64_t M,
+                   int L, uint8_t* fg, uint8_t* bg, int32_t* counts, void* stream) {
+  if (M < 0 || L <= 0 || L > 4096) return MGB_EINVAL;
+  if (M == 0) return MGB_OK;
+  if (M > INT32_MAX) return MGB_EUNSUPPORTED;
+  if (!rel || !r_fg || !fg || !bg) return MGB_EINVAL;
+  chip_masks_kernel<<<(unsigned)M, kThreads, 0, (cudaStream_t)stream>>>(rel, r_fg, r_inner, r_outer,
+                                                                       L, fg, bg, counts);
+  MGB_CUDA_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+// Host restatement of the reference's perimeter walk (utils.py:433-465): start at (0, -r), emit
+// the 8 mirror images of each octant point, step right while inside the circle, otherwise step
+// in (diagonally).  filled_circle_points (utils.py:398-430) fills every row between its
+// outermost perimeter pixels, so the disc is the span |dcol| <= hw[|drow|].
+int mgb_disc_halfwidths(int r, int32_t* host_hw) {
+  if (r < 1 || !host_hw) return MGB_EINVAL;
+  for (int i = 0; i <= r; ++i) host_hw[i] = 0;
+  auto mark = [&](long long row, long long col) {
+    const long long ar = row < 0 ? -row : row, ac = col < 0 ? -col : col;
+    if (ac > host_hw[ar]) host_hw[ar] = (int32_t)ac;
+  };
+  mark(0, -r); mark(-r, 0); mark(0, r); mark(r, 0);
+  long long a = 1, b = -(long long)r;
+  const long long r2 = (long long)r * r;
+  while (a < -b) {
+    mark(a, b); mark(b, a);   // the other six mirror images have the same (|row|, |col|)
+    if (a * a + b * b - r2 <= 0) {
+      ++a;
+    } else {
+      ++b;
+      ++a;
+    }
+  }
+  if (b == -a) mark(a, b);
+  return MGB_OK;
+}
+
+int mgb_bead_labels(const int32_t* beads, int64_t M, int64_t H, int64_t W, const int32_t* hw,
+                    int rmax, int32_t* labels, void* stream) {
+  if (M < 0 || H <= 0 || W <= 0 || rmax < 0) return MGB_EINVAL;
+  if (!labels) return MGB_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  MGB_CUDA_TRY(cudaMemsetAsync(labels, 0xff, (size_t)H * W * sizeof(int32_t), st));  // -1
+  if (M == 0) return MGB_OK;
+  if (M > INT32_MAX) return MGB_EUNSUPPORTED;
+  if (!beads || !hw) return MGB_EINVAL;
+  bead_labels_kernel<<<(unsigned)M, 128, 0, st>>>(beads, H, W, hw, rmax, labels);
+  MGB_CUDA_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+int mgb_bead_masks(const int32_t* labels, int64_t H, int64_t W, const int32_t* boxes, int64_t M,
+                   int L, uint8_t* fg, uint8_t* bg, int32_t* counts, void* stream) {
+  if (M < 0 || L <= 0 || L > 4096 || H < L || W < L) return MGB_EINVAL;
+  if (M == 0) return MGB_OK;
+  if (M > INT32_MAX) return MGB_EUNSUPPORTED;
+  if (!labels || !boxes || !fg || !bg) return MGB_EINVAL;
+  bead_masks_kernel<<<(unsigned)M, kThreads, 0, (cudaStream_t)stream>>>(labels, W, boxes, L, fg, bg,
+                                                                       counts);
+  MGB_CUDA_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+int mgb_abi_version(void) { return MGB_ABI_VERSION; }
+
+static unsigned long long g_launches = 0;
+void mgb_count_launch_(void) { __atomic_add_fetch(&g_launches, 1ULL, __ATOMIC_RELAXED); }
+int64_t mgb_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+const char* mgb_error_string(int code) {
+  switch (code) {
+    case MGB_OK: return "ok";
+    case MGB_EINVAL: return "invalid argument";
+    case MGB_EALIGN: return "pointer or pitch not aligned for the vectorised path";
+    case MGB_EUNSUPPORTED: return "shape or dtype not supported by this build";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "unknown magnify_b200 error";
+}
+
+}  // extern "C"

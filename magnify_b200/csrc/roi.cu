@@ -1,0 +1,353 @@
+// F3 / F4 / R: bounding boxes, ROI gather and masked per-ROI reductions, hand-written for
+// sm_100a.  Reference: src/magnify/utils.py:55-80 (bounding_box), find.py:160-169, 324-334,
+// 370-377, 589-602 (crop loops), identify.py:76-80 and filter.py:21-22,51 (reductions).
+//
+// HBM layout: image (C,T,H,W), roi (M,C,T,L,L), masks (M,Tm,L,L) uint8, stats (M,C,T,6) f64.
+// One CTA copies one ROI (m,c,t); CTAs are numbered in roi memory order so consecutive CTAs
+// write consecutive 2*L*L-byte blocks.  Reductions ride on the copy: the pixels are already in
+// registers, the masks (shared by all channels / copy-forward timepoints) come from L2.
+#include "common.cuh"
+
+namespace mgb {
+
+// ---- F3 ------------------------------------------------------------------------------------
+__device__ __forceinline__ void box_1d(long long c, int L, long long size, long long* lo) {
+  long long a = c - L / 2;
+  long long b = c + (L + 1) / 2;   // ceildiv(L, 2), utils.py:55-57
+  if (a < 0) { b -= a; a = 0; }
+  if (b > size) { a -= b - size; }
+  *lo = a;
+}
+
+__global__ void __launch_bounds__(kThreads)
+bounding_boxes_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n, int L,
+                      int64_t W, int64_t H, int32_t* __restrict__ boxes, int32_t* __restrict__ rel) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // Python round() on a float64 is round-half-to-even == cvt.rni.
+  const long long xr = __double2ll_rn(x[i]);
+  const long long yr = __double2ll_rn(y[i]);
+  long long top, left;
+  box_1d(yr, L, H, &top);
+  box_1d(xr, L, W, &left);
+  boxes[2 * i] = (int32_t)top;
+  boxes[2 * i + 1] = (int32_t)left;
+  if (rel) {
+    rel[2 * i] = (int32_t)(yr - top);
+    rel[2 * i + 1] = (int32_t)(xr - left);
+  }
+}
+
+// ---- F4 (+R) -------------------------------------------------------------------------------
+struct GatherParams {
+  const uint16_t* image;   // 16-bit units
+  uint16_t* roi;           // may be null when STATS
+  int64_t C, T, H, W;      // W in 16-bit units
+  const int32_t* boxes;    // (M,T,2) in elements
+  int unit;                // 16-bit units per element (itemsize / 2)
+  int L;                   // roi side in elements
+  int Lu;                  // roi row length in 16-bit units
+  uint32_t half;           // Lu / 2 words per row
+  uint32_t magic;          // ceil(2^32 / half)
+  uint32_t words;          // L * half
+  const int32_t* mask_t;
+  int64_t Tm;
+  const uint8_t* fg;
+  const uint8_t* bg;
+  double* stats;
+};
+
+__device__ __forceinline__ uint64_t block_sum_u32(uint32_t v, uint32_t* smem) {
+  v = __reduce_add_sync(0xffffffffu, v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) smem[w] = v;
+  __syncthreads();
+  uint64_t s = 0;
+#pragma unroll
+  for (int i = 0; i < kThreads / 32; ++i) s += smem[i];
+  return s;
+}
+
+// Word path: 2 x 16-bit units per thread step (Lu even).  ALIGNED: source words 4-byte aligned.
+template <bool STATS>
+__global__ void __launch_bounds__(kThreads) roi_gather_words_kernel(const GatherParams p) {
+  __shared__ uint32_t red[4][kThreads / 32];
+  const int64_t n = blockIdx.x;                 // (m*C + c)*T + t
+  const int64_t t = n % p.T;
+  const int64_t c = (n / p.T) % p.C;
+  const int64_t m = n / (p.T * p.C);
+  const int32_t top = p.boxes[(m * p.T + t) * 2];
+  const int32_t left = p.boxes[(m * p.T + t) * 2 + 1];
+  const uint16_t* src = p.image + ((c * p.T + t) * p.H + top) * p.W + (int64_t)left * p.unit;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 3u) == 0) && ((p.W & 1) == 0);
+  uint32_t* dst = p.roi ? reinterpret_cast<uint32_t*>(p.roi + n * (int64_t)p.L * p.Lu) : nullptr;
+  const uint16_t* fgp = nullptr;
+  const uint16_t* bgp = nullptr;
+  if constexpr (STATS) {
+    const int64_t mo = (m * p.Tm + p.mask_t[t]) * (int64_t)p.L * p.L;
+    fgp = reinterpret_cast<const uint16_t*>(p.fg + mo);
+    bgp = reinterpret_cast<const uint16_t*>(p.bg + mo);
+  }
+  uint32_t s_fg = 0, s_bg = 0, n_fg = 0, n_bg = 0;
+  for (uint32_t w = threadIdx.x; w < p.words; w += kThreads) {
+    const uint32_t row = __umulhi(w, p.magic);
+    const uint32_t col = w - row * p.half;
+    const uint16_t* sp = src + (int64_t)row * p.W + 2 * col;
+    uint32_t v;
+    if (aligned) {
+      v = __ldg(reinterpret_cast<const uint32_t*>(sp));
+    } else {
+      v = (uint32_t)__ldg(sp) | ((uint32_t)__ldg(sp + 1) << 16);
+    }
+    if (dst) dst[w] = v;
+    if constexpr (STATS) {
+      const uint32_t mf = __ldg(fgp + w);
+      const uint32_t mb = __ldg(bgp + w);
+      s_fg = __dp2a_lo(v, mf, s_fg);
+      s_bg = __dp2a_lo(v, mb, s_bg);
+      n_fg = __dp2a_lo(0x00010001u, mf, n_fg);
+      n_bg = __dp2a_lo(0x00010001u, mb, n_bg);
+    }
+  }
+  if constexpr (STATS) {
+    const uint64_t a = block_sum_u32(s_fg, red[0]);
+    const uint64_t b = block_sum_u32(s_bg, red[1]);
+    const uint64_t na = block_sum_u32(n_fg, red[2]);
+    const uint64_t nb = block_sum_u32(n_bg, red[3]);
+    if (threadIdx.x == 0) {
+      double* o = p.stats + n * 6;
+      o[0] = (double)na;
+      o[1] = (double)nb;
+      o[2] = (double)a;
+      o[3] = (double)b;
+      o[4] = (double)a / (double)na;   // 0/0 -> NaN, like nanmean over an empty mask
+      o[5] = (double)b / (double)nb;
+    }
+  }
+}
+
+// Scalar path: any unit type, any L (odd L, itemsize 1).
+template <typename U, bool STATS>
+__global__ void __launch_bounds__(kThreads)
+roi_gather_scalar_kernel(const U* __restrict__ image, U* __restrict__ roi, int64_t C, int64_t T,
+                         int64_t H, int64_t W, const int32_t* __restrict__ boxes, int L,
+                         const int32_t* __restrict__ mask_t, int64_t Tm,
+                         const uint8_t* __restrict__ fg, const uint8_t* __restrict__ bg,
+                         double* __restrict__ stats) {
+  __shared__ uint32_t red[4][kThreads / 32];
+  const int64_t n = blockIdx.x;
+  const int64_t t = n % T;
+  const int64_t c = (n / T) % C;
+  const int64_t m = n / (T * C);
+  const int32_t top = boxes[(m * T + t) * 2];
+  const int32_t left = boxes[(m * T + t) * 2 + 1];
+  const U* src = image + ((c * T + t) * H + top) * W + left;
+  U* dst = roi ? roi + n * (int64_t)L * L : nullptr;
+  const uint8_t* fgp = nullptr;
+  const uint8_t* bgp = nullptr;
+  if constexpr (STATS) {
+    const int64_t mo = (m * Tm + mask_t[t]) * (int64_t)L * L;
+    fgp = fg + mo;
+    bgp = bg + mo;
+  }
+  uint32_t s_fg = 0, s_bg = 0, n_fg = 0, n_bg = 0;
+  const int total = L * L;
+  for (int i = threadIdx.x; i < total; i += kThreads) {
+    const int row = i / L, col = i - row * L;
+    const U v = src[(int64_t)row * W + col];
+    if (dst) dst[i] = v;
+    if constexpr (STATS) {
+      const uint32_t f = fgp[i], b = bgp[i];
+      s_fg += f ? (uint32_t)v : 0u;
+      s_bg += b ? (uint32_t)v : 0u;
+      n_fg += f ? 1u : 0u;
+      n_bg += b ? 1u : 0u;
+    }
+  }
+  if constexpr (STATS) {
+    const uint64_t a = block_sum_u32(s_fg, red[0]);
+    const uint64_t b = block_sum_u32(s_bg, red[1]);
+    const uint64_t na = block_sum_u32(n_fg, red[2]);
+    const uint64_t nb = block_sum_u32(n_bg, red[3]);
+    if (threadIdx.x == 0) {
+      double* o = stats + n * 6;
+      o[0] = (double)na; o[1] = (double)nb; o[2] = (double)a; o[3] = (double)b;
+      o[4] = (double)a / (double)na; o[5] = (double)b / (double)nb;
+    }
+  }
+}
+
+// ---- masked median (exact) -----------------------------------------------------------------
+// One CTA per ROI.  Every thread keeps its pixels as 32-bit keys (masked-out -> 0xffffffff) in
+// registers; the k-th smallest is found by a 16-step binary search on the value with one block
+// count per step.  NPT = keys per thread.
+template <int NPT>
+__global__ void __launch_bounds__(kThreads)
+roi_median_u16_kernel(const uint16_t* __restrict__ roi, int64_t C, int64_t T, int L,
+                      const int32_t* __restrict__ mask_t, int64_t Tm,
+                      const uint8_t* __restrict__ mask, double* __restrict__ median) {
+  __shared__ uint32_t red[2][kThreads / 32];
+  const int64_t n = blockIdx.x;
+  const int64_t t = n % T;
+  const int64_t m = n / (T * C);
+  const int total = L * L;
+  const uint16_t* src = roi + n * (int64_t)total;
+  const uint8_t* mk = mask + (m * Tm + mask_t[t]) * (int64_t)total;
+  uint32_t key[NPT];
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int i = 0; i < NPT; ++i) {
+    const int idx = threadIdx.x + i * kThreads;
+    key[i] = 0xffffffffu;
+    if (idx < total && mk[idx]) { key[i] = src[idx]; ++cnt; }
+  }
+  int buf = 0;
+  auto block_count = [&](uint32_t c) -> uint32_t {
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) red[buf][threadIdx.x >> 5] = c;
+    __syncthreads();
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < kThreads / 32; ++i) s += red[buf][i];
+    buf ^= 1;
+    return s;
+  };
+  const uint32_t nvalid = block_count(cnt);
+  if (nvalid == 0) {
+    if (threadIdx.x == 0) median[n] = __longlong_as_double(0x7ff8000000000000LL);
+    return;
+  }
+  const uint32_t k1 = (nvalid - 1) >> 1;  // lower middle (0-based)
+  uint32_t lo = 0, hi = 65535;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) c += (key[i] <= mid) ? 1u : 0u;
+    const uint32_t tot = block_count(c);
+    if (tot >= k1 + 1) hi = mid; else lo = mid + 1;
+  }
+  const uint32_t v1 = lo;
+  uint32_t v2 = v1;
+  if ((nvalid & 1u) == 0) {
+    // upper middle: v1 again if enough copies, else the smallest value above v1
+    uint32_t c = 0, mn = 0xffffffffu;
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) {
+      c += (key[i] <= v1) ? 1u : 0u;
+      if (key[i] > v1) mn = min(mn, key[i]);
+    }
+    const uint32_t tot = block_count(c);
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    if ((threadIdx.x & 31) == 0) red[buf][threadIdx.x >> 5] = mn;
+    __syncthreads();
+    uint32_t g = 0xffffffffu;
+#pragma unroll
+    for (int i = 0; i < kThreads / 32; ++i) g = min(g, red[buf][i]);
+    if (tot < k1 + 2) v2 = g;
+  }
+  if (threadIdx.x == 0) median[n] = 0.5 * ((double)v1 + (double)v2);
+}
+
+static uint32_t magic_for(uint32_t d) { return (uint32_t)((0x100000000ULL + d - 1) / d); }
+
+}  // namespace mgb
+
+using namespace mgb;
+
+extern "C" {
+
+int mgb_bounding_boxes(const double* x, const double* y, int64_t n, int L, int64_t W, int64_t H,
+                       int32_t* boxes, int32_t* rel, void* stream) {
+  if (n < 0 || L <= 0 || W < L || H < L || W > INT32_MAX || H > INT32_MAX) return MGB_EINVAL;
+  if (n == 0) return MGB_OK;
+  if (!x || !y || !boxes) return MGB_EINVAL;
+  bounding_boxes_kernel<<<(unsigned)ceil_div(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      x, y, n, L, W, H, boxes, rel);
+  MGB_CUDA_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+static int gather_common(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
+                         const int32_t* boxes, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
+                         const uint8_t* bg, int64_t M, int L, void* roi, double* stats,
+                         cudaStream_t st) {
+  const bool with_stats = stats != nullptr;
+  if (M < 0 || C < 0 || T < 0 || L <= 0 || H < L || W < L) return MGB_EINVAL;
+  if (itemsize != 1 && itemsize != 2 && itemsize != 4 && itemsize != 8) return MGB_EINVAL;
+  if (L > 4096) return MGB_EUNSUPPORTED;
+  const int64_t n_roi = M * C * T;
+  if (n_roi == 0) return MGB_OK;
+  if (n_roi > INT32_MAX) return MGB_EUNSUPPORTED;
+  if (!image || !boxes || (!roi && !with_stats)) return MGB_EINVAL;
+  if (with_stats && (!mask_t || !fg || !bg || Tm <= 0 || itemsize != 2)) return MGB_EINVAL;
+  const int unit = itemsize / 2;
+  const int Lu = L * (unit ? unit : 1);
+  const bool word_path = itemsize >= 2 && (Lu % 2 == 0) &&
+                         ((reinterpret_cast<uintptr_t>(image) & 3u) == 0) &&
+                         (!roi || (reinterpret_cast<uintptr_t>(roi) & 3u) == 0) &&
+                         (!with_stats || ((reinterpret_cast<uintptr_t>(fg) & 1u) == 0 &&
+                                          (reinterpret_cast<uintptr_t>(bg) & 1u) == 0));
+  if (word_path) {
+    GatherParams p{};
+    p.image = (const uint16_t*)image; p.roi = (uint16_t*)roi;
+    p.C = C; p.T = T; p.H = H; p.W = W * unit; p.boxes = boxes; p.unit = unit; p.L = L; p.Lu = Lu;
+    p.half = (uint32_t)(Lu / 2); p.magic = magic_for(p.half); p.words = (uint32_t)L * p.half;
+    p.mask_t = mask_t; p.Tm = Tm; p.fg = fg; p.bg = bg; p.stats = stats;
+    if (with_stats) roi_gather_words_kernel<true><<<(unsigned)n_roi, kThreads, 0, st>>>(p);
+    else roi_gather_words_kernel<false><<<(unsigned)n_roi, kThreads, 0, st>>>(p);
+  } else if (with_stats) {
+    roi_gather_scalar_kernel<uint16_t, true><<<(unsigned)n_roi, kThreads, 0, st>>>(
+        (const uint16_t*)image, (uint16_t*)roi, C, T, H, W, boxes, L, mask_t, Tm, fg, bg, stats);
+  } else {
+    switch (itemsize) {
+      case 1: roi_gather_scalar_kernel<uint8_t, false><<<(unsigned)n_roi, kThreads, 0, st>>>((const uint8_t*)image, (uint8_t*)roi, C, T, H, W, boxes, L, nullptr, 0, nullptr, nullptr, nullptr); break;
+      case 2: roi_gather_scalar_kernel<uint16_t, false><<<(unsigned)n_roi, kThreads, 0, st>>>((const uint16_t*)image, (uint16_t*)roi, C, T, H, W, boxes, L, nullptr, 0, nullptr, nullptr, nullptr); break;
+      case 4: roi_gather_scalar_kernel<uint32_t, false><<<(unsigned)n_roi, kThreads, 0, st>>>((const uint32_t*)image, (uint32_t*)roi, C, T, H, W, boxes, L, nullptr, 0, nullptr, nullptr, nullptr); break;
+      default: roi_gather_scalar_kernel<uint64_t, false><<<(unsigned)n_roi, kThreads, 0, st>>>((const uint64_t*)image, (uint64_t*)roi, C, T, H, W, boxes, L, nullptr, 0, nullptr, nullptr, nullptr); break;
+    }
+  }
+  MGB_CUDA_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+int mgb_roi_gather(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
+                   const int32_t* boxes, int64_t M, int L, void* roi, void* stream) {
+  if (!roi && M * C * T > 0) return MGB_EINVAL;
+  return gather_common(image, C, T, H, W, itemsize, boxes, nullptr, 0, nullptr, nullptr, M, L, roi,
+                       nullptr, (cudaStream_t)stream);
+}
+
+int mgb_roi_gather_stats_u16(const uint16_t* image, int64_t C, int64_t T, int64_t H, int64_t W,
+                             const int32_t* boxes, const int32_t* mask_t, int64_t Tm,
+                             const uint8_t* fg, const uint8_t* bg, int64_t M, int L,
+                             uint16_t* roi, double* stats, void* stream) {
+  if (!stats && M * C * T > 0) return MGB_EINVAL;
+  return gather_common(image, C, T, H, W, 2, boxes, mask_t, Tm, fg, bg, M, L, roi, stats,
+                       (cudaStream_t)stream);
+}
+
+int mgb_roi_median_u16(const uint16_t* roi, int64_t M, int64_t C, int64_t T, int L,
+                       const int32_t* mask_t, int64_t Tm, const uint8_t* mask, double* median,
+                       void* stream) {
+  if (M < 0 || C < 0 || T < 0 || L <= 0) return MGB_EINVAL;
+  const int64_t n_roi = M * C * T;
+  if (n_roi == 0) return MGB_OK;
+  if (n_roi > INT32_MAX) return MGB_EUNSUPPORTED;
+  if (!roi || !mask_t || !mask || !median || Tm <= 0) return MGB_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int npt = (int)ceil_div((int64_t)L * L, kThreads);
+#define MGB_MED(N) roi_median_u16_kernel<N><<<(unsigned)n_roi, kThreads, 0, st>>>(roi, C, T, L, mask_t, Tm, mask, median)
+  if (npt <= 4) MGB_MED(4);
+  else if (npt <= 10) MGB_MED(10);
+  else if (npt <= 21) MGB_MED(21);
+  else if (npt <= 40) MGB_MED(40);
+  else if (npt <= 64) MGB_MED(64);
+  else if (npt <= 100) MGB_MED(100);
+  else return MGB_EUNSUPPORTED;   // L > 160
+#undef MGB_MED
+  MGB_CUDA_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,249 @@
+"""Drivers of the hot path over a (channel x time) stack on one GPU (one process per GPU).
+
+`QuantifyPlan` holds everything that is constant over a run (flat/dark tables, marker centres,
+boxes, masks) and runs
+
+    tiles --flat-field pass 1 (max)--> [all-reduce MAX] --pass 2 fused with stitch--> image
+          --ROI gather fused with masked reductions--> roi, stats
+
+either on tiles already resident in HBM (`run_device`) or from pinned host buffers with the
+host->device copies of timepoint t+1 overlapped with the max pass of timepoint t and the
+device->host copies of the results overlapped with the gather (`run_host`).
+
+Time sharding: every rank owns a contiguous block of timepoints; the
+only collectives are the all-reduce of the two flat-field maxima and the final gather of the
+per-marker summaries (`magnify_b200.dist`).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def copy_forward_sources(num_times: int, search_timesteps) -> np.ndarray:
+    """Source timestep of each timestep's centres and masks in ButtonFinder (find.py:143-151):
+    the latest search timestep <= t, or the first search timestep for earlier t."""
+    search = sorted({int(s) for s in np.atleast_1d(search_timesteps)})
+    if not search:
+        raise ValueError("at least one search timestep is required")
+    if search[0] < 0 or search[-1] >= num_times:
+        raise ValueError("search timestep out of range")
+    src = np.empty(num_times, dtype=np.int64)
+    for t in range(num_times):
+        if t < search[0]:
+            src[t] = search[0]
+        else:
+            src[t] = max(s for s in search if s <= t)
+    return src
+
+
+@dataclass
+class QuantifyResult:
+    image: Optional[torch.Tensor]      # (C,T,Him,Wim)
+    roi: Optional[torch.Tensor]        # (M,C,T,L,L)
+    fg: torch.Tensor                   # (M,Tm,L,L) uint8
+    bg: torch.Tensor                   # (M,Tm,L,L) uint8
+    mask_t: torch.Tensor               # (T,) int32 index into Tm
+    boxes: torch.Tensor                # (M,T,2) int32
+    stats: torch.Tensor                # (M,C,T,6) float64
+    maxima: Optional[torch.Tensor] = None
+    timings: dict = field(default_factory=dict)
+
+
+class QuantifyPlan:
+    """Static state of one run: tile geometry, flat-field plan, marker boxes and masks."""
+
+    def __init__(self, tile_shape, overlap: int, roi_length: int, flatfield=1.0, darkfield=0.0,
+                 device="cuda", group=None):
+        self.tile_shape = tuple(int(s) for s in tile_shape)
+        c, t, r, cc, h, w = self.tile_shape
+        ops.check_overlap(overlap, h, w)
+        self.overlap = int(overlap)
+        self.roi_length = int(roi_length)
+        self.device = torch.device(device)
+        self.group = group
+        self.image_shape = ops.stitched_shape(self.tile_shape, overlap)
+        self.ff = ops.FlatFieldPlan(self.tile_shape, flatfield, darkfield, device=self.device)
+        self.boxes = None
+        self.fg = self.bg = self.mask_t = None
+
+    # -- markers ------------------------------------------------------------------------------
+    def set_chip_markers(self, x, y, fg_radius, chamber_radius: int, max_button_radius: int,
+                         search_timesteps=0):
+        """Chip buttons (ButtonFinder, find.py:55-203 with the centre search done elsewhere).
+
+        x, y: (M, T) float64 centres in image coordinates for every timepoint (non-search
+        timepoints hold the copied-forward centres, find.py:156-157,174-175); fg_radius
+        (M, Ts) int -- refined radius or max_button_radius per search timestep."""
+        c, t = self.tile_shape[:2]
+        dev = self.device
+        x = torch.as_tensor(np.asarray(x, dtype=np.float64)).to(dev).contiguous()
+        y = torch.as_tensor(np.asarray(y, dtype=np.float64)).to(dev).contiguous()
+        if x.dim() != 2 or x.shape[1] != t or x.shape != y.shape:
+            raise ValueError(f"x and y must have shape (M, {t})")
+        m = x.shape[0]
+        src = copy_forward_sources(t, search_timesteps)
+        search = sorted(set(src.tolist()))
+        fg_radius = np.asarray(fg_radius, dtype=np.int32).reshape(m, -1)
+        if fg_radius.shape[1] != len(search):
+            raise ValueError("fg_radius must have one column per search timestep")
+        him, wim = self.image_shape[-2:]
+        self.boxes, rel = ops.bounding_boxes(x, y, self.roi_length, wim, him, want_rel=True)
+        fgs, bgs = [], []
+        for k, ts in enumerate(search):
+            f, b = ops.chip_masks(rel[:, ts].contiguous(), torch.from_numpy(fg_radius[:, k].copy()).to(dev),
+                                  int(max_button_radius), int(chamber_radius), self.roi_length)
+            fgs.append(f)
+            bgs.append(b)
+        self.fg = torch.stack(fgs, 1).contiguous()
+        self.bg = torch.stack(bgs, 1).contiguous()
+        index = {ts: k for k, ts in enumerate(search)}
+        self.mask_t = torch.tensor([index[int(s)] for s in src], dtype=torch.int32, device=dev)
+        self.x, self.y = x, y
+        return self
+
+    def set_bead_markers(self, beads):
+        """Beads (BeadFinder, find.py:503-605): beads (M,3) rows (row, col, radius), constant
+        over time (find.py:543-550); fg/bg from the label raster (find.py:561-586)."""
+        c, t = self.tile_shape[:2]
+        dev = self.device
+        beads = np.asarray(beads, dtype=np.float64).reshape(-1, 3)
+        m = len(beads)
+        him, wim = self.image_shape[-2:]
+        x = torch.from_numpy(np.repeat(beads[:, 1:2], t, axis=1)).to(dev).contiguous()
+        y = torch.from_numpy(np.repeat(beads[:, 0:1], t, axis=1)).to(dev).contiguous()
+        self.boxes = ops.bounding_boxes(x, y, self.roi_length, wim, him)
+        beads_i = torch.from_numpy(beads.astype(np.int64).astype(np.int32)).to(dev)   # astype(int), find.py:561
+        self.labels = ops.bead_labels(beads_i, him, wim)
+        box0 = self.boxes[:, 0].contiguous() if t > 0 else torch.zeros((m, 2), dtype=torch.int32, device=dev)
+        fg, bg = ops.bead_masks(self.labels, box0, self.roi_length)
+        self.fg, self.bg = fg[:, None].contiguous(), bg[:, None].contiguous()
+        self.mask_t = torch.zeros(t, dtype=torch.int32, device=dev)
+        self.x, self.y = x, y
+        return self
+
+    # -- device-resident run ------------------------------------------------------------------
+    def run_device(self, tiles: torch.Tensor, want_roi: bool = True, image_out=None, roi_out=None,
+                   stats_out=None, record: Optional[list] = None) -> QuantifyResult:
+        """Whole hot path on tiles already in HBM (all launches on the current stream).
+
+        record: optional list that receives (stage, start_event, end_event) CUDA-event triples
+        recorded on the launching stream (bench.py's per-kernel timing)."""
+        if self.boxes is None:
+            raise RuntimeError("set_chip_markers / set_bead_markers must be called first")
+        if tuple(tiles.shape) != self.tile_shape:
+            raise ValueError(f"tiles have shape {tuple(tiles.shape)}, plan was built for {self.tile_shape}")
+        stream = torch.cuda.current_stream(self.device)
+
+        def stage(name, fn):
+            if record is None:
+                return fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            out = fn()
+            b.record(stream)
+            record.append((name, a, b))
+            return out
+
+        ff = self.ff
+        maxima = None
+        if not ff.identity:
+            maxima = stage("flatfield_max", lambda: ops.flatfield_maxima(tiles, ff))
+            if self.group is not None:
+                import torch.distributed as dist
+
+                stage("allreduce_max", lambda: dist.all_reduce(maxima, op=dist.ReduceOp.MAX, group=self.group))
+        image = stage("flatfield_stitch", lambda: ops.flatfield_stitch(tiles, overlap=self.overlap, plan=ff,
+                                                                       maxima=maxima, out=image_out))
+        roi, stats = stage("roi_gather_stats", lambda: ops.roi_gather_stats(
+            image, self.boxes, self.fg, self.bg, self.roi_length, mask_t=self.mask_t, want_roi=want_roi,
+            out_roi=roi_out, out_stats=stats_out))
+        return QuantifyResult(image, roi, self.fg, self.bg, self.mask_t, self.boxes, stats, maxima)
+
+
+class HostStagedRunner:
+    """Pinned-host -> HBM staging loop around a QuantifyPlan (the replacement of the reference's
+    dask-chunk reads at find.py:121,155,590 and zarr writes at stitch.py:45, find.py:201,604).
+
+    The host side owns pinned buffers: `tiles_host` (C,T,R,Cc,H,W) in, `image_host`, `roi_host`,
+    `stats_host` out.  One timepoint (all channels) is a chunk.  A copy stream moves chunk t+1
+    to the GPU while the compute stream runs flat-field pass 1 on chunk t; after the maxima
+    all-reduce, pass 2 + gather run per chunk and a second copy stream drains the results."""
+
+    def __init__(self, plan: QuantifyPlan, want_image: bool = True, want_roi: bool = True):
+        self.plan = plan
+        c, t, r, cc, h, w = plan.tile_shape
+        dev = plan.device
+        self.want_image, self.want_roi = want_image, want_roi
+        self.tiles_dev = torch.empty(plan.tile_shape, dtype=torch.uint16, device=dev)
+        self.image_dev = torch.empty(plan.image_shape, dtype=torch.uint16, device=dev)
+        m = plan.boxes.shape[0]
+        length = plan.roi_length
+        self.roi_dev = torch.empty((m, c, t, length, length), dtype=torch.uint16, device=dev) if want_roi else None
+        self.stats_dev = torch.empty((m, c, t, 6), dtype=torch.float64, device=dev)
+        self.h2d = torch.cuda.Stream(device=dev)
+        self.d2h = torch.cuda.Stream(device=dev)
+        self.h2d_bytes = self.tiles_dev.numel() * 2
+        self.d2h_bytes = self.stats_dev.numel() * 8
+        if want_image:
+            self.d2h_bytes += self.image_dev.numel() * 2
+        if want_roi:
+            self.d2h_bytes += self.roi_dev.numel() * 2
+
+    def alloc_host_outputs(self):
+        pin = dict(pin_memory=True)
+        image = torch.empty(self.plan.image_shape, dtype=torch.uint16, **pin) if self.want_image else None
+        roi = torch.empty(tuple(self.roi_dev.shape), dtype=torch.uint16, **pin) if self.want_roi else None
+        stats = torch.empty(tuple(self.stats_dev.shape), dtype=torch.float64, **pin)
+        return image, roi, stats
+
+    def run(self, tiles_host: torch.Tensor, image_host, roi_host, stats_host) -> None:
+        plan = self.plan
+        c, t, r, cc, h, w = plan.tile_shape
+        compute = torch.cuda.current_stream(plan.device)
+        ff = plan.ff
+        # ---- stage in + pass 1 (per timepoint, per channel: each (c, t) block is contiguous)
+        if not ff.identity:
+            ff.maxima.zero_()
+        self.h2d.wait_stream(compute)
+        events = []
+        for ti in range(t):
+            with torch.cuda.stream(self.h2d):
+                for ci in range(c):
+                    self.tiles_dev[ci, ti].copy_(tiles_host[ci, ti], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.h2d)
+            events.append(ev)
+        for ti in range(t):
+            compute.wait_event(events[ti])
+            if not ff.identity:
+                for ci in range(c):
+                    ops.flatfield_maxima_accumulate(self.tiles_dev[ci, ti], ff, ci)
+        if not ff.identity and plan.group is not None:
+            import torch.distributed as dist
+
+            dist.all_reduce(ff.maxima, op=dist.ReduceOp.MAX, group=plan.group)
+        # ---- pass 2 + stitch, gather + reductions on the whole resident stack
+        image = ops.flatfield_stitch(self.tiles_dev, overlap=plan.overlap, plan=ff,
+                                     maxima=None if ff.identity else ff.maxima, out=self.image_dev)
+        done_image = torch.cuda.Event()
+        done_image.record(compute)
+        if self.want_image:
+            with torch.cuda.stream(self.d2h):
+                self.d2h.wait_event(done_image)
+                image_host.copy_(image, non_blocking=True)
+        roi, stats = ops.roi_gather_stats(image, plan.boxes, plan.fg, plan.bg, plan.roi_length, mask_t=plan.mask_t,
+                                          want_roi=self.want_roi, out_roi=self.roi_dev, out_stats=self.stats_dev)
+        done_roi = torch.cuda.Event()
+        done_roi.record(compute)
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(done_roi)
+            if self.want_roi:
+                roi_host.copy_(roi, non_blocking=True)
+            stats_host.copy_(stats, non_blocking=True)
+        compute.wait_stream(self.d2h)

@@ -1,0 +1,180 @@
+"""Generate the golden fixtures in tests/golden/ from the REAL reference helpers.
+
+Run in the build container only (needs /root/reference):  python tests/golden/make_golden.py
+It loads the reference's own src/magnify/utils.py in place (oracle/_refload.py; nothing is
+copied) and replays the reference's call sites for the hot path on small deterministic
+inputs, storing inputs and outputs as .npz.  The call sites replayed are quoted by file:line.
+The fixtures pin the oracle (tests/test_oracle_*.py, CPU) and the CUDA path (tests/test_gpu_*.py).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle._refload import load_reference_utils  # noqa: E402
+
+utils = load_reference_utils()
+if utils is None:
+    raise SystemExit("reference utils.py not available; run inside the build container")
+
+
+def pattern_image(c, t, h, w, salt=0):
+    """Deterministic uint16 image stack with every pixel distinct in its neighbourhood."""
+    cc, tt, yy, xx = np.meshgrid(np.arange(c), np.arange(t), np.arange(h), np.arange(w), indexing="ij")
+    v = cc * 7919 + tt * 10473 + yy * 131 + xx * 31 + (yy * xx) % 977 + salt * 2221
+    return (v % 65536).astype(np.uint16)
+
+
+def golden_geometry():
+    rng = np.random.default_rng(20261018)
+    # bounding_box known answers (utils.py:60-80), including boxes sliding off every edge.
+    n = 4000
+    w = rng.integers(1, 400, n)
+    h = rng.integers(1, 400, n)
+    length = rng.integers(1, 130, n)
+    x = rng.integers(-60, 460, n)
+    y = rng.integers(-60, 460, n)
+    out = np.array(
+        [utils.bounding_box(int(x[i]), int(y[i]), int(length[i]), int(w[i]), int(h[i])) for i in range(n)],
+        dtype=np.int64,
+    )
+    # filled_circle_points (utils.py:398-430): per-radius row half-widths and areas.
+    rmax = 160
+    hw = np.full((rmax + 1, rmax + 1), -1, dtype=np.int32)
+    area = np.zeros(rmax + 1, dtype=np.int64)
+    perim = np.zeros(rmax + 1, dtype=np.int64)
+    for r in range(1, rmax + 1):
+        pts = utils.filled_circle_points(r)
+        area[r] = len(pts)
+        perim[r] = len(utils.circle_points(r))
+        assert len(set(map(tuple, pts.tolist()))) == len(pts)
+        for d in range(0, r + 1):
+            cols = pts[pts[:, 0] == d, 1]
+            cols_neg = pts[pts[:, 0] == -d, 1]
+            assert cols.min() == -cols.max() and np.array_equal(np.sort(cols), np.sort(cols_neg))
+            assert len(cols) == 2 * cols.max() + 1  # one contiguous, centred span
+            hw[r, d] = cols.max()
+    np.savez_compressed(
+        os.path.join(HERE, "geometry.npz"),
+        bb_args=np.stack([x, y, length, w, h], 1), bb_out=out,
+        disc_halfwidth=hw, disc_area=area, perimeter_len=perim,
+    )
+
+
+def golden_beads():
+    """Replay BeadFinder's ROI/mask half, find.py:561-602, with the real utils."""
+    rng = np.random.default_rng(7)
+    c, t, h, w, length = 2, 2, 200, 232, 50
+    image = pattern_image(c, t, h, w, salt=1)
+    # (row, col, radius): isolated, overlapping pairs, a triple, border-straddling, corner.
+    beads = np.array(
+        [[60, 60, 10], [60, 75, 10], [120, 40, 12], [125, 52, 8], [118, 55, 6], [3, 100, 9],
+         [199, 231, 11], [100, 228, 7], [150, 150, 25], [30, 180, 5], [170, 30, 1], [90, 120, 16]],
+        dtype=np.float64,
+    )
+    labels = utils.circle_labels(beads.astype(int), h, w)  # find.py:561
+    x = beads[:, 1]
+    y = beads[:, 0]
+    m = len(beads)
+    fg = np.empty((m, length, length), dtype=bool)
+    bg = np.empty_like(fg)
+    roi = np.empty((m, c, t, length, length), dtype=image.dtype)
+    boxes = np.empty((m, 4), dtype=np.int64)
+    for i in range(m):
+        top, bottom, left, right = utils.bounding_box(round(x[i]), round(y[i]), length, w, h)  # :573-579
+        boxes[i] = (top, bottom, left, right)
+        sub = labels[top:bottom, left:right]
+        fg[i] = sub == i  # :582
+        bg[i] = sub == -1  # :584
+    for ch in range(c):
+        im = image[ch]  # (T, H, W)  :590
+        for j in range(m):
+            top, bottom, left, right = boxes[j]
+            roi[j, ch] = im[..., top:bottom, left:right]  # :601
+    np.savez_compressed(
+        os.path.join(HERE, "beads.npz"),
+        image_salt=1, image_shape=np.array([c, t, h, w]), roi_length=length, beads=beads,
+        labels=labels, fg=fg, bg=bg, roi=roi, boxes=boxes,
+    )
+
+
+def golden_chip():
+    """Replay ButtonFinder.find_rois' crop + masks (find.py:362-400) for pinned refinement
+    results, and the copy-forward crops (find.py:143-176), with the real utils."""
+    c, t, h, w = 2, 3, 300, 420
+    length, chamber_r, max_r = 72, 30, 15
+    image = pattern_image(c, t, h, w, salt=2)
+    rows, cols = 2, 3
+    # coarse (non-integer) centres incl. exact .5 ties and boxes clipped at the borders
+    gx = np.array([[20.5, 190.49, 400.5], [35.5, 200.5, 419.0]])
+    gy = np.array([[10.5, 40.2, 36.5], [250.5, 290.0, 299.49]])
+    # pinned outcome of the CPU refinement at search timestep 0: (y, x, r) in ROI coords or none
+    found = {(0, 1): (30, 41, 9), (1, 0): (36, 36, 12), (1, 2): (50, 60, 14)}
+    x = gx.copy()
+    y = gy.copy()
+    roi = np.empty((rows, cols, c, t, length, length), dtype=image.dtype)
+    fg = np.empty((rows, cols, t, length, length), dtype=bool)
+    bg = np.empty_like(fg)
+    rad = np.full((rows, cols), max_r, dtype=np.int32)
+    images0 = image[:, 0]
+    for i in range(rows):
+        for j in range(cols):
+            top, bottom, left, right = utils.bounding_box(round(x[i, j]), round(y[i, j]), length, w, h)  # :327-333
+            roi[i, j, :, 0] = images0[..., top:bottom, left:right]
+            if (i, j) in found:
+                by, bx, br = found[(i, j)]
+                y[i, j], x[i, j] = by, bx  # :365
+                x[i, j] += left  # :367
+                y[i, j] += top  # :368
+                top, bottom, left, right = utils.bounding_box(round(x[i, j]), round(y[i, j]), length, w, h)  # :370-376
+                roi[i, j, :, 0] = images0[..., top:bottom, left:right]  # :377
+                rad[i, j] = br  # :378
+            x_rel = round(x[i, j]) - left  # :380
+            y_rel = round(y[i, j]) - top  # :381
+            bg[i, j, 0] = utils.annulus((length, length), (y_rel, x_rel), outer_radius=chamber_r,
+                                        inner_radius=max_r, value=1)  # :384-390
+            fg[i, j, 0] = utils.circle((length, length), (y_rel, x_rel), radius=int(rad[i, j]), value=1)  # :392-397
+    for tt in range(1, t):  # find.py:143-176 with search_timesteps=[0] -> copy_t = t-1
+        for i in range(rows):
+            for j in range(cols):
+                top, bottom, left, right = utils.bounding_box(round(x[i, j]), round(y[i, j]), length, w, h)
+                roi[i, j, :, tt] = image[:, tt, top:bottom, left:right]
+        fg[:, :, tt] = fg[:, :, tt - 1]
+        bg[:, :, tt] = bg[:, :, tt - 1]
+    np.savez_compressed(
+        os.path.join(HERE, "chip.npz"),
+        image_salt=2, image_shape=np.array([c, t, h, w]), roi_length=length, chamber_radius=chamber_r,
+        max_button_radius=max_r, coarse_x=gx, coarse_y=gy, x=x, y=y, fg_radius=rad,
+        roi=roi.reshape((rows * cols,) + roi.shape[2:]),
+        fg=fg.reshape((rows * cols,) + fg.shape[2:]), bg=bg.reshape((rows * cols,) + bg.shape[2:]),
+    )
+
+
+def golden_masks_cv():
+    """cv.circle rasters through utils.circle / utils.annulus (utils.py:30-52) for clipped and
+    unclipped centres -- pins the closed form `dx^2+dy^2 <= r^2` used by oracle and kernel."""
+    cases = []
+    discs = []
+    rings = []
+    for (cy, cx, r, ro, ri) in [(36, 36, 10, 30, 15), (0, 0, 15, 30, 15), (71, 71, 7, 30, 15), (5, 66, 12, 30, 16),
+                                (36, 2, 15, 33, 15), (40, 40, 0, 20, 20), (-3, 30, 9, 30, 15), (36, 75, 14, 30, 15)]:
+        cases.append((cy, cx, r, ro, ri))
+        discs.append(utils.circle((72, 72), (cy, cx), r).astype(bool))
+        rings.append(utils.annulus((72, 72), (cy, cx), ro, ri, value=1).astype(bool))
+    np.savez_compressed(os.path.join(HERE, "masks_cv.npz"), cases=np.array(cases), disc=np.array(discs),
+                        ring=np.array(rings))
+
+
+if __name__ == "__main__":
+    golden_geometry()
+    golden_beads()
+    golden_chip()
+    golden_masks_cv()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -1,0 +1,101 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol the header
+declares; host-side logic (argument errors, copy-forward map, disc table, fast-path fuzz)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from magnify_b200.build import build_library
+    from magnify_b200 import _lib
+
+    build_library()
+    return _lib.load()
+
+
+def test_library_exports_header_symbols(lib):
+    header = open(os.path.join(ROOT, "include", "magnify_b200.h")).read()
+    declared = set(re.findall(r"\b(mgb_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 18
+    from magnify_b200 import _lib
+
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mgb_abi_version() == 1
+    assert lib.mgb_error_string(-2).decode().startswith("pointer")
+
+
+def test_sass_is_sm100a():
+    so = os.path.join(ROOT, "magnify_b200", "libmagnify_b200.so")
+    out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+
+
+def test_disc_halfwidths_host_entry_point(lib, golden):
+    from magnify_b200 import ops
+
+    d = golden("geometry")
+    hw = d["disc_halfwidth"]
+    table = ops.disc_halfwidth_table(hw.shape[0] - 1)
+    for r in range(1, hw.shape[0]):
+        np.testing.assert_array_equal(table[r, : r + 1], hw[r, : r + 1])
+    import ctypes
+
+    assert lib.mgb_disc_halfwidths(0, (ctypes.c_int32 * 1)()) == -1   # r = 0 raises in the reference
+
+
+def test_argument_errors_before_any_launch(lib):
+    """Validation happens on the host: these return MGB_EINVAL without touching a GPU."""
+    import ctypes
+
+    p = ctypes.c_void_p(0)
+    assert lib.mgb_stitch(p, p, 1, 1, 2, 2, 50, 50, -5, 2, None, p) == -1     # stitch.py:8-9
+    assert lib.mgb_stitch(p, p, 1, 1, 2, 2, 50, 50, 100, 2, None, p) == -1    # stitch.py:16-20
+    assert lib.mgb_stitch(p, p, 1, 1, 2, 2, 50, 50, 4, 3, None, p) == -1      # itemsize
+    assert lib.mgb_stitch(p, p, 0, 1, 2, 2, 50, 50, 4, 2, None, p) == 0       # empty: nothing to do
+    assert lib.mgb_bounding_boxes(p, p, 4, 72, 50, 50, p, p, p) == -1         # image smaller than box
+    assert lib.mgb_roi_gather(p, 1, 1, 100, 100, 2, p, 0, 72, p, p) == 0      # zero markers
+    assert lib.mgb_chip_masks(p, p, 15, 30, 0, 72, p, p, p, p) == 0
+
+
+def test_ops_refuse_cpu_tensors(lib):
+    import torch
+    from magnify_b200 import ops
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.stitch(torch.zeros((1, 1, 1, 1, 8, 8), dtype=torch.uint16), 0)
+    with pytest.raises(ValueError):
+        ops.check_overlap(-1)
+    with pytest.raises(ValueError):
+        ops.check_overlap(10, 10, 12)
+
+
+def test_copy_forward_sources_match_oracle():
+    from magnify_b200.pipeline import copy_forward_sources
+    from oracle.rois import chip_copy_forward
+
+    for t, search in [(5, 0), (6, [2, 4]), (4, [3]), (7, [0, 3, 6]), (3, [1])]:
+        np.testing.assert_array_equal(copy_forward_sources(t, search), chip_copy_forward(t, search))
+    with pytest.raises(ValueError):
+        copy_forward_sources(3, [5])
+
+
+def test_flatfield_fast_path_fuzz_host(tmp_path):
+    """The one-FMA fast path + guard band of ff_core.cuh, compiled for the host and fuzzed
+    against the reference's exact operation order (20M pixels incl. degenerate coefficients)."""
+    exe = tmp_path / "ff_fuzz"
+    src = os.path.join(ROOT, "tests", "csrc", "ff_fuzz.cpp")
+    subprocess.run(["g++", "-O2", "-o", str(exe), src], check=True)
+    out = subprocess.run([str(exe), "20000000"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("ok")

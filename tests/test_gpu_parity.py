@@ -1,0 +1,358 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.
+
+Integer / byte / index results must be bit-exact; the float summaries must agree to 1e-5
+relative (north_star) -- they are in fact exact rationals rounded once, so the test uses 1e-12.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import flatfield as o_ff
+from oracle import geometry as o_geo
+from oracle import reduce as o_red
+from oracle import rois as o_rois
+from oracle import stitch as o_st
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a, device):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+
+# ------------------------------------------------------------------------------------ stitch
+@pytest.mark.parametrize(
+    "shape,overlap,dtype",
+    [
+        ((1, 1, 2, 3, 40, 40), 5, np.float64),     # reference tests/test_stitch.py:9-26
+        ((1, 1, 1, 1, 30, 30), 5, np.float64),     # :28-45
+        ((2, 3, 2, 2, 25, 25), 8, np.float64),     # :47-76 (odd pitch -> element-wise kernel)
+        ((1, 1, 1, 2, 20, 20), 0, np.float64),     # :78-96
+        ((2, 2, 3, 4, 64, 64), 6, np.uint16),      # vector path, phases 0/2/4/6 like 2048/102
+        ((1, 2, 2, 5, 48, 56), 7, np.uint16),      # odd overlap, odd phases
+        ((1, 1, 2, 2, 32, 40), 9, np.uint8),       # 1-byte elements
+        ((2, 1, 2, 3, 32, 32), 4, np.float32),     # 4-byte elements
+        ((1, 1, 3, 3, 16, 24), 0, np.uint16),
+        ((0, 1, 2, 2, 16, 16), 2, np.uint16),      # empty
+    ],
+)
+def test_stitch_matches_oracle(cuda_device, shape, overlap, dtype):
+    from magnify_b200 import ops
+
+    rng = np.random.default_rng(1)
+    if np.issubdtype(dtype, np.floating):
+        tiles = rng.random(shape).astype(dtype)
+    else:
+        tiles = rng.integers(0, np.iinfo(dtype).max, shape, dtype=dtype, endpoint=True)
+    want = o_st.stitch(tiles, overlap)
+    got = ops.stitch(dev(tiles, cuda_device), overlap).cpu().numpy()
+    assert got.dtype == want.dtype and got.shape == want.shape
+    np.testing.assert_array_equal(got, want)
+
+
+def test_stitch_reference_golden_slices(cuda_device):
+    """The exact-slice assertions of the reference's tests/test_stitch.py:22-26,43-45,93-96."""
+    from magnify_b200 import ops
+
+    tile_data = np.random.rand(1, 1, 2, 3, 40, 40)
+    img = ops.stitch(dev(tile_data, cuda_device), 5).cpu().numpy()
+    assert img.shape[-2:] == (2 * 35, 3 * 35)
+    np.testing.assert_array_equal(img[0, 0, 35:70, 35:70], tile_data[0, 0, 1, 1, 2:37, 2:37])
+    tile_data = np.random.rand(1, 1, 1, 1, 30, 30)
+    img = ops.stitch(dev(tile_data, cuda_device), 5).cpu().numpy()
+    np.testing.assert_array_equal(img[0, 0], tile_data[0, 0, 0, 0, 2:27, 2:27])
+    tile_data = np.random.rand(1, 1, 1, 2, 20, 20)
+    img = ops.stitch(dev(tile_data, cuda_device), 0).cpu().numpy()
+    np.testing.assert_array_equal(img[0, 0, :, :20], tile_data[0, 0, 0, 0])
+    np.testing.assert_array_equal(img[0, 0, :, 20:], tile_data[0, 0, 0, 1])
+
+
+def test_stitch_errors(cuda_device):
+    from magnify_b200 import ops
+
+    t = torch.zeros((1, 1, 2, 2, 50, 50), dtype=torch.uint16, device=cuda_device)
+    with pytest.raises(ValueError):
+        ops.stitch(t, -5)      # tests/test_stitch.py:98-100
+    with pytest.raises(ValueError):
+        ops.stitch(t, 100)     # tests/test_stitch.py:112-125
+
+
+# -------------------------------------------------------------------------------- flat-field
+def _ff_case(rng, shape, per_channel=False, scalar_dark=False):
+    c, t, r, cc, h, w = shape
+    tiles = np.clip(rng.normal(3000, 1500, shape), 0, 65535).astype(np.uint16)
+    tiles[..., :3, :] = 0          # pixels below dark -> clipped to 0
+    tiles[0, 0, 0, 0, 5, 5] = 65535
+    yy, xx = np.mgrid[0:h, 0:w]
+    flat = 1.0 + 0.35 * np.cos(yy / h * 2.1) * np.sin(xx / w * 1.7 + 0.3)
+    dark = 100.0 + 5.0 * np.sin(yy * 0.37 + xx * 0.11)
+    if per_channel:
+        flat = np.stack([flat * (1 + 0.1 * k) for k in range(c)])[:, None, None, None]
+        dark = np.stack([dark + 3 * k for k in range(c)])[:, None, None, None]
+    if scalar_dark:
+        dark = 97.25
+    return tiles, flat, dark
+
+
+@pytest.mark.parametrize(
+    "shape,overlap,per_channel,scalar_dark",
+    [
+        ((2, 3, 2, 2, 64, 64), 6, False, False),
+        ((2, 2, 1, 4, 64, 64), 6, True, False),
+        ((1, 2, 2, 3, 48, 56), 7, False, True),
+        ((3, 1, 1, 1, 128, 128), 0, True, True),
+        ((1, 2, 2, 2, 50, 50), 4, False, False),   # W % 8 != 0 -> generic exact path + stitch
+    ],
+)
+def test_flatfield_stitch_bit_exact(cuda_device, shape, overlap, per_channel, scalar_dark):
+    from magnify_b200 import ops
+
+    rng = np.random.default_rng(3)
+    tiles, flat, dark = _ff_case(rng, shape, per_channel, scalar_dark)
+    want_tiles = o_ff.flatfield_correct(tiles, flat, dark)
+    want = o_st.stitch(want_tiles, overlap)
+    plan = ops.FlatFieldPlan(shape, flat, dark, device=cuda_device)
+    got = ops.flatfield_stitch(dev(tiles, cuda_device), overlap=overlap, plan=plan)
+    m_want = o_ff.flatfield_maxima(tiles, flat, dark)
+    assert tuple(plan.maxima.cpu().numpy()) == m_want           # bit-exact float64 maxima
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    got_tiles = ops.flatfield_correct(dev(tiles, cuda_device), flat, dark)
+    np.testing.assert_array_equal(got_tiles.cpu().numpy(), want_tiles)
+
+
+def test_flatfield_degenerate_coefficients_take_exact_path(cuda_device):
+    """flat = 1, integer dark: every corrected value is an exact integer, so every pixel sits on
+    the guard band and must come out of the exact path."""
+    from magnify_b200 import ops
+
+    rng = np.random.default_rng(5)
+    shape = (1, 2, 2, 2, 32, 32)
+    tiles = rng.integers(0, 65535, shape, dtype=np.uint16, endpoint=True)
+    for flat, dark in [(1.0, 100.0), (np.ones((32, 32)), np.full((32, 32), 7.0)), (0.5, 0.0), (2.0, 1.5)]:
+        want = o_st.stitch(o_ff.flatfield_correct(tiles, flat, dark), 4)
+        got = ops.flatfield_stitch(dev(tiles, cuda_device), flat, dark, overlap=4)
+        np.testing.assert_array_equal(got.cpu().numpy(), want)
+    # the defaults are the identity (preprocess.py:62 with registry.py:278-279)
+    got = ops.flatfield_stitch(dev(tiles, cuda_device), 1.0, 0.0, overlap=4)
+    np.testing.assert_array_equal(got.cpu().numpy(), o_st.stitch(o_ff.flatfield_correct(tiles), 4))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.uint8])
+def test_flatfield_other_dtypes(cuda_device, dtype):
+    from magnify_b200 import ops
+
+    rng = np.random.default_rng(6)
+    shape = (2, 1, 2, 2, 24, 32)
+    if dtype == np.uint8:
+        tiles = rng.integers(0, 255, shape, dtype=np.uint8, endpoint=True)
+        dark = 3.5
+    else:
+        tiles = (rng.random(shape) * 4000).astype(dtype)
+        dark = 100.25
+    flat = 0.7 + 0.6 * rng.random((24, 32))
+    want = o_st.stitch(o_ff.flatfield_correct(tiles, flat, dark), 2)
+    got = ops.flatfield_stitch(dev(tiles, cuda_device), flat, dark, overlap=2)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+
+
+def test_flatfield_rejects_nonpositive_flat(cuda_device):
+    from magnify_b200 import ops
+
+    with pytest.raises(ValueError):
+        ops.FlatFieldPlan((1, 1, 1, 1, 8, 8), np.zeros((8, 8)), 0.0, device=cuda_device)
+
+
+# ------------------------------------------------------------------------------------- boxes
+def test_bounding_boxes_golden(cuda_device, golden):
+    from magnify_b200 import ops
+
+    g = golden("geometry")
+    args, out = g["bb_args"], g["bb_out"]
+    ok = (args[:, 3] >= args[:, 2]) & (args[:, 4] >= args[:, 2])   # image at least as large as the box
+    for length in np.unique(args[ok, 2])[:40]:
+        for (w, h) in {(int(a[3]), int(a[4])) for a in args[ok & (args[:, 2] == length)]}:
+            sel = ok & (args[:, 2] == length) & (args[:, 3] == w) & (args[:, 4] == h)
+            x = dev(args[sel, 0].astype(np.float64), cuda_device)
+            y = dev(args[sel, 1].astype(np.float64), cuda_device)
+            boxes = ops.bounding_boxes(x, y, int(length), w, h).cpu().numpy()
+            np.testing.assert_array_equal(boxes[:, 0], out[sel, 0])
+            np.testing.assert_array_equal(boxes[:, 1], out[sel, 2])
+
+
+def test_bounding_boxes_round_half_even(cuda_device):
+    from magnify_b200 import ops
+
+    xs = np.array([0.5, 1.5, 2.5, 3.5, 10.49999, 10.5, 11.5, 99.5, 100.5, -0.5, 250.5, 251.5])
+    ys = xs[::-1].copy()
+    boxes, rel = ops.bounding_boxes(dev(xs, cuda_device), dev(ys, cuda_device), 21, 300, 280, want_rel=True)
+    want = o_geo.boxes_from_centres(xs, ys, 21, 300, 280)
+    np.testing.assert_array_equal(boxes.cpu().numpy(), want)
+    for i in range(len(xs)):
+        assert rel[i, 0].item() == round(float(ys[i])) - want[i, 0]
+        assert rel[i, 1].item() == round(float(xs[i])) - want[i, 1]
+
+
+# ------------------------------------------------------------------------------- beads golden
+def test_beads_golden(cuda_device, golden, make_pattern_image):
+    """Labels, fg/bg and ROI crops of BeadFinder's ROI half (find.py:561-602) -- fixture made
+    with the reference's real utils.py."""
+    from magnify_b200 import ops
+
+    g = golden("beads")
+    c, t, h, w = (int(v) for v in g["image_shape"])
+    length = int(g["roi_length"])
+    image = make_pattern_image(c, t, h, w, salt=int(g["image_salt"]))
+    beads = g["beads"]
+    m = len(beads)
+    beads_i = dev(beads.astype(np.int32), cuda_device)
+    labels = ops.bead_labels(beads_i, h, w)
+    np.testing.assert_array_equal(labels.cpu().numpy(), g["labels"])
+    x = dev(np.repeat(beads[:, 1:2], t, axis=1), cuda_device)
+    y = dev(np.repeat(beads[:, 0:1], t, axis=1), cuda_device)
+    boxes = ops.bounding_boxes(x, y, length, w, h)
+    np.testing.assert_array_equal(boxes[:, 0].cpu().numpy(), g["boxes"][:, [0, 2]])
+    fg, bg, counts = ops.bead_masks(labels, boxes[:, 0].contiguous(), length, want_counts=True)
+    np.testing.assert_array_equal(fg.cpu().numpy().astype(bool), g["fg"])
+    np.testing.assert_array_equal(bg.cpu().numpy().astype(bool), g["bg"])
+    np.testing.assert_array_equal(counts.cpu().numpy(), np.stack([g["fg"].sum((1, 2)), g["bg"].sum((1, 2))], 1))
+    roi, stats = ops.roi_gather_stats(dev(image, cuda_device), boxes, fg[:, None].contiguous(),
+                                      bg[:, None].contiguous(), length)
+    np.testing.assert_array_equal(roi.cpu().numpy(), g["roi"])
+    roi2 = ops.roi_gather(dev(image, cuda_device), boxes, length)
+    np.testing.assert_array_equal(roi2.cpu().numpy(), g["roi"])
+    want = o_red.masked_stats(g["roi"], np.repeat(g["fg"][:, None], t, 1), np.repeat(g["bg"][:, None], t, 1))
+    np.testing.assert_allclose(stats.cpu().numpy(), want, rtol=1e-12, equal_nan=True)
+    for mask, key in ((fg, "fg"), (bg, "bg")):
+        med = ops.roi_median(roi, mask[:, None].contiguous())
+        want_med = o_red.masked_median(g["roi"], np.repeat(g[key][:, None], t, 1))
+        np.testing.assert_array_equal(med.cpu().numpy(), want_med)
+    assert m == roi.shape[0]
+
+
+def test_beads_zero_markers(cuda_device):
+    """find.py:557-558 / tests/test_beads.py:219-232: no beads -> empty mark dimension."""
+    from magnify_b200 import ops
+
+    image = torch.zeros((2, 1, 64, 64), dtype=torch.uint16, device=cuda_device)
+    beads = torch.zeros((0, 3), dtype=torch.int32, device=cuda_device)
+    labels = ops.bead_labels(beads, 64, 64)
+    assert int((labels != -1).sum()) == 0
+    boxes = torch.zeros((0, 1, 2), dtype=torch.int32, device=cuda_device)
+    roi = ops.roi_gather(image, boxes, 20)
+    assert tuple(roi.shape) == (0, 2, 1, 20, 20)
+    fg, bg = ops.bead_masks(labels, boxes[:, 0].contiguous(), 20)
+    roi, stats = ops.roi_gather_stats(image, boxes, fg[:, None].contiguous(), bg[:, None].contiguous(), 20)
+    assert tuple(stats.shape) == (0, 2, 1, 6)
+
+
+# -------------------------------------------------------------------------------- chip golden
+def test_chip_golden(cuda_device, golden, make_pattern_image):
+    """ROI crops + disc/annulus masks of ButtonFinder.find_rois and the copy-forward loop
+    (find.py:143-176, 362-400) -- fixture made with the reference's real utils.py (cv.circle)."""
+    from magnify_b200 import ops
+
+    g = golden("chip")
+    c, t, h, w = (int(v) for v in g["image_shape"])
+    length = int(g["roi_length"])
+    image = make_pattern_image(c, t, h, w, salt=int(g["image_salt"]))
+    x = g["x"].reshape(-1)
+    y = g["y"].reshape(-1)
+    m = len(x)
+    xt = dev(np.repeat(x[:, None], t, 1), cuda_device)
+    yt = dev(np.repeat(y[:, None], t, 1), cuda_device)
+    boxes, rel = ops.bounding_boxes(xt, yt, length, w, h, want_rel=True)
+    fg, bg = ops.chip_masks(rel[:, 0].contiguous(), dev(g["fg_radius"].reshape(-1).astype(np.int32), cuda_device),
+                            int(g["max_button_radius"]), int(g["chamber_radius"]), length)
+    np.testing.assert_array_equal(fg.cpu().numpy().astype(bool), g["fg"][:, 0])
+    np.testing.assert_array_equal(bg.cpu().numpy().astype(bool), g["bg"][:, 0])
+    roi, stats = ops.roi_gather_stats(dev(image, cuda_device), boxes, fg[:, None].contiguous(),
+                                      bg[:, None].contiguous(), length)
+    np.testing.assert_array_equal(roi.cpu().numpy(), g["roi"])
+    want = o_red.masked_stats(g["roi"], g["fg"], g["bg"])
+    np.testing.assert_allclose(stats.cpu().numpy(), want, rtol=1e-12, equal_nan=True)
+    med = ops.roi_median(roi, bg[:, None].contiguous())
+    np.testing.assert_array_equal(med.cpu().numpy(), o_red.masked_median(g["roi"], g["bg"]))
+    assert m == 6
+
+
+def test_chip_masks_cv_golden(cuda_device, golden):
+    from magnify_b200 import ops
+
+    g = golden("masks_cv")
+    cases = g["cases"]
+    for (ro, ri) in {(int(a[3]), int(a[4])) for a in cases}:
+        sel = (cases[:, 3] == ro) & (cases[:, 4] == ri)
+        rel = dev(cases[sel][:, :2].astype(np.int32), cuda_device)
+        rad = dev(cases[sel][:, 2].astype(np.int32), cuda_device)
+        fg, bg, counts = ops.chip_masks(rel, rad, ri, ro, 72, want_counts=True)
+        np.testing.assert_array_equal(fg.cpu().numpy().astype(bool), g["disc"][sel])
+        np.testing.assert_array_equal(bg.cpu().numpy().astype(bool), g["ring"][sel])
+        np.testing.assert_array_equal(counts[:, 0].cpu().numpy(), g["disc"][sel].sum((1, 2)))
+
+
+# --------------------------------------------------------------------- randomized vs oracle
+@pytest.mark.parametrize("length,itemsize_dtype", [(72, np.uint16), (50, np.uint16), (51, np.uint16), (100, np.uint16),
+                                                    (24, np.float32), (17, np.uint8), (16, np.float64)])
+def test_roi_gather_random(cuda_device, length, itemsize_dtype):
+    from magnify_b200 import ops
+
+    rng = np.random.default_rng(11)
+    c, t, h, w, m = 3, 2, 260, 333 if length % 2 else 336, 37
+    if np.issubdtype(itemsize_dtype, np.floating):
+        image = rng.random((c, t, h, w)).astype(itemsize_dtype)
+    else:
+        image = rng.integers(0, np.iinfo(itemsize_dtype).max, (c, t, h, w), dtype=itemsize_dtype, endpoint=True)
+    x = rng.uniform(-20, w + 20, (m, t))
+    y = rng.uniform(-20, h + 20, (m, t))
+    x[:4] = np.round(x[:4]) + 0.5          # exact ties
+    want = o_rois.gather_rois(image, x, y, length)
+    boxes = ops.bounding_boxes(dev(x, cuda_device), dev(y, cuda_device), length, w, h)
+    got = ops.roi_gather(dev(image, cuda_device), boxes, length)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+
+
+def test_median_random(cuda_device):
+    from magnify_b200 import ops
+
+    rng = np.random.default_rng(12)
+    for length in (8, 50, 72, 100, 128):
+        m, c, t = 9, 2, 2
+        roi = rng.integers(390, 420, (m, c, t, length, length)).astype(np.uint16)   # many ties
+        roi[0] = rng.integers(0, 65535, roi[0].shape, endpoint=True)
+        mask = rng.random((m, t, length, length)) < 0.3
+        mask[1] = False                       # empty -> NaN
+        mask[2, :, 0, :3] = True
+        mask[3] = True
+        got = ops.roi_median(dev(roi, cuda_device), dev(mask.view(np.uint8), cuda_device)).cpu().numpy()
+        want = o_red.masked_median(roi, mask)
+        np.testing.assert_array_equal(got, want)
+
+
+def test_full_size_properties_c2(cuda_device):
+    """BASELINE config 2 at full size (4x4 tiles of 2048^2, overlap 102, 56x32 buttons, L=72):
+    size-independent properties instead of a CPU replay -- the stitched image equals torch
+    indexing of the tiles, ROI crops equal direct slices, sums of masked sums match."""
+    from magnify_b200 import ops
+
+    torch.manual_seed(0)
+    c, t, r, cc, h, w, ov, length = 2, 1, 4, 4, 2048, 2048, 102, 72
+    tiles = torch.randint(0, 65536, (c, t, r, cc, h, w), dtype=torch.int32, device=cuda_device).to(torch.uint16)
+    image = ops.stitch(tiles, ov)
+    kept = tiles[..., 51:2048 - 51, 51:2048 - 51]
+    ref = kept.permute(0, 1, 2, 4, 3, 5).reshape(c, t, r * 1946, cc * 1946)
+    assert torch.equal(image.view(torch.int16), ref.contiguous().view(torch.int16))
+    rows, cols = 56, 32
+    gy, gx = torch.meshgrid(torch.arange(rows, dtype=torch.float64), torch.arange(cols, dtype=torch.float64), indexing="ij")
+    x = (300.25 + gx * 232.9).reshape(-1, 1).to(cuda_device).contiguous()
+    y = (350.5 + gy * 126.1).reshape(-1, 1).to(cuda_device).contiguous()
+    boxes, rel = ops.bounding_boxes(x, y, length, image.shape[-1], image.shape[-2], want_rel=True)
+    rad = torch.full((rows * cols,), 15, dtype=torch.int32, device=cuda_device)
+    fg, bg = ops.chip_masks(rel[:, 0].contiguous(), rad, 15, 30, length)
+    roi, stats = ops.roi_gather_stats(image, boxes, fg[:, None].contiguous(), bg[:, None].contiguous(), length)
+    for m in (0, 17, 1000, rows * cols - 1):
+        top, left = (int(v) for v in boxes[m, 0])
+        assert torch.equal(roi[m, :, 0].contiguous().view(torch.int16),
+                           image[:, 0, top:top + length, left:left + length].contiguous().view(torch.int16))
+    sums = (roi.to(torch.float64) * fg[:, None, None].to(torch.float64)).sum((-1, -2))
+    assert torch.equal(sums, stats[..., 2])
+    assert torch.equal(stats[..., 0], fg.sum((-1, -2)).to(torch.float64)[:, None, None].expand(-1, c, t))

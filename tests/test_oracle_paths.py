@@ -1,0 +1,125 @@
+"""Oracle restatements of stitch / flat-field / ROI paths: the reference's own golden
+assertions (tests/test_stitch.py) and the golden fixtures replayed from the real utils.py."""
+import numpy as np
+import pytest
+
+from oracle import flatfield as ff
+from oracle import reduce as red
+from oracle import rois
+from oracle import stitch as st
+
+
+# ---- port of the reference's tests/test_stitch.py (array level) -------------------------------
+def test_stitcher_basic():  # tests/test_stitch.py:9-26
+    tile_data = np.random.rand(1, 1, 2, 3, 40, 40)
+    image = st.stitch(tile_data, 5)
+    assert image.shape[-2] == 2 * (40 - 5) and image.shape[-1] == 3 * (40 - 5)
+    np.testing.assert_array_equal(image[0, 0, 35:70, 35:70], tile_data[0, 0, 1, 1, 2:37, 2:37])
+
+
+def test_stitcher_single_tile():  # :28-45
+    tile_data = np.random.rand(1, 1, 1, 1, 30, 30)
+    image = st.stitch(tile_data, 5)
+    assert image.shape[-2:] == (25, 25)
+    np.testing.assert_array_equal(image[0, 0], tile_data[0, 0, 0, 0, 2:27, 2:27])
+
+
+def test_stitcher_preserves_channels_and_time():  # :47-76
+    image = st.stitch(np.random.rand(2, 3, 2, 2, 25, 25), 8)
+    assert image.shape[:2] == (2, 3)
+
+
+def test_stitcher_zero_overlap():  # :78-96
+    tile_data = np.random.rand(1, 1, 1, 2, 20, 20)
+    image = st.stitch(tile_data, 0)
+    assert image.shape[-2:] == (20, 40)
+    np.testing.assert_array_equal(image[0, 0, :, :20], tile_data[0, 0, 0, 0])
+    np.testing.assert_array_equal(image[0, 0, :, 20:], tile_data[0, 0, 0, 1])
+
+
+def test_stitcher_errors():  # :98-100, :112-125
+    with pytest.raises(ValueError):
+        st.check_overlap(-5)
+    with pytest.raises(ValueError):
+        st.stitch(np.random.rand(1, 1, 2, 2, 50, 50), 100)
+
+
+# ---- flat-field ------------------------------------------------------------------------------
+def test_flatfield_defaults_are_identity():
+    rng = np.random.default_rng(0)
+    tiles = rng.integers(0, 65535, (2, 2, 1, 2, 16, 16), dtype=np.uint16, endpoint=True)
+    np.testing.assert_array_equal(ff.flatfield_correct(tiles), tiles)
+
+
+def test_flatfield_formula_and_chunked_maxima():
+    rng = np.random.default_rng(1)
+    tiles = rng.integers(0, 5000, (2, 2, 2, 2, 12, 16), dtype=np.uint16)
+    flat = 0.7 + 0.6 * rng.random((12, 16))
+    dark = 90 + 20 * rng.random((12, 16))
+    out = ff.flatfield_correct(tiles, flat, dark)
+    t = np.clip(tiles.astype(np.float64) - dark, 0, None)
+    m1 = t.max()
+    u = t / flat
+    want = ((u * m1) / u.max()).astype(np.uint16)
+    np.testing.assert_array_equal(out, want)
+    assert out.max() <= np.floor(m1)
+    # chunked evaluation with precomputed maxima (the multi-GPU / CPU-baseline form) is identical
+    parts = [ff.flatfield_maxima(tiles[c], flat, dark) for c in range(2)]
+    maxima = (max(p[0] for p in parts), max(p[1] for p in parts))
+    assert maxima == ff.flatfield_maxima(tiles, flat, dark)
+    chunked = np.stack([ff.flatfield_correct(tiles[c], flat, dark, maxima=maxima) for c in range(2)])
+    np.testing.assert_array_equal(chunked, out)
+
+
+# ---- ROI paths against fixtures made with the reference's real utils.py -----------------------
+def test_beads_golden(golden, make_pattern_image):
+    d = golden("beads")
+    c, t, h, w = (int(v) for v in d["image_shape"])
+    image = make_pattern_image(c, t, h, w, salt=int(d["image_salt"]))
+    length = int(d["roi_length"])
+    beads = d["beads"]
+    labels, fg, bg = rois.bead_masks(beads, h, w, length)
+    np.testing.assert_array_equal(labels, d["labels"])
+    np.testing.assert_array_equal(fg, d["fg"])
+    np.testing.assert_array_equal(bg, d["bg"])
+    x = np.repeat(beads[:, 1:2], t, 1)
+    y = np.repeat(beads[:, 0:1], t, 1)
+    np.testing.assert_array_equal(rois.gather_rois(image, x, y, length), d["roi"])
+
+
+def test_chip_golden(golden, make_pattern_image):
+    d = golden("chip")
+    c, t, h, w = (int(v) for v in d["image_shape"])
+    image = make_pattern_image(c, t, h, w, salt=int(d["image_salt"]))
+    length = int(d["roi_length"])
+    x, y = d["x"].reshape(-1), d["y"].reshape(-1)
+    roi = rois.gather_rois(image, np.repeat(x[:, None], t, 1), np.repeat(y[:, None], t, 1), length)
+    np.testing.assert_array_equal(roi, d["roi"])
+    fg, bg = rois.chip_masks(x, y, d["fg_radius"].reshape(-1), length, int(d["chamber_radius"]),
+                             int(d["max_button_radius"]), w, h)
+    src = rois.chip_copy_forward(t, [0])
+    np.testing.assert_array_equal(src, np.zeros(t, dtype=np.int64))
+    for ti in range(t):
+        np.testing.assert_array_equal(fg, d["fg"][:, ti])
+        np.testing.assert_array_equal(bg, d["bg"][:, ti])
+
+
+def test_copy_forward_sources():
+    np.testing.assert_array_equal(rois.chip_copy_forward(6, [2, 4]), [2, 2, 2, 2, 4, 4])
+    np.testing.assert_array_equal(rois.chip_copy_forward(3, 0), [0, 0, 0])
+
+
+def test_masked_stats_and_median():
+    rng = np.random.default_rng(2)
+    roi = rng.integers(0, 65535, (3, 2, 2, 10, 10), dtype=np.uint16, endpoint=True)
+    fg = rng.random((3, 2, 10, 10)) < 0.3
+    bg = ~fg
+    fg[1] = False
+    s = red.masked_stats(roi, fg, bg)
+    assert s.shape == (3, 2, 2, 6)
+    assert np.isnan(s[1, :, :, 4]).all() and (s[1, :, :, 0] == 0).all()
+    m, c, t = 2, 1, 0
+    vals = roi[m, c, t][fg[m, t]]
+    assert s[m, c, t, 0] == vals.size and s[m, c, t, 2] == vals.sum() and s[m, c, t, 4] == vals.mean()
+    med = red.masked_median(roi, fg)
+    assert med[m, c, t] == np.median(vals) and np.isnan(med[1]).all()
