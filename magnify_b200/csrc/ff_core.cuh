@@ -51,41 +51,60 @@ MGB_HD uint16_t ff_exact_u16(uint16_t x, double flat, double dark, double M, dou
   return (uint16_t)(long long)v;
 }
 
-// Fast-path coefficients for one position; NaN marks "always take the exact path".
+MGB_HD double ff_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+  return __fma_rn(a, b, c);
+#else
+  return fma(a, b, c);
+#endif
+}
+
+MGB_HD double ff_from_hi(unsigned hi_word) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double((int)hi_word, 0);
+#else
+  union { double d; uint64_t u; } cv;
+  cv.u = (uint64_t)hi_word << 32;
+  return cv.d;
+#endif
+}
+
+// Fast-path coefficients for one position.  Coefficients are accepted only if s(x) stays in
+// [2^20, 2^21) for the two extreme pixel values (s is monotone in x because gain > 0), so the
+// per-pixel code needs no range check.  Rejected positions get gain = 0, bias = 2^20: then
+// s = 2^20 exactly, its low word is 0 < 2G and every pixel there takes the exact path.
 MGB_HD void ff_make_coeffs(double flat, double dark, double M, double M2, double* gain,
                            double* bias) {
+  *gain = 0.0;
+  *bias = 1048576.0;
   double k = M / M2;
   double g = (1.0 / flat) * k;
   bool ok = (flat > 0.0) && (M2 > 0.0) && (g > 0.0) && (g <= kFFMaxGain) &&
             (fabs(dark) <= kFFMaxDark) && (k == k);
-  if (!ok) {
-    *gain = NAN;
-    *bias = NAN;
-    return;
-  }
+  if (!ok) return;
+  double b = ff_fma(-(dark + 1048576.0), g, kFFOffset + kFFGuard);
+  double s_lo = ff_fma(ff_from_hi(kFFHiBase), g, b);             // x = 0
+  double s_hi = ff_fma(ff_from_hi(kFFHiBase | 0xffffu), g, b);   // x = 65535
+  if (!(s_lo >= 1048576.0) || !(s_hi < 2097152.0)) return;
   *gain = g;
-  *bias = fma(-(dark + 1048576.0), g, kFFOffset + kFFGuard);
+  *bias = b;
 }
 
 // One pixel of the fast path.  Returns the candidate output; *slow is OR-ed with "recompute
 // exactly".  hi_word = 0x41300000 | x, i.e. the double 2^20 + x with a zero low word.
 MGB_HD int ff_fast_px(unsigned hi_word, double gain, double bias, bool* slow) {
+  double s = ff_fma(ff_from_hi(hi_word), gain, bias);
 #if defined(__CUDA_ARCH__)
-  double xd = __hiloint2double((int)hi_word, 0);
-  double s = __fma_rn(xd, gain, bias);
   unsigned hi = (unsigned)__double2hiint(s);
   unsigned lo = (unsigned)__double2loint(s);
 #else
   union { double d; uint64_t u; } cv;
-  cv.u = (uint64_t)hi_word << 32;
-  double s = fma(cv.d, gain, bias);
   cv.d = s;
   unsigned hi = (unsigned)(cv.u >> 32);
   unsigned lo = (unsigned)cv.u;
 #endif
-  unsigned rp = hi - kFFHiBase;
-  *slow = *slow || (rp >= 0x100000u) || (lo < kFFGuardLo);
-  int o = (int)rp - 0x80000;
+  *slow = *slow || (lo < kFFGuardLo);
+  int o = (int)(hi - kFFHiBase) - 0x80000;
   return o < 0 ? 0 : o;
 }
 

@@ -180,8 +180,26 @@ __device__ __forceinline__ uint4 funnel8(const uint4& a, const uint4& b) {
   }
 }
 
+// Prefetch ring: every thread streams its own two 16-byte input vectors of the next
+// kStitchStages-1 tiles into shared memory with cp.async (LDGSTS, L1 bypass) and reads them
+// back itself, so the bytes in flight per SM (2 CTAs x 256 thr x 32 B x 5 = 80 KB) are decoupled
+// from the register file, which holds the 16 float64 coefficients.  A thread only ever reads
+// the slots it wrote: no block-level synchronisation is needed.
+constexpr int kStitchStages = 6;
+constexpr int kStitchSmemBytes = kStitchStages * 2 * kThreads * 16;
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 template <int MODE, int S>
 __global__ void __launch_bounds__(kThreads, 2) stitch_u16_kernel(const StitchParams p) {
+  extern __shared__ uint4 ring[];   // [stage][2][kThreads]
   const int xb = blockIdx.x % p.xblocks;
   const int y = blockIdx.x / p.xblocks;
   const int q = p.q;
@@ -205,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 2) stitch_u16_kernel(const StitchPar
   const int64_t ct_lo = ct_first + n_ct * split / p.ct_splits;
   const int64_t ct_hi = ct_first + n_ct * (split + 1) / p.ct_splits;
   const int cols_q = (p.Cc - q + p.P - 1) / p.P;   // tile columns q, q+P, ...
-  const int64_t n_iter = (ct_hi - ct_lo) * p.R * cols_q;
+  const int n_iter = (int)((ct_hi - ct_lo) * p.R * cols_q);   // host keeps this below 2^31
   if (n_iter <= 0) return;
 
   double g[8], b[8];
@@ -215,41 +233,68 @@ __global__ void __launch_bounds__(kThreads, 2) stitch_u16_kernel(const StitchPar
     for (int i = 0; i < 8; ++i) {
       const int xi = xin0 + i;
       const bool in = (xi >= 0) && (xi < p.W);
+      // out-of-row lanes: s = 2^20 + 2^19 + 0.5 never trips the guard (their result is not stored)
       g[i] = in ? p.gain[base + xi] : 0.0;
-      b[i] = in ? p.bias[base + xi] : 0.0;
+      b[i] = in ? p.bias[base + xi] : 1572864.5;
     }
   }
 
-  // Iteration state: (ct, r, cc) advanced like an odometer, cc fastest.
-  int64_t ct = ct_lo;
-  int r = 0, cc = q;
+  // Tiles are visited in (ct, r, cc) order, cc fastest with stride P.  Between consecutive
+  // tiles both offsets advance by a constant, except every cols_q-th step (next tile row; the
+  // step from the last tile row of an image to the next image is the same).
   const int64_t tile_stride = (int64_t)p.H * p.W;
-  auto in_ptr = [&](int64_t ct_, int r_, int cc_) {
-    return reinterpret_cast<const uint4*>(
-        p.tiles + (((ct_ * p.R + r_) * p.Cc + cc_) * tile_stride + (int64_t)(p.clip_y + y) * p.W)) + a0;
-  };
-  auto out_ptr = [&](int64_t ct_, int r_, int cc_) {
-    return p.image + ((ct_ * p.Him + (int64_t)r_ * p.h + y) * p.Wim + (int64_t)cc_ * p.w + xk0);
+  const int64_t in_step = (int64_t)p.P * tile_stride;
+  const int64_t in_wrap = (int64_t)(p.Cc - (cols_q - 1) * p.P) * tile_stride;
+  const int64_t in_step8 = in_step >> 3, in_wrap8 = in_wrap >> 3;   // in 16-byte vectors
+  const int64_t out_step = (int64_t)p.P * p.w;
+  const int64_t out_wrap = (int64_t)p.h * p.Wim - (int64_t)(cols_q - 1) * p.P * p.w;
+  const uint4* ip = reinterpret_cast<const uint4*>(
+                        p.tiles + ((ct_lo * p.R * p.Cc + q) * tile_stride + (int64_t)(p.clip_y + y) * p.W)) + a0;
+  uint16_t* op = p.image + ((ct_lo * p.Him + y) * p.Wim + (int64_t)q * p.w + xk0);
+  int ci_in = 0, ci_out = 0;
+
+  uint4* slot_a = ring + threadIdx.x;
+  uint4* slot_b = ring + kThreads + threadIdx.x;
+  const uint32_t sa = (uint32_t)__cvta_generic_to_shared(slot_a);
+  const uint32_t sb = (uint32_t)__cvta_generic_to_shared(slot_b);
+  constexpr int kStageVecs = 2 * kThreads;
+  if (!ld_a) {
+#pragma unroll
+    for (int s = 0; s < kStitchStages; ++s) slot_a[s * kStageVecs] = make_uint4(0, 0, 0, 0);
+  }
+  if (!ld_b) {
+#pragma unroll
+    for (int s = 0; s < kStitchStages; ++s) slot_b[s * kStageVecs] = make_uint4(0, 0, 0, 0);
+  }
+
+  auto issue = [&](int stage) {
+    if (ld_a) cp_async16(sa + stage * (kStageVecs * 16), ip);
+    if (ld_b) cp_async16(sb + stage * (kStageVecs * 16), ip + 1);
+    const bool wrap = (++ci_in == cols_q);
+    if (wrap) ci_in = 0;
+    ip += wrap ? in_wrap8 : in_step8;
   };
 
-  const uint4 zero = make_uint4(0, 0, 0, 0);
-  uint4 na = zero, nb = zero;
-  {
-    const uint4* ip = in_ptr(ct, r, cc);
-    if (ld_a) na = ldg_stream(ip);
-    if (ld_b) nb = ldg_stream(ip + 1);
+  // prologue: kStitchStages-1 tiles in flight
+#pragma unroll
+  for (int s = 0; s < kStitchStages - 1; ++s) {
+    if (s < n_iter) issue(s);
+    cp_async_commit();
   }
-  for (int64_t it = 0; it < n_iter; ++it) {
-    const uint4 va = na, vb = nb;
-    uint16_t* op = out_ptr(ct, r, cc);
-    // advance + prefetch the next tile's vectors before computing on this one
-    cc += p.P;
-    if (cc >= p.Cc) { cc = q; if (++r >= p.R) { r = 0; ++ct; } }
-    if (it + 1 < n_iter) {
-      const uint4* ip = in_ptr(ct, r, cc);
-      if (ld_a) na = ldg_stream(ip);
-      if (ld_b) nb = ldg_stream(ip + 1);
+  int stage = 0;
+  for (int it = 0; it < n_iter; ++it) {
+    // refill the slot consumed in the previous iteration, then wait for this iteration's data
+    if (it + kStitchStages - 1 < n_iter) {
+      int pf = stage + kStitchStages - 1;
+      if (pf >= kStitchStages) pf -= kStitchStages;
+      issue(pf);
     }
+    cp_async_commit();
+    cp_async_wait<kStitchStages - 1>();
+    const uint4 va = slot_a[stage * kStageVecs];
+    const uint4 vb = (S != 0) ? slot_b[stage * kStageVecs] : va;
+    if (++stage == kStitchStages) stage = 0;
+
     uint4 v = funnel8<S>(va, vb);
     if constexpr (MODE == 1) {
       const uint32_t win[4] = {v.x, v.y, v.z, v.w};
@@ -288,6 +333,9 @@ __global__ void __launch_bounds__(kThreads, 2) stitch_u16_kernel(const StitchPar
         if (xk >= 0 && xk < p.w) op[i] = (uint16_t)((wv[i >> 1] >> (16 * (i & 1))) & 0xffffu);
       }
     }
+    const bool owrap = (++ci_out == cols_q);
+    if (owrap) ci_out = 0;
+    op += owrap ? out_wrap : out_step;
   }
 }
 
@@ -335,7 +383,7 @@ template <int MODE>
 static int launch_stitch_fast(const StitchParams& p, int S, cudaStream_t st) {
   dim3 grid((unsigned)(p.h * p.xblocks), (unsigned)p.K, (unsigned)p.ct_splits);
 #define MGB_CASE(SS) \
-  case SS: stitch_u16_kernel<MODE, SS><<<grid, kThreads, 0, st>>>(p); break;
+  case SS: stitch_u16_kernel<MODE, SS><<<grid, kThreads, kStitchSmemBytes, st>>>(p); break;
   switch (S) {
     MGB_CASE(0) MGB_CASE(1) MGB_CASE(2) MGB_CASE(3) MGB_CASE(4) MGB_CASE(5) MGB_CASE(6) MGB_CASE(7)
     default: return MGB_EINVAL;
@@ -372,6 +420,7 @@ static int run_stitch_fast(StitchParams p, cudaStream_t st) {
   const int64_t base_ctas = (int64_t)p.h * p.xblocks * p.K;
   const int64_t n_ct = (p.K == 1) ? p.CT : p.T;
   const int64_t cols_q = (p.Cc + p.P - 1) / p.P;
+  if (n_ct * p.R * cols_q >= INT32_MAX) return MGB_EUNSUPPORTED;   // 32-bit tile loop counter
   int64_t splits = 1;
   while (base_ctas * splits < (int64_t)cached_sm_count() * 16 && splits * 2 <= n_ct &&
          (n_ct / (splits * 2)) * p.R * cols_q >= 16 && splits < 32768)

@@ -17,6 +17,10 @@ static void check(uint16_t x, double f, double d, double M, double M2) {
   ff_make_coeffs(f, d, M, M2, &g, &b);
   bool slow = false;
   int o = ff_fast_px(kFFHiBase | x, g, b, &slow);
+  {  // accepted coefficients keep s inside [2^20, 2^21): the kernel relies on it
+    double s = fma(ff_from_hi(kFFHiBase | x), g, b);
+    if (!(s >= 1048576.0 && s < 2097152.0)) { ++n_bad; return; }
+  }
   ++n_checked;
   if (slow) { ++n_slow; return; }
   uint16_t e = ff_exact_u16(x, f, d, M, M2);
