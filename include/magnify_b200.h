@@ -111,6 +111,12 @@ int mgb_flatfield_apply_generic(const void* tiles, void* out, int dtype, int64_t
 int mgb_bounding_boxes(const double* x, const double* y, int64_t n, int L, int64_t W, int64_t H,
                        int32_t* boxes, int32_t* rel, void* stream);
 
+/* The ROI gather has two implementations: TMA-staged (cp.async.bulk.tensor windows through
+ * shared memory, bulk store back) and a plain load/store kernel used when the image pitch is
+ * not a multiple of 16 bytes or the window does not fit shared memory.  This switch forces the
+ * plain kernels (tests cover both); returns the previous setting.  Default: enabled. */
+int mgb_set_tma_enabled(int enabled);
+
 /* ---- F4 (+R): ROI gather, reference find.py:160-169, 324-334, 370-377, 589-602 -------------
  * roi[m,c,t] = image[c,t, top:top+L, left:left+L] for any itemsize in {1,2,4,8}. */
 int mgb_roi_gather(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,

@@ -251,6 +251,13 @@ roi_median_u16_kernel(const uint16_t* __restrict__ roi, int64_t C, int64_t T, in
 
 static uint32_t magic_for(uint32_t d) { return (uint32_t)((0x100000000ULL + d - 1) / d); }
 
+// roi_tma.cu
+int roi_gather_tma(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
+                   const int32_t* boxes, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
+                   const uint8_t* bg, int64_t M, int L, void* roi, double* stats, cudaStream_t st);
+
+static int g_tma_enabled = 1;
+
 }  // namespace mgb
 
 using namespace mgb;
@@ -281,6 +288,11 @@ static int gather_common(const void* image, int64_t C, int64_t T, int64_t H, int
   if (n_roi > INT32_MAX) return MGB_EUNSUPPORTED;
   if (!image || !boxes || (!roi && !with_stats)) return MGB_EINVAL;
   if (with_stats && (!mask_t || !fg || !bg || Tm <= 0 || itemsize != 2)) return MGB_EINVAL;
+  if (g_tma_enabled) {
+    // TMA-staged path (roi_tma.cu); MGB_EALIGN means "not applicable here", fall through.
+    const int rc = roi_gather_tma(image, C, T, H, W, itemsize, boxes, mask_t, Tm, fg, bg, M, L, roi, stats, st);
+    if (rc != MGB_EALIGN) return rc;
+  }
   const int unit = itemsize / 2;
   const int Lu = L * (unit ? unit : 1);
   const bool word_path = itemsize >= 2 && (Lu % 2 == 0) &&
@@ -309,6 +321,12 @@ static int gather_common(const void* image, int64_t C, int64_t T, int64_t H, int
   }
   MGB_CUDA_LAUNCH_CHECK();
   return MGB_OK;
+}
+
+int mgb_set_tma_enabled(int enabled) {
+  const int old = g_tma_enabled;
+  g_tma_enabled = enabled ? 1 : 0;
+  return old;
 }
 
 int mgb_roi_gather(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,

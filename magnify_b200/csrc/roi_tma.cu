@@ -1,0 +1,394 @@
+// F4 + R, TMA path: ROI windows are staged through shared memory by the tensor-memory
+// accelerator (cp.async.bulk.tensor, SASS UTMALDG); the warp that owns a window re-aligns it
+// out of shared memory with 128-bit loads + a funnel shift, stores it with aligned 128-bit
+// streaming stores and accumulates the masked sums (dp2a) from the same registers.
+//
+// Measured constraint (tools/tma_probe2.cu on B200): a tiled TMA load faults ("illegal
+// instruction") unless coordinate[0] * elemsize is a multiple of 16 bytes.  ROI windows start at
+// arbitrary pixels, so the box is widened to start at the 16-byte boundary below `left` and the
+// residual shift (0..7 pixels, uniform per window) is applied while reading shared memory.
+//
+// One CTA = one marker m (x one mask timestep); its warps share the marker's fg/bg masks in
+// shared memory and each runs an independent NS-stage pipeline over its (channel, time) items:
+//
+//     lane 0:  expect_tx + TMA load of item k+NS-1  --->  mbarrier full[s]
+//     warp  :  wait full[s] -> realign + store roi[m,c,t] + masked sums
+//     lane 0:  (after __syncwarp) refill the stage item k-1 used
+//
+// Reference semantics: roi[m,c,t] = image[c,t, top:top+L, left:left+L] (find.py:160-169,
+// 324-334, 589-602); sums/means over fg/bg (identify.py:76-80, filter.py:21-22,51).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+
+namespace mgb {
+
+constexpr int kTmaMaxWarps = 8;
+
+struct TmaGatherParams {
+  uint16_t* roi;            // may be null (summaries only)
+  const int32_t* boxes;     // (M,T,2) in elements
+  const int32_t* mask_t;    // (T) or null when !stats
+  const uint8_t* fg;        // (M,Tm,rows,rows) or null
+  const uint8_t* bg;
+  double* stats;            // (M,C,T,6) or null
+  int64_t C, T, Tm;
+  int rows;                 // L
+  int wu;                   // row length in 16-bit units (L * unit)
+  int wpu;                  // TMA box width: roundup8(wu + 7) units
+  int unit;                 // 16-bit units per element
+  int n_stages;
+  int stage_bytes;          // rows * wpu * 2 rounded up to 128
+  uint32_t vpr;             // 16-byte vectors per roi row (wu / 8) when the vector path applies, else 0
+  uint32_t magic_vpr;       // ceil(2^32 / vpr)
+  uint32_t half;            // wu / 2 words per row when the word path applies, else 0
+  uint32_t magic_half;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// 8 consecutive 16-bit units starting S units into the 16 units of (a, b).
+template <int S>
+__device__ __forceinline__ uint4 shift_units(const uint4& a, const uint4& b) {
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  constexpr int o = S >> 1;
+  if constexpr ((S & 1) == 0) {
+    return make_uint4(w[o], w[o + 1], w[o + 2], w[o + 3]);
+  } else {
+    return make_uint4(__funnelshift_r(w[o], w[o + 1], 16), __funnelshift_r(w[o + 1], w[o + 2], 16),
+                      __funnelshift_r(w[o + 2], w[o + 3], 16), __funnelshift_r(w[o + 3], w[o + 4], 16));
+  }
+}
+
+// Vector path for one window: rows of wu = 8*vpr units, output 16-byte aligned.
+template <bool STATS, bool STORE, int S>
+__device__ __forceinline__ void consume_vec(const TmaGatherParams& p, const uint8_t* buf, uint16_t* dst,
+                                            const uint8_t* fgm, const uint8_t* bgm, int lane,
+                                            uint32_t* sf_out, uint32_t* sb_out) {
+  const uint4* s4 = reinterpret_cast<const uint4*>(buf);
+  const uint2* f2 = reinterpret_cast<const uint2*>(fgm);
+  const uint2* b2 = reinterpret_cast<const uint2*>(bgm);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+  const uint32_t nvec = p.rows * p.vpr, pitch = p.wpu >> 3;
+  uint32_t sf = 0, sb = 0;
+#pragma unroll 4
+  for (uint32_t v = lane; v < nvec; v += 32) {
+    const uint32_t row = __umulhi(v, p.magic_vpr);
+    const uint32_t sv = row * pitch + (v - row * p.vpr);
+    const uint4 a = s4[sv];
+    const uint4 b = (S != 0) ? s4[sv + 1] : a;
+    const uint4 d = shift_units<S>(a, b);
+    if constexpr (STORE) stg_stream(d4 + v, d);
+    if constexpr (STATS) {
+      const uint2 f = f2[v];
+      const uint2 g = b2[v];
+      sf = __dp2a_lo(d.x, f.x, sf); sf = __dp2a_hi(d.y, f.x, sf);
+      sf = __dp2a_lo(d.z, f.y, sf); sf = __dp2a_hi(d.w, f.y, sf);
+      sb = __dp2a_lo(d.x, g.x, sb); sb = __dp2a_hi(d.y, g.x, sb);
+      sb = __dp2a_lo(d.z, g.y, sb); sb = __dp2a_hi(d.w, g.y, sb);
+    }
+  }
+  *sf_out = sf;
+  *sb_out = sb;
+}
+
+// Word / unit path for rows that are not a whole number of 16-byte vectors (e.g. L = 50).
+template <bool STATS, bool STORE>
+__device__ __forceinline__ void consume_generic(const TmaGatherParams& p, const uint8_t* buf, uint16_t* dst,
+                                                const uint8_t* fgm, const uint8_t* bgm, int lane, int shift,
+                                                uint32_t* sf_out, uint32_t* sb_out) {
+  const uint16_t* s16 = reinterpret_cast<const uint16_t*>(buf);
+  uint32_t sf = 0, sb = 0;
+  if (p.half) {
+    uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+    const uint16_t* f16 = reinterpret_cast<const uint16_t*>(fgm);
+    const uint16_t* b16 = reinterpret_cast<const uint16_t*>(bgm);
+    const uint32_t words = p.rows * p.half;
+#pragma unroll 4
+    for (uint32_t w = lane; w < words; w += 32) {
+      const uint32_t row = __umulhi(w, p.magic_half);
+      const uint32_t u = row * p.wpu + shift + 2 * (w - row * p.half);
+      const uint32_t d = (uint32_t)s16[u] | ((uint32_t)s16[u + 1] << 16);
+      if constexpr (STORE) d32[w] = d;
+      if constexpr (STATS) {
+        sf = __dp2a_lo(d, (uint32_t)f16[w], sf);
+        sb = __dp2a_lo(d, (uint32_t)b16[w], sb);
+      }
+    }
+  } else {
+    const int total = p.rows * p.wu;
+    for (int e = lane; e < total; e += 32) {
+      const int row = e / p.wu;
+      const uint32_t d = s16[row * p.wpu + shift + (e - row * p.wu)];
+      if constexpr (STORE) dst[e] = (uint16_t)d;
+      if constexpr (STATS) {
+        sf += fgm[e] ? d : 0u;
+        sb += bgm[e] ? d : 0u;
+      }
+    }
+  }
+  *sf_out = sf;
+  *sb_out = sb;
+}
+
+template <bool STATS, bool STORE>
+__global__ void __launch_bounds__(kTmaMaxWarps * 32, 1)
+roi_gather_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGatherParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nw = blockDim.x >> 5;
+  const int64_t m = blockIdx.x;
+  const int tm = blockIdx.y;
+
+  // shared memory carve-up
+  uint8_t* stages = smem;                                                  // [warp][stage][stage_bytes]
+  const int mask_bytes = STATS ? ((p.rows * p.wu + 15) & ~15) : 0;         // dense (rows x wu), 1 B / unit
+  uint8_t* fgm = stages + (size_t)nw * p.n_stages * p.stage_bytes;
+  uint8_t* bgm = fgm + mask_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bgm + mask_bytes);          // [warp][8]
+  int32_t* tlist = reinterpret_cast<int32_t*>(bars + kTmaMaxWarps * 8);    // timepoints of this CTA
+  __shared__ int s_nt;
+  __shared__ uint32_t s_cnt[2][kTmaMaxWarps];
+
+  // timepoints whose mask timestep is tm (all of them when there are no masks)
+  if (warp == 0) {
+    int n = 0;
+    for (int64_t base = 0; base < p.T; base += 32) {
+      const int64_t t = base + lane;
+      const bool hit = (t < p.T) && (!STATS || p.mask_t[t] == tm);
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (hit) tlist[n + __popc(bal & ((1u << lane) - 1))] = (int32_t)t;
+      n += __popc(bal);
+    }
+    if (lane == 0) s_nt = n;
+  }
+  if constexpr (STATS) {
+    // masks of (m, tm) expanded to one byte per 16-bit unit; counts are per element
+    const uint8_t* f = p.fg + (m * p.Tm + tm) * (int64_t)p.rows * p.rows;
+    const uint8_t* b = p.bg + (m * p.Tm + tm) * (int64_t)p.rows * p.rows;
+    uint32_t nf = 0, nb = 0;
+    const int total = p.rows * p.wu;
+    for (int i = threadIdx.x; i < mask_bytes; i += blockDim.x) {
+      uint8_t vf = 0, vb = 0;
+      if (i < total) {
+        const int row = i / p.wu, col = i - row * p.wu;
+        const int e = row * p.rows + col / p.unit;
+        vf = f[e] != 0;
+        vb = b[e] != 0;
+        if (col % p.unit == 0) { nf += vf; nb += vb; }
+      }
+      fgm[i] = vf;
+      bgm[i] = vb;
+    }
+    nf = __reduce_add_sync(0xffffffffu, nf);
+    nb = __reduce_add_sync(0xffffffffu, nb);
+    if (lane == 0) { s_cnt[0][warp] = nf; s_cnt[1][warp] = nb; }
+  }
+  if (lane == 0) {
+    for (int s = 0; s < p.n_stages; ++s) mbar_init(smem_u32(&bars[warp * 8 + s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int nt = s_nt;
+  const int n_items = nt * (int)p.C;           // item i -> (c = i / nt, t = tlist[i % nt])
+  double cnt_fg = 0.0, cnt_bg = 0.0;
+  if constexpr (STATS) {
+    uint32_t a = 0, c = 0;
+    for (int i = 0; i < nw; ++i) { a += s_cnt[0][i]; c += s_cnt[1][i]; }
+    cnt_fg = (double)a;
+    cnt_bg = (double)c;
+  }
+
+  uint8_t* my_stages = stages + (size_t)warp * p.n_stages * p.stage_bytes;
+  const uint32_t my_stage0 = smem_u32(my_stages);
+  const uint32_t my_bar0 = smem_u32(&bars[warp * 8]);
+  const uint32_t tx_bytes = (uint32_t)(p.rows * p.wpu * 2);
+
+  auto item_ct = [&](int i, int64_t* c, int64_t* t) {
+    *c = i / nt;
+    *t = tlist[i - (int)(*c) * nt];
+  };
+  auto issue_load = [&](int i, int s) {       // lane 0 only
+    int64_t c, t;
+    item_ct(i, &c, &t);
+    const int32_t top = p.boxes[(m * p.T + t) * 2];
+    const int32_t left = p.boxes[(m * p.T + t) * 2 + 1];
+    const uint32_t bar = my_bar0 + s * 8;
+    mbar_expect_tx(bar, tx_bytes);
+    tma_load_3d(my_stage0 + s * p.stage_bytes, &tmap, bar, (left * p.unit) & ~7, top, (int)(c * p.T + t));
+  };
+
+  if (lane == 0) {
+    for (int s = 0; s < p.n_stages - 1; ++s) {
+      const int i = warp + s * nw;
+      if (i < n_items) issue_load(i, s);
+    }
+  }
+  int s = 0;
+  uint32_t parity = 0;
+  for (int i = warp; i < n_items; i += nw) {
+    int64_t c, t;
+    item_ct(i, &c, &t);
+    const int shift = (p.boxes[(m * p.T + t) * 2 + 1] * p.unit) & 7;
+    const int64_t n = (m * p.C + c) * p.T + t;
+    uint16_t* dst = STORE ? p.roi + n * (int64_t)p.rows * p.wu : nullptr;
+    const uint8_t* buf = my_stages + (size_t)s * p.stage_bytes;
+    mbar_wait(my_bar0 + s * 8, parity);
+    uint32_t sf = 0, sb = 0;
+    if (p.vpr) {
+      switch (shift) {
+        case 0: consume_vec<STATS, STORE, 0>(p, buf, dst, fgm, bgm, lane, &sf, &sb); break;
+        case 1: consume_vec<STATS, STORE, 1>(p, buf, dst, fgm, bgm, lane, &sf, &sb); break;
+        case 2: consume_vec<STATS, STORE, 2>(p, buf, dst, fgm, bgm, lane, &sf, &sb); break;
+        case 3: consume_vec<STATS, STORE, 3>(p, buf, dst, fgm, bgm, lane, &sf, &sb); break;
+        case 4: consume_vec<STATS, STORE, 4>(p, buf, dst, fgm, bgm, lane, &sf, &sb); break;
+        case 5: consume_vec<STATS, STORE, 5>(p, buf, dst, fgm, bgm, lane, &sf, &sb); break;
+        case 6: consume_vec<STATS, STORE, 6>(p, buf, dst, fgm, bgm, lane, &sf, &sb); break;
+        default: consume_vec<STATS, STORE, 7>(p, buf, dst, fgm, bgm, lane, &sf, &sb); break;
+      }
+    } else {
+      consume_generic<STATS, STORE>(p, buf, dst, fgm, bgm, lane, shift, &sf, &sb);
+    }
+    if constexpr (STATS) {
+      sf = __reduce_add_sync(0xffffffffu, sf);
+      sb = __reduce_add_sync(0xffffffffu, sb);
+      if (lane == 0) {
+        double* o = p.stats + n * 6;
+        o[0] = cnt_fg; o[1] = cnt_bg; o[2] = (double)sf; o[3] = (double)sb;
+        o[4] = (double)sf / cnt_fg; o[5] = (double)sb / cnt_bg;   // 0/0 = NaN like nanmean
+      }
+    }
+    __syncwarp();
+    // every lane is done reading this stage's predecessor: refill the stage item k-1 used
+    if (lane == 0) {
+      const int nxt = i + (p.n_stages - 1) * nw;
+      if (nxt < n_items) {
+        int rs = s + p.n_stages - 1;
+        if (rs >= p.n_stages) rs -= p.n_stages;
+        issue_load(nxt, rs);
+      }
+    }
+    if (++s == p.n_stages) { s = 0; parity ^= 1; }
+  }
+}
+
+static PFN_cuTensorMapEncodeTiled get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(ptr);
+  }
+  return fn;
+}
+
+static uint32_t magic_u32(uint32_t d) { return (uint32_t)((0x100000000ULL + d - 1) / d); }
+
+// Returns MGB_OK when launched, MGB_EALIGN when this path does not apply (caller falls back to
+// the LSU kernels of roi.cu), or an error.
+int roi_gather_tma(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
+                   const int32_t* boxes, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
+                   const uint8_t* bg, int64_t M, int L, void* roi, double* stats, cudaStream_t st) {
+  const bool with_stats = stats != nullptr;
+  if (itemsize < 2) return MGB_EALIGN;
+  const int unit = itemsize / 2;
+  const int64_t Wu = W * unit;
+  const int wu = L * unit;
+  const int wpu = (wu + 7 + 7) & ~7;            // any shift 0..7 plus the row, in whole vectors
+  if ((Wu * 2) % 16 != 0 || !aligned16(image) || wpu > 256 || L > 256) return MGB_EALIGN;
+  if (C * T > INT32_MAX || H > INT32_MAX || Wu > INT32_MAX || M > INT32_MAX) return MGB_EALIGN;
+  if (with_stats && Tm > 65535) return MGB_EALIGN;
+  PFN_cuTensorMapEncodeTiled encode = get_encode_fn();
+  if (!encode) return MGB_EALIGN;
+
+  TmaGatherParams p{};
+  p.roi = (uint16_t*)roi; p.boxes = boxes; p.mask_t = mask_t; p.fg = fg; p.bg = bg; p.stats = stats;
+  p.C = C; p.T = T; p.Tm = with_stats ? Tm : 1; p.rows = L; p.wu = wu; p.wpu = wpu; p.unit = unit;
+  p.stage_bytes = (L * wpu * 2 + 127) & ~127;
+  const bool out16 = !roi || aligned16(roi);
+  const bool out4 = !roi || (reinterpret_cast<uintptr_t>(roi) & 3u) == 0;
+  if (wu % 8 == 0 && out16) {
+    p.vpr = (uint32_t)(wu / 8);
+    p.magic_vpr = magic_u32(p.vpr);
+  } else if (wu % 2 == 0 && out4) {
+    p.half = (uint32_t)(wu / 2);
+    p.magic_half = magic_u32(p.half);
+  }
+  const size_t mask_bytes = with_stats ? 2 * (size_t)((L * wu + 15) & ~15) : 0;
+  const size_t fixed = mask_bytes + kTmaMaxWarps * 8 * sizeof(uint64_t) + (size_t)T * sizeof(int32_t) + 128;
+  int dev = 0, max_smem = 0;
+  MGB_CUDA_TRY(cudaGetDevice(&dev));
+  MGB_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const size_t budget = (size_t)max_smem > fixed + 1024 ? (size_t)max_smem - fixed - 1024 : 0;
+  int nw = kTmaMaxWarps;
+  int ns = (int)(budget / ((size_t)nw * p.stage_bytes));
+  if (ns < 2) {
+    nw = 4;
+    ns = (int)(budget / ((size_t)nw * p.stage_bytes));
+  }
+  if (ns > 4) ns = 4;
+  if (ns < 2) return MGB_EALIGN;
+  p.n_stages = ns;
+  const size_t smem_bytes = (size_t)nw * ns * p.stage_bytes + fixed;
+
+  CUtensorMap tmap;
+  const cuuint64_t gdim[3] = {(cuuint64_t)Wu, (cuuint64_t)H, (cuuint64_t)(C * T)};
+  const cuuint64_t gstride[2] = {(cuuint64_t)Wu * 2, (cuuint64_t)H * Wu * 2};
+  const cuuint32_t box[3] = {(cuuint32_t)wpu, (cuuint32_t)L, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(image), gdim, gstride, box,
+                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return MGB_EALIGN;
+
+  dim3 grid((unsigned)M, (unsigned)(with_stats ? Tm : 1));
+#define MGB_LAUNCH(ST, SO)                                                                              \
+  do {                                                                                                  \
+    MGB_CUDA_TRY(cudaFuncSetAttribute(roi_gather_tma_kernel<ST, SO>,                                    \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));   \
+    roi_gather_tma_kernel<ST, SO><<<grid, nw * 32, smem_bytes, st>>>(tmap, p);                          \
+  } while (0)
+  if (with_stats) {
+    if (roi) MGB_LAUNCH(true, true);
+    else MGB_LAUNCH(true, false);
+  } else {
+    MGB_LAUNCH(false, true);
+  }
+#undef MGB_LAUNCH
+  MGB_CUDA_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+}  // namespace mgb

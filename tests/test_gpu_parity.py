@@ -20,6 +20,16 @@ def dev(a, device):
     return torch.from_numpy(np.ascontiguousarray(a)).to(device)
 
 
+@pytest.fixture(params=["tma", "lsu"])
+def gather_path(request, cuda_device):
+    """Run the ROI-gather tests through both implementations: TMA-staged and plain load/store."""
+    from magnify_b200 import _lib
+
+    old = _lib.load().mgb_set_tma_enabled(1 if request.param == "tma" else 0)
+    yield request.param
+    _lib.load().mgb_set_tma_enabled(old)
+
+
 # ------------------------------------------------------------------------------------ stitch
 @pytest.mark.parametrize(
     "shape,overlap,dtype",
@@ -193,7 +203,7 @@ def test_bounding_boxes_round_half_even(cuda_device):
 
 
 # ------------------------------------------------------------------------------- beads golden
-def test_beads_golden(cuda_device, golden, make_pattern_image):
+def test_beads_golden(cuda_device, golden, make_pattern_image, gather_path):
     """Labels, fg/bg and ROI crops of BeadFinder's ROI half (find.py:561-602) -- fixture made
     with the reference's real utils.py."""
     from magnify_b200 import ops
@@ -229,7 +239,7 @@ def test_beads_golden(cuda_device, golden, make_pattern_image):
     assert m == roi.shape[0]
 
 
-def test_beads_zero_markers(cuda_device):
+def test_beads_zero_markers(cuda_device, gather_path):
     """find.py:557-558 / tests/test_beads.py:219-232: no beads -> empty mark dimension."""
     from magnify_b200 import ops
 
@@ -246,7 +256,7 @@ def test_beads_zero_markers(cuda_device):
 
 
 # -------------------------------------------------------------------------------- chip golden
-def test_chip_golden(cuda_device, golden, make_pattern_image):
+def test_chip_golden(cuda_device, golden, make_pattern_image, gather_path):
     """ROI crops + disc/annulus masks of ButtonFinder.find_rois and the copy-forward loop
     (find.py:143-176, 362-400) -- fixture made with the reference's real utils.py (cv.circle)."""
     from magnify_b200 import ops
@@ -293,7 +303,7 @@ def test_chip_masks_cv_golden(cuda_device, golden):
 # --------------------------------------------------------------------- randomized vs oracle
 @pytest.mark.parametrize("length,itemsize_dtype", [(72, np.uint16), (50, np.uint16), (51, np.uint16), (100, np.uint16),
                                                     (24, np.float32), (17, np.uint8), (16, np.float64)])
-def test_roi_gather_random(cuda_device, length, itemsize_dtype):
+def test_roi_gather_random(cuda_device, length, itemsize_dtype, gather_path):
     from magnify_b200 import ops
 
     rng = np.random.default_rng(11)
@@ -328,7 +338,7 @@ def test_median_random(cuda_device):
         np.testing.assert_array_equal(got, want)
 
 
-def test_full_size_properties_c2(cuda_device):
+def test_full_size_properties_c2(cuda_device, gather_path):
     """BASELINE config 2 at full size (4x4 tiles of 2048^2, overlap 102, 56x32 buttons, L=72):
     size-independent properties instead of a CPU replay -- the stitched image equals torch
     indexing of the tiles, ROI crops equal direct slices, sums of masked sums match."""
@@ -356,3 +366,32 @@ def test_full_size_properties_c2(cuda_device):
     sums = (roi.to(torch.float64) * fg[:, None, None].to(torch.float64)).sum((-1, -2))
     assert torch.equal(sums, stats[..., 2])
     assert torch.equal(stats[..., 0], fg.sum((-1, -2)).to(torch.float64)[:, None, None].expand(-1, c, t))
+
+
+@pytest.mark.parametrize("length", [72, 50, 33])
+def test_gather_stats_random_masks(cuda_device, gather_path, length):
+    """Fused gather + masked sums with arbitrary (overlapping, empty, full) masks and several
+    mask timesteps (chip with more than one search timestep, find.py:151,172-173)."""
+    from magnify_b200 import ops
+
+    rng = np.random.default_rng(21)
+    c, t, h, w, m = 3, 5, 200, 256, 11
+    image = rng.integers(0, 65535, (c, t, h, w), dtype=np.uint16, endpoint=True)
+    x = rng.uniform(0, w, (m, t))
+    y = rng.uniform(0, h, (m, t))
+    mask_t = np.array([0, 0, 1, 1, 1], dtype=np.int32)
+    fg = rng.random((m, 2, length, length)) < 0.3
+    bg = rng.random((m, 2, length, length)) < 0.5
+    fg[0] = False
+    bg[1] = True
+    want_roi = o_rois.gather_rois(image, x, y, length)
+    want = o_red.masked_stats(want_roi, fg[:, mask_t], bg[:, mask_t])
+    boxes = ops.bounding_boxes(dev(x, cuda_device), dev(y, cuda_device), length, w, h)
+    roi, stats = ops.roi_gather_stats(dev(image, cuda_device), boxes, dev(fg.view(np.uint8), cuda_device),
+                                      dev(bg.view(np.uint8), cuda_device), length, mask_t=dev(mask_t, cuda_device))
+    np.testing.assert_array_equal(roi.cpu().numpy(), want_roi)
+    np.testing.assert_allclose(stats.cpu().numpy(), want, rtol=1e-12, equal_nan=True)
+    _, stats2 = ops.roi_gather_stats(dev(image, cuda_device), boxes, dev(fg.view(np.uint8), cuda_device),
+                                     dev(bg.view(np.uint8), cuda_device), length, mask_t=dev(mask_t, cuda_device),
+                                     want_roi=False)
+    np.testing.assert_allclose(stats2.cpu().numpy(), want, rtol=1e-12, equal_nan=True)
