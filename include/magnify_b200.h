@@ -50,6 +50,10 @@ int mgb_sm_count(void);
 /* Kernels launched by this library in this process so far (bench.py's gpu_launches). */
 int64_t mgb_launch_count(void);
 
+/* Tuning knob of the vectorised stitch / flat-field+stitch kernel: prefetch-ring depth x CTAs per
+ * SM (0: 6x2, 1: 10x2, 2: 8x3).  Returns the previous value.  Results do not depend on it. */
+int mgb_set_stitch_variant(int variant);
+
 /* ---- F2: tile stitching, reference src/magnify/stitch.py:22-39 ----------------------------
  * image[c,t,y,x] = tiles[c,t, y/h, x/w, clip + y%h, clip + x%w], clip = overlap/2,
  * h = H-overlap, w = W-overlap.  Pure copy for any itemsize in {1,2,4,8}.  Argument checks

@@ -1,0 +1,430 @@
+"""Reference-facing components: the same names, arguments, exceptions and dataset schema as
+magnify's own (`src/magnify/preprocess.py:62-88`, `stitch.py:6-50`, `find.py:13-629`), with the
+pixel work done on the GPU through `magnify_b200.ops`.
+
+A component is a callable `Dataset -> Dataset`.  "Dataset" is an `xarray.Dataset` when xarray
+is installed, or `magnify_b200.dataset.Assay` (a minimal stand-in with the same accessors).
+`install()` registers the factories in `magnify.registry.components` under the reference's own
+names so that `mg.mrbles`, `mg.beads` and `mg.microfluidic_chip` pick them up unchanged
+(INTEGRATION.md).
+
+Centre finding is NOT part of this package (stochastic CPU RANSAC):
+`BeadFinder` / `ButtonFinder` take a `centers` hook, and fall back to the reference's own
+finder (`magnify.utils.find_circles`, `magnify.find.ButtonFinder.find_centers`) when the
+reference package is importable.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops, pipeline
+from .dataset import Assay
+
+TILE_DIMS = ("channel", "time", "tile_row", "tile_col", "tile_y", "tile_x")
+IMAGE_DIMS = ("channel", "time", "im_y", "im_x")
+
+
+# ---------------------------------------------------------------------------------------------
+# dataset adapters (xarray.Dataset or Assay)
+# ---------------------------------------------------------------------------------------------
+def _to_numpy(var) -> np.ndarray:
+    return var.to_numpy() if hasattr(var, "to_numpy") else np.asarray(var)
+
+
+def _device(device) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("magnify_b200 components need a CUDA device (there is no CPU fallback)")
+    return torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+
+
+def _tiles_to_device(assay, dev) -> torch.Tensor:
+    tile = assay["tile"]
+    if tuple(tile.dims) != TILE_DIMS:
+        raise ValueError(f"tile must have dims {TILE_DIMS} (run standardize_format first), got {tuple(tile.dims)}")
+    return torch.from_numpy(np.ascontiguousarray(_to_numpy(tile))).to(dev)
+
+
+def _read_tiff(path) -> np.ndarray:
+    import tifffile  # same dependency the reference uses at preprocess.py:75-81
+
+    with tifffile.TiffFile(os.fspath(path)) as tif:
+        return tif.asarray()
+
+
+# ---------------------------------------------------------------------------------------------
+# flatfield_correct  (preprocess.py:62-88)
+# ---------------------------------------------------------------------------------------------
+def flatfield_correct(xp, flatfield=1.0, darkfield=0.0, device=None):
+    if isinstance(flatfield, (str, os.PathLike)):
+        flatfield = _read_tiff(os.path.expanduser(flatfield))
+    if isinstance(darkfield, (str, os.PathLike)):
+        darkfield = _read_tiff(os.path.expanduser(darkfield))
+    dev = _device(device)
+    tiles = _tiles_to_device(xp, dev)
+    out = ops.flatfield_correct(tiles, flatfield, darkfield)
+    xp["tile"] = (TILE_DIMS, out.cpu().numpy())
+    return xp
+
+
+def make_flatfield_correct(flatfield=1.0, darkfield=0.0, device=None):
+    return lambda xp: flatfield_correct(xp, flatfield=flatfield, darkfield=darkfield, device=device)
+
+
+# ---------------------------------------------------------------------------------------------
+# stitch  (stitch.py:6-50)
+# ---------------------------------------------------------------------------------------------
+class Stitcher:
+    def __init__(self, overlap: int = 102, device=None):
+        if overlap < 0:
+            raise ValueError("Overlap must be non-negative.")  # stitch.py:8-9
+        self.overlap = overlap
+        self.device = device
+
+    def __call__(self, assay):
+        if "tile" not in assay:
+            raise AttributeError("Dataset must contain 'tile' data variable.")  # stitch.py:13-14
+        sizes = assay.sizes
+        ops.check_overlap(self.overlap, sizes["tile_y"], sizes["tile_x"])  # stitch.py:16-20
+        dev = _device(self.device)
+        image = ops.stitch(_tiles_to_device(assay, dev), self.overlap)
+        assay["image"] = (IMAGE_DIMS, image.cpu().numpy())
+        return assay
+
+
+def make_stitch(overlap: int = 102, device=None):
+    return Stitcher(overlap=overlap, device=device)
+
+
+class FlatfieldStitcher:
+    """flatfield_correct + stitch in one pass over the tiles (fused kernel); equivalent to the
+    two reference components back to back, minus the corrected `tile` variable (which the
+    predefined pipelines drop anyway, postprocess.py:6-17)."""
+
+    def __init__(self, flatfield=1.0, darkfield=0.0, overlap: int = 102, device=None):
+        if overlap < 0:
+            raise ValueError("Overlap must be non-negative.")
+        self.flatfield, self.darkfield, self.overlap, self.device = flatfield, darkfield, overlap, device
+
+    def __call__(self, assay):
+        if "tile" not in assay:
+            raise AttributeError("Dataset must contain 'tile' data variable.")
+        sizes = assay.sizes
+        ops.check_overlap(self.overlap, sizes["tile_y"], sizes["tile_x"])
+        flat, dark = self.flatfield, self.darkfield
+        if isinstance(flat, (str, os.PathLike)):
+            flat = _read_tiff(os.path.expanduser(flat))
+        if isinstance(dark, (str, os.PathLike)):
+            dark = _read_tiff(os.path.expanduser(dark))
+        dev = _device(self.device)
+        image = ops.flatfield_stitch(_tiles_to_device(assay, dev), flat, dark, overlap=self.overlap)
+        assay["image"] = (IMAGE_DIMS, image.cpu().numpy())
+        return assay
+
+
+# ---------------------------------------------------------------------------------------------
+# find_beads  (find.py:445-629)
+# ---------------------------------------------------------------------------------------------
+def _reference_utils():
+    try:
+        import magnify.utils as mu  # the reference package, when installed
+
+        return mu
+    except Exception:
+        return None
+
+
+class BeadFinder:
+    """ROI/mask half of the reference BeadFinder on the GPU (find.py:503-605).
+
+    centers: ndarray (M,3) of (row, col, radius) or a callable `assay -> ndarray`; when omitted
+    the reference's CPU finder is used (find.py:476-501), which needs `magnify` importable."""
+
+    def __init__(self, min_bead_diameter: int, max_bead_diameter: int, low_edge_quantile: float = 0.1,
+                 high_edge_quantile: float = 0.9, num_iter: int = 5000000, min_roundness: float = 0.3,
+                 roi_length: Optional[int] = None, search_channel=None, interactive: bool = False,
+                 centers=None, device=None):
+        if min_bead_diameter > max_bead_diameter:
+            raise ValueError("min_bead_diameter must be <= max_bead_diameter.")  # find.py:458-459
+        self.min_bead_radius = math.floor(min_bead_diameter / 2)
+        self.max_bead_radius = math.ceil(max_bead_diameter / 2)
+        self.low_edge_quantile, self.high_edge_quantile = low_edge_quantile, high_edge_quantile
+        self.num_iter, self.min_roundness = num_iter, min_roundness
+        self.roi_length = roi_length if roi_length is not None else 2 * max_bead_diameter  # find.py:467
+        self.search_channels = [] if search_channel is None else (
+            [search_channel] if isinstance(search_channel, str) else list(search_channel))
+        self.interactive = interactive
+        self.centers = centers
+        self.device = device
+
+    def find_centers(self, assay) -> np.ndarray:
+        if self.centers is not None:
+            beads = self.centers(assay) if callable(self.centers) else self.centers
+            return np.asarray(beads, dtype=np.float64).reshape(-1, 3)
+        mu = _reference_utils()
+        if mu is None:
+            raise ImportError("bead centre finding is delegated to the reference (magnify.utils.find_circles); "
+                              "magnify is not importable here -- pass centers=(M,3) array or callable")
+        import scipy.spatial
+
+        channels = self.search_channels or list(_to_numpy(assay["channel"]))
+        chan_index = list(_to_numpy(assay["channel"]))
+        image = _to_numpy(assay["image"])
+        beads = np.empty((0, 3))
+        for ch in channels:  # find.py:476-501
+            img = mu.to_uint8(image[chan_index.index(ch), 0])
+            b = mu.find_circles(img, low_edge_quantile=self.low_edge_quantile,
+                                high_edge_quantile=self.high_edge_quantile, grid_length=20, num_iter=self.num_iter,
+                                min_radius=self.min_bead_radius, max_radius=self.max_bead_radius,
+                                min_dist=self.min_bead_radius, min_roundness=self.min_roundness, gui=None)[0]
+            if len(beads) > 0 and len(b) > 0:
+                near = scipy.spatial.KDTree(beads[:, :2]).query_ball_point(b[:, :2], 2 * self.min_bead_radius)
+                b = b[~np.array([len(n) > 0 for n in near])]
+            beads = np.concatenate([beads, b])
+        return beads
+
+    def __call__(self, assay):
+        dev = _device(self.device)
+        beads = self.find_centers(assay)
+        image = torch.from_numpy(np.ascontiguousarray(_to_numpy(assay["image"]))).to(dev)
+        c, t, him, wim = image.shape
+        length = self.roi_length
+        m = len(beads)
+        x = np.repeat(beads[:, 1:2], t, axis=1)  # find.py:543-550
+        y = np.repeat(beads[:, 0:1], t, axis=1)
+        valid = np.ones((m, t), dtype=bool)  # find.py:551-554
+        if m == 0:  # find.py:557-558
+            roi = np.empty((0, c, t, length, length), dtype=_to_numpy(assay["image"]).dtype)
+            fg = np.empty((0, t, length, length), dtype=bool)
+            bg = fg.copy()
+        else:
+            xd = torch.from_numpy(x).to(dev).contiguous()
+            yd = torch.from_numpy(y).to(dev).contiguous()
+            boxes = ops.bounding_boxes(xd, yd, length, wim, him)
+            labels = ops.bead_labels(torch.from_numpy(beads.astype(np.int64).astype(np.int32)).to(dev), him, wim)
+            fg_d, bg_d = ops.bead_masks(labels, boxes[:, 0].contiguous(), length)
+            roi = ops.roi_gather(image, boxes, length).cpu().numpy()
+            # masks are time invariant (find.py:585-586): broadcast views, not copies
+            fg = np.broadcast_to(fg_d.cpu().numpy().astype(bool)[:, None], (m, t, length, length))
+            bg = np.broadcast_to(bg_d.cpu().numpy().astype(bool)[:, None], (m, t, length, length))
+        assay["roi"] = (("mark", "channel", "time", "roi_y", "roi_x"), roi)
+        return assay.assign_coords(
+            fg=(("mark", "time", "roi_y", "roi_x"), fg), bg=(("mark", "time", "roi_y", "roi_x"), bg),
+            x=(("mark", "time"), x), y=(("mark", "time"), y), valid=(("mark", "time"), valid))
+
+
+def make_find_beads(min_bead_diameter: int, max_bead_diameter: int, low_edge_quantile: float,
+                    high_edge_quantile: float, num_iter: int, min_roundness: float, roi_length: int,
+                    search_channel, interactive: bool, centers=None, device=None):
+    return BeadFinder(min_bead_diameter=min_bead_diameter, max_bead_diameter=max_bead_diameter,
+                      low_edge_quantile=low_edge_quantile, high_edge_quantile=high_edge_quantile, num_iter=num_iter,
+                      min_roundness=min_roundness, roi_length=roi_length, search_channel=search_channel,
+                      interactive=interactive, centers=centers, device=device)
+
+
+# ---------------------------------------------------------------------------------------------
+# find_buttons  (find.py:13-442)
+# ---------------------------------------------------------------------------------------------
+class ButtonFinder:
+    """ROI/mask half of the reference ButtonFinder on the GPU (find.py:143-181, 308-402).
+
+    centers: callable `(assay, t) -> (x, y, fg_radius)` giving, for a search timestep t, the final
+    button centres in image coordinates (rows x cols float64 each) and the foreground radii
+    (rows x cols int; max_button_radius where refinement found nothing, find.py:363,378).  When
+    omitted, the reference's own `find_centers` + per-ROI refinement run on the CPU (needs
+    `magnify`), with the refinement crops gathered by the GPU."""
+
+    def __init__(self, row_dist: float, col_dist: float, min_button_diameter: int, max_button_diameter: int,
+                 chamber_diameter: int, top_chamber=None, left_chamber=None, low_edge_quantile: float = 0.1,
+                 high_edge_quantile: float = 0.9, num_iter: int = 5000000, min_roundness: float = 0.20,
+                 cluster_penalty: float = 10, roi_length: Optional[int] = None, progress_bar: bool = False,
+                 search_timestep=0, search_channel=None, interactive: bool = False, centers: Optional[Callable] = None,
+                 device=None):
+        if min_button_diameter > max_button_diameter:
+            raise ValueError("min_button_diameter must be <= max_button_diameter.")  # find.py:34-35
+        self.row_dist, self.col_dist = row_dist, col_dist
+        self.min_button_radius = math.floor(min_button_diameter / 2)
+        self.max_button_radius = math.ceil(max_button_diameter / 2)
+        self.chamber_radius = round(chamber_diameter / 2)
+        self.roi_length = roi_length if roi_length is not None else round(1.2 * chamber_diameter)  # find.py:49
+        self.search_timesteps = sorted(np.atleast_1d(search_timestep).astype(int).tolist())
+        self.kwargs = dict(row_dist=row_dist, col_dist=col_dist, min_button_diameter=min_button_diameter,
+                           max_button_diameter=max_button_diameter, chamber_diameter=chamber_diameter,
+                           top_chamber=top_chamber, left_chamber=left_chamber, low_edge_quantile=low_edge_quantile,
+                           high_edge_quantile=high_edge_quantile, num_iter=num_iter, min_roundness=min_roundness,
+                           cluster_penalty=cluster_penalty, roi_length=roi_length, progress_bar=progress_bar,
+                           search_timestep=search_timestep, search_channel=search_channel, interactive=interactive)
+        self.centers = centers
+        self.device = device
+
+    def _reference_centers(self, assay, t):
+        try:
+            from magnify.find import ButtonFinder as RefFinder
+        except Exception as e:
+            raise ImportError("button centre finding is delegated to the reference (magnify.find.ButtonFinder); "
+                              "magnify is not importable here -- pass centers=callable") from e
+        ref = RefFinder(**self.kwargs)
+        if not ref.search_channels:
+            ref.search_channels = assay.channel
+        images = assay.image.isel(time=t).compute()
+        x, y = ref.find_centers(images.sel(channel=ref.search_channels), assay)
+        assay.x[..., t], assay.y[..., t] = x, y
+        # reference refinement loop (find.py:324-402): returns refined x, y and the fg masks, from
+        # which the per-button radius is recovered as the fg disc's row extent.
+        _, fg, _, x, y, _ = ref.find_rois(images, t, assay)
+        radius = (fg.any(axis=-1).sum(axis=-1) - 1) // 2
+        return np.asarray(x), np.asarray(y), radius.astype(np.int32)
+
+    def __call__(self, assay):
+        dev = _device(self.device)
+        image_np = _to_numpy(assay["image"])
+        image = torch.from_numpy(np.ascontiguousarray(image_np)).to(dev)
+        c, t, him, wim = image.shape
+        rows, cols = assay["tag"].shape
+        m = rows * cols
+        length = self.roi_length
+        src = pipeline.copy_forward_sources(t, self.search_timesteps)  # find.py:143-151
+        search = sorted(set(src.tolist()))
+        x = np.empty((rows, cols, t))
+        y = np.empty((rows, cols, t))
+        radius = np.empty((m, len(search)), dtype=np.int32)
+        if self.centers is None:
+            assay = assay.assign_coords(x=(("mark_row", "mark_col", "time"), x.copy()),
+                                        y=(("mark_row", "mark_col", "time"), y.copy()))
+        for k, ts in enumerate(search):
+            xs, ys, rs = self.centers(assay, ts) if self.centers is not None else self._reference_centers(assay, ts)
+            x[..., ts], y[..., ts], radius[:, k] = xs, ys, np.asarray(rs).reshape(m)
+        for ti in range(t):  # copy-forward of the centres, find.py:156-157,174-175
+            x[..., ti], y[..., ti] = x[..., src[ti]], y[..., src[ti]]
+        xd = torch.from_numpy(np.ascontiguousarray(x.reshape(m, t))).to(dev)
+        yd = torch.from_numpy(np.ascontiguousarray(y.reshape(m, t))).to(dev)
+        boxes, rel = ops.bounding_boxes(xd, yd, length, wim, him, want_rel=True)
+        fgs, bgs = [], []
+        for k, ts in enumerate(search):
+            f, b = ops.chip_masks(rel[:, ts].contiguous(), torch.from_numpy(radius[:, k].copy()).to(dev),
+                                  self.max_button_radius, self.chamber_radius, length)
+            fgs.append(f.cpu().numpy().astype(bool))
+            bgs.append(b.cpu().numpy().astype(bool))
+        index = {ts: k for k, ts in enumerate(search)}
+        mask_t = np.array([index[int(s)] for s in src])
+        fg = np.stack(fgs, 1)[:, mask_t]  # find.py:172-173
+        bg = np.stack(bgs, 1)[:, mask_t]
+        roi = ops.roi_gather(image, boxes, length).cpu().numpy()
+        valid = _to_numpy(assay["valid"]) if "valid" in assay else np.ones((rows, cols, t), dtype=bool)
+        valid = valid[:, :, src] if valid.ndim == 3 else valid
+        return self._emit(assay, roi, fg, bg, x, y, valid, rows, cols, t, length)
+
+    @staticmethod
+    def _emit(assay, roi, fg, bg, x, y, valid, rows, cols, t, length):
+        c = roi.shape[1]
+        try:
+            import xarray as xr
+        except Exception:
+            xr = None
+        if xr is not None and isinstance(assay, xr.Dataset):
+            assay["roi"] = (("mark_row", "mark_col", "channel", "time", "roi_y", "roi_x"),
+                            roi.reshape(rows, cols, c, t, length, length))
+            assay = assay.assign_coords(
+                fg=(("mark_row", "mark_col", "time", "roi_y", "roi_x"), fg.reshape(rows, cols, t, length, length)),
+                bg=(("mark_row", "mark_col", "time", "roi_y", "roi_x"), bg.reshape(rows, cols, t, length, length)),
+                x=(("mark_row", "mark_col", "time"), x), y=(("mark_row", "mark_col", "time"), y),
+                valid=(("mark_row", "mark_col", "time"), valid.reshape(rows, cols, t)))
+            return assay.stack(mark=("mark_row", "mark_col"), create_index=True).transpose("mark", ...)  # find.py:182
+        # Assay stand-in: the stacked `mark` dimension directly, row-major like xarray's stack
+        mr, mc = np.divmod(np.arange(rows * cols), cols)
+        assay = assay.drop_vars(["tag", "valid"], errors="ignore").assign_coords(
+            mark_row=(("mark",), mr), mark_col=(("mark",), mc),
+            tag=(("mark",), _to_numpy(assay["tag"]).reshape(-1)) if "tag" in assay else (("mark",), np.full(rows * cols, "default")),
+            fg=(("mark", "time", "roi_y", "roi_x"), fg), bg=(("mark", "time", "roi_y", "roi_x"), bg),
+            x=(("mark", "time"), x.reshape(rows * cols, t)), y=(("mark", "time"), y.reshape(rows * cols, t)),
+            valid=(("mark", "time"), np.asarray(valid).reshape(rows * cols, t)))
+        assay["roi"] = (("mark", "channel", "time", "roi_y", "roi_x"), roi)
+        return assay
+
+
+def make_find_buttons(row_dist, col_dist, min_button_diameter, max_button_diameter, chamber_diameter, top_chamber,
+                      left_chamber, low_edge_quantile, high_edge_quantile, num_iter, min_roundness, cluster_penalty,
+                      roi_length, progress_bar, search_timestep, search_channel, interactive, centers=None, device=None):
+    return ButtonFinder(row_dist, col_dist, min_button_diameter, max_button_diameter, chamber_diameter, top_chamber,
+                        left_chamber, low_edge_quantile, high_edge_quantile, num_iter, min_roundness, cluster_penalty,
+                        roi_length, progress_bar, search_timestep, search_channel, interactive, centers=centers,
+                        device=device)
+
+
+# ---------------------------------------------------------------------------------------------
+# quantify: the per-marker summaries the reference's consumers compute with xarray expressions
+# (identify.py:76-80, filter.py:21-22,51,74,82, README.md:21-22)
+# ---------------------------------------------------------------------------------------------
+def quantify(assay, median: bool = True, device=None):
+    """Adds fg_count/bg_count (mark,time) and fg_sum, bg_sum, fg_mean, bg_mean[, fg_median,
+    bg_median] (mark,channel,time) computed from roi/fg/bg: `roi.where(fg).mean(["roi_x","roi_y"])`
+    etc.  uint16 roi only."""
+    dev = _device(device)
+    roi = torch.from_numpy(np.ascontiguousarray(_to_numpy(assay["roi"]))).to(dev)
+    if roi.dtype != torch.uint16:
+        raise TypeError(f"quantify needs a uint16 roi, got {roi.dtype}")
+    m, c, t, length, _ = roi.shape
+    fg = torch.from_numpy(np.ascontiguousarray(_to_numpy(assay["fg"])).view(np.uint8)).to(dev)
+    bg = torch.from_numpy(np.ascontiguousarray(_to_numpy(assay["bg"])).view(np.uint8)).to(dev)
+    dims = ("mark", "channel", "time")
+    if m == 0:
+        empty = np.empty((0, c, t))
+        for name in ("fg_sum", "bg_sum", "fg_mean", "bg_mean") + (("fg_median", "bg_median") if median else ()):
+            assay[name] = (dims, empty.copy())
+        return assay
+    # an roi is its own image: boxes at the origin of a (M*C... ) stack would cost a copy, so
+    # reduce in place with the gather kernel reading each roi as a (C,T,L,L) image per marker.
+    stats = torch.empty((m, c, t, 6), dtype=torch.float64, device=dev)
+    zero_box = torch.zeros((1, t, 2), dtype=torch.int32, device=dev)
+    for i in range(m):
+        ops.roi_gather_stats(roi[i], zero_box, fg[i:i + 1], bg[i:i + 1], length, want_roi=False, out_stats=stats[i:i + 1])
+    s = stats.cpu().numpy()
+    assay["fg_sum"], assay["bg_sum"] = (dims, s[..., 2]), (dims, s[..., 3])
+    assay["fg_mean"], assay["bg_mean"] = (dims, s[..., 4]), (dims, s[..., 5])
+    assay["fg_count"], assay["bg_count"] = (("mark", "time"), s[:, 0, :, 0]), (("mark", "time"), s[:, 0, :, 1])
+    if median:
+        assay["fg_median"] = (dims, ops.roi_median(roi, fg).cpu().numpy())
+        assay["bg_median"] = (dims, ops.roi_median(roi, bg).cpu().numpy())
+    return assay
+
+
+def make_quantify(median: bool = True, device=None):
+    return lambda xp: quantify(xp, median=median, device=device)
+
+
+# ---------------------------------------------------------------------------------------------
+# registration
+# ---------------------------------------------------------------------------------------------
+FACTORIES = {
+    "flatfield_correct": make_flatfield_correct,
+    "stitch": make_stitch,
+    "find_beads": make_find_beads,
+    "find_buttons": make_find_buttons,
+}
+EXTRA_FACTORIES = {
+    "flatfield_stitch_b200": lambda flatfield=1.0, darkfield=0.0, overlap=102, device=None: FlatfieldStitcher(
+        flatfield, darkfield, overlap, device),
+    "quantify": make_quantify,
+}
+
+
+def install(override: bool = True):
+    """Register the GPU components in magnify's registry (registry.py:12-13).  With override the
+    reference's own names are replaced, so the predefined pipelines use them unchanged; the
+    `<name>_b200` aliases and "quantify" are always added."""
+    try:
+        import magnify.registry as registry
+    except Exception as e:
+        raise ImportError("magnify (and its dependencies xarray, dask, catalogue) must be importable to "
+                          "install the magnify_b200 components into its registry") from e
+    for name, factory in FACTORIES.items():
+        registry.components.register(name + "_b200")(factory)
+        if override:
+            registry.components.register(name)(factory)
+    for name, factory in EXTRA_FACTORIES.items():
+        registry.components.register(name)(factory)
+    return sorted(list(FACTORIES) + [n + "_b200" for n in FACTORIES] + list(EXTRA_FACTORIES))

@@ -155,7 +155,6 @@ struct StitchParams {
   int64_t Wim;     // Cc * w
   int64_t Him;     // R * h
   int P;           // tile-column period of the output phase
-  int q;           // this launch handles tile columns q, q+P, ...
   int K;           // number of coefficient tables (1 or C)
   int ct_splits;   // CTAs sharing one (row, x-block, q, k)
   int xblocks;     // ceil((w + 7) / 8 / 256)
@@ -180,13 +179,12 @@ __device__ __forceinline__ uint4 funnel8(const uint4& a, const uint4& b) {
   }
 }
 
-// Prefetch ring: every thread streams its own two 16-byte input vectors of the next
-// kStitchStages-1 tiles into shared memory with cp.async (LDGSTS, L1 bypass) and reads them
-// back itself, so the bytes in flight per SM (2 CTAs x 256 thr x 32 B x 5 = 80 KB) are decoupled
-// from the register file, which holds the 16 float64 coefficients.  A thread only ever reads
-// the slots it wrote: no block-level synchronisation is needed.
-constexpr int kStitchStages = 6;
-constexpr int kStitchSmemBytes = kStitchStages * 2 * kThreads * 16;
+// Prefetch ring: every thread streams its own aligned 16-byte input chunk of the next
+// kStitchStages tiles into shared memory with cp.async (LDGSTS, L1 bypass), so the bytes in
+// flight per SM are decoupled from the register file, which holds the 16 float64 coefficients.
+// A thread reads back its own slot and (for a shifted vector) its right neighbour's, which
+// needs only warp-level synchronisation; every input byte is requested from L2 once.
+constexpr int stitch_smem_bytes(int stages) { return stages * (kThreads + kThreads / 32) * 16; }
 
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
@@ -197,25 +195,28 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-template <int MODE, int S>
-__global__ void __launch_bounds__(kThreads, 2) stitch_u16_kernel(const StitchParams p) {
-  extern __shared__ uint4 ring[];   // [stage][2][kThreads]
+template <int MODE, int S, int kStitchStages>
+__device__ __forceinline__ void stitch_u16_body(const StitchParams& p, uint4* ring, int q, int k, int split) {
   const int xb = blockIdx.x % p.xblocks;
   const int y = blockIdx.x / p.xblocks;
-  const int q = p.q;
-  const int k = blockIdx.y;
-  const int split = blockIdx.z;
 
   const int phase = (int)(((int64_t)q * p.w) & 7);
   const int j = xb * kThreads + threadIdx.x;   // output vector index within the kept row
   const int xk0 = 8 * j - phase;               // first kept pixel of this thread
-  if (xk0 >= p.w) return;                      // whole vector right of the kept row
+  // a warp whose first vector is already right of the kept row has nothing to do (the last
+  // active lane of the previous warp streams its own extra chunk)
+  if (8 * (j - (int)(threadIdx.x & 31)) - phase >= p.w) return;
+  const bool active = xk0 < p.w;               // lanes right of the kept row only feed neighbours
   const int xin0 = p.clip + xk0;               // may be negative for the first vector
   const int a0 = (xin0 - S) >> 3;              // aligned input chunk (exact: xin0 - S = 8 * a0)
   const int chunks = p.W >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // Every thread streams ONE aligned 16-byte chunk per tile; the second chunk a shifted vector
+  // needs (S != 0) is the next lane's chunk, read back from its ring slot after a __syncwarp.
+  // Lane 31 has no next lane in its warp, so it also streams chunk a0+1 into a per-warp slot.
   const bool ld_a = (a0 >= 0) && (a0 < chunks);
-  const bool ld_b = (S != 0) && (a0 + 1 >= 0) && (a0 + 1 < chunks);
-  const bool full = (xk0 >= 0) && (xk0 + 8 <= p.w);
+  const bool ld_x = (S != 0) && (lane == 31) && (a0 + 1 >= 0) && (a0 + 1 < chunks);
+  const bool full = active && (xk0 >= 0) && (xk0 + 8 <= p.w);
 
   // Images handled by this CTA: table k covers ct in [k*T, (k+1)*T) when K > 1.
   const int64_t n_ct = (p.K == 1) ? p.CT : p.T;
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 2) stitch_u16_kernel(const StitchPar
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int xi = xin0 + i;
-      const bool in = (xi >= 0) && (xi < p.W);
+      const bool in = active && (xi >= 0) && (xi < p.W);
       // out-of-row lanes: s = 2^20 + 2^19 + 0.5 never trips the guard (their result is not stored)
       g[i] = in ? p.gain[base + xi] : 0.0;
       b[i] = in ? p.bias[base + xi] : 1572864.5;
@@ -253,23 +254,23 @@ __global__ void __launch_bounds__(kThreads, 2) stitch_u16_kernel(const StitchPar
   uint16_t* op = p.image + ((ct_lo * p.Him + y) * p.Wim + (int64_t)q * p.w + xk0);
   int ci_in = 0, ci_out = 0;
 
+  constexpr int kStageVecs = kThreads + kThreads / 32;       // 256 chunks + one spare per warp
   uint4* slot_a = ring + threadIdx.x;
-  uint4* slot_b = ring + kThreads + threadIdx.x;
+  uint4* slot_b = (lane < 31) ? slot_a + 1 : ring + kThreads + warp;
   const uint32_t sa = (uint32_t)__cvta_generic_to_shared(slot_a);
-  const uint32_t sb = (uint32_t)__cvta_generic_to_shared(slot_b);
-  constexpr int kStageVecs = 2 * kThreads;
+  const uint32_t sx = (uint32_t)__cvta_generic_to_shared(ring + kThreads + warp);
   if (!ld_a) {
 #pragma unroll
     for (int s = 0; s < kStitchStages; ++s) slot_a[s * kStageVecs] = make_uint4(0, 0, 0, 0);
   }
-  if (!ld_b) {
+  if (S != 0 && lane == 31 && !ld_x) {
 #pragma unroll
-    for (int s = 0; s < kStitchStages; ++s) slot_b[s * kStageVecs] = make_uint4(0, 0, 0, 0);
+    for (int s = 0; s < kStitchStages; ++s) ring[s * kStageVecs + kThreads + warp] = make_uint4(0, 0, 0, 0);
   }
 
   auto issue = [&](int stage) {
     if (ld_a) cp_async16(sa + stage * (kStageVecs * 16), ip);
-    if (ld_b) cp_async16(sb + stage * (kStageVecs * 16), ip + 1);
+    if (ld_x) cp_async16(sx + stage * (kStageVecs * 16), ip + 1);
     const bool wrap = (++ci_in == cols_q);
     if (wrap) ci_in = 0;
     ip += wrap ? in_wrap8 : in_step8;
@@ -283,7 +284,9 @@ __global__ void __launch_bounds__(kThreads, 2) stitch_u16_kernel(const StitchPar
   }
   int stage = 0;
   for (int it = 0; it < n_iter; ++it) {
-    // refill the slot consumed in the previous iteration, then wait for this iteration's data
+    // refill the stage consumed in the previous iteration (all lanes are past reading it), then
+    // wait for this iteration's chunk -- and, for a shifted vector, the neighbours' chunks
+    if constexpr (S != 0) __syncwarp();
     if (it + kStitchStages - 1 < n_iter) {
       int pf = stage + kStitchStages - 1;
       if (pf >= kStitchStages) pf -= kStitchStages;
@@ -291,6 +294,7 @@ __global__ void __launch_bounds__(kThreads, 2) stitch_u16_kernel(const StitchPar
     }
     cp_async_commit();
     cp_async_wait<kStitchStages - 1>();
+    if constexpr (S != 0) __syncwarp();
     const uint4 va = slot_a[stage * kStageVecs];
     const uint4 vb = (S != 0) ? slot_b[stage * kStageVecs] : va;
     if (++stage == kStitchStages) stage = 0;
@@ -339,6 +343,30 @@ __global__ void __launch_bounds__(kThreads, 2) stitch_u16_kernel(const StitchPar
   }
 }
 
+// One launch covers every output phase: blockIdx.y = k * P + q.  The input shift S is uniform per
+// CTA, so the tile loop is instantiated once per S and selected with a CTA-uniform switch; all
+// tile columns of an image row are then written in the same time window and the tiles are read in
+// their natural order, which is what DRAM likes.
+template <int MODE, int kStitchStages, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) stitch_u16_kernel(const StitchParams p) {
+  extern __shared__ uint4 ring[];   // [stage][2][kThreads]
+  const int q = blockIdx.y % p.P;
+  const int k = blockIdx.y / p.P;
+  const int split = blockIdx.z;
+  const int phase = (int)(((int64_t)q * p.w) & 7);
+  const int S = (((p.clip - phase) % 8) + 8) % 8;
+  switch (S) {
+    case 0: stitch_u16_body<MODE, 0, kStitchStages>(p, ring, q, k, split); break;
+    case 1: stitch_u16_body<MODE, 1, kStitchStages>(p, ring, q, k, split); break;
+    case 2: stitch_u16_body<MODE, 2, kStitchStages>(p, ring, q, k, split); break;
+    case 3: stitch_u16_body<MODE, 3, kStitchStages>(p, ring, q, k, split); break;
+    case 4: stitch_u16_body<MODE, 4, kStitchStages>(p, ring, q, k, split); break;
+    case 5: stitch_u16_body<MODE, 5, kStitchStages>(p, ring, q, k, split); break;
+    case 6: stitch_u16_body<MODE, 6, kStitchStages>(p, ring, q, k, split); break;
+    default: stitch_u16_body<MODE, 7, kStitchStages>(p, ring, q, k, split); break;
+  }
+}
+
 // Element-wise fallbacks (any itemsize / any shape).
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
@@ -379,18 +407,29 @@ ff_apply_generic_kernel(const T* __restrict__ tiles, T* __restrict__ out, int64_
   }
 }
 
-template <int MODE>
-static int launch_stitch_fast(const StitchParams& p, int S, cudaStream_t st) {
-  dim3 grid((unsigned)(p.h * p.xblocks), (unsigned)p.K, (unsigned)p.ct_splits);
-#define MGB_CASE(SS) \
-  case SS: stitch_u16_kernel<MODE, SS><<<grid, kThreads, kStitchSmemBytes, st>>>(p); break;
-  switch (S) {
-    MGB_CASE(0) MGB_CASE(1) MGB_CASE(2) MGB_CASE(3) MGB_CASE(4) MGB_CASE(5) MGB_CASE(6) MGB_CASE(7)
-    default: return MGB_EINVAL;
+static int g_stitch_variant = 0;   // tuning knob: 0 = 6 stages x 2 CTAs/SM, 1 = 10 x 2, 2 = 8 x 3
+
+template <int MODE, int D, int B>
+static int launch_stitch_variant(const StitchParams& p, cudaStream_t st) {
+  dim3 grid((unsigned)(p.h * p.xblocks), (unsigned)(p.K * p.P), (unsigned)p.ct_splits);
+  constexpr int smem = stitch_smem_bytes(D);
+  static bool attr_set = false;
+  if (!attr_set && smem > 48 * 1024) {
+    MGB_CUDA_TRY(cudaFuncSetAttribute(stitch_u16_kernel<MODE, D, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
   }
-#undef MGB_CASE
+  stitch_u16_kernel<MODE, D, B><<<grid, kThreads, smem, st>>>(p);
   MGB_CUDA_LAUNCH_CHECK();
   return MGB_OK;
+}
+
+template <int MODE>
+static int launch_stitch_fast(const StitchParams& p, cudaStream_t st) {
+  switch (g_stitch_variant) {
+    case 1: return launch_stitch_variant<MODE, 11, 2>(p, st);
+    case 2: return launch_stitch_variant<MODE, 8, 3>(p, st);
+    default: return launch_stitch_variant<MODE, 6, 2>(p, st);
+  }
 }
 
 static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
@@ -417,7 +456,7 @@ static int run_stitch_fast(StitchParams p, cudaStream_t st) {
   p.xblocks = (int)ceil_div(ceil_div((int64_t)p.w + 7, 8), kThreads);
   // Enough CTAs for several waves at 2 CTAs/SM without shortening the per-thread tile loop
   // below ~16 iterations (the register-resident coefficients are loaded once per CTA).
-  const int64_t base_ctas = (int64_t)p.h * p.xblocks * p.K;
+  const int64_t base_ctas = (int64_t)p.h * p.xblocks * p.K * p.P;
   const int64_t n_ct = (p.K == 1) ? p.CT : p.T;
   const int64_t cols_q = (p.Cc + p.P - 1) / p.P;
   if (n_ct * p.R * cols_q >= INT32_MAX) return MGB_EUNSUPPORTED;   // 32-bit tile loop counter
@@ -426,14 +465,8 @@ static int run_stitch_fast(StitchParams p, cudaStream_t st) {
          (n_ct / (splits * 2)) * p.R * cols_q >= 16 && splits < 32768)
     splits *= 2;
   p.ct_splits = (int)splits;
-  for (int q = 0; q < p.P; ++q) {
-    const int phase = (int)(((int64_t)q * p.w) & 7);
-    const int S = (((p.clip - phase) % 8) + 8) % 8;
-    p.q = q;
-    const int rc = launch_stitch_fast<MODE>(p, S, st);
-    if (rc != MGB_OK) return rc;
-  }
-  return MGB_OK;
+  if ((int64_t)p.K * p.P > 65535 || splits > 65535) return MGB_EUNSUPPORTED;
+  return launch_stitch_fast<MODE>(p, st);
 }
 
 static int grid_for(int64_t n) {
@@ -451,6 +484,12 @@ using namespace mgb;
 extern "C" {
 
 int mgb_sm_count(void) { return cached_sm_count(); }
+
+int mgb_set_stitch_variant(int variant) {
+  const int old = g_stitch_variant;
+  if (variant >= 0 && variant <= 2) g_stitch_variant = variant;
+  return old;
+}
 
 int mgb_stitch(const void* tiles, void* image, int64_t C, int64_t T, int64_t R, int64_t Cc,
                int64_t H, int64_t W, int64_t overlap, int itemsize, int* host_used_fast,
