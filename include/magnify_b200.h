@@ -120,6 +120,10 @@ int mgb_bounding_boxes(const double* x, const double* y, int64_t n, int L, int64
  * not a multiple of 16 bytes or the window does not fit shared memory.  This switch forces the
  * plain kernels (tests cover both); returns the previous setting.  Default: enabled. */
 int mgb_set_tma_enabled(int enabled);
+/* Loader of the staged gather: 0 = TMA tensor copy (cp.async.bulk.tensor, default), 1 = per-warp
+ * cp.async 16-byte chunks.  Both measured within 1% of each other on B200 (DRAM fetches 128-byte
+ * lines for the row fragments either way).  Returns the previous value; results do not depend on it. */
+int mgb_set_gather_loader(int loader);
 
 /* ---- F4 (+R): ROI gather, reference find.py:160-169, 324-334, 370-377, 589-602 -------------
  * roi[m,c,t] = image[c,t, top:top+L, left:left+L] for any itemsize in {1,2,4,8}. */

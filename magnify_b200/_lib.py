@@ -32,6 +32,7 @@ SIGNATURES = {
     "mgb_launch_count": [],
     "mgb_set_tma_enabled": [c_int],
     "mgb_set_stitch_variant": [c_int],
+    "mgb_set_gather_loader": [c_int],
     "mgb_stitch": [_P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _I64, c_int, POINTER(c_int), _P],
     "mgb_flatfield_tilemax_u16": [_P, _I64, _I64, _I64, c_int, c_int, _P, _P],
     "mgb_flatfield_maxima": [_P, c_int, c_int, _I64, _P, _P, _P, _P],
@@ -49,7 +50,7 @@ SIGNATURES = {
     "mgb_bead_masks": [_P, _I64, _I64, _P, _I64, c_int, _P, _P, _P, _P],
 }
 _SPECIAL_RESTYPE = {"mgb_error_string": c_char_p, "mgb_launch_count": c_int64}
-_NO_STATUS = {"mgb_abi_version", "mgb_error_string", "mgb_sm_count", "mgb_launch_count", "mgb_set_tma_enabled", "mgb_set_stitch_variant"}
+_NO_STATUS = {"mgb_abi_version", "mgb_error_string", "mgb_sm_count", "mgb_launch_count", "mgb_set_tma_enabled", "mgb_set_stitch_variant", "mgb_set_gather_loader"}
 
 _lib = None
 

@@ -256,6 +256,8 @@ int roi_gather_tma(const void* image, int64_t C, int64_t T, int64_t H, int64_t W
                    const int32_t* boxes, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
                    const uint8_t* bg, int64_t M, int L, void* roi, double* stats, cudaStream_t st);
 
+extern int g_gather_loader;
+
 static int g_tma_enabled = 1;
 
 }  // namespace mgb
@@ -326,6 +328,12 @@ static int gather_common(const void* image, int64_t C, int64_t T, int64_t H, int
 int mgb_set_tma_enabled(int enabled) {
   const int old = g_tma_enabled;
   g_tma_enabled = enabled ? 1 : 0;
+  return old;
+}
+
+int mgb_set_gather_loader(int loader) {
+  const int old = g_gather_loader;
+  if (loader == 0 || loader == 1) g_gather_loader = loader;
   return old;
 }
 

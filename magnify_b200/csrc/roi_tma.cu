@@ -17,6 +17,8 @@
 //
 // Reference semantics: roi[m,c,t] = image[c,t, top:top+L, left:left+L] (find.py:160-169,
 // 324-334, 589-602); sums/means over fg/bg (identify.py:76-80, filter.py:21-22,51).
+#include <cstdlib>
+
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -39,6 +41,9 @@ struct TmaGatherParams {
   int wpu;                  // TMA box width: roundup8(wu + 7) units
   int unit;                 // 16-bit units per element
   int n_stages;
+  int loader;               // 0 = TMA tensor copy, 1 = cp.async chunks (sector granularity)
+  const uint16_t* image;    // 16-bit units, for the cp.async loader
+  int64_t H, Wu;
   int stage_bytes;          // rows * wpu * 2 rounded up to 128
   uint32_t vpr;             // 16-byte vectors per roi row (wu / 8) when the vector path applies, else 0
   uint32_t magic_vpr;       // ceil(2^32 / vpr)
@@ -91,31 +96,54 @@ __device__ __forceinline__ uint4 shift_units(const uint4& a, const uint4& b) {
 }
 
 // Vector path for one window: rows of wu = 8*vpr units, output 16-byte aligned.
-template <bool STATS, bool STORE, int S>
+// VPL > 0: the loop over this lane's vectors is fully unrolled and the lane's mask bytes and
+// shared-memory offsets (which do not depend on the window) live in registers for the whole CTA.
+template <bool STATS, bool STORE, int S, int VPL>
 __device__ __forceinline__ void consume_vec(const TmaGatherParams& p, const uint8_t* buf, uint16_t* dst,
                                             const uint8_t* fgm, const uint8_t* bgm, int lane,
+                                            const uint2* fm, const uint2* bm, const uint32_t* svo,
                                             uint32_t* sf_out, uint32_t* sb_out) {
   const uint4* s4 = reinterpret_cast<const uint4*>(buf);
-  const uint2* f2 = reinterpret_cast<const uint2*>(fgm);
-  const uint2* b2 = reinterpret_cast<const uint2*>(bgm);
   uint4* d4 = reinterpret_cast<uint4*>(dst);
-  const uint32_t nvec = p.rows * p.vpr, pitch = p.wpu >> 3;
+  const uint32_t nvec = p.rows * p.vpr;
   uint32_t sf = 0, sb = 0;
+  if constexpr (VPL > 0) {
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const uint32_t v = lane + 32 * k;
+      if (v < nvec) {
+        const uint4 a = s4[svo[k]];
+        const uint4 b = (S != 0) ? s4[svo[k] + 1] : a;
+        const uint4 d = shift_units<S>(a, b);
+        if constexpr (STORE) stg_stream(d4 + v, d);
+        if constexpr (STATS) {
+          sf = __dp2a_lo(d.x, fm[k].x, sf); sf = __dp2a_hi(d.y, fm[k].x, sf);
+          sf = __dp2a_lo(d.z, fm[k].y, sf); sf = __dp2a_hi(d.w, fm[k].y, sf);
+          sb = __dp2a_lo(d.x, bm[k].x, sb); sb = __dp2a_hi(d.y, bm[k].x, sb);
+          sb = __dp2a_lo(d.z, bm[k].y, sb); sb = __dp2a_hi(d.w, bm[k].y, sb);
+        }
+      }
+    }
+  } else {
+    const uint2* f2 = reinterpret_cast<const uint2*>(fgm);
+    const uint2* b2 = reinterpret_cast<const uint2*>(bgm);
+    const uint32_t pitch = p.wpu >> 3;
 #pragma unroll 4
-  for (uint32_t v = lane; v < nvec; v += 32) {
-    const uint32_t row = __umulhi(v, p.magic_vpr);
-    const uint32_t sv = row * pitch + (v - row * p.vpr);
-    const uint4 a = s4[sv];
-    const uint4 b = (S != 0) ? s4[sv + 1] : a;
-    const uint4 d = shift_units<S>(a, b);
-    if constexpr (STORE) stg_stream(d4 + v, d);
-    if constexpr (STATS) {
-      const uint2 f = f2[v];
-      const uint2 g = b2[v];
-      sf = __dp2a_lo(d.x, f.x, sf); sf = __dp2a_hi(d.y, f.x, sf);
-      sf = __dp2a_lo(d.z, f.y, sf); sf = __dp2a_hi(d.w, f.y, sf);
-      sb = __dp2a_lo(d.x, g.x, sb); sb = __dp2a_hi(d.y, g.x, sb);
-      sb = __dp2a_lo(d.z, g.y, sb); sb = __dp2a_hi(d.w, g.y, sb);
+    for (uint32_t v = lane; v < nvec; v += 32) {
+      const uint32_t row = __umulhi(v, p.magic_vpr);
+      const uint32_t sv = row * pitch + (v - row * p.vpr);
+      const uint4 a = s4[sv];
+      const uint4 b = (S != 0) ? s4[sv + 1] : a;
+      const uint4 d = shift_units<S>(a, b);
+      if constexpr (STORE) stg_stream(d4 + v, d);
+      if constexpr (STATS) {
+        const uint2 f = f2[v];
+        const uint2 g = b2[v];
+        sf = __dp2a_lo(d.x, f.x, sf); sf = __dp2a_hi(d.y, f.x, sf);
+        sf = __dp2a_lo(d.z, f.y, sf); sf = __dp2a_hi(d.w, f.y, sf);
+        sb = __dp2a_lo(d.x, g.x, sb); sb = __dp2a_hi(d.y, g.x, sb);
+        sb = __dp2a_lo(d.z, g.y, sb); sb = __dp2a_hi(d.w, g.y, sb);
+      }
     }
   }
   *sf_out = sf;
@@ -161,7 +189,11 @@ __device__ __forceinline__ void consume_generic(const TmaGatherParams& p, const 
   *sb_out = sb;
 }
 
-template <bool STATS, bool STORE>
+__device__ __forceinline__ void cp_async16_cg(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+
+template <bool STATS, bool STORE, int VPL>
 __global__ void __launch_bounds__(kTmaMaxWarps * 32, 1)
 roi_gather_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGatherParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -214,7 +246,7 @@ roi_gather_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGatherP
     nb = __reduce_add_sync(0xffffffffu, nb);
     if (lane == 0) { s_cnt[0][warp] = nf; s_cnt[1][warp] = nb; }
   }
-  if (lane == 0) {
+  if (p.loader == 0 && lane == 0) {
     for (int s = 0; s < p.n_stages; ++s) mbar_init(smem_u32(&bars[warp * 8 + s]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -229,52 +261,128 @@ roi_gather_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGatherP
     cnt_bg = (double)c;
   }
 
+  // window-independent per-lane state of the unrolled vector path
+  constexpr int kV = VPL > 0 ? VPL : 1;
+  uint2 fm[kV], bm[kV];
+  uint32_t svo[kV];
+  if constexpr (VPL > 0) {
+    const uint32_t nvec = p.rows * p.vpr, pitch = p.wpu >> 3;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const uint32_t v = lane + 32 * k;
+      const uint32_t vv = v < nvec ? v : 0;
+      const uint32_t row = __umulhi(vv, p.magic_vpr);
+      svo[k] = row * pitch + (vv - row * p.vpr);
+      if constexpr (STATS) {
+        fm[k] = reinterpret_cast<const uint2*>(fgm)[vv];
+        bm[k] = reinterpret_cast<const uint2*>(bgm)[vv];
+      } else {
+        fm[k] = make_uint2(0, 0);
+        bm[k] = make_uint2(0, 0);
+      }
+    }
+  }
+
   uint8_t* my_stages = stages + (size_t)warp * p.n_stages * p.stage_bytes;
   const uint32_t my_stage0 = smem_u32(my_stages);
   const uint32_t my_bar0 = smem_u32(&bars[warp * 8]);
   const uint32_t tx_bytes = (uint32_t)(p.rows * p.wpu * 2);
+  const int cpr = p.wpu >> 3;                   // 16-byte chunks per staged row
+  const int n_chunks = p.rows * cpr;
 
   auto item_ct = [&](int i, int64_t* c, int64_t* t) {
     *c = i / nt;
     *t = tlist[i - (int)(*c) * nt];
   };
-  auto issue_load = [&](int i, int s) {       // lane 0 only
+  // TMA loader: lane 0 arms the stage's mbarrier and issues one tensor copy for the window.
+  auto issue_tma = [&](int i, int s) {
+    if (lane == 0) {
+      int64_t c, t;
+      item_ct(i, &c, &t);
+      const int32_t top = p.boxes[(m * p.T + t) * 2];
+      const int32_t left = p.boxes[(m * p.T + t) * 2 + 1];
+      const uint32_t bar = my_bar0 + s * 8;
+      mbar_expect_tx(bar, tx_bytes);
+      tma_load_3d(my_stage0 + s * p.stage_bytes, &tmap, bar, (left * p.unit) & ~7, top, (int)(c * p.T + t));
+    }
+  };
+  // LSU loader: the warp streams the window's 16-byte chunks with cp.async (32-byte sector
+  // granularity in L2/DRAM instead of the 128-byte lines TMA fetches); chunks that start right of
+  // the image row or that the shifted row does not touch are skipped.
+  auto issue_lsu = [&](int i, int s) {
     int64_t c, t;
     item_ct(i, &c, &t);
     const int32_t top = p.boxes[(m * p.T + t) * 2];
-    const int32_t left = p.boxes[(m * p.T + t) * 2 + 1];
-    const uint32_t bar = my_bar0 + s * 8;
-    mbar_expect_tx(bar, tx_bytes);
-    tma_load_3d(my_stage0 + s * p.stage_bytes, &tmap, bar, (left * p.unit) & ~7, top, (int)(c * p.T + t));
+    const int32_t left_u = p.boxes[(m * p.T + t) * 2 + 1] * p.unit;
+    const int left_al = left_u & ~7;
+    const int last_chunk = ((left_u & 7) + p.wu - 1) >> 3;               // last chunk the row touches
+    const int max_chunk = (int)((p.Wu - left_al) >> 3) - 1;              // last chunk inside the image row
+    const int lim = last_chunk < max_chunk ? last_chunk : max_chunk;
+    const uint16_t* base = p.image + ((c * p.T + t) * p.H + top) * p.Wu + left_al;
+    const uint32_t dst0 = my_stage0 + s * p.stage_bytes;
+    int row = lane / cpr, col = lane - row * cpr;
+    const int drow = 32 / cpr, dcol = 32 - drow * cpr;
+    for (int j = lane; j < n_chunks; j += 32) {
+      if (col <= lim) cp_async16_cg(dst0 + j * 16, base + (int64_t)row * p.Wu + col * 8);
+      row += drow;
+      col += dcol;
+      if (col >= cpr) { col -= cpr; ++row; }
+    }
   };
 
-  if (lane == 0) {
+  if (p.loader == 0) {
     for (int s = 0; s < p.n_stages - 1; ++s) {
       const int i = warp + s * nw;
-      if (i < n_items) issue_load(i, s);
+      if (i < n_items) issue_tma(i, s);
+    }
+  } else {
+    for (int s = 0; s < p.n_stages - 1; ++s) {
+      const int i = warp + s * nw;
+      if (i < n_items) issue_lsu(i, s);
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
   }
   int s = 0;
   uint32_t parity = 0;
   for (int i = warp; i < n_items; i += nw) {
+    // refill the stage the previous item used (every lane is past reading it)
+    {
+      const int nxt = i + (p.n_stages - 1) * nw;
+      int rs = s + p.n_stages - 1;
+      if (rs >= p.n_stages) rs -= p.n_stages;
+      if (p.loader == 0) {
+        if (nxt < n_items) issue_tma(nxt, rs);
+      } else {
+        if (nxt < n_items) issue_lsu(nxt, rs);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+    }
     int64_t c, t;
     item_ct(i, &c, &t);
     const int shift = (p.boxes[(m * p.T + t) * 2 + 1] * p.unit) & 7;
     const int64_t n = (m * p.C + c) * p.T + t;
     uint16_t* dst = STORE ? p.roi + n * (int64_t)p.rows * p.wu : nullptr;
     const uint8_t* buf = my_stages + (size_t)s * p.stage_bytes;
-    mbar_wait(my_bar0 + s * 8, parity);
+    if (p.loader == 0) {
+      mbar_wait(my_bar0 + s * 8, parity);
+    } else {
+      // all but the newest n_stages-1 groups are complete -> this item's chunks have landed
+      switch (p.n_stages) {
+        case 2: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+      }
+      __syncwarp();
+    }
     uint32_t sf = 0, sb = 0;
     if (p.vpr) {
       switch (shift) {
-        case 0: consume_vec<STATS, STORE, 0>(p, buf, dst, fgm, bgm, lane, &sf, &sb); break;
-        case 1: consume_vec<STATS, STORE, 1>(p, buf, dst, fgm, bgm, lane, &sf, &sb); break;
-        case 2: consume_vec<STATS, STORE, 2>(p, buf, dst, fgm, bgm, lane, &sf, &sb); break;
-        case 3: consume_vec<STATS, STORE, 3>(p, buf, dst, fgm, bgm, lane, &sf, &sb); break;
-        case 4: consume_vec<STATS, STORE, 4>(p, buf, dst, fgm, bgm, lane, &sf, &sb); break;
-        case 5: consume_vec<STATS, STORE, 5>(p, buf, dst, fgm, bgm, lane, &sf, &sb); break;
-        case 6: consume_vec<STATS, STORE, 6>(p, buf, dst, fgm, bgm, lane, &sf, &sb); break;
-        default: consume_vec<STATS, STORE, 7>(p, buf, dst, fgm, bgm, lane, &sf, &sb); break;
+#define MGB_CONSUME(SS) \
+  case SS: consume_vec<STATS, STORE, SS, VPL>(p, buf, dst, fgm, bgm, lane, fm, bm, svo, &sf, &sb); break;
+        MGB_CONSUME(0) MGB_CONSUME(1) MGB_CONSUME(2) MGB_CONSUME(3)
+        MGB_CONSUME(4) MGB_CONSUME(5) MGB_CONSUME(6)
+        default: consume_vec<STATS, STORE, 7, VPL>(p, buf, dst, fgm, bgm, lane, fm, bm, svo, &sf, &sb); break;
+#undef MGB_CONSUME
       }
     } else {
       consume_generic<STATS, STORE>(p, buf, dst, fgm, bgm, lane, shift, &sf, &sb);
@@ -289,15 +397,6 @@ roi_gather_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGatherP
       }
     }
     __syncwarp();
-    // every lane is done reading this stage's predecessor: refill the stage item k-1 used
-    if (lane == 0) {
-      const int nxt = i + (p.n_stages - 1) * nw;
-      if (nxt < n_items) {
-        int rs = s + p.n_stages - 1;
-        if (rs >= p.n_stages) rs -= p.n_stages;
-        issue_load(nxt, rs);
-      }
-    }
     if (++s == p.n_stages) { s = 0; parity ^= 1; }
   }
 }
@@ -313,6 +412,8 @@ static PFN_cuTensorMapEncodeTiled get_encode_fn() {
   }
   return fn;
 }
+
+int g_gather_loader = 0;   // 0 = TMA tensor copies (default), 1 = cp.async chunks; equal within 1% on B200
 
 static uint32_t magic_u32(uint32_t d) { return (uint32_t)((0x100000000ULL + d - 1) / d); }
 
@@ -353,6 +454,7 @@ int roi_gather_tma(const void* image, int64_t C, int64_t T, int64_t H, int64_t W
   MGB_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const size_t budget = (size_t)max_smem > fixed + 1024 ? (size_t)max_smem - fixed - 1024 : 0;
   int nw = kTmaMaxWarps;
+  if (const char* e = getenv("MGB_GATHER_WARPS")) nw = atoi(e) == 4 ? 4 : kTmaMaxWarps;   // tuning only
   int ns = (int)(budget / ((size_t)nw * p.stage_bytes));
   if (ns < 2) {
     nw = 4;
@@ -373,19 +475,32 @@ int roi_gather_tma(const void* image, int64_t C, int64_t T, int64_t H, int64_t W
                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return MGB_EALIGN;
 
+  p.loader = g_gather_loader;
+  p.image = (const uint16_t*)image;
+  p.H = H;
+  p.Wu = Wu;
+  const int vpl = p.vpr ? (int)((L * p.vpr + 31) / 32) : 0;       // vectors per lane
   dim3 grid((unsigned)M, (unsigned)(with_stats ? Tm : 1));
-#define MGB_LAUNCH(ST, SO)                                                                              \
+#define MGB_LAUNCH(ST, SO, VP)                                                                          \
   do {                                                                                                  \
-    MGB_CUDA_TRY(cudaFuncSetAttribute(roi_gather_tma_kernel<ST, SO>,                                    \
+    MGB_CUDA_TRY(cudaFuncSetAttribute(roi_gather_tma_kernel<ST, SO, VP>,                                \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));   \
-    roi_gather_tma_kernel<ST, SO><<<grid, nw * 32, smem_bytes, st>>>(tmap, p);                          \
+    roi_gather_tma_kernel<ST, SO, VP><<<grid, nw * 32, smem_bytes, st>>>(tmap, p);                      \
+  } while (0)
+#define MGB_LAUNCH_V(ST, SO)                                  \
+  do {                                                        \
+    if (vpl > 0 && vpl <= 12) MGB_LAUNCH(ST, SO, 12);         \
+    else if (vpl > 12 && vpl <= 21) MGB_LAUNCH(ST, SO, 21);   \
+    else if (vpl > 21 && vpl <= 36) MGB_LAUNCH(ST, SO, 36);   \
+    else MGB_LAUNCH(ST, SO, 0);                               \
   } while (0)
   if (with_stats) {
-    if (roi) MGB_LAUNCH(true, true);
-    else MGB_LAUNCH(true, false);
+    if (roi) MGB_LAUNCH_V(true, true);
+    else MGB_LAUNCH_V(true, false);
   } else {
-    MGB_LAUNCH(false, true);
+    MGB_LAUNCH_V(false, true);
   }
+#undef MGB_LAUNCH_V
 #undef MGB_LAUNCH
   MGB_CUDA_LAUNCH_CHECK();
   return MGB_OK;

@@ -20,14 +20,18 @@ def dev(a, device):
     return torch.from_numpy(np.ascontiguousarray(a)).to(device)
 
 
-@pytest.fixture(params=["tma", "lsu"])
+@pytest.fixture(params=["staged_cpasync", "staged_tma", "plain"])
 def gather_path(request, cuda_device):
-    """Run the ROI-gather tests through both implementations: TMA-staged and plain load/store."""
+    """Run the ROI-gather tests through every implementation: windows staged in shared memory by
+    cp.async chunks (default) or by TMA tensor copies, and the plain load/store kernels."""
     from magnify_b200 import _lib
 
-    old = _lib.load().mgb_set_tma_enabled(1 if request.param == "tma" else 0)
+    lib = _lib.load()
+    old_tma = lib.mgb_set_tma_enabled(0 if request.param == "plain" else 1)
+    old_loader = lib.mgb_set_gather_loader(0 if request.param == "staged_tma" else 1)
     yield request.param
-    _lib.load().mgb_set_tma_enabled(old)
+    lib.mgb_set_tma_enabled(old_tma)
+    lib.mgb_set_gather_loader(old_loader)
 
 
 # ------------------------------------------------------------------------------------ stitch

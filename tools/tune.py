@@ -38,12 +38,18 @@ for v in (0, 1, 2):
 m, c, t, L = plan.boxes.shape[0], 4, T, case.roi_length
 roi = torch.empty((m, c, t, L, L), dtype=torch.uint16, device=dev)
 stats = torch.empty((m, c, t, 6), dtype=torch.float64, device=dev)
-for tma in (1, 0):
-    lib.mgb_set_tma_enabled(tma)
-    ms = timeit(lambda: ops.roi_gather_stats(image, plan.boxes, plan.fg, plan.bg, L, mask_t=plan.mask_t, out_roi=roi, out_stats=stats))
-    print(f"gather+stats tma={tma}: {ms:.3f} ms  {4 * roi.numel() / ms / 1e6:.0f} GB/s")
-    ms = timeit(lambda: ops.roi_gather(image, plan.boxes, L, out=roi))
-    print(f"gather only  tma={tma}: {ms:.3f} ms  {4 * roi.numel() / ms / 1e6:.0f} GB/s")
+for gran in (0,):
+  for name, tma, loader in (("staged cp.async", 1, 1), ("staged TMA", 1, 0), ("plain LSU", 0, 1)):
+      lib.mgb_set_tma_enabled(tma)
+      lib.mgb_set_gather_loader(loader)
+      ms = timeit(lambda: ops.roi_gather_stats(image, plan.boxes, plan.fg, plan.bg, L, mask_t=plan.mask_t, out_roi=roi, out_stats=stats))
+      chk = float(stats[..., 2:4].sum().item())
+      print(f"gather+stats {name}: {ms:.3f} ms  {4 * roi.numel() / ms / 1e6:.0f} GB/s  (stats checksum {chk:.0f})")
+      ms = timeit(lambda: ops.roi_gather(image, plan.boxes, L, out=roi))
+      print(f"gather only  {name}: {ms:.3f} ms  {4 * roi.numel() / ms / 1e6:.0f} GB/s")
+      ms = timeit(lambda: ops.roi_gather_stats(image, plan.boxes, plan.fg, plan.bg, L, mask_t=plan.mask_t, want_roi=False, out_stats=stats))
+      print(f"stats only   {name}: {ms:.3f} ms  {2 * roi.numel() / ms / 1e6:.0f} GB/s (read only)")
+lib.mgb_set_tma_enabled(1); lib.mgb_set_gather_loader(1)
 ms = timeit(lambda: ops.flatfield_maxima(case.tiles, plan.ff))
 print(f"flatfield max pass: {ms:.3f} ms {2 * px / ms / 1e6:.0f} GB/s")
 # pure elementwise flat-field (every tile its own image, overlap 0, S = 0, contiguous)
