@@ -329,6 +329,7 @@ def run_b200_arm(args, cfg):
         cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": "1 timepoint x 1 channel of the C3 stack (16 tiles of 2048^2, 1792 ROIs), "
                                   f"2 timed passes of {sec:.2f} s, NumPy oracle over a {threads}-thread pool, data in RAM"}
+    line = None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -337,10 +338,10 @@ def run_b200_arm(args, cfg):
             "config": workload_config(cfg, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "stages": stages, "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier(group=group)
         dist.destroy_process_group()
+    return line
 
 
 def measure_e2e(args, cfg, case, plan, dev, world, rank, group, barrier):
@@ -401,6 +402,23 @@ def measure_e2e(args, cfg, case, plan, dev, world, rank, group, barrier):
     }
 
 
+class StdoutToStderr:
+    """Everything written to fd 1 while active goes to stderr (NCCL prints its version banner to
+    stdout); the JSON line is printed after restoring, so stdout carries exactly one line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -417,7 +435,10 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, cfg)
     else:
-        run_b200_arm(args, cfg)
+        with StdoutToStderr():
+            line = run_b200_arm(args, cfg)
+        if line is not None:
+            print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -138,6 +138,11 @@ int mgb_roi_gather_stats_u16(const uint16_t* image, int64_t C, int64_t T, int64_
                              const int32_t* boxes, const int32_t* mask_t, int64_t Tm,
                              const uint8_t* fg, const uint8_t* bg, int64_t M, int L,
                              uint16_t* roi, double* stats, void* stream);
+/* The same summaries from an roi that already exists (the `quantify` component on a dataset
+ * produced elsewhere): roi (M,C,T,L,L) uint16 -> stats (M,C,T,6). */
+int mgb_roi_stats_u16(const uint16_t* roi, int64_t M, int64_t C, int64_t T, int L,
+                      const int32_t* mask_t, int64_t Tm, const uint8_t* fg, const uint8_t* bg,
+                      double* stats, void* stream);
 /* Exact masked median per (m,c,t) of a uint16 roi (M,C,T,L,L) (identify.py:79, filter.py:21-22):
  * mean of the two middle values for even counts, NaN for an empty mask, as np.nanmedian. */
 int mgb_roi_median_u16(const uint16_t* roi, int64_t M, int64_t C, int64_t T, int L,

@@ -376,12 +376,7 @@ def quantify(assay, median: bool = True, device=None):
         for name in ("fg_sum", "bg_sum", "fg_mean", "bg_mean") + (("fg_median", "bg_median") if median else ()):
             assay[name] = (dims, empty.copy())
         return assay
-    # an roi is its own image: boxes at the origin of a (M*C... ) stack would cost a copy, so
-    # reduce in place with the gather kernel reading each roi as a (C,T,L,L) image per marker.
-    stats = torch.empty((m, c, t, 6), dtype=torch.float64, device=dev)
-    zero_box = torch.zeros((1, t, 2), dtype=torch.int32, device=dev)
-    for i in range(m):
-        ops.roi_gather_stats(roi[i], zero_box, fg[i:i + 1], bg[i:i + 1], length, want_roi=False, out_stats=stats[i:i + 1])
+    stats = ops.roi_stats(roi, fg, bg)
     s = stats.cpu().numpy()
     assay["fg_sum"], assay["bg_sum"] = (dims, s[..., 2]), (dims, s[..., 3])
     assay["fg_mean"], assay["bg_mean"] = (dims, s[..., 4]), (dims, s[..., 5])

@@ -43,7 +43,8 @@ struct GatherParams {
   const uint16_t* image;   // 16-bit units
   uint16_t* roi;           // may be null when STATS
   int64_t C, T, H, W;      // W in 16-bit units
-  const int32_t* boxes;    // (M,T,2) in elements
+  const int32_t* boxes;    // (M,T,2) in elements; null = every box at (0, 0)
+  int64_t marker_stride;   // 16-bit units between markers' images (0: all markers share `image`)
   int unit;                // 16-bit units per element (itemsize / 2)
   int L;                   // roi side in elements
   int Lu;                  // roi row length in 16-bit units
@@ -76,9 +77,9 @@ __global__ void __launch_bounds__(kThreads) roi_gather_words_kernel(const Gather
   const int64_t t = n % p.T;
   const int64_t c = (n / p.T) % p.C;
   const int64_t m = n / (p.T * p.C);
-  const int32_t top = p.boxes[(m * p.T + t) * 2];
-  const int32_t left = p.boxes[(m * p.T + t) * 2 + 1];
-  const uint16_t* src = p.image + ((c * p.T + t) * p.H + top) * p.W + (int64_t)left * p.unit;
+  const int32_t top = p.boxes ? p.boxes[(m * p.T + t) * 2] : 0;
+  const int32_t left = p.boxes ? p.boxes[(m * p.T + t) * 2 + 1] : 0;
+  const uint16_t* src = p.image + m * p.marker_stride + ((c * p.T + t) * p.H + top) * p.W + (int64_t)left * p.unit;
   const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 3u) == 0) && ((p.W & 1) == 0);
   uint32_t* dst = p.roi ? reinterpret_cast<uint32_t*>(p.roi + n * (int64_t)p.L * p.Lu) : nullptr;
   const uint16_t* fgp = nullptr;
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(kThreads) roi_gather_words_kernel(const Gather
 template <typename U, bool STATS>
 __global__ void __launch_bounds__(kThreads)
 roi_gather_scalar_kernel(const U* __restrict__ image, U* __restrict__ roi, int64_t C, int64_t T,
-                         int64_t H, int64_t W, const int32_t* __restrict__ boxes, int L,
+                         int64_t H, int64_t W, const int32_t* __restrict__ boxes, int64_t marker_stride, int L,
                          const int32_t* __restrict__ mask_t, int64_t Tm,
                          const uint8_t* __restrict__ fg, const uint8_t* __restrict__ bg,
                          double* __restrict__ stats) {
@@ -139,9 +140,9 @@ roi_gather_scalar_kernel(const U* __restrict__ image, U* __restrict__ roi, int64
   const int64_t t = n % T;
   const int64_t c = (n / T) % C;
   const int64_t m = n / (T * C);
-  const int32_t top = boxes[(m * T + t) * 2];
-  const int32_t left = boxes[(m * T + t) * 2 + 1];
-  const U* src = image + ((c * T + t) * H + top) * W + left;
+  const int32_t top = boxes ? boxes[(m * T + t) * 2] : 0;
+  const int32_t left = boxes ? boxes[(m * T + t) * 2 + 1] : 0;
+  const U* src = image + m * marker_stride + ((c * T + t) * H + top) * W + left;
   U* dst = roi ? roi + n * (int64_t)L * L : nullptr;
   const uint8_t* fgp = nullptr;
   const uint8_t* bgp = nullptr;
@@ -278,7 +279,7 @@ int mgb_bounding_boxes(const double* x, const double* y, int64_t n, int L, int64
 }
 
 static int gather_common(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
-                         const int32_t* boxes, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
+                         const int32_t* boxes, int64_t marker_stride, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
                          const uint8_t* bg, int64_t M, int L, void* roi, double* stats,
                          cudaStream_t st) {
   const bool with_stats = stats != nullptr;
@@ -288,9 +289,9 @@ static int gather_common(const void* image, int64_t C, int64_t T, int64_t H, int
   const int64_t n_roi = M * C * T;
   if (n_roi == 0) return MGB_OK;
   if (n_roi > INT32_MAX) return MGB_EUNSUPPORTED;
-  if (!image || !boxes || (!roi && !with_stats)) return MGB_EINVAL;
+  if (!image || (!boxes && marker_stride == 0) || (!roi && !with_stats)) return MGB_EINVAL;
   if (with_stats && (!mask_t || !fg || !bg || Tm <= 0 || itemsize != 2)) return MGB_EINVAL;
-  if (g_tma_enabled) {
+  if (g_tma_enabled && marker_stride == 0) {
     // TMA-staged path (roi_tma.cu); MGB_EALIGN means "not applicable here", fall through.
     const int rc = roi_gather_tma(image, C, T, H, W, itemsize, boxes, mask_t, Tm, fg, bg, M, L, roi, stats, st);
     if (rc != MGB_EALIGN) return rc;
@@ -305,20 +306,21 @@ static int gather_common(const void* image, int64_t C, int64_t T, int64_t H, int
   if (word_path) {
     GatherParams p{};
     p.image = (const uint16_t*)image; p.roi = (uint16_t*)roi;
-    p.C = C; p.T = T; p.H = H; p.W = W * unit; p.boxes = boxes; p.unit = unit; p.L = L; p.Lu = Lu;
+    p.C = C; p.T = T; p.H = H; p.W = W * unit; p.boxes = boxes; p.marker_stride = marker_stride * unit;
+    p.unit = unit; p.L = L; p.Lu = Lu;
     p.half = (uint32_t)(Lu / 2); p.magic = magic_for(p.half); p.words = (uint32_t)L * p.half;
     p.mask_t = mask_t; p.Tm = Tm; p.fg = fg; p.bg = bg; p.stats = stats;
     if (with_stats) roi_gather_words_kernel<true><<<(unsigned)n_roi, kThreads, 0, st>>>(p);
     else roi_gather_words_kernel<false><<<(unsigned)n_roi, kThreads, 0, st>>>(p);
   } else if (with_stats) {
     roi_gather_scalar_kernel<uint16_t, true><<<(unsigned)n_roi, kThreads, 0, st>>>(
-        (const uint16_t*)image, (uint16_t*)roi, C, T, H, W, boxes, L, mask_t, Tm, fg, bg, stats);
+        (const uint16_t*)image, (uint16_t*)roi, C, T, H, W, boxes, marker_stride, L, mask_t, Tm, fg, bg, stats);
   } else {
     switch (itemsize) {
-      case 1: roi_gather_scalar_kernel<uint8_t, false><<<(unsigned)n_roi, kThreads, 0, st>>>((const uint8_t*)image, (uint8_t*)roi, C, T, H, W, boxes, L, nullptr, 0, nullptr, nullptr, nullptr); break;
-      case 2: roi_gather_scalar_kernel<uint16_t, false><<<(unsigned)n_roi, kThreads, 0, st>>>((const uint16_t*)image, (uint16_t*)roi, C, T, H, W, boxes, L, nullptr, 0, nullptr, nullptr, nullptr); break;
-      case 4: roi_gather_scalar_kernel<uint32_t, false><<<(unsigned)n_roi, kThreads, 0, st>>>((const uint32_t*)image, (uint32_t*)roi, C, T, H, W, boxes, L, nullptr, 0, nullptr, nullptr, nullptr); break;
-      default: roi_gather_scalar_kernel<uint64_t, false><<<(unsigned)n_roi, kThreads, 0, st>>>((const uint64_t*)image, (uint64_t*)roi, C, T, H, W, boxes, L, nullptr, 0, nullptr, nullptr, nullptr); break;
+      case 1: roi_gather_scalar_kernel<uint8_t, false><<<(unsigned)n_roi, kThreads, 0, st>>>((const uint8_t*)image, (uint8_t*)roi, C, T, H, W, boxes, marker_stride, L, nullptr, 0, nullptr, nullptr, nullptr); break;
+      case 2: roi_gather_scalar_kernel<uint16_t, false><<<(unsigned)n_roi, kThreads, 0, st>>>((const uint16_t*)image, (uint16_t*)roi, C, T, H, W, boxes, marker_stride, L, nullptr, 0, nullptr, nullptr, nullptr); break;
+      case 4: roi_gather_scalar_kernel<uint32_t, false><<<(unsigned)n_roi, kThreads, 0, st>>>((const uint32_t*)image, (uint32_t*)roi, C, T, H, W, boxes, marker_stride, L, nullptr, 0, nullptr, nullptr, nullptr); break;
+      default: roi_gather_scalar_kernel<uint64_t, false><<<(unsigned)n_roi, kThreads, 0, st>>>((const uint64_t*)image, (uint64_t*)roi, C, T, H, W, boxes, marker_stride, L, nullptr, 0, nullptr, nullptr, nullptr); break;
     }
   }
   MGB_CUDA_LAUNCH_CHECK();
@@ -340,7 +342,7 @@ int mgb_set_gather_loader(int loader) {
 int mgb_roi_gather(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
                    const int32_t* boxes, int64_t M, int L, void* roi, void* stream) {
   if (!roi && M * C * T > 0) return MGB_EINVAL;
-  return gather_common(image, C, T, H, W, itemsize, boxes, nullptr, 0, nullptr, nullptr, M, L, roi,
+  return gather_common(image, C, T, H, W, itemsize, boxes, 0, nullptr, 0, nullptr, nullptr, M, L, roi,
                        nullptr, (cudaStream_t)stream);
 }
 
@@ -349,8 +351,16 @@ int mgb_roi_gather_stats_u16(const uint16_t* image, int64_t C, int64_t T, int64_
                              const uint8_t* fg, const uint8_t* bg, int64_t M, int L,
                              uint16_t* roi, double* stats, void* stream) {
   if (!stats && M * C * T > 0) return MGB_EINVAL;
-  return gather_common(image, C, T, H, W, 2, boxes, mask_t, Tm, fg, bg, M, L, roi, stats,
+  return gather_common(image, C, T, H, W, 2, boxes, 0, mask_t, Tm, fg, bg, M, L, roi, stats,
                        (cudaStream_t)stream);
+}
+
+int mgb_roi_stats_u16(const uint16_t* roi, int64_t M, int64_t C, int64_t T, int L, const int32_t* mask_t,
+                      int64_t Tm, const uint8_t* fg, const uint8_t* bg, double* stats, void* stream) {
+  if (!stats && M * C * T > 0) return MGB_EINVAL;
+  // every marker's roi block (C,T,L,L) is read as its own little image with the box at the origin
+  return gather_common(roi, C, T, L, L, 2, nullptr, C * T * (int64_t)L * L, mask_t, Tm, fg, bg, M, L, nullptr,
+                       stats, (cudaStream_t)stream);
 }
 
 int mgb_roi_median_u16(const uint16_t* roi, int64_t M, int64_t C, int64_t T, int L,

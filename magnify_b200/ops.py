@@ -113,7 +113,7 @@ def _as_table(value, name: str, tile_shape, device) -> torch.Tensor:
         raise NotImplementedError(f"{name} varying over time or tile position is not supported (shape {arr.shape})")
     k = full.shape[0]
     table = np.broadcast_to(full[:, 0, 0, 0], (k, h, w))
-    return torch.from_numpy(np.ascontiguousarray(table)).to(device)
+    return torch.from_numpy(np.array(table, dtype=np.float64, order="C")).to(device)
 
 
 class FlatFieldPlan:
@@ -380,6 +380,31 @@ def roi_gather_stats(
         _lib.call("mgb_roi_gather_stats_u16", _ptr(image), c, t, h, w, _ptr(boxes), _ptr(mask_t), tm, _ptr(fg),
                   _ptr(bg), m, int(roi_length), _ptr(roi), _ptr(stats), _stream())
     return roi, stats
+
+
+def roi_stats(roi: torch.Tensor, fg: torch.Tensor, bg: torch.Tensor, mask_t: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Masked sums / counts / means of an existing roi (M,C,T,L,L) uint16 -> (M,C,T,6) float64."""
+    _check(roi, "roi", dtype=torch.uint16, ndim=5)
+    m, c, t, length, _ = roi.shape
+    fg = fg.view(torch.uint8) if fg.dtype == torch.bool else fg
+    bg = bg.view(torch.uint8) if bg.dtype == torch.bool else bg
+    _check(fg, "fg", dtype=torch.uint8, ndim=4)
+    _check(bg, "bg", dtype=torch.uint8, ndim=4)
+    tm = fg.shape[1]
+    if tuple(fg.shape) != (m, tm, length, length) or fg.shape != bg.shape:
+        raise ValueError(f"fg/bg must have shape ({m}, Tm, {length}, {length})")
+    if mask_t is None:
+        if tm == 1:
+            mask_t = torch.zeros(t, dtype=torch.int32, device=roi.device)
+        elif tm == t:
+            mask_t = torch.arange(t, dtype=torch.int32, device=roi.device)
+        else:
+            raise ValueError("mask_t is required when fg/bg hold neither 1 nor T timesteps")
+    stats = torch.empty((m, c, t, 6), dtype=torch.float64, device=roi.device)
+    with torch.cuda.device(roi.device):
+        _lib.call("mgb_roi_stats_u16", _ptr(roi), m, c, t, int(length), _ptr(mask_t), tm, _ptr(fg), _ptr(bg),
+                  _ptr(stats), _stream())
+    return stats
 
 
 def roi_median(roi: torch.Tensor, mask: torch.Tensor, mask_t: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -1,0 +1,160 @@
+"""The reference-facing components (magnify_b200.components) on the Assay stand-in: same
+arguments, exceptions and dataset schema as the reference's Stitcher / flatfield_correct /
+BeadFinder / ButtonFinder, pixel values against the oracle and the golden fixtures."""
+import numpy as np
+import pytest
+
+from oracle import flatfield as o_ff
+from oracle import reduce as o_red
+from oracle import stitch as o_st
+
+pytestmark = pytest.mark.gpu
+
+TILE_DIMS = ("channel", "time", "tile_row", "tile_col", "tile_y", "tile_x")
+
+
+def tile_assay(tile_data):
+    from magnify_b200.dataset import Assay
+
+    return Assay({"tile": (TILE_DIMS, tile_data)})
+
+
+# ---- port of the reference's tests/test_stitch.py against the component ----------------------
+def test_stitcher_basic(cuda_device):  # tests/test_stitch.py:9-26
+    from magnify_b200.components import Stitcher
+
+    tile_data = np.random.rand(1, 1, 2, 3, 40, 40)
+    result = Stitcher(overlap=5)(tile_assay(tile_data))
+    assert "image" in result.data_vars
+    assert result.sizes["im_y"] == 2 * (40 - 5)
+    assert result.sizes["im_x"] == 3 * (40 - 5)
+    np.testing.assert_array_equal(result.image[0, 0, 35:70, 35:70], tile_data[0, 0, 1, 1, 2:37, 2:37])
+
+
+def test_stitcher_single_tile_and_zero_overlap(cuda_device):  # :28-45, :78-96
+    from magnify_b200.components import Stitcher
+
+    tile_data = np.random.rand(1, 1, 1, 1, 30, 30)
+    result = Stitcher(overlap=5)(tile_assay(tile_data))
+    assert result.sizes["im_y"] == 25 and result.sizes["im_x"] == 25
+    np.testing.assert_array_equal(result.image[0, 0], tile_data[0, 0, 0, 0, 2:27, 2:27])
+    tile_data = np.random.rand(1, 1, 1, 2, 20, 20)
+    result = Stitcher(overlap=0)(tile_assay(tile_data))
+    assert result.sizes["im_y"] == 20 and result.sizes["im_x"] == 40
+    np.testing.assert_array_equal(result.image[0, 0, :, :20], tile_data[0, 0, 0, 0])
+    np.testing.assert_array_equal(result.image[0, 0, :, 20:], tile_data[0, 0, 0, 1])
+
+
+def test_stitcher_preserves_channels_and_time(cuda_device):  # :47-76
+    from magnify_b200.components import Stitcher
+
+    result = Stitcher(overlap=8)(tile_assay(np.random.rand(2, 3, 2, 2, 25, 25)))
+    assert result.image.dims == ("channel", "time", "im_y", "im_x")
+    assert result.sizes["channel"] == 2 and result.sizes["time"] == 3
+
+
+def test_stitcher_errors(cuda_device):  # :98-125
+    from magnify_b200.components import Stitcher
+    from magnify_b200.dataset import Assay
+
+    with pytest.raises(ValueError):
+        Stitcher(overlap=-5)
+    with pytest.raises(AttributeError):
+        Stitcher(overlap=10)(Assay({"other_data": (("x",), np.array([1, 2, 3]))}))
+    with pytest.raises(ValueError):
+        Stitcher(overlap=100)(tile_assay(np.random.rand(1, 1, 2, 2, 50, 50)))
+
+
+# ---- flat-field ------------------------------------------------------------------------------
+def test_flatfield_components(cuda_device):
+    from magnify_b200.components import FlatfieldStitcher, Stitcher, flatfield_correct
+
+    rng = np.random.default_rng(0)
+    tiles = np.clip(rng.normal(2000, 800, (2, 2, 2, 2, 64, 64)), 0, 65535).astype(np.uint16)
+    flat = 0.7 + 0.6 * rng.random((64, 64))
+    dark = 90.0 + 10 * rng.random((64, 64))
+    want_tiles = o_ff.flatfield_correct(tiles, flat, dark)
+    xp = flatfield_correct(tile_assay(tiles.copy()), flatfield=flat, darkfield=dark)
+    np.testing.assert_array_equal(xp.tile.values, want_tiles)
+    xp = Stitcher(overlap=6)(xp)
+    np.testing.assert_array_equal(xp.image.values, o_st.stitch(want_tiles, 6))
+    fused = FlatfieldStitcher(flat, dark, overlap=6)(tile_assay(tiles.copy()))
+    np.testing.assert_array_equal(fused.image.values, o_st.stitch(want_tiles, 6))
+    # defaults are the identity (registry.py:278-279)
+    xp = flatfield_correct(tile_assay(tiles.copy()))
+    np.testing.assert_array_equal(xp.tile.values, tiles)
+
+
+# ---- find_beads / find_buttons ---------------------------------------------------------------
+def test_bead_finder_schema_and_values(cuda_device, golden, make_pattern_image):
+    from magnify_b200.components import BeadFinder, quantify
+    from magnify_b200.dataset import Assay
+
+    g = golden("beads")
+    c, t, h, w = (int(v) for v in g["image_shape"])
+    image = make_pattern_image(c, t, h, w, salt=int(g["image_salt"]))
+    assay = Assay({"image": (("channel", "time", "im_y", "im_x"), image)},
+                  coords={"channel": (("channel",), np.array(["a", "b"]))})
+    finder = BeadFinder(min_bead_diameter=2, max_bead_diameter=50, roi_length=int(g["roi_length"]), centers=g["beads"])
+    out = finder(assay)
+    assert out.roi.dims == ("mark", "channel", "time", "roi_y", "roi_x")          # find.py:533
+    assert out.fg.dims == ("mark", "time", "roi_y", "roi_x") and out.fg.dtype == bool
+    assert out.x.dims == ("mark", "time") and out.valid.dtype == bool
+    np.testing.assert_array_equal(out.roi.values, g["roi"])
+    np.testing.assert_array_equal(out.fg.values, np.repeat(g["fg"][:, None], t, 1))
+    np.testing.assert_array_equal(out.bg.values, np.repeat(g["bg"][:, None], t, 1))
+    np.testing.assert_array_equal(out.x.values[:, 0], g["beads"][:, 1])
+    np.testing.assert_array_equal(out.y.values[:, 0], g["beads"][:, 0])
+    assert out.valid.values.all()
+    q = quantify(out)
+    fgt, bgt = np.repeat(g["fg"][:, None], t, 1), np.repeat(g["bg"][:, None], t, 1)
+    want = o_red.masked_stats(g["roi"], fgt, bgt)
+    np.testing.assert_allclose(q.fg_mean.values, want[..., 4], rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(q.bg_mean.values, want[..., 5], rtol=1e-12, equal_nan=True)
+    np.testing.assert_array_equal(q.bg_median.values, o_red.masked_median(g["roi"], bgt))
+    # identify.py:76-80: mean(fg) - median(bg)
+    intensity = q.fg_mean.values - q.bg_median.values
+    assert intensity.shape == (len(g["beads"]), c, t)
+    with pytest.raises(ValueError):
+        BeadFinder(min_bead_diameter=30, max_bead_diameter=10)                     # find.py:458-459
+
+
+def test_bead_finder_no_beads(cuda_device):  # find.py:557-558, tests/test_beads.py:219-232
+    from magnify_b200.components import BeadFinder
+    from magnify_b200.dataset import Assay
+
+    assay = Assay({"image": (("channel", "time", "im_y", "im_x"), np.zeros((1, 1, 128, 128), np.uint16))})
+    out = BeadFinder(16, 24, centers=np.empty((0, 3)))(assay)
+    assert out.sizes["mark"] == 0 and out.roi.shape == (0, 1, 1, 48, 48)
+
+
+def test_button_finder_schema_and_values(cuda_device, golden, make_pattern_image):
+    from magnify_b200.components import ButtonFinder
+    from magnify_b200.dataset import Assay
+
+    g = golden("chip")
+    c, t, h, w = (int(v) for v in g["image_shape"])
+    image = make_pattern_image(c, t, h, w, salt=int(g["image_salt"]))
+    rows, cols = g["x"].shape
+    assay = Assay({"image": (("channel", "time", "im_y", "im_x"), image)},
+                  coords={"tag": (("mark_row", "mark_col"), np.full((rows, cols), "default")),
+                          "valid": (("mark_row", "mark_col", "time"), np.ones((rows, cols, t), bool))})
+
+    def centers(assay, ts):   # pinned outcome of the CPU centre search + refinement at timestep ts
+        assert ts == 0
+        return g["x"], g["y"], g["fg_radius"]
+
+    finder = ButtonFinder(row_dist=100, col_dist=150, min_button_diameter=16, max_button_diameter=30,
+                          chamber_diameter=60, search_timestep=0, centers=centers)
+    assert finder.roi_length == 72 and finder.chamber_radius == 30 and finder.max_button_radius == 15
+    out = finder(assay)
+    np.testing.assert_array_equal(out.roi.values, g["roi"])
+    np.testing.assert_array_equal(out.fg.values, g["fg"])
+    np.testing.assert_array_equal(out.bg.values, g["bg"])
+    # copy-forward: identical x, y on non-searched timesteps (tests/test_chip.py:449-456)
+    for ti in range(1, t):
+        np.testing.assert_array_equal(out.x.values[:, ti], out.x.values[:, 0])
+        np.testing.assert_array_equal(out.y.values[:, ti], out.y.values[:, 0])
+    assert out.tag.dims == ("mark",) and out.valid.dims == ("mark", "time")
+    with pytest.raises(ValueError):
+        ButtonFinder(100, 100, 30, 10, 60)                                          # find.py:34-35
