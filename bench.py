@@ -375,20 +375,23 @@ def measure_e2e(args, cfg, case, plan, dev, world, rank, group, barrier):
     torch.cuda.synchronize(dev)
     runner = pipeline.HostStagedRunner(sub, want_image=True, want_roi=True)
     image_h, roi_h, stats_h = runner.alloc_host_outputs()
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, min(args.steps, 6))
 
     def step():
         runner.run(tiles_host, image_h, roi_h, stats_h)
 
     step()
+    runner.synchronize()
     barrier()
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    start.record()
+    # Wall clock around fully synchronised ends: the region contains every H2D copy, kernel and D2H
+    # copy of `steps` assays (the D2H of assay k overlaps the H2D of assay k+1 -- PCIe full duplex).
+    t0 = time.perf_counter()
     for _ in range(steps):
         step()
-    end.record()
+    runner.synchronize()
+    elapsed = time.perf_counter() - t0
     barrier()
-    ms = torch.tensor([start.elapsed_time(end)], dtype=torch.float64, device=dev)
+    ms = torch.tensor([elapsed * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX, group=group)
     sec = float(ms.item()) / 1e3
@@ -399,6 +402,7 @@ def measure_e2e(args, cfg, case, plan, dev, world, rank, group, barrier):
         "ms_per_step": sec * 1e3 / steps,
         "h2d_plus_d2h_GBps_per_gpu": (runner.h2d_bytes + runner.d2h_bytes) * steps / sec / 1e9,
         "outputs_copied_back": "stitched image + roi + summaries",
+        "pipelining": "D2H of assay k overlaps H2D of assay k+1; timed with host clock around synchronised ends",
     }
 
 

@@ -203,13 +203,16 @@ class HostStagedRunner:
         return image, roi, stats
 
     def run(self, tiles_host: torch.Tensor, image_host, roi_host, stats_host) -> None:
+        """Enqueue one assay.  Returns as soon as everything is queued: the device->host copies of
+        this assay overlap the host->device copies of the next `run()` (PCIe is full duplex), so a
+        sequence of assays is bounded by max(H2D, D2H) + compute instead of their sum.  Call
+        `synchronize()` before reading the host outputs."""
         plan = self.plan
         c, t, r, cc, h, w = plan.tile_shape
         compute = torch.cuda.current_stream(plan.device)
         ff = plan.ff
-        # ---- stage in + pass 1 (per timepoint, per channel: each (c, t) block is contiguous)
-        if not ff.identity:
-            ff.maxima.zero_()
+        # ---- stage in + pass 1 (per timepoint, per channel: each (c, t) block is contiguous).
+        # tiles_dev may be overwritten once the previous assay's kernels are done with it.
         self.h2d.wait_stream(compute)
         events = []
         for ti in range(t):
@@ -219,6 +222,8 @@ class HostStagedRunner:
                 ev = torch.cuda.Event()
                 ev.record(self.h2d)
             events.append(ev)
+        if not ff.identity:
+            ff.maxima.zero_()
         for ti in range(t):
             compute.wait_event(events[ti])
             if not ff.identity:
@@ -228,7 +233,9 @@ class HostStagedRunner:
             import torch.distributed as dist
 
             dist.all_reduce(ff.maxima, op=dist.ReduceOp.MAX, group=plan.group)
-        # ---- pass 2 + stitch, gather + reductions on the whole resident stack
+        # ---- pass 2 + stitch, gather + reductions on the whole resident stack.  image_dev /
+        # roi_dev / stats_dev are reused: wait until the previous assay's results have left them.
+        compute.wait_stream(self.d2h)
         image = ops.flatfield_stitch(self.tiles_dev, overlap=plan.overlap, plan=ff,
                                      maxima=None if ff.identity else ff.maxima, out=self.image_dev)
         done_image = torch.cuda.Event()
@@ -246,4 +253,8 @@ class HostStagedRunner:
             if self.want_roi:
                 roi_host.copy_(roi, non_blocking=True)
             stats_host.copy_(stats, non_blocking=True)
-        compute.wait_stream(self.d2h)
+
+    def synchronize(self) -> None:
+        """Wait until every queued assay's results are in the host buffers."""
+        self.d2h.synchronize()
+        torch.cuda.current_stream(self.plan.device).synchronize()
