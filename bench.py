@@ -44,6 +44,13 @@ C3 = dict(c=4, t=50, r=4, cc=4, h=2048, w=2048, overlap=102, rows=56, cols=32, r
           roi_length=72, chamber_radius=30, max_button_radius=15)
 
 
+# BASELINE config 5 geometry, one rank's shard ("C5"): 20480^2 images as 10x10 tiles of 2048^2 with overlap 0,
+# 4 channels, 100k beads, roi_length 50 (beads_pipe default, registry.py:572-573); 12 timepoints per rank
+# (100 timepoints over 8 GPUs = 12.5).  Not the default workload: `--config c5`.
+C5 = dict(c=4, t=12, r=10, cc=10, h=2048, w=2048, overlap=0, n_beads=100000, min_radius=4, max_radius=12,
+          roi_length=50)
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -203,6 +210,16 @@ def workload_config(cfg, n_gpus):
     }
 
 
+def c5_config(cfg, n_gpus):
+    return {
+        "workload": "C5 bead screen shard: flat-field + stitch + bead label raster/masks + ROI gather + masked sums/means",
+        "tiles_per_rank": [cfg["c"], cfg["t"], cfg["r"], cfg["cc"], cfg["h"], cfg["w"]], "overlap": cfg["overlap"],
+        "markers": cfg["n_beads"], "roi_length": cfg["roi_length"],
+        "sharding": f"time x{n_gpus} (each rank its own {cfg['t']} timepoints)",
+        "cache": "inputs (40 GB/rank) far exceed the 126 MB L2; no explicit flush",
+    }
+
+
 def run_b200_arm(args, cfg):
     import torch
     import torch.distributed as dist
@@ -216,6 +233,9 @@ def run_b200_arm(args, cfg):
         raise RuntimeError("bench.py needs a CUDA device; magnify_b200 has no CPU path")
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
+    from magnify_b200 import numa
+
+    bound_cpus = numa.bind_to_gpu_numa(local_rank) if world > 1 else []
     group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -225,13 +245,20 @@ def run_b200_arm(args, cfg):
     peak, peak_src = load_peaks()
 
     c, t = cfg["c"], cfg["t"]
-    gen_keys = ("c", "t", "r", "cc", "h", "w", "overlap", "rows", "cols", "row_dist", "col_dist", "roi_length",
-                "chamber_radius", "max_button_radius")
-    case = synth.chip_case(**{k: cfg[k] for k in gen_keys}, seed=rank, device=dev)
-    plan = pipeline.QuantifyPlan(case.tiles.shape, case.overlap, case.roi_length, case.flat, case.dark, device=dev,
-                                 group=group)
-    plan.set_chip_markers(case.x, case.y, case.fg_radius, case.chamber_radius, case.max_button_radius)
-    m = case.x.shape[0]
+    if args.config == "c5":
+        case = synth.bead_case(**cfg, seed=rank, device=dev)
+        plan = pipeline.QuantifyPlan(case.tiles.shape, case.overlap, case.roi_length, case.flat, case.dark,
+                                     device=dev, group=group)
+        plan.set_bead_markers(case.beads)
+        m = len(case.beads)
+    else:
+        gen_keys = ("c", "t", "r", "cc", "h", "w", "overlap", "rows", "cols", "row_dist", "col_dist", "roi_length",
+                    "chamber_radius", "max_button_radius")
+        case = synth.chip_case(**{k: cfg[k] for k in gen_keys}, seed=rank, device=dev)
+        plan = pipeline.QuantifyPlan(case.tiles.shape, case.overlap, case.roi_length, case.flat, case.dark,
+                                     device=dev, group=group)
+        plan.set_chip_markers(case.x, case.y, case.fg_radius, case.chamber_radius, case.max_button_radius)
+        m = case.x.shape[0]
     length = case.roi_length
     image_out = torch.empty(plan.image_shape, dtype=torch.uint16, device=dev)
     roi_out = torch.empty((m, c, t, length, length), dtype=torch.uint16, device=dev)
@@ -298,6 +325,8 @@ def run_b200_arm(args, cfg):
             entry.update({"algorithmic_GB": stage_bytes[name] / 1e9, "GB/s": gbs, "frac_of_peak": gbs / peak})
         stages[name] = entry
     dom = "flatfield_stitch"
+    if args.config != "c3":
+        stage_bytes["roi_gather_stats"] = 4.0 * roi_px_rank
     achieved = stages.get(dom, {}).get("GB/s")
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from ncu --set full
@@ -317,13 +346,16 @@ def run_b200_arm(args, cfg):
 
     # ---- end to end from pinned host buffers -------------------------------------------------
     e2e = None
-    try:
-        e2e = measure_e2e(args, cfg, case, plan, dev, world, rank, group, barrier)
-    except Exception as exc:  # keep the device numbers even if the host leg cannot allocate
-        e2e = {"value": None, "unit": UNIT, "error": repr(exc)[:300]}
+    if args.config == "c5":
+        e2e = {"value": None, "unit": UNIT, "note": "host leg is measured on the default workload (config 3) only"}
+    else:
+        try:
+            e2e = measure_e2e(args, cfg, case, plan, dev, world, rank, group, barrier)
+        except Exception as exc:  # keep the device numbers even if the host leg cannot allocate
+            e2e = {"value": None, "unit": UNIT, "error": repr(exc)[:300]}
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == "c3":
         threads = os.cpu_count() or 1
         v, sec, _ = time_cpu(cfg, 1, steps=2, warmup=1, threads=threads)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
@@ -335,7 +367,7 @@ def run_b200_arm(args, cfg):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_s * 1e3 / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u16 (f64 flat-field arithmetic)", "data": "synthetic",
-            "config": workload_config(cfg, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "config": workload_config(cfg, world) if args.config == "c3" else c5_config(cfg, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "stages": stages, "cpu_baseline": cpu_baseline,
         }
     if world > 1:
@@ -402,6 +434,7 @@ def measure_e2e(args, cfg, case, plan, dev, world, rank, group, barrier):
         "ms_per_step": sec * 1e3 / steps,
         "h2d_plus_d2h_GBps_per_gpu": (runner.h2d_bytes + runner.d2h_bytes) * steps / sec / 1e9,
         "outputs_copied_back": "stitched image + roi + summaries",
+        "numa_bound_cpus": len(os.sched_getaffinity(0)),
         "pipelining": "D2H of assay k overlaps H2D of assay k+1; timed with host clock around synchronised ends",
     }
 
@@ -432,8 +465,10 @@ def main():
     ap.add_argument("--timepoints", type=int, default=None, help="timepoints per rank (default 50 = config 3)")
     ap.add_argument("--e2e-timepoints", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c3", choices=["c3", "c5"],
+                    help="c3 = BASELINE config 3 (default, the metric's workload); c5 = one rank's shard of config 5")
     args = ap.parse_args()
-    cfg = dict(C3)
+    cfg = dict(C3 if args.config == "c3" else C5)
     if args.timepoints:
         cfg["t"] = args.timepoints
     if args.impl == "reference":
