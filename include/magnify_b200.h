@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MGB_ABI_VERSION 1
+#define MGB_ABI_VERSION 2
 
 #define MGB_OK 0
 #define MGB_EINVAL (-1)      /* bad argument (null pointer, negative size, bad itemsize ...) */
@@ -126,17 +126,21 @@ int mgb_set_tma_enabled(int enabled);
 int mgb_set_gather_loader(int loader);
 
 /* ---- F4 (+R): ROI gather, reference find.py:160-169, 324-334, 370-377, 589-602 -------------
- * roi[m,c,t] = image[c,t, top:top+L, left:left+L] for any itemsize in {1,2,4,8}. */
+ * roi[m,c,t] = image[c,t, top:top+L, left:left+L] for any itemsize in {1,2,4,8}.
+ * order (M) int32, nullable: a permutation giving the order in which markers are processed (results
+ * are independent of it).  Spatially sorted markers let windows that overlap or share DRAM lines
+ * hit in L2 (dense bead screens). */
 int mgb_roi_gather(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
-                   const int32_t* boxes, int64_t M, int L, void* roi, void* stream);
+                   const int32_t* boxes, const int32_t* order, int64_t M, int L, void* roi,
+                   void* stream);
 /* Gather fused with the masked reductions the consumers run (identify.py:76-80,
  * filter.py:21-22,51, README.md:21-22): uint16 only.  mask_t (T) int32 maps each timepoint to
  * its mask timestep in fg/bg (M, Tm, L, L) (beads: all 0, find.py:585-586; chip: the source
  * search timestep, find.py:151,172-173).  roi may be NULL (summaries only).  stats (M,C,T,6)
  * float64: exact integer sums, mean = sum / count (NaN for an empty mask, like nanmean). */
 int mgb_roi_gather_stats_u16(const uint16_t* image, int64_t C, int64_t T, int64_t H, int64_t W,
-                             const int32_t* boxes, const int32_t* mask_t, int64_t Tm,
-                             const uint8_t* fg, const uint8_t* bg, int64_t M, int L,
+                             const int32_t* boxes, const int32_t* order, const int32_t* mask_t,
+                             int64_t Tm, const uint8_t* fg, const uint8_t* bg, int64_t M, int L,
                              uint16_t* roi, double* stats, void* stream);
 /* The same summaries from an roi that already exists (the `quantify` component on a dataset
  * produced elsewhere): roi (M,C,T,L,L) uint16 -> stats (M,C,T,6). */

@@ -41,8 +41,8 @@ SIGNATURES = {
     "mgb_flatfield_stitch_u16": [_P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _I64, c_int, _P, _P, _P, _P, _P, _P],
     "mgb_flatfield_apply_generic": [_P, _P, c_int, _I64, _I64, _I64, c_int, _P, _P, _P, _P],
     "mgb_bounding_boxes": [_P, _P, _I64, c_int, _I64, _I64, _P, _P, _P],
-    "mgb_roi_gather": [_P, _I64, _I64, _I64, _I64, c_int, _P, _I64, c_int, _P, _P],
-    "mgb_roi_gather_stats_u16": [_P, _I64, _I64, _I64, _I64, _P, _P, _I64, _P, _P, _I64, c_int, _P, _P, _P],
+    "mgb_roi_gather": [_P, _I64, _I64, _I64, _I64, c_int, _P, _P, _I64, c_int, _P, _P],
+    "mgb_roi_gather_stats_u16": [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _I64, _P, _P, _I64, c_int, _P, _P, _P],
     "mgb_roi_stats_u16": [_P, _I64, _I64, _I64, c_int, _P, _I64, _P, _P, _P, _P],
     "mgb_roi_median_u16": [_P, _I64, _I64, _I64, c_int, _P, _I64, _P, _P, _P],
     "mgb_chip_masks": [_P, _P, c_int, c_int, _I64, c_int, _P, _P, _P, _P],
@@ -71,7 +71,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.argtypes = argtypes
         fn.restype = _SPECIAL_RESTYPE.get(name, c_int)
-    if lib.mgb_abi_version() != 1:
+    if lib.mgb_abi_version() != 2:
         raise ImportError("libmagnify_b200.so ABI version mismatch; rebuild with `python -m magnify_b200.build --force`")
     _lib = lib
     return lib

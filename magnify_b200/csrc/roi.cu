@@ -254,7 +254,7 @@ static uint32_t magic_for(uint32_t d) { return (uint32_t)((0x100000000ULL + d - 
 
 // roi_tma.cu
 int roi_gather_tma(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
-                   const int32_t* boxes, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
+                   const int32_t* boxes, const int32_t* order, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
                    const uint8_t* bg, int64_t M, int L, void* roi, double* stats, cudaStream_t st);
 
 extern int g_gather_loader;
@@ -279,7 +279,7 @@ int mgb_bounding_boxes(const double* x, const double* y, int64_t n, int L, int64
 }
 
 static int gather_common(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
-                         const int32_t* boxes, int64_t marker_stride, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
+                         const int32_t* boxes, const int32_t* order, int64_t marker_stride, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
                          const uint8_t* bg, int64_t M, int L, void* roi, double* stats,
                          cudaStream_t st) {
   const bool with_stats = stats != nullptr;
@@ -293,7 +293,7 @@ static int gather_common(const void* image, int64_t C, int64_t T, int64_t H, int
   if (with_stats && (!mask_t || !fg || !bg || Tm <= 0 || itemsize != 2)) return MGB_EINVAL;
   if (g_tma_enabled && marker_stride == 0) {
     // TMA-staged path (roi_tma.cu); MGB_EALIGN means "not applicable here", fall through.
-    const int rc = roi_gather_tma(image, C, T, H, W, itemsize, boxes, mask_t, Tm, fg, bg, M, L, roi, stats, st);
+    const int rc = roi_gather_tma(image, C, T, H, W, itemsize, boxes, order, mask_t, Tm, fg, bg, M, L, roi, stats, st);
     if (rc != MGB_EALIGN) return rc;
   }
   const int unit = itemsize / 2;
@@ -340,18 +340,18 @@ int mgb_set_gather_loader(int loader) {
 }
 
 int mgb_roi_gather(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
-                   const int32_t* boxes, int64_t M, int L, void* roi, void* stream) {
+                   const int32_t* boxes, const int32_t* order, int64_t M, int L, void* roi, void* stream) {
   if (!roi && M * C * T > 0) return MGB_EINVAL;
-  return gather_common(image, C, T, H, W, itemsize, boxes, 0, nullptr, 0, nullptr, nullptr, M, L, roi,
+  return gather_common(image, C, T, H, W, itemsize, boxes, order, 0, nullptr, 0, nullptr, nullptr, M, L, roi,
                        nullptr, (cudaStream_t)stream);
 }
 
 int mgb_roi_gather_stats_u16(const uint16_t* image, int64_t C, int64_t T, int64_t H, int64_t W,
-                             const int32_t* boxes, const int32_t* mask_t, int64_t Tm,
+                             const int32_t* boxes, const int32_t* order, const int32_t* mask_t, int64_t Tm,
                              const uint8_t* fg, const uint8_t* bg, int64_t M, int L,
                              uint16_t* roi, double* stats, void* stream) {
   if (!stats && M * C * T > 0) return MGB_EINVAL;
-  return gather_common(image, C, T, H, W, 2, boxes, 0, mask_t, Tm, fg, bg, M, L, roi, stats,
+  return gather_common(image, C, T, H, W, 2, boxes, order, 0, mask_t, Tm, fg, bg, M, L, roi, stats,
                        (cudaStream_t)stream);
 }
 
@@ -359,7 +359,7 @@ int mgb_roi_stats_u16(const uint16_t* roi, int64_t M, int64_t C, int64_t T, int 
                       int64_t Tm, const uint8_t* fg, const uint8_t* bg, double* stats, void* stream) {
   if (!stats && M * C * T > 0) return MGB_EINVAL;
   // every marker's roi block (C,T,L,L) is read as its own little image with the box at the origin
-  return gather_common(roi, C, T, L, L, 2, nullptr, C * T * (int64_t)L * L, mask_t, Tm, fg, bg, M, L, nullptr,
+  return gather_common(roi, C, T, L, L, 2, nullptr, nullptr, C * T * (int64_t)L * L, mask_t, Tm, fg, bg, M, L, nullptr,
                        stats, (cudaStream_t)stream);
 }
 

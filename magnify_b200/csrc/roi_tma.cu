@@ -31,6 +31,7 @@ constexpr int kTmaMaxWarps = 8;
 struct TmaGatherParams {
   uint16_t* roi;            // may be null (summaries only)
   const int32_t* boxes;     // (M,T,2) in elements
+  const int32_t* order;     // (M) processing order of the markers, or null
   const int32_t* mask_t;    // (T) or null when !stats
   const uint8_t* fg;        // (M,Tm,rows,rows) or null
   const uint8_t* bg;
@@ -199,7 +200,9 @@ roi_gather_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGatherP
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nw = blockDim.x >> 5;
-  const int64_t m = blockIdx.x;
+  // Markers may be visited in a caller-given order (spatially sorted: CTAs that run together then
+  // touch neighbouring image rows, and DRAM lines shared by overlapping windows hit in L2).
+  const int64_t m = p.order ? p.order[blockIdx.x] : blockIdx.x;
   const int tm = blockIdx.y;
 
   // shared memory carve-up
@@ -420,7 +423,7 @@ static uint32_t magic_u32(uint32_t d) { return (uint32_t)((0x100000000ULL + d - 
 // Returns MGB_OK when launched, MGB_EALIGN when this path does not apply (caller falls back to
 // the LSU kernels of roi.cu), or an error.
 int roi_gather_tma(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
-                   const int32_t* boxes, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
+                   const int32_t* boxes, const int32_t* order, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
                    const uint8_t* bg, int64_t M, int L, void* roi, double* stats, cudaStream_t st) {
   const bool with_stats = stats != nullptr;
   if (itemsize < 2) return MGB_EALIGN;
@@ -435,7 +438,7 @@ int roi_gather_tma(const void* image, int64_t C, int64_t T, int64_t H, int64_t W
   if (!encode) return MGB_EALIGN;
 
   TmaGatherParams p{};
-  p.roi = (uint16_t*)roi; p.boxes = boxes; p.mask_t = mask_t; p.fg = fg; p.bg = bg; p.stats = stats;
+  p.roi = (uint16_t*)roi; p.boxes = boxes; p.order = order; p.mask_t = mask_t; p.fg = fg; p.bg = bg; p.stats = stats;
   p.C = C; p.T = T; p.Tm = with_stats ? Tm : 1; p.rows = L; p.wu = wu; p.wpu = wpu; p.unit = unit;
   p.stage_bytes = (L * wpu * 2 + 127) & ~127;
   const bool out16 = !roi || aligned16(roi);

@@ -313,7 +313,28 @@ def _check_boxes(boxes, m, t):
         raise ValueError(f"boxes must have shape ({m}, {t}, 2), got {tuple(boxes.shape)}")
 
 
-def roi_gather(image: torch.Tensor, boxes: torch.Tensor, roi_length: int, out: Optional[torch.Tensor] = None):
+def spatial_order(boxes: torch.Tensor, band: int = 32) -> torch.Tensor:
+    """Permutation of the markers sorted by (top // band, left) of their first box: markers that
+    are processed together then read neighbouring image rows, so DRAM lines shared by nearby or
+    overlapping windows are fetched once and hit in L2 afterwards.  boxes (M,T,2) or (M,2)."""
+    b = boxes[:, 0] if boxes.dim() == 3 else boxes
+    if b.shape[0] == 0:
+        return torch.zeros(0, dtype=torch.int32, device=boxes.device)
+    key = (b[:, 0].to(torch.int64) // band) * (1 << 32) + b[:, 1].to(torch.int64)
+    return torch.argsort(key).to(torch.int32).contiguous()
+
+
+def _check_order(order, m):
+    if order is None:
+        return None
+    _check(order, "order", dtype=torch.int32, ndim=1)
+    if order.numel() != m:
+        raise ValueError("order must be a permutation of the markers")
+    return order
+
+
+def roi_gather(image: torch.Tensor, boxes: torch.Tensor, roi_length: int, out: Optional[torch.Tensor] = None,
+               order: Optional[torch.Tensor] = None):
     """roi[m,c,t] = image[c,t, top:top+L, left:left+L]  (find.py:160-169,324-334,589-602)."""
     _check(image, "image", ndim=4)
     c, t, h, w = image.shape
@@ -325,8 +346,8 @@ def roi_gather(image: torch.Tensor, boxes: torch.Tensor, roi_length: int, out: O
     elif tuple(out.shape) != shape or out.dtype != image.dtype:
         raise ValueError(f"out must have shape {shape} and dtype {image.dtype}")
     with torch.cuda.device(image.device):
-        _lib.call("mgb_roi_gather", _ptr(image), c, t, h, w, image.element_size(), _ptr(boxes), m, int(roi_length),
-                  _ptr(out), _stream())
+        _lib.call("mgb_roi_gather", _ptr(image), c, t, h, w, image.element_size(), _ptr(boxes),
+                  _ptr(_check_order(order, m)), m, int(roi_length), _ptr(out), _stream())
     return out
 
 
@@ -340,6 +361,7 @@ def roi_gather_stats(
     want_roi: bool = True,
     out_roi: Optional[torch.Tensor] = None,
     out_stats: Optional[torch.Tensor] = None,
+    order: Optional[torch.Tensor] = None,
 ):
     """Gather fused with per-(marker, channel, time) masked sums / counts / means.
 
@@ -377,8 +399,8 @@ def roi_gather_stats(
     if tuple(stats.shape) != (m, c, t, 6) or stats.dtype != torch.float64:
         raise ValueError("out_stats must be float64 with shape (M, C, T, 6)")
     with torch.cuda.device(image.device):
-        _lib.call("mgb_roi_gather_stats_u16", _ptr(image), c, t, h, w, _ptr(boxes), _ptr(mask_t), tm, _ptr(fg),
-                  _ptr(bg), m, int(roi_length), _ptr(roi), _ptr(stats), _stream())
+        _lib.call("mgb_roi_gather_stats_u16", _ptr(image), c, t, h, w, _ptr(boxes), _ptr(_check_order(order, m)),
+                  _ptr(mask_t), tm, _ptr(fg), _ptr(bg), m, int(roi_length), _ptr(roi), _ptr(stats), _stream())
     return roi, stats
 
 

@@ -70,6 +70,7 @@ class QuantifyPlan:
         self.image_shape = ops.stitched_shape(self.tile_shape, overlap)
         self.ff = ops.FlatFieldPlan(self.tile_shape, flatfield, darkfield, device=self.device)
         self.boxes = None
+        self.order = None
         self.fg = self.bg = self.mask_t = None
 
     # -- markers ------------------------------------------------------------------------------
@@ -104,6 +105,7 @@ class QuantifyPlan:
         self.bg = torch.stack(bgs, 1).contiguous()
         index = {ts: k for k, ts in enumerate(search)}
         self.mask_t = torch.tensor([index[int(s)] for s in src], dtype=torch.int32, device=dev)
+        self.order = ops.spatial_order(self.boxes)
         self.x, self.y = x, y
         return self
 
@@ -124,6 +126,7 @@ class QuantifyPlan:
         fg, bg = ops.bead_masks(self.labels, box0, self.roi_length)
         self.fg, self.bg = fg[:, None].contiguous(), bg[:, None].contiguous()
         self.mask_t = torch.zeros(t, dtype=torch.int32, device=dev)
+        self.order = ops.spatial_order(self.boxes) if t > 0 else None
         self.x, self.y = x, y
         return self
 
@@ -162,7 +165,7 @@ class QuantifyPlan:
                                                                        maxima=maxima, out=image_out))
         roi, stats = stage("roi_gather_stats", lambda: ops.roi_gather_stats(
             image, self.boxes, self.fg, self.bg, self.roi_length, mask_t=self.mask_t, want_roi=want_roi,
-            out_roi=roi_out, out_stats=stats_out))
+            out_roi=roi_out, out_stats=stats_out, order=self.order))
         return QuantifyResult(image, roi, self.fg, self.bg, self.mask_t, self.boxes, stats, maxima)
 
 
@@ -245,7 +248,8 @@ class HostStagedRunner:
                 self.d2h.wait_event(done_image)
                 image_host.copy_(image, non_blocking=True)
         roi, stats = ops.roi_gather_stats(image, plan.boxes, plan.fg, plan.bg, plan.roi_length, mask_t=plan.mask_t,
-                                          want_roi=self.want_roi, out_roi=self.roi_dev, out_stats=self.stats_dev)
+                                          want_roi=self.want_roi, out_roi=self.roi_dev, out_stats=self.stats_dev,
+                                          order=plan.order)
         done_roi = torch.cuda.Event()
         done_roi.record(compute)
         with torch.cuda.stream(self.d2h):

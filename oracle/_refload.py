@@ -67,3 +67,72 @@ def load_reference_utils():
                 sys.modules[k] = v
     _cached = mod
     return mod
+
+
+_cached_pre = None
+
+
+class NdarrayAssay:
+    """Stand-in for the xarray.Dataset argument of the reference's `flatfield_correct`: `.tile` is a
+    plain ndarray (which has the same astype/clip/max/arithmetic surface the function uses) and
+    item assignment stores the result."""
+
+    def __init__(self, tile):
+        self.tile = tile
+
+    def __setitem__(self, key, value):
+        setattr(self, key, value)
+
+
+def load_reference_preprocess():
+    """The reference's `src/magnify/preprocess.py`, loaded in place with stub modules for its
+    imports (dask.array, tifffile, xarray, magnify.registry, magnify.utils), or None.  Gives access
+    to the reference's OWN `flatfield_correct` source (preprocess.py:62-88), which only needs
+    ndarray-like operands for scalar / ndarray flat and dark fields."""
+    global _cached_pre
+    if _cached_pre is not None:
+        return _cached_pre
+    path = os.path.join(REFERENCE_ROOT, "src", "magnify", "preprocess.py")
+    if not os.path.exists(path):
+        return None
+    xr = types.ModuleType("xarray")
+    xr.Dataset = type("Dataset", (), {})
+    xr.DataArray = type("DataArray", (), {})
+    dask = types.ModuleType("dask")
+    dask_array = types.ModuleType("dask.array")
+    dask.array = dask_array
+    tifffile = types.ModuleType("tifffile")
+    pkg = types.ModuleType("magnify")
+    pkg.__path__ = []
+    registry = types.ModuleType("magnify.registry")
+    registry.component = lambda name: (lambda func: func)   # registry.py:16-29 returns func itself
+    utils = types.ModuleType("magnify.utils")
+    pkg.registry, pkg.utils = registry, utils
+    stubs = {"xarray": xr, "dask": dask, "dask.array": dask_array, "tifffile": tifffile, "magnify": pkg,
+             "magnify.registry": registry, "magnify.utils": utils}
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        spec = importlib.util.spec_from_file_location("_magnify_reference_preprocess", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    except Exception:
+        mod = None
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _cached_pre = mod
+    return mod
+
+
+def reference_flatfield_correct(tiles, flatfield=1.0, darkfield=0.0):
+    """Run the reference's own flatfield_correct on an ndarray tile stack; None if unavailable."""
+    mod = load_reference_preprocess()
+    if mod is None:
+        return None
+    xp = NdarrayAssay(tiles)
+    mod.flatfield_correct(xp, flatfield=flatfield, darkfield=darkfield)
+    return xp.tile

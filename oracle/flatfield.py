@@ -1,8 +1,9 @@
 """Flat-field correction of the reference, restated in NumPy.
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY UNPINNED by the reference's own suite:
-`flatfield_correct` has no test and its xarray wrapper cannot be imported here, so this file
-is a line-by-line restatement of src/magnify/preprocess.py:83-87.
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Line-by-line restatement of
+src/magnify/preprocess.py:83-87, pinned by tests/golden/flatfield.npz, which holds the outputs of
+the reference's own `flatfield_correct` source executed in place on ndarray operands
+(oracle/_refload.py::reference_flatfield_correct; the reference's suite has no flat-field test).
 """
 from __future__ import annotations
 

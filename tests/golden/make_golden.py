@@ -170,8 +170,41 @@ def golden_masks_cv():
                         ring=np.array(rings))
 
 
+def golden_flatfield():
+    """Run the reference's OWN flatfield_correct source (preprocess.py:62-88, loaded in place with
+    stub imports, ndarray operands) on small deterministic stacks."""
+    from oracle._refload import reference_flatfield_correct
+
+    rng = np.random.default_rng(99)
+    c, t, r, cc, h, w = 2, 2, 1, 2, 32, 40
+    tiles = np.clip(rng.normal(2500, 1500, (c, t, r, cc, h, w)), 0, 65535).astype(np.uint16)
+    tiles[0, 0, 0, 0, 3, 4] = 65535
+    tiles[..., :2, :] = 0
+    yy, xx = np.mgrid[0:h, 0:w]
+    flat = 1.0 + 0.35 * np.cos(yy / h * 2.0) * np.sin(xx / w * 1.5 + 0.2)
+    dark = 100.0 + 5.0 * np.sin(yy * 0.37 + xx * 0.11)
+    flat_c = np.stack([flat, flat * 1.1])[:, None, None, None]
+    dark_c = np.stack([dark, dark + 3.0])[:, None, None, None]
+    cases = {
+        "arrays": (flat, dark), "scalars": (0.5, 97.25), "defaults": (1.0, 0.0), "integer_dark": (1.0, 100.0),
+        "per_channel": (flat_c, dark_c), "scalar_flat_array_dark": (1.25, dark),
+    }
+    out = {"tiles": tiles}
+    for name, (f, d) in cases.items():
+        res = reference_flatfield_correct(tiles, f, d)
+        assert res is not None and res.dtype == tiles.dtype and res.shape == tiles.shape
+        out[f"{name}__flat"] = np.asarray(f, dtype=np.float64)
+        out[f"{name}__dark"] = np.asarray(d, dtype=np.float64)
+        out[f"{name}__out"] = res
+    tiles32 = (rng.random((1, 1, 1, 2, 16, 24)) * 3000).astype(np.float32)
+    out["f32_tiles"] = tiles32
+    out["f32__out"] = reference_flatfield_correct(tiles32, flat[:16, :24], dark[:16, :24])
+    np.savez_compressed(os.path.join(HERE, "flatfield.npz"), **out)
+
+
 if __name__ == "__main__":
     golden_geometry()
+    golden_flatfield()
     golden_beads()
     golden_chip()
     golden_masks_cv()

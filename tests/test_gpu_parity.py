@@ -169,6 +169,23 @@ def test_flatfield_other_dtypes(cuda_device, dtype):
     np.testing.assert_array_equal(got.cpu().numpy(), want)
 
 
+def test_flatfield_golden_from_reference_source(cuda_device, golden):
+    """CUDA path against the outputs of the reference's own flatfield_correct source
+    (tests/golden/flatfield.npz, made by tests/golden/make_golden.py::golden_flatfield)."""
+    from magnify_b200 import ops
+
+    g = golden("flatfield")
+    tiles = dev(g["tiles"], cuda_device)
+    for name in ("arrays", "scalars", "defaults", "integer_dark", "per_channel", "scalar_flat_array_dark"):
+        f, d = g[name + "__flat"], g[name + "__dark"]
+        f = float(f) if f.ndim == 0 else f
+        d = float(d) if d.ndim == 0 else d
+        got = ops.flatfield_correct(tiles, f, d)
+        np.testing.assert_array_equal(got.cpu().numpy(), g[name + "__out"], err_msg=name)
+    got = ops.flatfield_correct(dev(g["f32_tiles"], cuda_device), g["arrays__flat"][:16, :24], g["arrays__dark"][:16, :24])
+    np.testing.assert_array_equal(got.cpu().numpy(), g["f32__out"])
+
+
 def test_flatfield_rejects_nonpositive_flat(cuda_device):
     from magnify_b200 import ops
 

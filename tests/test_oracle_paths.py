@@ -71,6 +71,37 @@ def test_flatfield_formula_and_chunked_maxima():
     np.testing.assert_array_equal(chunked, out)
 
 
+FF_CASES = ("arrays", "scalars", "defaults", "integer_dark", "per_channel", "scalar_flat_array_dark")
+
+
+def _ff_operand(a):
+    return float(a) if a.ndim == 0 else a
+
+
+def test_flatfield_golden_from_reference_source(golden):
+    """tests/golden/flatfield.npz = outputs of the reference's own preprocess.py:62-88."""
+    g = golden("flatfield")
+    for name in FF_CASES:
+        got = ff.flatfield_correct(g["tiles"], _ff_operand(g[name + "__flat"]), _ff_operand(g[name + "__dark"]))
+        np.testing.assert_array_equal(got, g[name + "__out"], err_msg=name)
+    got = ff.flatfield_correct(g["f32_tiles"], g["arrays__flat"][:16, :24], g["arrays__dark"][:16, :24])
+    assert got.dtype == np.float32
+    np.testing.assert_array_equal(got, g["f32__out"])
+
+
+def test_flatfield_against_reference_source_when_present():
+    from oracle._refload import reference_flatfield_correct
+
+    rng = np.random.default_rng(7)
+    tiles = rng.integers(0, 65535, (2, 1, 2, 2, 16, 16), dtype=np.uint16, endpoint=True)
+    flat = 0.6 + 0.8 * rng.random((16, 16))
+    dark = 80 + 40 * rng.random((16, 16))
+    want = reference_flatfield_correct(tiles, flat, dark)
+    if want is None:
+        pytest.skip("/root/reference not available (GPU box); the golden fixture covers this")
+    np.testing.assert_array_equal(ff.flatfield_correct(tiles, flat, dark), want)
+
+
 # ---- ROI paths against fixtures made with the reference's real utils.py -----------------------
 def test_beads_golden(golden, make_pattern_image):
     d = golden("beads")
