@@ -1,0 +1,105 @@
+"""QuantifyPlan / HostStagedRunner end to end against the oracle: several search timesteps with
+copy-forward (find.py:143-181), per-channel flat fields, the pinned-host staging loop."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import flatfield as o_ff
+from oracle import reduce as o_red
+from oracle import rois as o_rois
+from oracle import stitch as o_st
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_chip(tiles, flat, dark, overlap, x, y, radius, search, length, chamber_r, max_r):
+    image = o_st.stitch(o_ff.flatfield_correct(tiles, flat, dark), overlap)
+    t = tiles.shape[1]
+    src = o_rois.chip_copy_forward(t, search)
+    roi = o_rois.gather_rois(image, x, y, length)
+    m = x.shape[0]
+    fg = np.empty((m, t, length, length), bool)
+    bg = np.empty_like(fg)
+    searched = sorted(set(src.tolist()))
+    for k, ts in enumerate(searched):
+        f, b = o_rois.chip_masks(x[:, ts], y[:, ts], radius[:, k], length, chamber_r, max_r, image.shape[-1], image.shape[-2])
+        for ti in np.where(src == ts)[0]:
+            fg[:, ti], bg[:, ti] = f, b
+    return image, roi, fg, bg, o_red.masked_stats(roi, fg, bg)
+
+
+@pytest.mark.parametrize("search,per_channel", [([0], False), ([1, 3], True)])
+def test_chip_plan_matches_oracle(cuda_device, search, per_channel):
+    from magnify_b200 import pipeline
+
+    rng = np.random.default_rng(8)
+    c, t, r, cc, h, w, ov, length = 2, 5, 2, 4, 128, 128, 22, 40
+    tiles = np.clip(rng.normal(3000, 900, (c, t, r, cc, h, w)), 0, 65535).astype(np.uint16)
+    flat = 0.7 + 0.6 * rng.random((h, w))
+    dark = 95.0 + 10 * rng.random((h, w))
+    if per_channel:
+        flat = np.stack([flat, flat * 1.2])[:, None, None, None]
+        dark = np.stack([dark, dark - 4.0])[:, None, None, None]
+    him, wim = r * (h - ov), cc * (w - ov)
+    m = 7
+    src = o_rois.chip_copy_forward(t, search)
+    x_s = rng.uniform(0, wim, (m, t))
+    y_s = rng.uniform(0, him, (m, t))
+    x, y = x_s[:, src], y_s[:, src]        # centres of non-search timesteps are copied forward
+    radius = rng.integers(3, 9, (m, len(set(src.tolist())))).astype(np.int32)
+    plan = pipeline.QuantifyPlan(tiles.shape, ov, length, flat, dark, device=cuda_device)
+    plan.set_chip_markers(x, y, radius, chamber_radius=16, max_button_radius=9, search_timesteps=search)
+    res = plan.run_device(torch.from_numpy(tiles).to(cuda_device))
+    image, roi, fg, bg, stats = oracle_chip(tiles, flat, dark, ov, x, y, radius, search, length, 16, 9)
+    np.testing.assert_array_equal(res.image.cpu().numpy(), image)
+    np.testing.assert_array_equal(res.roi.cpu().numpy(), roi)
+    mask_t = res.mask_t.cpu().numpy()
+    np.testing.assert_array_equal(res.fg.cpu().numpy().astype(bool)[:, mask_t], fg)
+    np.testing.assert_array_equal(res.bg.cpu().numpy().astype(bool)[:, mask_t], bg)
+    np.testing.assert_allclose(res.stats.cpu().numpy(), stats, rtol=1e-12, equal_nan=True)
+
+
+def test_host_staged_runner_equals_device_run(cuda_device):
+    from magnify_b200 import pipeline, synth
+
+    case = synth.chip_case(c=2, t=3, r=2, cc=4, h=256, w=256, overlap=22, rows=3, cols=3, row_dist=126.1,
+                           col_dist=250.0, seed=2, device=cuda_device)
+    plan = pipeline.QuantifyPlan(case.tiles.shape, case.overlap, case.roi_length, case.flat, case.dark,
+                                 device=cuda_device)
+    plan.set_chip_markers(case.x, case.y, case.fg_radius, case.chamber_radius, case.max_button_radius)
+    ref = plan.run_device(case.tiles)
+    image_ref, roi_ref, stats_ref = ref.image.cpu(), ref.roi.cpu(), ref.stats.cpu()
+    runner = pipeline.HostStagedRunner(plan)
+    tiles_host = case.tiles.cpu().pin_memory()
+    image_h, roi_h, stats_h = runner.alloc_host_outputs()
+    for _ in range(3):                 # back-to-back assays reuse the device buffers safely
+        image_h.zero_(); roi_h.zero_(); stats_h.zero_()
+        runner.run(tiles_host, image_h, roi_h, stats_h)
+        runner.synchronize()
+        assert torch.equal(image_h.view(torch.int16), image_ref.view(torch.int16))
+        assert torch.equal(roi_h.view(torch.int16), roi_ref.view(torch.int16))
+        assert torch.equal(stats_h, stats_ref)
+    assert runner.h2d_bytes == tiles_host.numel() * 2
+
+
+def test_bead_plan_time_series(cuda_device):
+    """Beads over several timepoints: masks are computed once and broadcast (find.py:585-586)."""
+    from magnify_b200 import pipeline
+
+    rng = np.random.default_rng(9)
+    c, t, h, w, length = 3, 4, 256, 320, 50
+    tiles = rng.integers(0, 65535, (c, t, 1, 1, h, w), dtype=np.uint16, endpoint=True)
+    beads = np.stack([rng.integers(0, h, 25), rng.integers(0, w, 25), rng.integers(1, 14, 25)], 1).astype(np.float64)
+    plan = pipeline.QuantifyPlan(tiles.shape, 0, length, device=cuda_device)
+    plan.set_bead_markers(beads)
+    res = plan.run_device(torch.from_numpy(tiles).to(cuda_device))
+    image = o_st.stitch(tiles, 0)
+    labels, fg, bg = o_rois.bead_masks(beads, h, w, length)
+    x = np.repeat(beads[:, 1:2], t, 1)
+    y = np.repeat(beads[:, 0:1], t, 1)
+    roi = o_rois.gather_rois(image, x, y, length)
+    np.testing.assert_array_equal(res.image.cpu().numpy(), image)
+    np.testing.assert_array_equal(res.roi.cpu().numpy(), roi)
+    np.testing.assert_array_equal(res.fg[:, 0].cpu().numpy().astype(bool), fg)
+    want = o_red.masked_stats(roi, np.repeat(fg[:, None], t, 1), np.repeat(bg[:, None], t, 1))
+    np.testing.assert_allclose(res.stats.cpu().numpy(), want, rtol=1e-12, equal_nan=True)
