@@ -387,6 +387,56 @@ def quantify(assay, median: bool = True, device=None):
     return assay
 
 
+def _time0_medians(assay, channel_index: int, dev):
+    """GPU medians of fg and bg at time 0 for one channel -> two (M,) float64 arrays."""
+    roi = np.ascontiguousarray(_to_numpy(assay["roi"])[:, channel_index : channel_index + 1, :1])
+    fg = np.ascontiguousarray(_to_numpy(assay["fg"])[:, :1]).view(np.uint8)
+    bg = np.ascontiguousarray(_to_numpy(assay["bg"])[:, :1]).view(np.uint8)
+    roi_d = torch.from_numpy(roi).to(dev)
+    if roi_d.dtype != torch.uint16:
+        raise TypeError(f"needs a uint16 roi, got {roi_d.dtype}")
+    fgm = ops.roi_median(roi_d, torch.from_numpy(fg).to(dev)).cpu().numpy()[:, 0, 0]
+    bgm = ops.roi_median(roi_d, torch.from_numpy(bg).to(dev)).cpu().numpy()[:, 0, 0]
+    return fgm, bgm
+
+
+def filter_expression(assay, search_channel=None, min_contrast=None, device=None):
+    """`filter_expression` of the reference (filter.py:11-37) with the masked medians computed on
+    the GPU.  The pairwise-difference statistic is the reference's
+    own expression (O(M^2) on the host, like the reference)."""
+    dev = _device(device)
+    channels = list(_to_numpy(assay["channel"])) if "channel" in assay else list(range(assay["roi"].shape[1]))
+    wanted = channels if search_channel is None else ([search_channel] if isinstance(search_channel, str)
+                                                      or np.isscalar(search_channel) else list(search_channel))
+    valid = _to_numpy(assay["valid"]).astype(bool)
+    expressed = np.zeros_like(valid)
+    for ch in wanted:
+        fgm, bgm = _time0_medians(assay, channels.index(ch), dev)
+        if min_contrast is None:
+            diffs = bgm[:, np.newaxis] - bgm[np.newaxis, :]
+            offdiag = np.ones_like(diffs, dtype=bool) & (~np.eye(len(diffs), dtype=bool))
+            upper = 4 * diffs[offdiag].std()
+        else:
+            upper = min_contrast
+        hit = fgm - bgm > upper
+        expressed |= hit.reshape((-1,) + (1,) * (valid.ndim - 1))
+    return assay.assign_coords(valid=(tuple(assay["valid"].dims), valid & expressed))
+
+
+def mrbles_intensities(assay, channels=None, device=None) -> np.ndarray:
+    """The per-bead intensities `identify_mrbles` starts from (identify.py:76-80): mean of the
+    foreground minus median of the background at time 0, (mark, channel)."""
+    dev = _device(device)
+    names = list(_to_numpy(assay["channel"])) if "channel" in assay else list(range(assay["roi"].shape[1]))
+    idx = list(range(len(names))) if channels is None else [names.index(c) for c in channels]
+    roi = torch.from_numpy(np.ascontiguousarray(_to_numpy(assay["roi"])[:, idx, :1])).to(dev)
+    fg = torch.from_numpy(np.ascontiguousarray(_to_numpy(assay["fg"])[:, :1]).view(np.uint8)).to(dev)
+    bg = torch.from_numpy(np.ascontiguousarray(_to_numpy(assay["bg"])[:, :1]).view(np.uint8)).to(dev)
+    mean_fg = ops.roi_stats(roi, fg, bg)[:, :, 0, 4]
+    med_bg = ops.roi_median(roi, bg)[:, :, 0]
+    return (mean_fg - med_bg).cpu().numpy()
+
+
 def make_quantify(median: bool = True, device=None):
     return lambda xp: quantify(xp, median=median, device=device)
 
@@ -404,6 +454,8 @@ EXTRA_FACTORIES = {
     "flatfield_stitch_b200": lambda flatfield=1.0, darkfield=0.0, overlap=102, device=None: FlatfieldStitcher(
         flatfield, darkfield, overlap, device),
     "quantify": make_quantify,
+    "filter_expression_b200": lambda search_channel=None, min_contrast=None, device=None: (
+        lambda xp: filter_expression(xp, search_channel=search_channel, min_contrast=min_contrast, device=device)),
 }
 
 

@@ -40,3 +40,30 @@ def masked_median(roi: np.ndarray, mask: np.ndarray) -> np.ndarray:
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", RuntimeWarning)
         return np.nanmedian(flat, axis=-1)
+
+
+def mrbles_intensities(roi: np.ndarray, fg: np.ndarray, bg: np.ndarray) -> np.ndarray:
+    """identify.py:76-80 at time 0: `sel.where(sel.fg).mean(...) - sel.where(sel.bg).median(...)`.
+    roi (M,C,T,L,L), fg/bg (M,T,L,L) -> (M,C)."""
+    r0, f0, b0 = roi[:, :, :1], fg[:, :1], bg[:, :1]
+    return masked_stats(r0, f0, b0)[:, :, 0, 4] - masked_median(r0, b0)[:, :, 0]
+
+
+def filter_expression_valid(roi: np.ndarray, fg: np.ndarray, bg: np.ndarray, valid: np.ndarray, channels,
+                            min_contrast=None) -> np.ndarray:
+    """filter.py:11-37: per search channel, medians of fg and bg at time 0; markers whose fg-bg
+    exceeds 4 standard deviations of all pairwise background differences (or `min_contrast`) are
+    expressed; `valid &= any-channel-expressed`.  valid (M,T) bool; channels = channel indices."""
+    expressed = np.zeros(valid.shape, dtype=bool)
+    for c in channels:
+        r0 = roi[:, c : c + 1, :1]
+        fgm = masked_median(r0, fg[:, :1])[:, 0, 0]
+        bgm = masked_median(r0, bg[:, :1])[:, 0, 0]
+        if min_contrast is None:
+            diffs = bgm[:, np.newaxis] - bgm[np.newaxis, :]          # :26-29
+            offdiag = np.ones_like(diffs, dtype=bool) & (~np.eye(len(diffs), dtype=bool))
+            upper = 4 * diffs[offdiag].std()                          # :32
+        else:
+            upper = min_contrast
+        expressed |= (fgm - bgm > upper)[:, None]                     # :35 (broadcast over time)
+    return valid & expressed

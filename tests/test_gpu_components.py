@@ -158,3 +158,32 @@ def test_button_finder_schema_and_values(cuda_device, golden, make_pattern_image
     assert out.tag.dims == ("mark",) and out.valid.dims == ("mark", "time")
     with pytest.raises(ValueError):
         ButtonFinder(100, 100, 30, 10, 60)                                          # find.py:34-35
+
+
+def test_filter_expression_and_mrbles_intensities(cuda_device):
+    """the consumers of the summaries (filter.py:11-37,
+    identify.py:76-80) on GPU medians / means, against the NumPy restatement."""
+    from magnify_b200.components import filter_expression, mrbles_intensities
+    from magnify_b200.dataset import Assay
+
+    rng = np.random.default_rng(17)
+    m, c, t, length = 40, 3, 2, 24
+    roi = rng.integers(380, 420, (m, c, t, length, length)).astype(np.uint16)
+    yy, xx = np.mgrid[0:length, 0:length]
+    fg0 = (yy - 12) ** 2 + (xx - 12) ** 2 <= 25
+    fg = np.broadcast_to(fg0, (m, t, length, length)).copy()
+    bg = ~np.broadcast_to((yy - 12) ** 2 + (xx - 12) ** 2 <= 64, (m, t, length, length))
+    roi[: m // 2, 1][:, :, fg0] += 300            # half of the markers are expressed in channel 1
+    valid = np.ones((m, t), bool)
+    valid[3] = False
+    assay = Assay({"roi": (("mark", "channel", "time", "roi_y", "roi_x"), roi)},
+                  coords={"fg": (("mark", "time", "roi_y", "roi_x"), fg), "bg": (("mark", "time", "roi_y", "roi_x"), bg),
+                          "valid": (("mark", "time"), valid), "channel": (("channel",), np.array(["a", "b", "c"]))})
+    out = filter_expression(assay, search_channel="b")
+    want = o_red.filter_expression_valid(roi, fg, bg, valid, channels=[1])
+    np.testing.assert_array_equal(out.valid.values, want)
+    assert want[: m // 2].sum() >= (m // 2 - 1) * t and not want[m // 2 :].any()
+    out2 = filter_expression(assay, min_contrast=1000)
+    np.testing.assert_array_equal(out2.valid.values, o_red.filter_expression_valid(roi, fg, bg, valid, [0, 1, 2], 1000))
+    inten = mrbles_intensities(assay, channels=["a", "b"])
+    np.testing.assert_allclose(inten, o_red.mrbles_intensities(roi[:, :2], fg, bg), rtol=1e-12)
