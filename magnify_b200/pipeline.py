@@ -6,9 +6,10 @@ boxes, masks) and runs
     tiles --flat-field pass 1 (max)--> [all-reduce MAX] --pass 2 fused with stitch--> image
           --ROI gather fused with masked reductions--> roi, stats
 
-either on tiles already resident in HBM (`run_device`) or from pinned host buffers with the
-host->device copies of timepoint t+1 overlapped with the max pass of timepoint t and the
-device->host copies of the results overlapped with the gather (`run_host`).
+either on tiles already resident in HBM (`QuantifyPlan.run_device`), from pinned host buffers
+(`HostStagedRunner.run`: the host->device copies of block k+1 overlap the max pass of block k, and
+the device->host copies of one assay overlap the host->device copies of the next), or from an
+iterable of pageable chunks such as dask blocks (`ChunkStager.feed` + `HostStagedRunner.finish`).
 
 Time sharding: every rank owns a contiguous block of timepoints; the
 only collectives are the all-reduce of the two flat-field maxima and the final gather of the
@@ -232,6 +233,14 @@ class HostStagedRunner:
             if not ff.identity:
                 for ci in range(c):
                     ops.flatfield_maxima_accumulate(self.tiles_dev[ci, ti], ff, ci)
+        self.finish(image_host, roi_host, stats_host)
+
+    def finish(self, image_host, roi_host, stats_host) -> None:
+        """All tiles are on the device and pass 1 has run: all-reduce the maxima, run pass 2 +
+        stitch + gather + reductions and queue the device->host copies."""
+        plan = self.plan
+        ff = plan.ff
+        compute = torch.cuda.current_stream(plan.device)
         if not ff.identity and plan.group is not None:
             import torch.distributed as dist
 
@@ -262,3 +271,81 @@ class HostStagedRunner:
         """Wait until every queued assay's results are in the host buffers."""
         self.d2h.synchronize()
         torch.cuda.current_stream(self.plan.device).synchronize()
+
+
+class ChunkStager:
+    """Chunk provider -> pinned ring -> HBM: the staging loop for tiles that are NOT already in
+    pinned memory (the reference's per-page dask chunks, reader.py:265-292, or any iterable of
+    NumPy blocks).
+
+    `chunks` yields `((channel, time), ndarray)` with ndarray shaped (R, Cc, H, W) -- one
+    (channel, timepoint) block of the tile stack, in any order.  Each block is copied into one of
+    `depth` pinned staging buffers by a small thread pool (NumPy copies release the GIL, so the
+    pageable->pinned memcpy of block k+1 overlaps the PCIe copy of block k) and then sent to its
+    slot of the device tile stack on the copy stream; flat-field pass 1 runs on the compute stream
+    as blocks land.  After `feed()` the runner's `finish()` does pass 2 + gather + drain.
+    """
+
+    def __init__(self, runner: HostStagedRunner, depth: int = 4, threads: int = 4):
+        from concurrent.futures import ThreadPoolExecutor
+
+        self.runner = runner
+        c, t, r, cc, h, w = runner.plan.tile_shape
+        self.block_shape = (r, cc, h, w)
+        self.staging = [torch.empty(self.block_shape, dtype=torch.uint16, pin_memory=True) for _ in range(depth)]
+        self.free_events = [None] * depth
+        self.pool = ThreadPoolExecutor(max_workers=threads)
+        self.threads = threads
+
+    def _fill(self, slot: int, block) -> None:
+        dst = self.staging[slot].numpy()
+        src = np.asarray(block)
+        if src.shape != dst.shape:
+            raise ValueError(f"chunk has shape {src.shape}, expected {dst.shape}")
+        if src.dtype != np.uint16:
+            raise TypeError(f"chunk has dtype {src.dtype}, expected uint16")
+        # split the copy over the pool's threads (row blocks of the first axis)
+        parts = np.array_split(np.arange(dst.shape[0] * dst.shape[1]), self.threads)
+        d2, s2 = dst.reshape((-1,) + dst.shape[2:]), src.reshape((-1,) + src.shape[2:])
+        list(self.pool.map(lambda idx: np.copyto(d2[idx[0]:idx[-1] + 1], s2[idx[0]:idx[-1] + 1]) if len(idx) else None,
+                           parts))
+
+    def feed(self, chunks) -> int:
+        """Stage every chunk and run flat-field pass 1 on it.  Returns the number of blocks."""
+        runner, plan = self.runner, self.runner.plan
+        compute = torch.cuda.current_stream(plan.device)
+        ff = plan.ff
+        runner.h2d.wait_stream(compute)
+        if not ff.identity:
+            ff.maxima.zero_()
+        n = 0
+        for (ci, ti), block in chunks:
+            slot = n % len(self.staging)
+            if self.free_events[slot] is not None:
+                self.free_events[slot].synchronize()      # the slot's previous H2D has left it
+            self._fill(slot, block)
+            with torch.cuda.stream(runner.h2d):
+                runner.tiles_dev[ci, ti].copy_(self.staging[slot], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(runner.h2d)
+            self.free_events[slot] = ev
+            compute.wait_event(ev)
+            if not ff.identity:
+                ops.flatfield_maxima_accumulate(runner.tiles_dev[ci, ti], ff, ci)
+            n += 1
+        return n
+
+    def close(self):
+        self.pool.shutdown(wait=True)
+
+
+def iter_blocks(tiles):
+    """((channel, time), block) chunks of a (C,T,R,Cc,H,W) array-like (NumPy, or a dask array whose
+    chunks are computed block by block) in channel-major order."""
+    c, t = tiles.shape[:2]
+    for ci in range(c):
+        for ti in range(t):
+            block = tiles[ci, ti]
+            if hasattr(block, "compute"):       # dask: materialise this block only
+                block = block.compute()
+            yield (ci, ti), block
