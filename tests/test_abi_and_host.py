@@ -99,3 +99,22 @@ def test_flatfield_fast_path_fuzz_host(tmp_path):
     out = subprocess.run([str(exe), "20000000"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.startswith("ok")
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No CPU fallback: without the built .so the binding raises instead of degrading."""
+    from magnify_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libmagnify_b200.so"))
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_product_package_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under magnify_b200/ may import it."""
+    import pathlib
+
+    for path in pathlib.Path(ROOT, "magnify_b200").rglob("*.py"):
+        text = path.read_text()
+        assert "import oracle" not in text and "from oracle" not in text, path
