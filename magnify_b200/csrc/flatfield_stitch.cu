@@ -230,19 +230,6 @@ __device__ __forceinline__ void stitch_u16_body(const StitchParams& p, uint4* ri
   const int n_iter = (int)((ct_hi - ct_lo) * p.R * cols_q);   // host keeps this below 2^31
   if (n_iter <= 0) return;
 
-  double g[8], b[8];
-  if constexpr (MODE == 1) {
-    const int64_t base = ((int64_t)k * p.H + (p.clip_y + y)) * p.W;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int xi = xin0 + i;
-      const bool in = active && (xi >= 0) && (xi < p.W);
-      // out-of-row lanes: s = 2^20 + 2^19 + 0.5 never trips the guard (their result is not stored)
-      g[i] = in ? p.gain[base + xi] : 0.0;
-      b[i] = in ? p.bias[base + xi] : 1572864.5;
-    }
-  }
-
   // Tiles are visited in (ct, r, cc) order, cc fastest with stride P.  Between consecutive
   // tiles both offsets advance by a constant, except every cols_q-th step (next tile row; the
   // step from the last tile row of an image to the next image is the same).
@@ -285,6 +272,20 @@ __device__ __forceinline__ void stitch_u16_body(const StitchParams& p, uint4* ri
     if (s < n_iter) issue(s);
     cp_async_commit();
   }
+  // coefficient loads are issued after the ring prologue so that both are in flight together
+  double g[8], b[8];
+  if constexpr (MODE == 1) {
+    const int64_t base = ((int64_t)k * p.H + (p.clip_y + y)) * p.W;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int xi = xin0 + i;
+      const bool in = active && (xi >= 0) && (xi < p.W);
+      // out-of-row lanes: s = 2^20 + 2^19 + 0.5 never trips the guard (their result is not stored)
+      g[i] = in ? p.gain[base + xi] : 0.0;
+      b[i] = in ? p.bias[base + xi] : 1572864.5;
+    }
+  }
+
   int stage = 0;
   for (int it = 0; it < n_iter; ++it) {
     // refill the stage consumed in the previous iteration (all lanes are past reading it), then
@@ -468,7 +469,7 @@ static int run_stitch_fast(StitchParams p, cudaStream_t st) {
   // CTA walks ~kTargetIters tiles: blockIdx.z is the slowest grid index, so the resident CTAs all
   // work on the same narrow band of tiles (DRAM page locality; long loops let CTAs drift apart and
   // measured 15-20% slower), while the register-resident coefficients are still amortised.
-  int64_t target_iters = MODE == 1 ? 128 : 32;   // the copy-only kernel has no coefficients to amortise
+  int64_t target_iters = MODE == 1 ? 160 : 32;   // the copy-only kernel has no coefficients to amortise
   if (const char* e = getenv("MGB_STITCH_ITERS")) target_iters = atoll(e) > 0 ? atoll(e) : target_iters;  // tuning
   const int64_t iters_per_ct = p.R * cols_q;
   int64_t splits = (n_ct * iters_per_ct + target_iters - 1) / target_iters;
