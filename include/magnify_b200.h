@@ -51,7 +51,7 @@ int mgb_sm_count(void);
 int64_t mgb_launch_count(void);
 
 /* Tuning knob of the vectorised stitch / flat-field+stitch kernel: prefetch-ring depth x CTAs per
- * SM (0: 6x2, 1: 10x2, 2: 8x3).  Returns the previous value.  Results do not depend on it. */
+ * SM (0: 6x2 default, 1: 11x2, 2: 8x3).  Returns the previous value.  Results do not depend on it. */
 int mgb_set_stitch_variant(int variant);
 
 /* ---- F2: tile stitching, reference src/magnify/stitch.py:22-39 ----------------------------
@@ -91,8 +91,9 @@ int mgb_flatfield_maxima_generic(const void* tiles, int dtype, int64_t C, int64_
 /* Pass 2 preparation: per-position fast-path coefficients gain[k,p], bias[k,p] (float64) from
  * flat, dark and the (all-reduced) maxima.  The apply kernel evaluates one FMA per pixel,
  * s = (2^20 + x) * gain + bias, whose mantissa holds floor(v) in its high word and frac(v) in
- * its low word; pixels within 2^-24 of an integer (or with unusable coefficients, flagged
- * NaN here) are recomputed with the reference's exact operation order. */
+ * its low word; pixels within 2^-24 of an integer (or with unusable coefficients, encoded here
+ * as gain = 0, bias = 2^20 so that the guard always fires) are recomputed with the reference's
+ * exact operation order. */
 int mgb_flatfield_tables(const double* flat, const double* dark, int K, int64_t HW,
                          const double* maxima, double* gain, double* bias, void* stream);
 /* Pass 2: flat-field apply fused with the stitch (read 2 B, write 2*phi B per tile pixel).
@@ -115,9 +116,9 @@ int mgb_flatfield_apply_generic(const void* tiles, void* out, int dtype, int64_t
 int mgb_bounding_boxes(const double* x, const double* y, int64_t n, int L, int64_t W, int64_t H,
                        int32_t* boxes, int32_t* rel, void* stream);
 
-/* The ROI gather has two implementations: TMA-staged (cp.async.bulk.tensor windows through
- * shared memory, bulk store back) and a plain load/store kernel used when the image pitch is
- * not a multiple of 16 bytes or the window does not fit shared memory.  This switch forces the
+/* The ROI gather has two implementations: windows staged through shared memory (TMA tensor copies
+ * or cp.async chunks, re-aligned and stored with 128-bit stores) and plain load/store kernels used
+ * when the image pitch is not a multiple of 16 bytes or the window does not fit shared memory.  This switch forces the
  * plain kernels (tests cover both); returns the previous setting.  Default: enabled. */
 int mgb_set_tma_enabled(int enabled);
 /* Loader of the staged gather: 0 = TMA tensor copy (cp.async.bulk.tensor, default), 1 = per-warp
