@@ -416,3 +416,37 @@ def test_gather_stats_random_masks(cuda_device, gather_path, length):
                                      dev(bg.view(np.uint8), cuda_device), length, mask_t=dev(mask_t, cuda_device),
                                      want_roi=False)
     np.testing.assert_allclose(stats2.cpu().numpy(), want, rtol=1e-12, equal_nan=True)
+
+
+def test_flatfield_extreme_coefficients(cuda_device):
+    """Flat fields with a huge dynamic range.  (a) wild values everywhere; (b) a dim band with a
+    tiny flat value next to bright pixels with flat = 1: there gain = (1/f)(M/M2) exceeds the fast
+    path's budget (gain > 16), the positions are encoded as "always exact" (gain 0) and must still
+    be bit-exact, mixed with ordinary positions in the same 8-pixel vectors."""
+    from magnify_b200 import ops
+
+    rng = np.random.default_rng(31)
+    shape = (2, 3, 2, 2, 64, 64)
+    tiles = rng.integers(0, 65535, shape, dtype=np.uint16, endpoint=True)
+    flat = np.exp(rng.uniform(np.log(0.004), np.log(3.0), (64, 64)))
+    flat[::7, ::5] = 1e-6
+    flat[3, :] = 1e3
+    dark = rng.uniform(0, 300, (64, 64))
+    dark[:, ::9] = 0.0
+    want = o_st.stitch(o_ff.flatfield_correct(tiles, flat, dark), 6)
+    plan = ops.FlatFieldPlan(shape, flat, dark, device=cuda_device)
+    got = ops.flatfield_stitch(dev(tiles, cuda_device), overlap=6, plan=plan)
+    assert tuple(plan.maxima.cpu().numpy()) == o_ff.flatfield_maxima(tiles, flat, dark)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+
+    tiles_b = tiles.copy()
+    tiles_b[..., 10:20, :] = rng.integers(100, 400, tiles_b[..., 10:20, :].shape)
+    flat_b = np.ones((64, 64))
+    flat_b[10:20, 3::4] = 0.01
+    dark_b = np.full((64, 64), 100.0)
+    want = o_st.stitch(o_ff.flatfield_correct(tiles_b, flat_b, dark_b), 6)
+    plan = ops.FlatFieldPlan(shape, flat_b, dark_b, device=cuda_device)
+    got = ops.flatfield_stitch(dev(tiles_b, cuda_device), overlap=6, plan=plan)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    gain = plan.gain.cpu().numpy()
+    assert (gain[0, 10:20, 3::4] == 0).all() and (gain[0, 30:, :] > 0).all()   # both encodings exercised
