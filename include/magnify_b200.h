@@ -123,7 +123,9 @@ int mgb_bounding_boxes(const double* x, const double* y, int64_t n, int L, int64
 int mgb_set_tma_enabled(int enabled);
 /* Loader of the staged gather: 0 = TMA tensor copy (cp.async.bulk.tensor, default), 1 = per-warp
  * cp.async 16-byte chunks.  Both measured within 1% of each other on B200 (DRAM fetches 128-byte
- * lines for the row fragments either way).  Returns the previous value; results do not depend on it. */
+ * lines for the row fragments either way).  Adding 2 (values 2, 3) disables the warp-per-marker
+ * kernel that otherwise handles many-marker / few-window shapes (bead screens).  Returns the
+ * previous value; results do not depend on it. */
 int mgb_set_gather_loader(int loader);
 
 /* ---- F4 (+R): ROI gather, reference find.py:160-169, 324-334, 370-377, 589-602 -------------

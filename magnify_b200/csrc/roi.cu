@@ -276,6 +276,7 @@ int roi_gather_tma(const void* image, int64_t C, int64_t T, int64_t H, int64_t W
                    const uint8_t* bg, int64_t M, int L, void* roi, double* stats, cudaStream_t st);
 
 extern int g_gather_loader;
+extern int g_gather_wpm;
 
 static int g_tma_enabled = 1;
 
@@ -352,8 +353,12 @@ int mgb_set_tma_enabled(int enabled) {
 }
 
 int mgb_set_gather_loader(int loader) {
-  const int old = g_gather_loader;
-  if (loader == 0 || loader == 1) g_gather_loader = loader;
+  // bit 0: loader (0 TMA, 1 cp.async); value 2/3 additionally disables the warp-per-marker kernel
+  const int old = g_gather_loader | (g_gather_wpm ? 0 : 2);
+  if (loader >= 0 && loader <= 3) {
+    g_gather_loader = loader & 1;
+    g_gather_wpm = (loader & 2) ? 0 : 1;
+  }
   return old;
 }
 

@@ -18,6 +18,7 @@
 // Reference semantics: roi[m,c,t] = image[c,t, top:top+L, left:left+L] (find.py:160-169,
 // 324-334, 589-602); sums/means over fg/bg (identify.py:76-80, filter.py:21-22,51).
 #include <cstdlib>
+#include <type_traits>
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -404,6 +405,165 @@ roi_gather_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGatherP
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-per-marker variant for MANY markers with FEW windows each (bead screens: 1e5 markers x 48
+// windows of 50x50).  With one CTA per marker the mask set-up, the block barrier and the pipeline
+// fill are paid once per 48 windows and spread over 8 warps (6 windows each); here every warp owns
+// a marker for all its windows, keeps the marker's mask bytes in registers and runs one long
+// TMA pipeline -- no block-level synchronisation after the start.  Window rows that are not a
+// whole number of 16-byte vectors (50 px = 100 B) are handled as 8-byte quads: the flat roi is
+// 4-pixel aligned (L*L*2 is a multiple of 8 for even L), a quad is one or two pixel pairs of one or
+// two window rows, each pair one or two aligned 32-bit shared-memory words funnel-shifted by the
+// window's parity.  QPL = quads per lane (unrolled, offsets and masks in registers).
+// ---------------------------------------------------------------------------------------------
+template <int PAR>
+__device__ __forceinline__ uint32_t load_pair(const uint32_t* s32, uint32_t unit_off) {
+  const uint32_t w = unit_off >> 1;
+  if constexpr (PAR == 0) {
+    return s32[w];
+  } else {
+    return __funnelshift_r(s32[w], s32[w + 1], 16);
+  }
+}
+
+template <bool STATS, bool STORE, int QPL>
+__global__ void __launch_bounds__(kTmaMaxWarps * 32, 1)
+roi_gather_wpm_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGatherParams p, int64_t M) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nw = blockDim.x >> 5;
+  const int tm = blockIdx.y;
+
+  uint8_t* stages = smem;                                                  // [warp][stage][stage_bytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)nw * p.n_stages * p.stage_bytes);
+  int32_t* tlist = reinterpret_cast<int32_t*>(bars + kTmaMaxWarps * 8);
+  __shared__ int s_nt;
+  if (warp == 0) {
+    int n = 0;
+    for (int64_t base = 0; base < p.T; base += 32) {
+      const int64_t t = base + lane;
+      const bool hit = (t < p.T) && (!STATS || p.mask_t[t] == tm);
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (hit) tlist[n + __popc(bal & ((1u << lane) - 1))] = (int32_t)t;
+      n += __popc(bal);
+    }
+    if (lane == 0) s_nt = n;
+  }
+  if (lane == 0) {
+    for (int s = 0; s < p.n_stages; ++s) mbar_init(smem_u32(&bars[warp * 8 + s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t mi = (int64_t)blockIdx.x * nw + warp;
+  if (mi >= M) return;
+  const int64_t m = p.order ? p.order[mi] : mi;
+  const int nt = s_nt;
+  const int n_items = nt * (int)p.C;
+
+  // window-independent per-lane state: for each quad its two pixel pairs' offsets in the staged
+  // window (16-bit units, without the window's shift) and the 4+4 mask bytes
+  const int nquads = (p.rows * p.wu) >> 2;
+  uint32_t offa[QPL], offb[QPL], fm[QPL], bm[QPL];
+  uint32_t nf = 0, nb = 0;
+  const uint32_t* f32 = STATS ? reinterpret_cast<const uint32_t*>(p.fg + (m * p.Tm + tm) * (int64_t)p.rows * p.rows) : nullptr;
+  const uint32_t* b32 = STATS ? reinterpret_cast<const uint32_t*>(p.bg + (m * p.Tm + tm) * (int64_t)p.rows * p.rows) : nullptr;
+#pragma unroll
+  for (int k = 0; k < QPL; ++k) {
+    const int q = lane + 32 * k;
+    const int u = q < nquads ? 4 * q : 0;
+    const int row = u / p.wu, col = u - row * p.wu;
+    offa[k] = row * p.wpu + col;
+    offb[k] = (col + 2 < p.wu) ? offa[k] + 2 : (row + 1) * p.wpu;     // second pair wraps to the next row
+    fm[k] = bm[k] = 0;
+    if constexpr (STATS) {
+      if (q < nquads) {
+        fm[k] = __ldg(f32 + q);
+        bm[k] = __ldg(b32 + q);
+        // masks are 0/1 bytes by contract (bool arrays are)
+        nf += __popc(fm[k] & 0x01010101u);
+        nb += __popc(bm[k] & 0x01010101u);
+      }
+    }
+  }
+  double cnt_fg = 0.0, cnt_bg = 0.0;
+  if constexpr (STATS) {
+    cnt_fg = (double)__reduce_add_sync(0xffffffffu, nf);
+    cnt_bg = (double)__reduce_add_sync(0xffffffffu, nb);
+  }
+
+  uint8_t* my_stages = stages + (size_t)warp * p.n_stages * p.stage_bytes;
+  const uint32_t my_stage0 = smem_u32(my_stages);
+  const uint32_t my_bar0 = smem_u32(&bars[warp * 8]);
+  const uint32_t tx_bytes = (uint32_t)(p.rows * p.wpu * 2);
+
+  auto item_ct = [&](int i, int64_t* c, int64_t* t) {
+    *c = i / nt;
+    *t = tlist[i - (int)(*c) * nt];
+  };
+  auto issue_tma = [&](int i, int s) {
+    if (lane == 0) {
+      int64_t c, t;
+      item_ct(i, &c, &t);
+      const int32_t top = p.boxes[(m * p.T + t) * 2];
+      const int32_t left = p.boxes[(m * p.T + t) * 2 + 1];
+      const uint32_t bar = my_bar0 + s * 8;
+      mbar_expect_tx(bar, tx_bytes);
+      tma_load_3d(my_stage0 + s * p.stage_bytes, &tmap, bar, (left * p.unit) & ~7, top, (int)(c * p.T + t));
+    }
+  };
+  for (int s = 0; s < p.n_stages - 1; ++s)
+    if (s < n_items) issue_tma(s, s);
+  int s = 0;
+  uint32_t parity = 0;
+  for (int i = 0; i < n_items; ++i) {
+    {
+      const int nxt = i + p.n_stages - 1;
+      int rs = s + p.n_stages - 1;
+      if (rs >= p.n_stages) rs -= p.n_stages;
+      if (nxt < n_items) issue_tma(nxt, rs);
+    }
+    int64_t c, t;
+    item_ct(i, &c, &t);
+    const uint32_t shift = (uint32_t)(p.boxes[(m * p.T + t) * 2 + 1] * p.unit) & 7u;
+    const int64_t n = (m * p.C + c) * p.T + t;
+    uint2* dst = STORE ? reinterpret_cast<uint2*>(p.roi + n * (int64_t)p.rows * p.wu) : nullptr;
+    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(my_stages + (size_t)s * p.stage_bytes);
+    mbar_wait(my_bar0 + s * 8, parity);
+    uint32_t sf = 0, sb = 0;
+    auto consume = [&](auto par) {
+      constexpr int PAR = decltype(par)::value;
+#pragma unroll
+      for (int k = 0; k < QPL; ++k) {
+        const int q = lane + 32 * k;
+        if (q < nquads) {
+          const uint32_t lo = load_pair<PAR>(s32, offa[k] + shift);
+          const uint32_t hi = load_pair<PAR>(s32, offb[k] + shift);
+          if constexpr (STORE) {
+            asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(dst + q), "r"(lo), "r"(hi) : "memory");
+          }
+          if constexpr (STATS) {
+            sf = __dp2a_lo(lo, fm[k], sf); sf = __dp2a_hi(hi, fm[k], sf);
+            sb = __dp2a_lo(lo, bm[k], sb); sb = __dp2a_hi(hi, bm[k], sb);
+          }
+        }
+      }
+    };
+    if (shift & 1u) consume(std::integral_constant<int, 1>{});
+    else consume(std::integral_constant<int, 0>{});
+    if constexpr (STATS) {
+      sf = __reduce_add_sync(0xffffffffu, sf);
+      sb = __reduce_add_sync(0xffffffffu, sb);
+      if (lane == 0) {
+        double* o = p.stats + n * 6;
+        o[0] = cnt_fg; o[1] = cnt_bg; o[2] = (double)sf; o[3] = (double)sb;
+        o[4] = (double)sf / cnt_fg; o[5] = (double)sb / cnt_bg;
+      }
+    }
+    __syncwarp();
+    if (++s == p.n_stages) { s = 0; parity ^= 1; }
+  }
+}
+
 static PFN_cuTensorMapEncodeTiled get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled fn = nullptr;
   if (!fn) {
@@ -416,6 +576,7 @@ static PFN_cuTensorMapEncodeTiled get_encode_fn() {
   return fn;
 }
 
+int g_gather_wpm = 1;      // warp-per-marker kernel for many-marker shapes (tuning switch)
 int g_gather_loader = 0;   // 0 = TMA tensor copies (default), 1 = cp.async chunks; equal within 1% on B200
 
 static uint32_t magic_u32(uint32_t d) { return (uint32_t)((0x100000000ULL + d - 1) / d); }
@@ -482,6 +643,48 @@ int roi_gather_tma(const void* image, int64_t C, int64_t T, int64_t H, int64_t W
   p.image = (const uint16_t*)image;
   p.H = H;
   p.Wu = Wu;
+
+  // Many markers, rows that are not whole 16-byte vectors, few quads per lane: warp-per-marker.
+  const int nquads = (L * wu) / 4;
+  const int qpl = (nquads + 31) / 32;
+  const bool masks_0_1_words = !with_stats || (((size_t)L * L) % 4 == 0 && (reinterpret_cast<uintptr_t>(fg) & 3u) == 0 &&
+                                               (reinterpret_cast<uintptr_t>(bg) & 3u) == 0);
+  const bool out8 = !roi || (reinterpret_cast<uintptr_t>(roi) & 7u) == 0;
+  if (g_gather_wpm && unit == 1 && p.vpr == 0 && wu % 2 == 0 && (L * wu) % 4 == 0 && qpl <= 24 && M >= 2048 &&
+      masks_0_1_words && out8) {
+    const size_t fixed_w = kTmaMaxWarps * 8 * sizeof(uint64_t) + (size_t)T * sizeof(int32_t) + 128;
+    const size_t budget_w = (size_t)max_smem > fixed_w + 1024 ? (size_t)max_smem - fixed_w - 1024 : 0;
+    int ns_w = (int)(budget_w / ((size_t)kTmaMaxWarps * p.stage_bytes));
+    if (ns_w > 4) ns_w = 4;
+    if (ns_w >= 2) {
+      TmaGatherParams pw = p;
+      pw.n_stages = ns_w;
+      const size_t smem_w = (size_t)kTmaMaxWarps * ns_w * p.stage_bytes + fixed_w;
+      dim3 grid_w((unsigned)((M + kTmaMaxWarps - 1) / kTmaMaxWarps), (unsigned)(with_stats ? Tm : 1));
+#define MGB_LAUNCH_W(ST, SO, QP)                                                                       \
+  do {                                                                                                 \
+    MGB_CUDA_TRY(cudaFuncSetAttribute(roi_gather_wpm_kernel<ST, SO, QP>,                               \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));      \
+    roi_gather_wpm_kernel<ST, SO, QP><<<grid_w, kTmaMaxWarps * 32, smem_w, st>>>(tmap, pw, M);         \
+  } while (0)
+#define MGB_LAUNCH_WQ(ST, SO)                      \
+  do {                                             \
+    if (qpl <= 12) MGB_LAUNCH_W(ST, SO, 12);       \
+    else if (qpl <= 20) MGB_LAUNCH_W(ST, SO, 20);  \
+    else MGB_LAUNCH_W(ST, SO, 24);                 \
+  } while (0)
+      if (with_stats) {
+        if (roi) MGB_LAUNCH_WQ(true, true);
+        else MGB_LAUNCH_WQ(true, false);
+      } else {
+        MGB_LAUNCH_WQ(false, true);
+      }
+#undef MGB_LAUNCH_WQ
+#undef MGB_LAUNCH_W
+      MGB_CUDA_LAUNCH_CHECK();
+      return MGB_OK;
+    }
+  }
   const int vpl = p.vpr ? (int)((L * p.vpr + 31) / 32) : 0;       // vectors per lane
   dim3 grid((unsigned)M, (unsigned)(with_stats ? Tm : 1));
 #define MGB_LAUNCH(ST, SO, VP)                                                                          \

@@ -450,3 +450,45 @@ def test_flatfield_extreme_coefficients(cuda_device):
     np.testing.assert_array_equal(got.cpu().numpy(), want)
     gain = plan.gain.cpu().numpy()
     assert (gain[0, 10:20, 3::4] == 0).all() and (gain[0, 30:, :] > 0).all()   # both encodings exercised
+
+
+@pytest.mark.parametrize("length", [50, 34, 22])
+def test_gather_warp_per_marker_kernel(cuda_device, length):
+    """Many markers x few windows (bead-screen shape) takes the warp-per-marker quad kernel: it
+    must agree bit for bit with the CTA-per-marker staged kernel and the plain kernels, and with
+    the oracle on a sample of markers."""
+    from magnify_b200 import _lib, ops
+
+    lib = _lib.load()
+    rng = np.random.default_rng(41)
+    c, t, h, w, m = 2, 3, 600, 1024, 3000
+    image = rng.integers(0, 65535, (c, t, h, w), dtype=np.uint16, endpoint=True)
+    x = rng.uniform(-10, w + 10, (m, t))
+    y = rng.uniform(-10, h + 10, (m, t))
+    mask_t = np.array([0, 1, 1], dtype=np.int32)
+    fg = rng.random((m, 2, length, length)) < 0.25
+    bg = rng.random((m, 2, length, length)) < 0.5
+    fg[5] = False
+    image_d = dev(image, cuda_device)
+    boxes = ops.bounding_boxes(dev(x, cuda_device), dev(y, cuda_device), length, w, h)
+    args = (image_d, boxes, dev(fg.view(np.uint8), cuda_device), dev(bg.view(np.uint8), cuda_device), length)
+    order = ops.spatial_order(boxes)
+    results = {}
+    for name, tma, loader in (("wpm", 1, 0), ("cta", 1, 2), ("plain", 0, 0)):
+        old_t, old_l = lib.mgb_set_tma_enabled(tma), lib.mgb_set_gather_loader(loader)
+        try:
+            roi, stats = ops.roi_gather_stats(*args, mask_t=dev(mask_t, cuda_device), order=order if name == "wpm" else None)
+            _, stats_only = ops.roi_gather_stats(*args, mask_t=dev(mask_t, cuda_device), want_roi=False)
+            roi_only = ops.roi_gather(image_d, boxes, length)
+        finally:
+            lib.mgb_set_tma_enabled(old_t)
+            lib.mgb_set_gather_loader(old_l)
+        results[name] = (roi.cpu().numpy(), stats.cpu().numpy(), stats_only.cpu().numpy(), roi_only.cpu().numpy())
+    for name in ("cta", "plain"):
+        for a, b in zip(results["wpm"], results[name]):
+            np.testing.assert_array_equal(a, b, err_msg=name)
+    sample = np.r_[0:8, 1500:1504, m - 4:m]
+    want_roi = o_rois.gather_rois(image, x[sample], y[sample], length)
+    np.testing.assert_array_equal(results["wpm"][0][sample], want_roi)
+    want = o_red.masked_stats(want_roi, fg[sample][:, mask_t], bg[sample][:, mask_t])
+    np.testing.assert_allclose(results["wpm"][1][sample], want, rtol=1e-12, equal_nan=True)
