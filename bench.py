@@ -264,11 +264,25 @@ def run_b200_arm(args, cfg):
     roi_out = torch.empty((m, c, t, length, length), dtype=torch.uint16, device=dev)
     stats_out = torch.empty((m, c, t, 6), dtype=torch.float64, device=dev)
     gathered = torch.empty((world,) + tuple(stats_out.shape), dtype=torch.float64, device=dev) if world > 1 else None
+    symm = None
+    if world > 1 and not args.no_fused_gather:
+        try:  # summaries all-gathered by the gather kernel itself over NVLink peer memory
+            from magnify_b200.dist import SymmetricSummaries
+
+            symm = SymmetricSummaries(stats_out.shape, dev, group)
+        except Exception as exc:
+            print(f"[bench] symmetric memory unavailable ({exc!r}); using NCCL all_gather", file=sys.stderr)
+            symm = None
     roi_px_rank = m * c * t * length * length
     tile_px_rank = case.tiles.numel()
     phi = (plan.image_shape[-1] * plan.image_shape[-2]) / (cfg["r"] * cfg["cc"] * cfg["h"] * cfg["w"])
 
     def step(record=None):
+        if symm is not None:
+            plan.run_device(case.tiles, want_roi=True, image_out=image_out, roi_out=roi_out, record=record,
+                            peer_stats=symm.peer_blocks)
+            symm.barrier()
+            return
         plan.run_device(case.tiles, want_roi=True, image_out=image_out, roi_out=roi_out, stats_out=stats_out,
                         record=record)
         if world > 1:
@@ -282,6 +296,13 @@ def run_b200_arm(args, cfg):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    if symm is not None:   # the fused gather must equal the NCCL all-gather of the same summaries
+        plan.run_device(case.tiles, want_roi=False, image_out=image_out, stats_out=stats_out)
+        dist.all_gather_into_tensor(gathered, stats_out, group=group)
+        torch.cuda.synchronize(dev)
+        same = torch.equal(torch.nan_to_num(gathered, nan=-1.0), torch.nan_to_num(symm.gathered, nan=-1.0))
+        if not same:
+            raise RuntimeError("fused peer-store gather of the summaries differs from the NCCL all_gather")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -367,7 +388,10 @@ def run_b200_arm(args, cfg):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_s * 1e3 / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u16 (f64 flat-field arithmetic)", "data": "synthetic",
-            "config": workload_config(cfg, world) if args.config == "c3" else c5_config(cfg, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "config": dict(workload_config(cfg, world) if args.config == "c3" else c5_config(cfg, world),
+                           summary_gather=("fused peer stores over NVLink (symmetric memory)" if symm is not None
+                                           else ("nccl all_gather" if world > 1 else "single rank"))),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "stages": stages, "cpu_baseline": cpu_baseline,
         }
     if world > 1:
@@ -465,6 +489,8 @@ def main():
     ap.add_argument("--timepoints", type=int, default=None, help="timepoints per rank (default 50 = config 3)")
     ap.add_argument("--e2e-timepoints", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fused-gather", action="store_true",
+                    help="N>1: gather the summaries with NCCL all_gather instead of peer stores from the kernel")
     ap.add_argument("--config", default="c3", choices=["c3", "c5"],
                     help="c3 = BASELINE config 3 (default, the metric's workload); c5 = one rank's shard of config 5")
     args = ap.parse_args()

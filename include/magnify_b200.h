@@ -145,6 +145,16 @@ int mgb_roi_gather_stats_u16(const uint16_t* image, int64_t C, int64_t T, int64_
                              const int32_t* boxes, const int32_t* order, const int32_t* mask_t,
                              int64_t Tm, const uint8_t* fg, const uint8_t* bg, int64_t M, int L,
                              uint16_t* roi, double* stats, void* stream);
+/* Multi-GPU variant: the summaries are written by the kernel itself into the gathered buffer of
+ * EVERY rank over NVLink peer memory (no separate all-gather).  host_peer_stats[j] (host array of
+ * n_peers <= 8 device addresses) points at THIS rank's (M,C,T,6) block inside rank j's gathered
+ * (ranks,M,C,T,6) buffer (peer-mapped, e.g. torch symmetric memory); the caller synchronises the
+ * ranks afterwards.  Needs the staged kernels (else MGB_EUNSUPPORTED). */
+int mgb_roi_gather_stats_peers_u16(const uint16_t* image, int64_t C, int64_t T, int64_t H, int64_t W,
+                                   const int32_t* boxes, const int32_t* order, const int32_t* mask_t,
+                                   int64_t Tm, const uint8_t* fg, const uint8_t* bg, int64_t M, int L,
+                                   uint16_t* roi, const uint64_t* host_peer_stats, int n_peers,
+                                   void* stream);
 /* The same summaries from an roi that already exists (the `quantify` component on a dataset
  * produced elsewhere): roi (M,C,T,L,L) uint16 -> stats (M,C,T,6). */
 int mgb_roi_stats_u16(const uint16_t* roi, int64_t M, int64_t C, int64_t T, int L,

@@ -43,6 +43,8 @@ SIGNATURES = {
     "mgb_bounding_boxes": [_P, _P, _I64, c_int, _I64, _I64, _P, _P, _P],
     "mgb_roi_gather": [_P, _I64, _I64, _I64, _I64, c_int, _P, _P, _I64, c_int, _P, _P],
     "mgb_roi_gather_stats_u16": [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _I64, _P, _P, _I64, c_int, _P, _P, _P],
+    "mgb_roi_gather_stats_peers_u16": [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _I64, _P, _P, _I64, c_int, _P,
+                                       POINTER(ctypes.c_uint64), c_int, _P],
     "mgb_roi_stats_u16": [_P, _I64, _I64, _I64, c_int, _P, _I64, _P, _P, _P, _P],
     "mgb_roi_median_u16": [_P, _I64, _I64, _I64, c_int, _P, _I64, _P, _P, _P],
     "mgb_chip_masks": [_P, _P, c_int, c_int, _I64, c_int, _P, _P, _P, _P],

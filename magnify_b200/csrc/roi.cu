@@ -273,7 +273,8 @@ static uint32_t magic_for(uint32_t d) { return (uint32_t)((0x100000000ULL + d - 
 // roi_tma.cu
 int roi_gather_tma(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
                    const int32_t* boxes, const int32_t* order, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
-                   const uint8_t* bg, int64_t M, int L, void* roi, double* stats, cudaStream_t st);
+                   const uint8_t* bg, int64_t M, int L, void* roi, double* stats, const uint64_t* host_peers,
+                   int n_peers, cudaStream_t st);
 
 extern int g_gather_loader;
 extern int g_gather_wpm;
@@ -300,7 +301,7 @@ int mgb_bounding_boxes(const double* x, const double* y, int64_t n, int L, int64
 static int gather_common(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
                          const int32_t* boxes, const int32_t* order, int64_t marker_stride, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
                          const uint8_t* bg, int64_t M, int L, void* roi, double* stats,
-                         cudaStream_t st) {
+                         cudaStream_t st, const uint64_t* host_peers = nullptr, int n_peers = 0) {
   const bool with_stats = stats != nullptr;
   if (M < 0 || C < 0 || T < 0 || L <= 0 || H < L || W < L) return MGB_EINVAL;
   if (itemsize != 1 && itemsize != 2 && itemsize != 4 && itemsize != 8) return MGB_EINVAL;
@@ -312,9 +313,11 @@ static int gather_common(const void* image, int64_t C, int64_t T, int64_t H, int
   if (with_stats && (!mask_t || !fg || !bg || Tm <= 0 || itemsize != 2)) return MGB_EINVAL;
   if (g_tma_enabled && marker_stride == 0) {
     // TMA-staged path (roi_tma.cu); MGB_EALIGN means "not applicable here", fall through.
-    const int rc = roi_gather_tma(image, C, T, H, W, itemsize, boxes, order, mask_t, Tm, fg, bg, M, L, roi, stats, st);
+    const int rc = roi_gather_tma(image, C, T, H, W, itemsize, boxes, order, mask_t, Tm, fg, bg, M, L, roi, stats,
+                                  host_peers, n_peers, st);
     if (rc != MGB_EALIGN) return rc;
   }
+  if (n_peers > 0) return MGB_EUNSUPPORTED;   // peer write-out exists only in the staged kernels
   const int unit = itemsize / 2;
   const int Lu = L * (unit ? unit : 1);
   const bool word_path = itemsize >= 2 && (Lu % 2 == 0) &&
@@ -376,6 +379,17 @@ int mgb_roi_gather_stats_u16(const uint16_t* image, int64_t C, int64_t T, int64_
   if (!stats && M * C * T > 0) return MGB_EINVAL;
   return gather_common(image, C, T, H, W, 2, boxes, order, 0, mask_t, Tm, fg, bg, M, L, roi, stats,
                        (cudaStream_t)stream);
+}
+
+int mgb_roi_gather_stats_peers_u16(const uint16_t* image, int64_t C, int64_t T, int64_t H, int64_t W,
+                                   const int32_t* boxes, const int32_t* order, const int32_t* mask_t,
+                                   int64_t Tm, const uint8_t* fg, const uint8_t* bg, int64_t M, int L,
+                                   uint16_t* roi, const uint64_t* host_peer_stats, int n_peers, void* stream) {
+  if (!host_peer_stats || n_peers < 1 || n_peers > 8) return MGB_EINVAL;
+  if (M * C * T == 0) return MGB_OK;
+  // `stats` only flags "with summaries" here; every record is written through the peer pointers
+  return gather_common(image, C, T, H, W, 2, boxes, order, 0, mask_t, Tm, fg, bg, M, L, roi,
+                       reinterpret_cast<double*>(host_peer_stats[0]), (cudaStream_t)stream, host_peer_stats, n_peers);
 }
 
 int mgb_roi_stats_u16(const uint16_t* roi, int64_t M, int64_t C, int64_t T, int L, const int32_t* mask_t,

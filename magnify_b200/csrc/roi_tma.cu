@@ -37,6 +37,8 @@ struct TmaGatherParams {
   const uint8_t* fg;        // (M,Tm,rows,rows) or null
   const uint8_t* bg;
   double* stats;            // (M,C,T,6) or null
+  double* peer_stats[8];    // peer-mapped copies of the gathered (ranks,M,C,T,6) buffer, this rank's block
+  int n_peers;              // 0: write only `stats`
   int64_t C, T, Tm;
   int rows;                 // L
   int wu;                   // row length in 16-bit units (L * unit)
@@ -94,6 +96,23 @@ __device__ __forceinline__ uint4 shift_units(const uint4& a, const uint4& b) {
   } else {
     return make_uint4(__funnelshift_r(w[o], w[o + 1], 16), __funnelshift_r(w[o + 1], w[o + 2], 16),
                       __funnelshift_r(w[o + 2], w[o + 3], 16), __funnelshift_r(w[o + 3], w[o + 4], 16));
+  }
+}
+
+// Summary write-out.  With peers, the 48-byte record goes straight into this rank's block of the
+// gathered buffer of EVERY rank (NVLink peer stores): the per-marker summaries are all-gathered by
+// the kernel that computes them, no separate collective.
+__device__ __forceinline__ void write_stats(const TmaGatherParams& p, int64_t n, double cf, double cb, double sf,
+                                            double sb) {
+  const double v0 = cf, v1 = cb, v2 = sf, v3 = sb, v4 = sf / cf, v5 = sb / cb;   // 0/0 = NaN like nanmean
+  if (p.n_peers == 0) {
+    double* o = p.stats + n * 6;
+    o[0] = v0; o[1] = v1; o[2] = v2; o[3] = v3; o[4] = v4; o[5] = v5;
+  } else {
+    for (int j = 0; j < p.n_peers; ++j) {
+      double* o = p.peer_stats[j] + n * 6;
+      o[0] = v0; o[1] = v1; o[2] = v2; o[3] = v3; o[4] = v4; o[5] = v5;
+    }
   }
 }
 
@@ -394,11 +413,7 @@ roi_gather_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGatherP
     if constexpr (STATS) {
       sf = __reduce_add_sync(0xffffffffu, sf);
       sb = __reduce_add_sync(0xffffffffu, sb);
-      if (lane == 0) {
-        double* o = p.stats + n * 6;
-        o[0] = cnt_fg; o[1] = cnt_bg; o[2] = (double)sf; o[3] = (double)sb;
-        o[4] = (double)sf / cnt_fg; o[5] = (double)sb / cnt_bg;   // 0/0 = NaN like nanmean
-      }
+      if (lane == 0) write_stats(p, n, cnt_fg, cnt_bg, (double)sf, (double)sb);
     }
     __syncwarp();
     if (++s == p.n_stages) { s = 0; parity ^= 1; }
@@ -553,11 +568,7 @@ roi_gather_wpm_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGatherP
     if constexpr (STATS) {
       sf = __reduce_add_sync(0xffffffffu, sf);
       sb = __reduce_add_sync(0xffffffffu, sb);
-      if (lane == 0) {
-        double* o = p.stats + n * 6;
-        o[0] = cnt_fg; o[1] = cnt_bg; o[2] = (double)sf; o[3] = (double)sb;
-        o[4] = (double)sf / cnt_fg; o[5] = (double)sb / cnt_bg;
-      }
+      if (lane == 0) write_stats(p, n, cnt_fg, cnt_bg, (double)sf, (double)sb);
     }
     __syncwarp();
     if (++s == p.n_stages) { s = 0; parity ^= 1; }
@@ -585,7 +596,8 @@ static uint32_t magic_u32(uint32_t d) { return (uint32_t)((0x100000000ULL + d - 
 // the LSU kernels of roi.cu), or an error.
 int roi_gather_tma(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
                    const int32_t* boxes, const int32_t* order, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
-                   const uint8_t* bg, int64_t M, int L, void* roi, double* stats, cudaStream_t st) {
+                   const uint8_t* bg, int64_t M, int L, void* roi, double* stats, const uint64_t* host_peers,
+                   int n_peers, cudaStream_t st) {
   const bool with_stats = stats != nullptr;
   if (itemsize < 2) return MGB_EALIGN;
   const int unit = itemsize / 2;
@@ -601,6 +613,12 @@ int roi_gather_tma(const void* image, int64_t C, int64_t T, int64_t H, int64_t W
   TmaGatherParams p{};
   p.roi = (uint16_t*)roi; p.boxes = boxes; p.order = order; p.mask_t = mask_t; p.fg = fg; p.bg = bg; p.stats = stats;
   p.C = C; p.T = T; p.Tm = with_stats ? Tm : 1; p.rows = L; p.wu = wu; p.wpu = wpu; p.unit = unit;
+  p.n_peers = 0;
+  if (host_peers && n_peers > 0) {
+    if (n_peers > 8 || !with_stats) return MGB_EINVAL;
+    p.n_peers = n_peers;
+    for (int j = 0; j < n_peers; ++j) p.peer_stats[j] = reinterpret_cast<double*>(host_peers[j]);
+  }
   p.stage_bytes = (L * wpu * 2 + 127) & ~127;
   const bool out16 = !roi || aligned16(roi);
   const bool out4 = !roi || (reinterpret_cast<uintptr_t>(roi) & 3u) == 0;

@@ -75,3 +75,32 @@ def broadcast_centres(centres: Optional[torch.Tensor], src: int = 0, group=None,
         centres = torch.empty(tuple(int(v) for v in shape), dtype=torch.float64, device=device)
     dist.broadcast(centres, src=src, group=group)
     return centres
+
+
+class SymmetricSummaries:
+    """Gathered per-marker summaries (ranks, M, C, T, K) in peer-mapped (symmetric) memory.
+
+    Every rank allocates the same buffer, the ranks exchange handles once (`rendezvous`), and the
+    gather kernel of rank r stores its records directly into block r of EVERY rank's buffer over
+    NVLink (`peer_blocks` are those block addresses, one per rank).  After `barrier()` the whole
+    gathered tensor is valid on every rank: the all-gather of the summaries is fused into the
+    kernel that computes them.  Raises if symmetric memory is unavailable; callers fall back to
+    `gather_summaries` (NCCL all-gather)."""
+
+    def __init__(self, shape_local, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.shape_local = tuple(int(s) for s in shape_local)
+        self.gathered = symm_mem.empty((self.world,) + self.shape_local, dtype=torch.float64, device=device)
+        self.handle = symm_mem.rendezvous(self.gathered, group)
+        block_bytes = 8
+        for s in self.shape_local:
+            block_bytes *= s
+        self.peer_blocks = [int(ptr) + self.rank * block_bytes for ptr in self.handle.buffer_ptrs]
+
+    def barrier(self) -> None:
+        """Cross-rank barrier on the current stream: every rank's stores have landed everywhere."""
+        self.handle.barrier()

@@ -362,6 +362,7 @@ def roi_gather_stats(
     out_roi: Optional[torch.Tensor] = None,
     out_stats: Optional[torch.Tensor] = None,
     order: Optional[torch.Tensor] = None,
+    peer_stats: Optional[Sequence[int]] = None,
 ):
     """Gather fused with per-(marker, channel, time) masked sums / counts / means.
 
@@ -395,6 +396,16 @@ def roi_gather_stats(
         roi = out_roi if out_roi is not None else torch.empty(shape, dtype=image.dtype, device=image.device)
         if tuple(roi.shape) != shape or roi.dtype != image.dtype:
             raise ValueError(f"out_roi must have shape {shape} and dtype {image.dtype}")
+    if peer_stats is not None:
+        # Multi-GPU: the kernel writes every summary record into this rank's block of each rank's
+        # gathered buffer (peer-mapped addresses, see magnify_b200.dist.SymmetricSummaries).
+        n_peers = len(peer_stats)
+        arr = (ctypes.c_uint64 * n_peers)(*[int(a) for a in peer_stats])
+        with torch.cuda.device(image.device):
+            _lib.call("mgb_roi_gather_stats_peers_u16", _ptr(image), c, t, h, w, _ptr(boxes),
+                      _ptr(_check_order(order, m)), _ptr(mask_t), tm, _ptr(fg), _ptr(bg), m, int(roi_length),
+                      _ptr(roi), arr, n_peers, _stream())
+        return roi, None
     stats = out_stats if out_stats is not None else torch.empty((m, c, t, 6), dtype=torch.float64, device=image.device)
     if tuple(stats.shape) != (m, c, t, 6) or stats.dtype != torch.float64:
         raise ValueError("out_stats must be float64 with shape (M, C, T, 6)")

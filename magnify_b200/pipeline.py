@@ -133,11 +133,13 @@ class QuantifyPlan:
 
     # -- device-resident run ------------------------------------------------------------------
     def run_device(self, tiles: torch.Tensor, want_roi: bool = True, image_out=None, roi_out=None,
-                   stats_out=None, record: Optional[list] = None) -> QuantifyResult:
+                   stats_out=None, record: Optional[list] = None, peer_stats=None) -> QuantifyResult:
         """Whole hot path on tiles already in HBM (all launches on the current stream).
 
         record: optional list that receives (stage, start_event, end_event) CUDA-event triples
-        recorded on the launching stream (bench.py's per-kernel timing)."""
+        recorded on the launching stream (bench.py's per-kernel timing).
+        peer_stats: `SymmetricSummaries.peer_blocks` -- the gather kernel then writes the summaries
+        into every rank's gathered buffer over NVLink instead of `stats_out` (result.stats is None)."""
         if self.boxes is None:
             raise RuntimeError("set_chip_markers / set_bead_markers must be called first")
         if tuple(tiles.shape) != self.tile_shape:
@@ -166,7 +168,7 @@ class QuantifyPlan:
                                                                        maxima=maxima, out=image_out))
         roi, stats = stage("roi_gather_stats", lambda: ops.roi_gather_stats(
             image, self.boxes, self.fg, self.bg, self.roi_length, mask_t=self.mask_t, want_roi=want_roi,
-            out_roi=roi_out, out_stats=stats_out, order=self.order))
+            out_roi=roi_out, out_stats=stats_out, order=self.order, peer_stats=peer_stats))
         return QuantifyResult(image, roi, self.fg, self.bg, self.mask_t, self.boxes, stats, maxima)
 
 
