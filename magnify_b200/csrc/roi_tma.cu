@@ -100,19 +100,23 @@ __device__ __forceinline__ uint4 shift_units(const uint4& a, const uint4& b) {
 }
 
 // Summary write-out.  With peers, the 48-byte record goes straight into this rank's block of the
-// gathered buffer of EVERY rank (NVLink peer stores): the per-marker summaries are all-gathered by
-// the kernel that computes them, no separate collective.
-__device__ __forceinline__ void write_stats(const TmaGatherParams& p, int64_t n, double cf, double cb, double sf,
-                                            double sb) {
-  const double v0 = cf, v1 = cb, v2 = sf, v3 = sb, v4 = sf / cf, v5 = sb / cb;   // 0/0 = NaN like nanmean
+// gathered buffer of EVERY rank (NVLink peer stores, one lane per peer): the per-marker summaries
+// are all-gathered by the kernel that computes them, no separate collective.
+__device__ __forceinline__ void write_stats(const TmaGatherParams& p, int lane, int64_t n, double cf, double cb,
+                                            double sf, double sb) {
+  // called by the whole warp (all lanes hold the reduced sums): lane 0 writes the local record, or
+  // lane j writes the record to peer j (one 48-byte record = three 16-byte stores per peer)
+  double* o = nullptr;
   if (p.n_peers == 0) {
-    double* o = p.stats + n * 6;
-    o[0] = v0; o[1] = v1; o[2] = v2; o[3] = v3; o[4] = v4; o[5] = v5;
-  } else {
-    for (int j = 0; j < p.n_peers; ++j) {
-      double* o = p.peer_stats[j] + n * 6;
-      o[0] = v0; o[1] = v1; o[2] = v2; o[3] = v3; o[4] = v4; o[5] = v5;
-    }
+    if (lane == 0) o = p.stats + n * 6;
+  } else if (lane < p.n_peers) {
+    o = p.peer_stats[lane] + n * 6;
+  }
+  if (o) {
+    double2* o2 = reinterpret_cast<double2*>(o);
+    o2[0] = make_double2(cf, cb);
+    o2[1] = make_double2(sf, sb);
+    o2[2] = make_double2(sf / cf, sb / cb);   // 0/0 = NaN like nanmean
   }
 }
 
@@ -413,7 +417,7 @@ roi_gather_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGatherP
     if constexpr (STATS) {
       sf = __reduce_add_sync(0xffffffffu, sf);
       sb = __reduce_add_sync(0xffffffffu, sb);
-      if (lane == 0) write_stats(p, n, cnt_fg, cnt_bg, (double)sf, (double)sb);
+      write_stats(p, lane, n, cnt_fg, cnt_bg, (double)sf, (double)sb);
     }
     __syncwarp();
     if (++s == p.n_stages) { s = 0; parity ^= 1; }
@@ -568,7 +572,7 @@ roi_gather_wpm_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGatherP
     if constexpr (STATS) {
       sf = __reduce_add_sync(0xffffffffu, sf);
       sb = __reduce_add_sync(0xffffffffu, sb);
-      if (lane == 0) write_stats(p, n, cnt_fg, cnt_bg, (double)sf, (double)sb);
+      write_stats(p, lane, n, cnt_fg, cnt_bg, (double)sf, (double)sb);
     }
     __syncwarp();
     if (++s == p.n_stages) { s = 0; parity ^= 1; }
