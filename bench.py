@@ -185,9 +185,9 @@ def run_reference_arm(args, cfg):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    channels = 1
+    channels = cfg["c"]
     value, sec_per_step, roi_px = time_cpu(cfg, channels, args.steps, args.warmup, threads)
-    sample = (f"1 timepoint x {channels} channel of the C3 stack per step ({cfg['r']}x{cfg['cc']} tiles of "
+    sample = (f"1 timepoint x {channels} channels of the C3 stack per step ({cfg['r']}x{cfg['cc']} tiles of "
               f"{cfg['h']}x{cfg['w']}, {cfg['rows'] * cfg['cols']} ROIs of {cfg['roi_length']}^2), data in RAM")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -378,10 +378,11 @@ def run_b200_arm(args, cfg):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == "c3":
         threads = os.cpu_count() or 1
-        v, sec, _ = time_cpu(cfg, 1, steps=2, warmup=1, threads=threads)
+        v, sec, _ = time_cpu(cfg, cfg["c"], steps=4, warmup=1, threads=threads)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": "1 timepoint x 1 channel of the C3 stack (16 tiles of 2048^2, 1792 ROIs), "
-                                  f"2 timed passes of {sec:.2f} s, NumPy oracle over a {threads}-thread pool, data in RAM"}
+                        "sample": f"1 timepoint x {cfg['c']} channels of the C3 stack (64 tiles of 2048^2, 1792 ROIs x 4), "
+                                  f"4 timed passes of {sec:.2f} s (~{5 * sec * threads:.0f} core-seconds), NumPy oracle over a "
+                                  f"{threads}-thread pool, data in RAM"}
     line = None
     if rank == 0:
         line = {
