@@ -17,13 +17,13 @@ from __future__ import annotations
 
 import math
 import os
-from typing import Callable, Optional, Sequence
+from typing import Callable, Optional
 
 import numpy as np
 import torch
 
 from . import ops, pipeline
-from .dataset import Assay
+from .dataset import Assay  # noqa: F401  (re-exported: the stand-in Dataset type of this module)
 
 TILE_DIMS = ("channel", "time", "tile_row", "tile_col", "tile_y", "tile_x")
 IMAGE_DIMS = ("channel", "time", "im_y", "im_x")
