@@ -261,7 +261,9 @@ def run_b200_arm(args, cfg):
         plan.set_chip_markers(case.x, case.y, case.fg_radius, case.chamber_radius, case.max_button_radius)
         m = case.x.shape[0]
     length = case.roi_length
-    image_out = torch.empty(plan.image_shape, dtype=torch.uint16, device=dev)
+    from magnify_b200 import ops as _ops
+
+    image_out = _ops.alloc_image(plan.image_shape, torch.uint16, dev)
     roi_out = torch.empty((m, c, t, length, length), dtype=torch.uint16, device=dev)
     stats_out = torch.empty((m, c, t, 6), dtype=torch.float64, device=dev)
     gathered = torch.empty((world,) + tuple(stats_out.shape), dtype=torch.float64, device=dev) if world > 1 else None

@@ -14,7 +14,11 @@
  *
  * Array layouts (row-major, contiguous):
  *   tiles  (C, T, R, Cc, H, W)   the reference's canonical tile stack (preprocess.py:24)
- *   image  (C, T, Him, Wim)      stitched images, Him = R*(H-ov), Wim = Cc*(W-ov) (stitch.py:23-39)
+ *   image  (C, T, Him, Wim)      stitched images, Him = R*(H-ov), Wim = Cc*(W-ov) (stitch.py:23-39);
+ *                                rows may be padded: `image_pitch` = elements between row starts
+ *                                (0 or Wim = dense).  A pitch that makes rows 16-byte aligned keeps
+ *                                the vectorised kernels usable for any tile grid (e.g. 10x10 tiles
+ *                                with overlap 102: Wim = 19460 is not a multiple of 8).
  *   boxes  (M, T, 2) int32       (top, left) of every marker's ROI at every timepoint
  *   roi    (M, C, T, L, L)       find.py:533 / find.py:89-92 after the stack at :182
  *   fg,bg  (M, Tm, L, L) uint8   0/1 masks; Tm = number of distinct mask timesteps
@@ -29,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MGB_ABI_VERSION 2
+#define MGB_ABI_VERSION 3
 
 #define MGB_OK 0
 #define MGB_EINVAL (-1)      /* bad argument (null pointer, negative size, bad itemsize ...) */
@@ -58,10 +62,10 @@ int mgb_set_stitch_variant(int variant);
  * image[c,t,y,x] = tiles[c,t, y/h, x/w, clip + y%h, clip + x%w], clip = overlap/2,
  * h = H-overlap, w = W-overlap.  Pure copy for any itemsize in {1,2,4,8}.  Argument checks
  * mirror stitch.py:8-9,16-20 (overlap < 0 or >= tile size -> MGB_EINVAL).  Picks a 128-bit
- * vectorised kernel when W*itemsize and Wim*itemsize are multiples of 16 bytes, else an
+ * vectorised kernel when W*itemsize and image_pitch*itemsize are multiples of 16 bytes, else an
  * element-wise kernel; `used_fast` (host pointer, may be NULL) reports which. */
-int mgb_stitch(const void* tiles, void* image, int64_t C, int64_t T, int64_t R, int64_t Cc,
-               int64_t H, int64_t W, int64_t overlap, int itemsize, int* host_used_fast,
+int mgb_stitch(const void* tiles, void* image, int64_t image_pitch, int64_t C, int64_t T, int64_t R,
+               int64_t Cc, int64_t H, int64_t W, int64_t overlap, int itemsize, int* host_used_fast,
                void* stream);
 
 /* ---- F1: flat-field correction, reference src/magnify/preprocess.py:83-87 -----------------
@@ -98,16 +102,22 @@ int mgb_flatfield_tables(const double* flat, const double* dark, int K, int64_t 
                          const double* maxima, double* gain, double* bias, void* stream);
 /* Pass 2: flat-field apply fused with the stitch (read 2 B, write 2*phi B per tile pixel).
  * With overlap = 0 and R = Cc = 1 this is flat-field alone.  uint16 only; needs W % 8 == 0,
- * (Cc*(W-overlap)) % 8 == 0 and 16-byte aligned base pointers, else MGB_EALIGN (the caller
+ * image_pitch % 8 == 0 and 16-byte aligned base pointers, else MGB_EALIGN (the caller
  * then uses mgb_flatfield_apply_generic + mgb_stitch). */
-int mgb_flatfield_stitch_u16(const uint16_t* tiles, uint16_t* image, int64_t C, int64_t T,
-                             int64_t R, int64_t Cc, int64_t H, int64_t W, int64_t overlap, int K,
+int mgb_flatfield_stitch_u16(const uint16_t* tiles, uint16_t* image, int64_t image_pitch, int64_t C,
+                             int64_t T, int64_t R, int64_t Cc, int64_t H, int64_t W, int64_t overlap, int K,
                              const double* flat, const double* dark, const double* gain,
                              const double* bias, const double* maxima, void* stream);
 /* Any-dtype exact flat-field apply in tile layout (no stitch): out[i] = cast(v(x[i])). */
 int mgb_flatfield_apply_generic(const void* tiles, void* out, int dtype, int64_t C, int64_t P,
                                 int64_t HW, int K, const double* flat, const double* dark,
                                 const double* maxima, void* stream);
+
+/* Pitched device <-> host copy (cudaMemcpy2DAsync): rows of `width_bytes` between buffers with
+ * different row pitches, e.g. a padded device image into a dense pinned host array.  kind: 1 = host
+ * to device, 2 = device to host, 3 = device to device. */
+int mgb_copy2d_async(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes,
+                     int64_t width_bytes, int64_t rows, int kind, void* stream);
 
 /* ---- F3: bounding boxes, reference src/magnify/utils.py:55-80 and the callers' round() -----
  * boxes[i] = (top, left) of bounding_box(round(x[i]), round(y[i]), L, W, H) with Python's
@@ -133,16 +143,16 @@ int mgb_set_gather_loader(int loader);
  * order (M) int32, nullable: a permutation giving the order in which markers are processed (results
  * are independent of it).  Spatially sorted markers let windows that overlap or share DRAM lines
  * hit in L2 (dense bead screens). */
-int mgb_roi_gather(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
-                   const int32_t* boxes, const int32_t* order, int64_t M, int L, void* roi,
+int mgb_roi_gather(const void* image, int64_t image_pitch, int64_t C, int64_t T, int64_t H, int64_t W,
+                   int itemsize, const int32_t* boxes, const int32_t* order, int64_t M, int L, void* roi,
                    void* stream);
 /* Gather fused with the masked reductions the consumers run (identify.py:76-80,
  * filter.py:21-22,51, README.md:21-22): uint16 only.  mask_t (T) int32 maps each timepoint to
  * its mask timestep in fg/bg (M, Tm, L, L) (beads: all 0, find.py:585-586; chip: the source
  * search timestep, find.py:151,172-173).  roi may be NULL (summaries only).  stats (M,C,T,6)
  * float64: exact integer sums, mean = sum / count (NaN for an empty mask, like nanmean). */
-int mgb_roi_gather_stats_u16(const uint16_t* image, int64_t C, int64_t T, int64_t H, int64_t W,
-                             const int32_t* boxes, const int32_t* order, const int32_t* mask_t,
+int mgb_roi_gather_stats_u16(const uint16_t* image, int64_t image_pitch, int64_t C, int64_t T, int64_t H,
+                             int64_t W, const int32_t* boxes, const int32_t* order, const int32_t* mask_t,
                              int64_t Tm, const uint8_t* fg, const uint8_t* bg, int64_t M, int L,
                              uint16_t* roi, double* stats, void* stream);
 /* Multi-GPU variant: the summaries are written by the kernel itself into the gathered buffer of
@@ -150,8 +160,8 @@ int mgb_roi_gather_stats_u16(const uint16_t* image, int64_t C, int64_t T, int64_
  * n_peers <= 8 device addresses) points at THIS rank's (M,C,T,6) block inside rank j's gathered
  * (ranks,M,C,T,6) buffer (peer-mapped, e.g. torch symmetric memory); the caller synchronises the
  * ranks afterwards.  Needs the staged kernels (else MGB_EUNSUPPORTED). */
-int mgb_roi_gather_stats_peers_u16(const uint16_t* image, int64_t C, int64_t T, int64_t H, int64_t W,
-                                   const int32_t* boxes, const int32_t* order, const int32_t* mask_t,
+int mgb_roi_gather_stats_peers_u16(const uint16_t* image, int64_t image_pitch, int64_t C, int64_t T,
+                                   int64_t H, int64_t W, const int32_t* boxes, const int32_t* order, const int32_t* mask_t,
                                    int64_t Tm, const uint8_t* fg, const uint8_t* bg, int64_t M, int L,
                                    uint16_t* roi, const uint64_t* host_peer_stats, int n_peers,
                                    void* stream);

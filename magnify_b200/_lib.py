@@ -33,17 +33,18 @@ SIGNATURES = {
     "mgb_set_tma_enabled": [c_int],
     "mgb_set_stitch_variant": [c_int],
     "mgb_set_gather_loader": [c_int],
-    "mgb_stitch": [_P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _I64, c_int, POINTER(c_int), _P],
+    "mgb_stitch": [_P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, c_int, POINTER(c_int), _P],
     "mgb_flatfield_tilemax_u16": [_P, _I64, _I64, _I64, c_int, c_int, _P, _P],
     "mgb_flatfield_maxima": [_P, c_int, c_int, _I64, _P, _P, _P, _P],
     "mgb_flatfield_maxima_generic": [_P, c_int, _I64, _I64, _I64, c_int, _P, _P, _P, _P],
     "mgb_flatfield_tables": [_P, _P, c_int, _I64, _P, _P, _P, _P],
-    "mgb_flatfield_stitch_u16": [_P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _I64, c_int, _P, _P, _P, _P, _P, _P],
+    "mgb_flatfield_stitch_u16": [_P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, c_int, _P, _P, _P, _P, _P, _P],
     "mgb_flatfield_apply_generic": [_P, _P, c_int, _I64, _I64, _I64, c_int, _P, _P, _P, _P],
+    "mgb_copy2d_async": [_P, _I64, _P, _I64, _I64, _I64, c_int, _P],
     "mgb_bounding_boxes": [_P, _P, _I64, c_int, _I64, _I64, _P, _P, _P],
-    "mgb_roi_gather": [_P, _I64, _I64, _I64, _I64, c_int, _P, _P, _I64, c_int, _P, _P],
-    "mgb_roi_gather_stats_u16": [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _I64, _P, _P, _I64, c_int, _P, _P, _P],
-    "mgb_roi_gather_stats_peers_u16": [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _I64, _P, _P, _I64, c_int, _P,
+    "mgb_roi_gather": [_P, _I64, _I64, _I64, _I64, _I64, c_int, _P, _P, _I64, c_int, _P, _P],
+    "mgb_roi_gather_stats_u16": [_P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _I64, _P, _P, _I64, c_int, _P, _P, _P],
+    "mgb_roi_gather_stats_peers_u16": [_P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _I64, _P, _P, _I64, c_int, _P,
                                        POINTER(ctypes.c_uint64), c_int, _P],
     "mgb_roi_stats_u16": [_P, _I64, _I64, _I64, c_int, _P, _I64, _P, _P, _P, _P],
     "mgb_roi_median_u16": [_P, _I64, _I64, _I64, c_int, _P, _I64, _P, _P, _P],
@@ -73,7 +74,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.argtypes = argtypes
         fn.restype = _SPECIAL_RESTYPE.get(name, c_int)
-    if lib.mgb_abi_version() != 2:
+    if lib.mgb_abi_version() != 3:
         raise ImportError("libmagnify_b200.so ABI version mismatch; rebuild with `python -m magnify_b200.build --force`")
     _lib = lib
     return lib

@@ -42,6 +42,15 @@ def _device(device) -> torch.device:
     return torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
 
 
+def _image_to_device(assay, dev) -> torch.Tensor:
+    """Upload assay["image"] into an x-padded device image (aligned rows for the staged gather)."""
+    arr = np.ascontiguousarray(_to_numpy(assay["image"]))
+    host = torch.from_numpy(arr)
+    image = ops.alloc_image(host.shape, host.dtype, dev)
+    image.copy_(host)
+    return image
+
+
 def _tiles_to_device(assay, dev) -> torch.Tensor:
     tile = assay["tile"]
     if tuple(tile.dims) != TILE_DIMS:
@@ -92,7 +101,7 @@ class Stitcher:
         ops.check_overlap(self.overlap, sizes["tile_y"], sizes["tile_x"])  # stitch.py:16-20
         dev = _device(self.device)
         image = ops.stitch(_tiles_to_device(assay, dev), self.overlap)
-        assay["image"] = (IMAGE_DIMS, image.cpu().numpy())
+        assay["image"] = (IMAGE_DIMS, ops.to_host_dense(image, non_blocking=False).numpy())
         return assay
 
 
@@ -122,7 +131,7 @@ class FlatfieldStitcher:
             dark = _read_tiff(os.path.expanduser(dark))
         dev = _device(self.device)
         image = ops.flatfield_stitch(_tiles_to_device(assay, dev), flat, dark, overlap=self.overlap)
-        assay["image"] = (IMAGE_DIMS, image.cpu().numpy())
+        assay["image"] = (IMAGE_DIMS, ops.to_host_dense(image, non_blocking=False).numpy())
         return assay
 
 
@@ -190,7 +199,7 @@ class BeadFinder:
     def __call__(self, assay):
         dev = _device(self.device)
         beads = self.find_centers(assay)
-        image = torch.from_numpy(np.ascontiguousarray(_to_numpy(assay["image"]))).to(dev)
+        image = _image_to_device(assay, dev)
         c, t, him, wim = image.shape
         length = self.roi_length
         m = len(beads)
@@ -281,8 +290,7 @@ class ButtonFinder:
 
     def __call__(self, assay):
         dev = _device(self.device)
-        image_np = _to_numpy(assay["image"])
-        image = torch.from_numpy(np.ascontiguousarray(image_np)).to(dev)
+        image = _image_to_device(assay, dev)
         c, t, him, wim = image.shape
         rows, cols = assay["tag"].shape
         m = rows * cols

@@ -154,7 +154,7 @@ struct StitchParams {
   int clip;        // first kept pixel (16-bit units along x), rows use clip_y
   int clip_y;
   int h, w;        // kept rows / kept 16-bit units per tile
-  int64_t Wim;     // Cc * w
+  int64_t Wim;     // image row pitch in 16-bit units (>= Cc * w; padded so that rows are 16-byte aligned)
   int64_t Him;     // R * h
   int P;           // tile-column period of the output phase
   int K;           // number of coefficient tables (1 or C)
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) stitch_u16_kernel(const 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 stitch_generic_kernel(const T* __restrict__ tiles, T* __restrict__ image, int64_t CT, int R, int Cc,
-                      int H, int W, int clip, int h, int w) {
+                      int H, int W, int clip, int h, int w, int64_t pitch) {
   const int64_t Wim = (int64_t)Cc * w, Him = (int64_t)R * h;
   const int64_t total = CT * Him * Wim;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -386,7 +386,7 @@ stitch_generic_kernel(const T* __restrict__ tiles, T* __restrict__ image, int64_
     const int64_t ct = i / (Wim * Him);
     const int cc = (int)(X / w), x = (int)(X % w);
     const int r = (int)(Y / h), y = (int)(Y % h);
-    image[i] = tiles[(((ct * R + r) * Cc + cc) * H + clip + y) * (int64_t)W + clip + x];
+    image[(ct * Him + Y) * pitch + X] = tiles[(((ct * R + r) * Cc + cc) * H + clip + y) * (int64_t)W + clip + x];
   }
 }
 
@@ -504,8 +504,8 @@ int mgb_set_stitch_variant(int variant) {
   return old;
 }
 
-int mgb_stitch(const void* tiles, void* image, int64_t C, int64_t T, int64_t R, int64_t Cc,
-               int64_t H, int64_t W, int64_t overlap, int itemsize, int* host_used_fast,
+int mgb_stitch(const void* tiles, void* image, int64_t image_pitch, int64_t C, int64_t T, int64_t R,
+               int64_t Cc, int64_t H, int64_t W, int64_t overlap, int itemsize, int* host_used_fast,
                void* stream) {
   if (host_used_fast) *host_used_fast = 0;
   if (C < 0 || T < 0 || R < 0 || Cc < 0 || H <= 0 || W <= 0) return MGB_EINVAL;
@@ -519,7 +519,9 @@ int mgb_stitch(const void* tiles, void* image, int64_t C, int64_t T, int64_t R, 
   if (!tiles || !image) return MGB_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t Wim = Cc * w;
-  const bool fast = itemsize >= 2 && (W * itemsize) % 16 == 0 && (Wim * itemsize) % 16 == 0 &&
+  const int64_t pitch = image_pitch > 0 ? image_pitch : Wim;
+  if (pitch < Wim) return MGB_EINVAL;
+  const bool fast = itemsize >= 2 && (W * itemsize) % 16 == 0 && (pitch * itemsize) % 16 == 0 &&
                     aligned16(tiles) && aligned16(image);
   if (fast) {
     const int u = itemsize / 2;  // 16-bit units per element
@@ -527,17 +529,17 @@ int mgb_stitch(const void* tiles, void* image, int64_t C, int64_t T, int64_t R, 
     p.tiles = (const uint16_t*)tiles; p.image = (uint16_t*)image;
     p.CT = CT; p.T = (int)T; p.R = (int)R; p.Cc = (int)Cc;
     p.H = (int)H; p.W = (int)(W * u); p.clip = clip * u; p.clip_y = clip; p.h = h; p.w = w * u;
-    p.Wim = Wim * u; p.Him = R * h; p.K = 1;
+    p.Wim = pitch * u; p.Him = R * h; p.K = 1;
     if (host_used_fast) *host_used_fast = 1;
     return run_stitch_fast<0>(p, st);
   }
   const int64_t total = CT * R * h * Wim;
   const int g = grid_for(total);
   switch (itemsize) {
-    case 1: stitch_generic_kernel<uint8_t><<<g, kThreads, 0, st>>>((const uint8_t*)tiles, (uint8_t*)image, CT, (int)R, (int)Cc, (int)H, (int)W, clip, h, w); break;
-    case 2: stitch_generic_kernel<uint16_t><<<g, kThreads, 0, st>>>((const uint16_t*)tiles, (uint16_t*)image, CT, (int)R, (int)Cc, (int)H, (int)W, clip, h, w); break;
-    case 4: stitch_generic_kernel<uint32_t><<<g, kThreads, 0, st>>>((const uint32_t*)tiles, (uint32_t*)image, CT, (int)R, (int)Cc, (int)H, (int)W, clip, h, w); break;
-    default: stitch_generic_kernel<uint64_t><<<g, kThreads, 0, st>>>((const uint64_t*)tiles, (uint64_t*)image, CT, (int)R, (int)Cc, (int)H, (int)W, clip, h, w); break;
+    case 1: stitch_generic_kernel<uint8_t><<<g, kThreads, 0, st>>>((const uint8_t*)tiles, (uint8_t*)image, CT, (int)R, (int)Cc, (int)H, (int)W, clip, h, w, pitch); break;
+    case 2: stitch_generic_kernel<uint16_t><<<g, kThreads, 0, st>>>((const uint16_t*)tiles, (uint16_t*)image, CT, (int)R, (int)Cc, (int)H, (int)W, clip, h, w, pitch); break;
+    case 4: stitch_generic_kernel<uint32_t><<<g, kThreads, 0, st>>>((const uint32_t*)tiles, (uint32_t*)image, CT, (int)R, (int)Cc, (int)H, (int)W, clip, h, w, pitch); break;
+    default: stitch_generic_kernel<uint64_t><<<g, kThreads, 0, st>>>((const uint64_t*)tiles, (uint64_t*)image, CT, (int)R, (int)Cc, (int)H, (int)W, clip, h, w, pitch); break;
   }
   MGB_CUDA_LAUNCH_CHECK();
   return MGB_OK;
@@ -593,8 +595,8 @@ int mgb_flatfield_tables(const double* flat, const double* dark, int K, int64_t 
   return MGB_OK;
 }
 
-int mgb_flatfield_stitch_u16(const uint16_t* tiles, uint16_t* image, int64_t C, int64_t T,
-                             int64_t R, int64_t Cc, int64_t H, int64_t W, int64_t overlap, int K,
+int mgb_flatfield_stitch_u16(const uint16_t* tiles, uint16_t* image, int64_t image_pitch, int64_t C,
+                             int64_t T, int64_t R, int64_t Cc, int64_t H, int64_t W, int64_t overlap, int K,
                              const double* flat, const double* dark, const double* gain,
                              const double* bias, const double* maxima, void* stream) {
   if (C < 0 || T < 0 || R < 0 || Cc < 0 || H <= 0 || W <= 0) return MGB_EINVAL;
@@ -605,11 +607,13 @@ int mgb_flatfield_stitch_u16(const uint16_t* tiles, uint16_t* image, int64_t C, 
   if (H > INT32_MAX / 8 || W > INT32_MAX / 8 || R > INT32_MAX || Cc > INT32_MAX || K > 65535) return MGB_EUNSUPPORTED;
   const int w = (int)(W - overlap), h = (int)(H - overlap);
   const int64_t Wim = Cc * w;
-  if (W % 8 != 0 || Wim % 8 != 0 || !aligned16(tiles) || !aligned16(image)) return MGB_EALIGN;
+  const int64_t pitch = image_pitch > 0 ? image_pitch : Wim;
+  if (pitch < Wim) return MGB_EINVAL;
+  if (W % 8 != 0 || pitch % 8 != 0 || !aligned16(tiles) || !aligned16(image)) return MGB_EALIGN;
   StitchParams p{};
   p.tiles = tiles; p.image = image; p.CT = C * T; p.T = (int)T; p.R = (int)R; p.Cc = (int)Cc;
   p.H = (int)H; p.W = (int)W; p.clip = (int)(overlap / 2); p.clip_y = p.clip; p.h = h; p.w = w;
-  p.Wim = Wim; p.Him = R * h; p.K = K;
+  p.Wim = pitch; p.Him = R * h; p.K = K;
   p.gain = gain; p.bias = bias; p.flat = flat; p.dark = dark; p.maxima = maxima;
   return run_stitch_fast<1>(p, (cudaStream_t)stream);
 }

@@ -183,6 +183,17 @@ int mgb_bead_masks(const int32_t* labels, int64_t H, int64_t W, const int32_t* b
   return MGB_OK;
 }
 
+int mgb_copy2d_async(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes,
+                     int64_t width_bytes, int64_t rows, int kind, void* stream) {
+  if (rows < 0 || width_bytes < 0 || dst_pitch_bytes < width_bytes || src_pitch_bytes < width_bytes) return MGB_EINVAL;
+  if (rows == 0 || width_bytes == 0) return MGB_OK;
+  if (!dst || !src || kind < 1 || kind > 3) return MGB_EINVAL;
+  const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : (kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+  MGB_CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)dst_pitch_bytes, src, (size_t)src_pitch_bytes, (size_t)width_bytes,
+                                 (size_t)rows, k, (cudaStream_t)stream));
+  return MGB_OK;
+}
+
 int mgb_abi_version(void) { return MGB_ABI_VERSION; }
 
 static unsigned long long g_launches = 0;

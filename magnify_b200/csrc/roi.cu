@@ -42,7 +42,7 @@ bounding_boxes_kernel(const double* __restrict__ x, const double* __restrict__ y
 struct GatherParams {
   const uint16_t* image;   // 16-bit units
   uint16_t* roi;           // may be null when STATS
-  int64_t C, T, H, W;      // W in 16-bit units
+  int64_t C, T, H, W;      // W = image row pitch in 16-bit units (>= logical width)
   const int32_t* boxes;    // (M,T,2) in elements; null = every box at (0, 0)
   int64_t marker_stride;   // 16-bit units between markers' images (0: all markers share `image`)
   int unit;                // 16-bit units per element (itemsize / 2)
@@ -271,7 +271,7 @@ roi_median_u16_kernel(const uint16_t* __restrict__ roi, int64_t C, int64_t T, in
 static uint32_t magic_for(uint32_t d) { return (uint32_t)((0x100000000ULL + d - 1) / d); }
 
 // roi_tma.cu
-int roi_gather_tma(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
+int roi_gather_tma(const void* image, int64_t pitch, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
                    const int32_t* boxes, const int32_t* order, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
                    const uint8_t* bg, int64_t M, int L, void* roi, double* stats, const uint64_t* host_peers,
                    int n_peers, cudaStream_t st);
@@ -298,12 +298,14 @@ int mgb_bounding_boxes(const double* x, const double* y, int64_t n, int L, int64
   return MGB_OK;
 }
 
-static int gather_common(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
-                         const int32_t* boxes, const int32_t* order, int64_t marker_stride, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
+static int gather_common(const void* image, int64_t image_pitch, int64_t C, int64_t T, int64_t H, int64_t W,
+                         int itemsize, const int32_t* boxes, const int32_t* order, int64_t marker_stride, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
                          const uint8_t* bg, int64_t M, int L, void* roi, double* stats,
                          cudaStream_t st, const uint64_t* host_peers = nullptr, int n_peers = 0) {
   const bool with_stats = stats != nullptr;
   if (M < 0 || C < 0 || T < 0 || L <= 0 || H < L || W < L) return MGB_EINVAL;
+  const int64_t pitch = image_pitch > 0 ? image_pitch : W;   // row pitch in elements
+  if (pitch < W) return MGB_EINVAL;
   if (itemsize != 1 && itemsize != 2 && itemsize != 4 && itemsize != 8) return MGB_EINVAL;
   if (L > 4096) return MGB_EUNSUPPORTED;
   const int64_t n_roi = M * C * T;
@@ -313,7 +315,7 @@ static int gather_common(const void* image, int64_t C, int64_t T, int64_t H, int
   if (with_stats && (!mask_t || !fg || !bg || Tm <= 0 || itemsize != 2)) return MGB_EINVAL;
   if (g_tma_enabled && marker_stride == 0) {
     // TMA-staged path (roi_tma.cu); MGB_EALIGN means "not applicable here", fall through.
-    const int rc = roi_gather_tma(image, C, T, H, W, itemsize, boxes, order, mask_t, Tm, fg, bg, M, L, roi, stats,
+    const int rc = roi_gather_tma(image, pitch, C, T, H, W, itemsize, boxes, order, mask_t, Tm, fg, bg, M, L, roi, stats,
                                   host_peers, n_peers, st);
     if (rc != MGB_EALIGN) return rc;
   }
@@ -328,7 +330,7 @@ static int gather_common(const void* image, int64_t C, int64_t T, int64_t H, int
   if (word_path) {
     GatherParams p{};
     p.image = (const uint16_t*)image; p.roi = (uint16_t*)roi;
-    p.C = C; p.T = T; p.H = H; p.W = W * unit; p.boxes = boxes; p.marker_stride = marker_stride * unit;
+    p.C = C; p.T = T; p.H = H; p.W = pitch * unit; p.boxes = boxes; p.marker_stride = marker_stride * unit;
     p.unit = unit; p.L = L; p.Lu = Lu;
     p.half = (uint32_t)(Lu / 2); p.magic = magic_for(p.half); p.words = (uint32_t)L * p.half;
     p.mask_t = mask_t; p.Tm = Tm; p.fg = fg; p.bg = bg; p.stats = stats;
@@ -336,13 +338,13 @@ static int gather_common(const void* image, int64_t C, int64_t T, int64_t H, int
     else roi_gather_words_kernel<false><<<(unsigned)n_roi, kThreads, 0, st>>>(p);
   } else if (with_stats) {
     roi_gather_scalar_kernel<uint16_t, true><<<(unsigned)n_roi, kThreads, 0, st>>>(
-        (const uint16_t*)image, (uint16_t*)roi, C, T, H, W, boxes, marker_stride, L, mask_t, Tm, fg, bg, stats);
+        (const uint16_t*)image, (uint16_t*)roi, C, T, H, pitch, boxes, marker_stride, L, mask_t, Tm, fg, bg, stats);
   } else {
     switch (itemsize) {
-      case 1: roi_gather_scalar_kernel<uint8_t, false><<<(unsigned)n_roi, kThreads, 0, st>>>((const uint8_t*)image, (uint8_t*)roi, C, T, H, W, boxes, marker_stride, L, nullptr, 0, nullptr, nullptr, nullptr); break;
-      case 2: roi_gather_scalar_kernel<uint16_t, false><<<(unsigned)n_roi, kThreads, 0, st>>>((const uint16_t*)image, (uint16_t*)roi, C, T, H, W, boxes, marker_stride, L, nullptr, 0, nullptr, nullptr, nullptr); break;
-      case 4: roi_gather_scalar_kernel<uint32_t, false><<<(unsigned)n_roi, kThreads, 0, st>>>((const uint32_t*)image, (uint32_t*)roi, C, T, H, W, boxes, marker_stride, L, nullptr, 0, nullptr, nullptr, nullptr); break;
-      default: roi_gather_scalar_kernel<uint64_t, false><<<(unsigned)n_roi, kThreads, 0, st>>>((const uint64_t*)image, (uint64_t*)roi, C, T, H, W, boxes, marker_stride, L, nullptr, 0, nullptr, nullptr, nullptr); break;
+      case 1: roi_gather_scalar_kernel<uint8_t, false><<<(unsigned)n_roi, kThreads, 0, st>>>((const uint8_t*)image, (uint8_t*)roi, C, T, H, pitch, boxes, marker_stride, L, nullptr, 0, nullptr, nullptr, nullptr); break;
+      case 2: roi_gather_scalar_kernel<uint16_t, false><<<(unsigned)n_roi, kThreads, 0, st>>>((const uint16_t*)image, (uint16_t*)roi, C, T, H, pitch, boxes, marker_stride, L, nullptr, 0, nullptr, nullptr, nullptr); break;
+      case 4: roi_gather_scalar_kernel<uint32_t, false><<<(unsigned)n_roi, kThreads, 0, st>>>((const uint32_t*)image, (uint32_t*)roi, C, T, H, pitch, boxes, marker_stride, L, nullptr, 0, nullptr, nullptr, nullptr); break;
+      default: roi_gather_scalar_kernel<uint64_t, false><<<(unsigned)n_roi, kThreads, 0, st>>>((const uint64_t*)image, (uint64_t*)roi, C, T, H, pitch, boxes, marker_stride, L, nullptr, 0, nullptr, nullptr, nullptr); break;
     }
   }
   MGB_CUDA_LAUNCH_CHECK();
@@ -365,30 +367,31 @@ int mgb_set_gather_loader(int loader) {
   return old;
 }
 
-int mgb_roi_gather(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
-                   const int32_t* boxes, const int32_t* order, int64_t M, int L, void* roi, void* stream) {
+int mgb_roi_gather(const void* image, int64_t image_pitch, int64_t C, int64_t T, int64_t H, int64_t W,
+                   int itemsize, const int32_t* boxes, const int32_t* order, int64_t M, int L, void* roi,
+                   void* stream) {
   if (!roi && M * C * T > 0) return MGB_EINVAL;
-  return gather_common(image, C, T, H, W, itemsize, boxes, order, 0, nullptr, 0, nullptr, nullptr, M, L, roi,
+  return gather_common(image, image_pitch, C, T, H, W, itemsize, boxes, order, 0, nullptr, 0, nullptr, nullptr, M, L, roi,
                        nullptr, (cudaStream_t)stream);
 }
 
-int mgb_roi_gather_stats_u16(const uint16_t* image, int64_t C, int64_t T, int64_t H, int64_t W,
-                             const int32_t* boxes, const int32_t* order, const int32_t* mask_t, int64_t Tm,
+int mgb_roi_gather_stats_u16(const uint16_t* image, int64_t image_pitch, int64_t C, int64_t T, int64_t H,
+                             int64_t W, const int32_t* boxes, const int32_t* order, const int32_t* mask_t, int64_t Tm,
                              const uint8_t* fg, const uint8_t* bg, int64_t M, int L,
                              uint16_t* roi, double* stats, void* stream) {
   if (!stats && M * C * T > 0) return MGB_EINVAL;
-  return gather_common(image, C, T, H, W, 2, boxes, order, 0, mask_t, Tm, fg, bg, M, L, roi, stats,
+  return gather_common(image, image_pitch, C, T, H, W, 2, boxes, order, 0, mask_t, Tm, fg, bg, M, L, roi, stats,
                        (cudaStream_t)stream);
 }
 
-int mgb_roi_gather_stats_peers_u16(const uint16_t* image, int64_t C, int64_t T, int64_t H, int64_t W,
-                                   const int32_t* boxes, const int32_t* order, const int32_t* mask_t,
+int mgb_roi_gather_stats_peers_u16(const uint16_t* image, int64_t image_pitch, int64_t C, int64_t T, int64_t H,
+                                   int64_t W, const int32_t* boxes, const int32_t* order, const int32_t* mask_t,
                                    int64_t Tm, const uint8_t* fg, const uint8_t* bg, int64_t M, int L,
                                    uint16_t* roi, const uint64_t* host_peer_stats, int n_peers, void* stream) {
   if (!host_peer_stats || n_peers < 1 || n_peers > 8) return MGB_EINVAL;
   if (M * C * T == 0) return MGB_OK;
   // `stats` only flags "with summaries" here; every record is written through the peer pointers
-  return gather_common(image, C, T, H, W, 2, boxes, order, 0, mask_t, Tm, fg, bg, M, L, roi,
+  return gather_common(image, image_pitch, C, T, H, W, 2, boxes, order, 0, mask_t, Tm, fg, bg, M, L, roi,
                        reinterpret_cast<double*>(host_peer_stats[0]), (cudaStream_t)stream, host_peer_stats, n_peers);
 }
 
@@ -396,7 +399,7 @@ int mgb_roi_stats_u16(const uint16_t* roi, int64_t M, int64_t C, int64_t T, int 
                       int64_t Tm, const uint8_t* fg, const uint8_t* bg, double* stats, void* stream) {
   if (!stats && M * C * T > 0) return MGB_EINVAL;
   // every marker's roi block (C,T,L,L) is read as its own little image with the box at the origin
-  return gather_common(roi, C, T, L, L, 2, nullptr, nullptr, C * T * (int64_t)L * L, mask_t, Tm, fg, bg, M, L, nullptr,
+  return gather_common(roi, 0, C, T, L, L, 2, nullptr, nullptr, C * T * (int64_t)L * L, mask_t, Tm, fg, bg, M, L, nullptr,
                        stats, (cudaStream_t)stream);
 }
 

@@ -598,18 +598,19 @@ static uint32_t magic_u32(uint32_t d) { return (uint32_t)((0x100000000ULL + d - 
 
 // Returns MGB_OK when launched, MGB_EALIGN when this path does not apply (caller falls back to
 // the LSU kernels of roi.cu), or an error.
-int roi_gather_tma(const void* image, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
+int roi_gather_tma(const void* image, int64_t pitch, int64_t C, int64_t T, int64_t H, int64_t W, int itemsize,
                    const int32_t* boxes, const int32_t* order, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
                    const uint8_t* bg, int64_t M, int L, void* roi, double* stats, const uint64_t* host_peers,
                    int n_peers, cudaStream_t st) {
   const bool with_stats = stats != nullptr;
   if (itemsize < 2) return MGB_EALIGN;
   const int unit = itemsize / 2;
-  const int64_t Wu = W * unit;
+  const int64_t Wu = W * unit;            // logical row length in 16-bit units
+  const int64_t Pu = pitch * unit;        // row pitch in 16-bit units
   const int wu = L * unit;
   const int wpu = (wu + 7 + 7) & ~7;            // any shift 0..7 plus the row, in whole vectors
-  if ((Wu * 2) % 16 != 0 || !aligned16(image) || wpu > 256 || L > 256) return MGB_EALIGN;
-  if (C * T > INT32_MAX || H > INT32_MAX || Wu > INT32_MAX || M > INT32_MAX) return MGB_EALIGN;
+  if ((Pu * 2) % 16 != 0 || !aligned16(image) || wpu > 256 || L > 256) return MGB_EALIGN;
+  if (C * T > INT32_MAX || H > INT32_MAX || Pu > INT32_MAX || M > INT32_MAX) return MGB_EALIGN;
   if (with_stats && Tm > 65535) return MGB_EALIGN;
   PFN_cuTensorMapEncodeTiled encode = get_encode_fn();
   if (!encode) return MGB_EALIGN;
@@ -652,8 +653,9 @@ int roi_gather_tma(const void* image, int64_t C, int64_t T, int64_t H, int64_t W
   const size_t smem_bytes = (size_t)nw * ns * p.stage_bytes + fixed;
 
   CUtensorMap tmap;
-  const cuuint64_t gdim[3] = {(cuuint64_t)Wu, (cuuint64_t)H, (cuuint64_t)(C * T)};
-  const cuuint64_t gstride[2] = {(cuuint64_t)Wu * 2, (cuuint64_t)H * Wu * 2};
+  // the tensor covers the whole pitch: the padding columns are real memory, never needed by a window
+  const cuuint64_t gdim[3] = {(cuuint64_t)Pu, (cuuint64_t)H, (cuuint64_t)(C * T)};
+  const cuuint64_t gstride[2] = {(cuuint64_t)Pu * 2, (cuuint64_t)H * Pu * 2};
   const cuuint32_t box[3] = {(cuuint32_t)wpu, (cuuint32_t)L, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(image), gdim, gstride, box,
@@ -664,7 +666,7 @@ int roi_gather_tma(const void* image, int64_t C, int64_t T, int64_t H, int64_t W
   p.loader = g_gather_loader;
   p.image = (const uint16_t*)image;
   p.H = H;
-  p.Wu = Wu;
+  p.Wu = Pu;
 
   // Many markers, rows that are not whole 16-byte vectors, few quads per lane: warp-per-marker.
   const int nquads = (L * wu) / 4;

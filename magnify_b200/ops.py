@@ -71,20 +71,75 @@ def stitched_shape(tile_shape: Sequence[int], overlap: int):
     return (c, t, r * (h - overlap), cc * (w - overlap))
 
 
+def alloc_image(shape: Sequence[int], dtype, device) -> torch.Tensor:
+    """(C,T,Him,Wim) image whose rows start on 16-byte boundaries: a view `[..., :Wim]` of a buffer
+    padded along x.  The vectorised stitch and the staged gather need aligned rows; padding the
+    pitch keeps them usable for any tile grid (10x10 tiles at overlap 102 give Wim = 19460, not a
+    multiple of 8).  Dense (`is_contiguous()`) whenever Wim already is aligned."""
+    c, t, him, wim = (int(v) for v in shape)
+    itemsize = torch.empty(0, dtype=dtype).element_size()
+    quantum = max(1, 16 // itemsize)
+    pitch = -(-wim // quantum) * quantum
+    buf = torch.empty((c, t, him, pitch), dtype=dtype, device=device)
+    return buf[..., :wim] if pitch != wim else buf
+
+
+def image_pitch(image: torch.Tensor) -> int:
+    """Row pitch (elements) of a dense or x-padded (C,T,H,W) image; raises for other layouts."""
+    if image.dim() != 4 or not image.is_cuda:
+        raise ValueError("image must be a 4-d CUDA tensor (C,T,H,W)")
+    c, t, h, w = image.shape
+    if image.numel() == 0:
+        return int(w)
+    pitch = int(image.stride(2)) if h > 1 else int(w)
+    ok = image.stride(3) == 1 and pitch >= w
+    ok = ok and (t == 1 or image.stride(1) == h * pitch) and (c == 1 or image.stride(0) == t * h * pitch)
+    if not ok:
+        raise ValueError(f"image must be dense or padded along x only, got strides {tuple(image.stride())}")
+    return pitch
+
+
+def to_host_dense(image: torch.Tensor, out: Optional[torch.Tensor] = None, non_blocking: bool = True) -> torch.Tensor:
+    """Copy a dense or x-padded device image into a dense (pinned) host tensor with one pitched
+    copy on the current stream (no intermediate contiguous device copy)."""
+    pitch = image_pitch(image)
+    if out is None:
+        out = torch.empty(tuple(image.shape), dtype=image.dtype, pin_memory=True)
+    if tuple(out.shape) != tuple(image.shape) or out.dtype != image.dtype or not out.is_contiguous():
+        raise ValueError("out must be a dense host tensor with the image's shape and dtype")
+    c, t, h, w = image.shape
+    if pitch == w:
+        out.copy_(image, non_blocking=non_blocking)
+        return out
+    es = image.element_size()
+    with torch.cuda.device(image.device):
+        _lib.call("mgb_copy2d_async", ctypes.c_void_p(out.data_ptr()), w * es, _ptr(image), pitch * es, w * es,
+                  c * t * h, 2, _stream())
+    if not non_blocking:
+        torch.cuda.current_stream(image.device).synchronize()
+    return out
+
+
+def _image_out(out: Optional[torch.Tensor], shape, dtype, device) -> torch.Tensor:
+    if out is None:
+        return alloc_image(shape, dtype, device)
+    if not isinstance(out, torch.Tensor) or not out.is_cuda or out.dtype != dtype:
+        raise TypeError(f"out must be a CUDA tensor of dtype {dtype}")
+    if tuple(out.shape) != tuple(shape):
+        raise ValueError(f"out has shape {tuple(out.shape)}, expected {tuple(shape)}")
+    image_pitch(out)   # validates the layout
+    return out
+
+
 def stitch(tiles: torch.Tensor, overlap: int = 102, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """(C,T,R,Cc,H,W) -> (C,T,R*(H-ov),Cc*(W-ov)); pure copy for any 1/2/4/8-byte dtype."""
+    """(C,T,R,Cc,H,W) -> (C,T,R*(H-ov),Cc*(W-ov)); pure copy for any 1/2/4/8-byte dtype.  The result
+    is dense or padded along x (see `alloc_image`); `.contiguous()` / `to_host_dense` densify it."""
     _check(tiles, "tiles", ndim=6)
     c, t, r, cc, h, w = tiles.shape
     check_overlap(overlap, h, w)
-    shape = stitched_shape(tiles.shape, overlap)
-    if out is None:
-        out = torch.empty(shape, dtype=tiles.dtype, device=tiles.device)
-    else:
-        _check(out, "out", dtype=tiles.dtype)
-        if tuple(out.shape) != tuple(shape):
-            raise ValueError(f"out has shape {tuple(out.shape)}, expected {shape}")
+    out = _image_out(out, stitched_shape(tiles.shape, overlap), tiles.dtype, tiles.device)
     with torch.cuda.device(tiles.device):
-        _lib.call("mgb_stitch", _ptr(tiles), _ptr(out), c, t, r, cc, h, w, int(overlap),
+        _lib.call("mgb_stitch", _ptr(tiles), _ptr(out), image_pitch(out), c, t, r, cc, h, w, int(overlap),
                   tiles.element_size(), None, _stream())
     return out
 
@@ -230,11 +285,7 @@ def flatfield_stitch(
     if plan.identity:
         # (x * M) / M == x exactly for integers below 2^53: the defaults are the identity.
         return stitch(tiles, overlap, out=out)
-    shape = stitched_shape(tiles.shape, overlap)
-    if out is None:
-        out = torch.empty(shape, dtype=tiles.dtype, device=tiles.device)
-    elif tuple(out.shape) != tuple(shape) or out.dtype != tiles.dtype:
-        raise ValueError(f"out must have shape {shape} and dtype {tiles.dtype}")
+    out = _image_out(out, stitched_shape(tiles.shape, overlap), tiles.dtype, tiles.device)
     if tiles.numel() == 0:
         return out
     with torch.cuda.device(tiles.device):
@@ -253,7 +304,8 @@ def flatfield_stitch(
         if tiles.dtype == torch.uint16:
             _lib.call("mgb_flatfield_tables", _ptr(plan.flat), _ptr(plan.dark), plan.k, h * w, _ptr(maxima),
                       _ptr(plan.gain), _ptr(plan.bias), _stream())
-            rc = _lib.try_call("mgb_flatfield_stitch_u16", _ptr(tiles), _ptr(out), c, t, r, cc, h, w, int(overlap),
+            rc = _lib.try_call("mgb_flatfield_stitch_u16", _ptr(tiles), _ptr(out), image_pitch(out), c, t, r, cc, h, w,
+                               int(overlap),
                                plan.k, _ptr(plan.flat), _ptr(plan.dark), _ptr(plan.gain), _ptr(plan.bias),
                                _ptr(maxima), _stream())
             if rc not in (0, _lib.MGB_EALIGN):
@@ -279,7 +331,8 @@ def flatfield_correct(tiles: torch.Tensor, flatfield=1.0, darkfield=0.0, plan=No
     # Every tile is its own 1x1 "image": same kernel, overlap 0.
     as_images = tiles.view(c, t * r * cc, 1, 1, h, w)
     plan_shape = plan.tile_shape
-    out = flatfield_stitch(as_images, overlap=0, plan=plan, maxima=maxima, group=group)
+    dense = torch.empty((c, t * r * cc, h, w), dtype=tiles.dtype, device=tiles.device)   # tile layout is dense
+    out = flatfield_stitch(as_images, overlap=0, plan=plan, maxima=maxima, group=group, out=dense)
     plan.tile_shape = plan_shape
     return out.view(tiles.shape)
 
@@ -336,7 +389,7 @@ def _check_order(order, m):
 def roi_gather(image: torch.Tensor, boxes: torch.Tensor, roi_length: int, out: Optional[torch.Tensor] = None,
                order: Optional[torch.Tensor] = None):
     """roi[m,c,t] = image[c,t, top:top+L, left:left+L]  (find.py:160-169,324-334,589-602)."""
-    _check(image, "image", ndim=4)
+    pitch = image_pitch(image)
     c, t, h, w = image.shape
     m = boxes.shape[0]
     _check_boxes(boxes, m, t)
@@ -346,7 +399,7 @@ def roi_gather(image: torch.Tensor, boxes: torch.Tensor, roi_length: int, out: O
     elif tuple(out.shape) != shape or out.dtype != image.dtype:
         raise ValueError(f"out must have shape {shape} and dtype {image.dtype}")
     with torch.cuda.device(image.device):
-        _lib.call("mgb_roi_gather", _ptr(image), c, t, h, w, image.element_size(), _ptr(boxes),
+        _lib.call("mgb_roi_gather", _ptr(image), pitch, c, t, h, w, image.element_size(), _ptr(boxes),
                   _ptr(_check_order(order, m)), m, int(roi_length), _ptr(out), _stream())
     return out
 
@@ -369,7 +422,9 @@ def roi_gather_stats(
     fg, bg: (M, Tm, L, L) uint8 (0/1) or bool; mask_t (T,) int32 maps timepoints to mask
     timesteps (default: all 0 when Tm == 1, identity when Tm == T).  Returns (roi | None, stats)
     with stats (M,C,T,6) float64 in `STATS` order."""
-    _check(image, "image", dtype=torch.uint16, ndim=4)
+    if image.dtype != torch.uint16:
+        raise TypeError(f"image must have dtype torch.uint16, got {image.dtype}")
+    pitch = image_pitch(image)
     c, t, h, w = image.shape
     m = boxes.shape[0]
     _check_boxes(boxes, m, t)
@@ -402,7 +457,7 @@ def roi_gather_stats(
         n_peers = len(peer_stats)
         arr = (ctypes.c_uint64 * n_peers)(*[int(a) for a in peer_stats])
         with torch.cuda.device(image.device):
-            _lib.call("mgb_roi_gather_stats_peers_u16", _ptr(image), c, t, h, w, _ptr(boxes),
+            _lib.call("mgb_roi_gather_stats_peers_u16", _ptr(image), pitch, c, t, h, w, _ptr(boxes),
                       _ptr(_check_order(order, m)), _ptr(mask_t), tm, _ptr(fg), _ptr(bg), m, int(roi_length),
                       _ptr(roi), arr, n_peers, _stream())
         return roi, None
@@ -410,7 +465,7 @@ def roi_gather_stats(
     if tuple(stats.shape) != (m, c, t, 6) or stats.dtype != torch.float64:
         raise ValueError("out_stats must be float64 with shape (M, C, T, 6)")
     with torch.cuda.device(image.device):
-        _lib.call("mgb_roi_gather_stats_u16", _ptr(image), c, t, h, w, _ptr(boxes), _ptr(_check_order(order, m)),
+        _lib.call("mgb_roi_gather_stats_u16", _ptr(image), pitch, c, t, h, w, _ptr(boxes), _ptr(_check_order(order, m)),
                   _ptr(mask_t), tm, _ptr(fg), _ptr(bg), m, int(roi_length), _ptr(roi), _ptr(stats), _stream())
     return roi, stats
 

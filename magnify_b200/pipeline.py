@@ -45,7 +45,7 @@ def copy_forward_sources(num_times: int, search_timesteps) -> np.ndarray:
 
 @dataclass
 class QuantifyResult:
-    image: Optional[torch.Tensor]      # (C,T,Him,Wim)
+    image: Optional[torch.Tensor]      # (C,T,Him,Wim); dense, or a view padded along x (ops.alloc_image)
     roi: Optional[torch.Tensor]        # (M,C,T,L,L)
     fg: torch.Tensor                   # (M,Tm,L,L) uint8
     bg: torch.Tensor                   # (M,Tm,L,L) uint8
@@ -187,7 +187,7 @@ class HostStagedRunner:
         dev = plan.device
         self.want_image, self.want_roi = want_image, want_roi
         self.tiles_dev = torch.empty(plan.tile_shape, dtype=torch.uint16, device=dev)
-        self.image_dev = torch.empty(plan.image_shape, dtype=torch.uint16, device=dev)
+        self.image_dev = ops.alloc_image(plan.image_shape, torch.uint16, dev)   # x-padded when Wim % 8 != 0
         m = plan.boxes.shape[0]
         length = plan.roi_length
         self.roi_dev = torch.empty((m, c, t, length, length), dtype=torch.uint16, device=dev) if want_roi else None
@@ -257,7 +257,7 @@ class HostStagedRunner:
         if self.want_image:
             with torch.cuda.stream(self.d2h):
                 self.d2h.wait_event(done_image)
-                image_host.copy_(image, non_blocking=True)
+                ops.to_host_dense(image, out=image_host)   # one pitched copy, also for a padded image
         roi, stats = ops.roi_gather_stats(image, plan.boxes, plan.fg, plan.bg, plan.roi_length, mask_t=plan.mask_t,
                                           want_roi=self.want_roi, out_roi=self.roi_dev, out_stats=self.stats_dev,
                                           order=plan.order)

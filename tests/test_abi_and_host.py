@@ -29,7 +29,7 @@ def test_library_exports_header_symbols(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mgb_abi_version() == 2
+    assert lib.mgb_abi_version() == 3
     assert lib.mgb_error_string(-2).decode().startswith("pointer")
 
 
@@ -59,12 +59,12 @@ def test_argument_errors_before_any_launch(lib):
     import ctypes
 
     p = ctypes.c_void_p(0)
-    assert lib.mgb_stitch(p, p, 1, 1, 2, 2, 50, 50, -5, 2, None, p) == -1     # stitch.py:8-9
-    assert lib.mgb_stitch(p, p, 1, 1, 2, 2, 50, 50, 100, 2, None, p) == -1    # stitch.py:16-20
-    assert lib.mgb_stitch(p, p, 1, 1, 2, 2, 50, 50, 4, 3, None, p) == -1      # itemsize
-    assert lib.mgb_stitch(p, p, 0, 1, 2, 2, 50, 50, 4, 2, None, p) == 0       # empty: nothing to do
+    assert lib.mgb_stitch(p, p, 0, 1, 1, 2, 2, 50, 50, -5, 2, None, p) == -1     # stitch.py:8-9
+    assert lib.mgb_stitch(p, p, 0, 1, 1, 2, 2, 50, 50, 100, 2, None, p) == -1    # stitch.py:16-20
+    assert lib.mgb_stitch(p, p, 0, 1, 1, 2, 2, 50, 50, 4, 3, None, p) == -1      # itemsize
+    assert lib.mgb_stitch(p, p, 0, 0, 1, 2, 2, 50, 50, 4, 2, None, p) == 0       # empty: nothing to do
     assert lib.mgb_bounding_boxes(p, p, 4, 72, 50, 50, p, p, p) == -1         # image smaller than box
-    assert lib.mgb_roi_gather(p, 1, 1, 100, 100, 2, p, p, 0, 72, p, p) == 0   # zero markers
+    assert lib.mgb_roi_gather(p, 0, 1, 1, 100, 100, 2, p, p, 0, 72, p, p) == 0  # zero markers
     assert lib.mgb_chip_masks(p, p, 15, 30, 0, 72, p, p, p, p) == 0
 
 
