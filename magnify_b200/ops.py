@@ -91,7 +91,7 @@ def image_pitch(image: torch.Tensor) -> int:
     c, t, h, w = image.shape
     if image.numel() == 0:
         return int(w)
-    pitch = int(image.stride(2)) if h > 1 else int(w)
+    pitch = int(image.stride(2)) if (h > 1 or image.stride(2) >= w) else int(w)
     ok = image.stride(3) == 1 and pitch >= w
     ok = ok and (t == 1 or image.stride(1) == h * pitch) and (c == 1 or image.stride(0) == t * h * pitch)
     if not ok:
