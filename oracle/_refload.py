@@ -136,3 +136,127 @@ def reference_flatfield_correct(tiles, flatfield=1.0, darkfield=0.0):
     xp = NdarrayAssay(tiles)
     mod.flatfield_correct(xp, flatfield=flatfield, darkfield=darkfield)
     return xp.tile
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference's own Stitcher (src/magnify/stitch.py) executed in place on a minimal named-array
+# stand-in for xarray.DataArray: only the calls Stitcher.__call__ makes are implemented
+# (indexing with Ellipsis + slices, transpose by name, iteration over the first dimension,
+# rename, chunk, and xr.concat along an existing dimension).
+# ---------------------------------------------------------------------------------------------
+class NamedArray:
+    def __init__(self, values, dims):
+        import numpy as np
+
+        self.values = np.asarray(values)
+        self.dims = tuple(dims)
+        assert self.values.ndim == len(self.dims)
+
+    shape = property(lambda self: self.values.shape)
+    sizes = property(lambda self: dict(zip(self.dims, self.values.shape)))
+
+    def __getitem__(self, key):
+        out = self.values[key]
+        assert out.ndim == self.values.ndim, "only slicing (no integer indexing) is supported"
+        return NamedArray(out, self.dims)
+
+    def __iter__(self):   # like DataArray: iterate over the first dimension, dropping it
+        for i in range(self.values.shape[0]):
+            yield NamedArray(self.values[i], self.dims[1:])
+
+    def transpose(self, *names):
+        order = [self.dims.index(n) for n in names]
+        return NamedArray(self.values.transpose(order), names)
+
+    def rename(self, **mapping):
+        return NamedArray(self.values, [mapping.get(d, d) for d in self.dims])
+
+    def chunk(self, chunks):
+        return self
+
+
+class NamedAssay:
+    def __init__(self, tile=None):
+        self._vars = {}
+        if tile is not None:
+            self._vars["tile"] = tile
+        self.mg = type("Mg", (), {"cache": staticmethod(lambda *a, **k: None)})()
+
+    def __contains__(self, name):
+        return name in self._vars
+
+    def __getattr__(self, name):
+        try:
+            return self.__dict__["_vars"][name]
+        except KeyError:
+            raise AttributeError(name) from None
+
+    def __setitem__(self, name, value):
+        self._vars[name] = value
+
+    @property
+    def sizes(self):
+        out = {}
+        for v in self._vars.values():
+            out.update(v.sizes)
+        return out
+
+
+def _named_concat(arrays, dim, **_ignored):
+    import numpy as np
+
+    arrays = list(arrays)
+    axis = arrays[0].dims.index(dim)
+    return NamedArray(np.concatenate([a.values for a in arrays], axis=axis), arrays[0].dims)
+
+
+_cached_stitch = None
+
+
+def load_reference_stitch():
+    """The reference's `src/magnify/stitch.py` loaded in place with stub imports, or None."""
+    global _cached_stitch
+    if _cached_stitch is not None:
+        return _cached_stitch
+    path = os.path.join(REFERENCE_ROOT, "src", "magnify", "stitch.py")
+    if not os.path.exists(path):
+        return None
+    xr = types.ModuleType("xarray")
+    xr.Dataset = type("Dataset", (), {})
+    xr.concat = _named_concat
+    pkg = types.ModuleType("magnify")
+    pkg.__path__ = []
+    registry = types.ModuleType("magnify.registry")
+    registry.components = type("Components", (), {"register": staticmethod(lambda name: (lambda f: f))})()
+    pkg.registry = registry
+    stubs = {"xarray": xr, "magnify": pkg, "magnify.registry": registry}
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        spec = importlib.util.spec_from_file_location("_magnify_reference_stitch", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    except Exception:
+        mod = None
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _cached_stitch = mod
+    return mod
+
+
+def reference_stitch(tiles, overlap):
+    """Run the reference's own Stitcher on a (C,T,R,Cc,H,W) ndarray; None if unavailable.  Raises
+    what the reference raises (ValueError for bad overlaps)."""
+    mod = load_reference_stitch()
+    if mod is None:
+        return None
+    dims = ("channel", "time", "tile_row", "tile_col", "tile_y", "tile_x")
+    assay = NamedAssay(NamedArray(tiles, dims))
+    out = mod.Stitcher(overlap=overlap)(assay)
+    image = out.image
+    assert image.dims == ("channel", "time", "im_y", "im_x")
+    return image.values

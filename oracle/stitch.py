@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE (see oracle/__init__.py).  Follows src/magnify/stitch.py:7-46; pinned by
 the exact-slice assertions of the reference's tests/test_stitch.py (ported in
-tests/test_oracle_stitch.py).
+tests/test_oracle_paths.py) and by tests/golden/stitch.npz, the outputs of the reference's own
+Stitcher source executed in place (oracle/_refload.py::reference_stitch).
 """
 from __future__ import annotations
 

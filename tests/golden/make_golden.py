@@ -202,9 +202,38 @@ def golden_flatfield():
     np.savez_compressed(os.path.join(HERE, "flatfield.npz"), **out)
 
 
+def golden_stitch():
+    """Run the reference's OWN Stitcher source (stitch.py:12-46, loaded in place, named-array
+    stand-in for xarray) on small stacks: odd / even / zero overlap, several channels and times."""
+    from oracle._refload import reference_stitch
+
+    rng = np.random.default_rng(123)
+    out = {}
+    for name, shape, ov, dtype in [("odd", (2, 2, 2, 3, 20, 24), 5, np.uint16), ("even", (1, 3, 3, 2, 16, 16), 6, np.float64),
+                                   ("zero", (1, 1, 2, 2, 8, 12), 0, np.uint16), ("single", (1, 1, 1, 1, 30, 30), 5, np.float32),
+                                   ("max", (1, 1, 2, 2, 10, 10), 9, np.uint8)]:
+        tiles = (rng.random(shape) * 200).astype(dtype)
+        res = reference_stitch(tiles, ov)
+        assert res is not None
+        out[name + "__tiles"], out[name + "__overlap"], out[name + "__image"] = tiles, ov, res
+    for bad in (-5,):
+        try:
+            reference_stitch(np.zeros((1, 1, 2, 2, 50, 50)), bad)
+            raise AssertionError("reference accepted a negative overlap")
+        except ValueError:
+            pass
+    try:
+        reference_stitch(np.zeros((1, 1, 2, 2, 50, 50)), 100)
+        raise AssertionError("reference accepted overlap >= tile size")
+    except ValueError:
+        pass
+    np.savez_compressed(os.path.join(HERE, "stitch.npz"), **out)
+
+
 if __name__ == "__main__":
     golden_geometry()
     golden_flatfield()
+    golden_stitch()
     golden_beads()
     golden_chip()
     golden_masks_cv()

@@ -81,6 +81,16 @@ def test_stitch_reference_golden_slices(cuda_device):
     np.testing.assert_array_equal(img[0, 0, :, 20:], tile_data[0, 0, 0, 1])
 
 
+def test_stitch_golden_from_reference_source(cuda_device, golden):
+    """CUDA stitch against the outputs of the reference's own Stitcher source (tests/golden/stitch.npz)."""
+    from magnify_b200 import ops
+
+    g = golden("stitch")
+    for name in ("odd", "even", "zero", "single", "max"):
+        got = ops.stitch(dev(g[name + "__tiles"], cuda_device), int(g[name + "__overlap"]))
+        np.testing.assert_array_equal(got.cpu().numpy(), g[name + "__image"], err_msg=name)
+
+
 def test_stitch_errors(cuda_device):
     from magnify_b200 import ops
 

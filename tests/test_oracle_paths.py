@@ -44,6 +44,30 @@ def test_stitcher_errors():  # :98-100, :112-125
         st.stitch(np.random.rand(1, 1, 2, 2, 50, 50), 100)
 
 
+STITCH_CASES = ("odd", "even", "zero", "single", "max")
+
+
+def test_stitch_golden_from_reference_source(golden):
+    """tests/golden/stitch.npz = outputs of the reference's own Stitcher source (stitch.py:12-46)."""
+    g = golden("stitch")
+    for name in STITCH_CASES:
+        got = st.stitch(g[name + "__tiles"], int(g[name + "__overlap"]))
+        assert got.dtype == g[name + "__image"].dtype
+        np.testing.assert_array_equal(got, g[name + "__image"], err_msg=name)
+
+
+def test_stitch_against_reference_source_when_present():
+    from oracle._refload import reference_stitch
+
+    rng = np.random.default_rng(3)
+    tiles = rng.integers(0, 65535, (2, 2, 3, 2, 14, 18), dtype=np.uint16, endpoint=True)
+    for ov in (0, 1, 4, 7, 13):
+        want = reference_stitch(tiles, ov)
+        if want is None:
+            pytest.skip("/root/reference not available (GPU box); the golden fixture covers this")
+        np.testing.assert_array_equal(st.stitch(tiles, ov), want)
+
+
 # ---- flat-field ------------------------------------------------------------------------------
 def test_flatfield_defaults_are_identity():
     rng = np.random.default_rng(0)
