@@ -260,3 +260,293 @@ def reference_stitch(tiles, overlap):
     image = out.image
     assert image.dims == ("channel", "time", "im_y", "im_x")
     return image.values
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference's own BeadFinder (src/magnify/find.py:445-605) executed in place: dask.array is
+# replaced by NumPy, xarray by the labelled stand-ins below, and `utils.find_circles` -- the
+# stochastic centre finder, out of scope -- by a function that returns the pinned beads.
+# Everything after the centres (find.py:503-605: boxes, label raster, fg/bg, crops, schema) is
+# the reference's code.
+# ---------------------------------------------------------------------------------------------
+class LabelledArray:
+    """ndarray + dim names + the owner's coordinate labels (for .sel)."""
+
+    def __init__(self, values, dims, coords):
+        import numpy as np
+
+        self.values = values if isinstance(values, np.ndarray) else np.asarray(values)
+        self.dims = tuple(dims)
+        self.coords = coords
+
+    shape = property(lambda self: self.values.shape)
+    dtype = property(lambda self: self.values.dtype)
+    sizes = property(lambda self: dict(zip(self.dims, self.values.shape)))
+
+    def to_numpy(self):
+        return self.values
+
+    def __array__(self, dtype=None, copy=None):
+        return self.values if dtype is None else self.values.astype(dtype)
+
+    def __iter__(self):
+        return iter(self.values)
+
+    def __len__(self):
+        return len(self.values)
+
+    def __getitem__(self, key):
+        import numpy as np
+
+        out = self.values[key]
+        if isinstance(out, np.ndarray) and out.ndim > 0:
+            return LabelledArray(out, tuple(f"_{i}" for i in range(out.ndim)), self.coords)
+        return out
+
+    def __setitem__(self, key, value):
+        import numpy as np
+
+        self.values[key] = np.asarray(value)
+
+    def compute(self):
+        return self
+
+    def persist(self):
+        return self
+
+    def chunk(self, chunks=None):
+        return self
+
+    def max(self):
+        return self.values.max()
+
+    def _index(self, indexers):
+        import numpy as np
+
+        key, dims = [], []
+        for d in self.dims:
+            if d in indexers:
+                k = indexers[d]
+                key.append(k)
+                if not np.isscalar(k):
+                    dims.append(d)
+            else:
+                key.append(slice(None))
+                dims.append(d)
+        return LabelledArray(self.values[tuple(key)], dims, self.coords)
+
+    def isel(self, **indexers):
+        return self._index(indexers)
+
+    def sel(self, **indexers):
+        import numpy as np
+
+        resolved = {}
+        for d, label in indexers.items():
+            labels = list(self.coords[d])
+            if isinstance(label, (list, tuple, np.ndarray, LabelledArray)):
+                resolved[d] = [labels.index(v) for v in list(label)]
+            else:
+                resolved[d] = labels.index(label)
+        return self._index(resolved)
+
+
+class LabelledAssay:
+    def __init__(self, variables=None, coords=None):
+        self._vars = dict(variables or {})
+        self._coords = dict(coords or {})
+        self.attrs = {}
+        self.mg = type("Mg", (), {"cache": staticmethod(lambda *a, **k: None)})()
+
+    def _wrap(self, name):
+        dims, values = self._vars[name]
+        return LabelledArray(values, dims, self._coords)
+
+    def __contains__(self, name):
+        return name in self._vars or name in self._coords
+
+    def __getattr__(self, name):
+        d = self.__dict__
+        if name in d.get("_vars", {}):
+            return self._wrap(name)
+        if name in d.get("_coords", {}):
+            return LabelledArray(d["_coords"][name], (name,), d["_coords"])
+        raise AttributeError(name)
+
+    def __getitem__(self, name):
+        return getattr(self, name)
+
+    def __setitem__(self, name, value):
+        if isinstance(value, tuple):
+            dims, values = value
+        else:
+            dims, values = value.dims, value.values
+        self._vars[name] = (tuple(dims), values)
+
+    @property
+    def sizes(self):
+        out = {}
+        for dims, values in self._vars.values():
+            out.update(dict(zip(dims, values.shape)))
+        return out
+
+    def assign_coords(self, **coords):
+        new = LabelledAssay(self._vars, self._coords)
+        for name, (dims, values) in coords.items():
+            new._vars[name] = (tuple(dims), values)
+        return new
+
+    def stack(self, create_index=True, **dims):
+        """xarray's Dataset.stack for ONE new dimension: every variable that has all the stacked
+        dims gets them merged (row-major) into the new one, placed where the first of them was."""
+        import numpy as np
+
+        (new_dim, old), = dims.items()
+        new = LabelledAssay({}, self._coords)
+        for name, (vdims, values) in self._vars.items():
+            if all(d in vdims for d in old):
+                order = [d for d in vdims if d not in old]
+                first = min(vdims.index(d) for d in old)
+                perm = [vdims.index(d) for d in order[:first]] + [vdims.index(d) for d in old] + \
+                       [vdims.index(d) for d in order[first:]]
+                v = np.transpose(values, perm)
+                shape = v.shape[:first] + (-1,) + v.shape[first + len(old):]
+                new._vars[name] = (tuple(order[:first]) + (new_dim,) + tuple(order[first:]), v.reshape(shape))
+            else:
+                new._vars[name] = (vdims, values)
+        return new
+
+    def transpose(self, *names):
+        """`.transpose("mark", ...)`: move the named leading dims to the front of every variable."""
+        import numpy as np
+
+        lead = [n for n in names if n is not Ellipsis]
+        new = LabelledAssay({}, self._coords)
+        for name, (vdims, values) in self._vars.items():
+            front = [d for d in lead if d in vdims]
+            order = front + [d for d in vdims if d not in front]
+            new._vars[name] = (tuple(order), np.transpose(values, [vdims.index(d) for d in order]))
+        return new
+
+
+_cached_find = None
+
+
+def load_reference_find():
+    """The reference's `src/magnify/find.py` loaded in place (NumPy for dask.array, the real
+    `utils.py`, stubs for xarray / registry / the GUI), or None."""
+    global _cached_find
+    if _cached_find is not None:
+        return _cached_find
+    path = os.path.join(REFERENCE_ROOT, "src", "magnify", "find.py")
+    utils = load_reference_utils()
+    if not os.path.exists(path) or utils is None:
+        return None
+    import numpy as np
+
+    xr = types.ModuleType("xarray")
+    xr.Dataset = type("Dataset", (), {})
+    xr.DataArray = type("DataArray", (), {})
+    dask = types.ModuleType("dask")
+    da = types.ModuleType("dask.array")
+    da.empty = lambda shape, dtype=float, chunks=None: np.empty(shape, dtype=dtype)
+    da.empty_like = lambda a, dtype=None, chunks=None: np.empty_like(a, dtype=dtype)
+    dask.array = da
+    pkg = types.ModuleType("magnify")
+    pkg.__path__ = []
+    registry = types.ModuleType("magnify.registry")
+    registry.components = type("Components", (), {"register": staticmethod(lambda name: (lambda f: f))})()
+    plot = types.ModuleType("magnify.plot")
+    plot.__path__ = []
+    vis = types.ModuleType("magnify.plot.vis")
+    vis.InteractiveUI = type("InteractiveUI", (), {})
+    pkg.registry, pkg.utils = registry, utils
+    stubs = {"xarray": xr, "dask": dask, "dask.array": da, "magnify": pkg, "magnify.registry": registry,
+             "magnify.utils": utils, "magnify.plot": plot, "magnify.plot.vis": vis}
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        spec = importlib.util.spec_from_file_location("_magnify_reference_find", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    except Exception:
+        mod = None
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _cached_find = mod
+    return mod
+
+
+def reference_bead_finder(image, channels, beads, roi_length, min_bead_diameter=2, max_bead_diameter=60):
+    """Run the reference's own BeadFinder.__call__ with the centre finder replaced by the pinned
+    `beads` (M,3 rows of (row, col, radius)).  image (C,T,H,W); returns dict(roi, fg, bg, x, y, valid)."""
+    import numpy as np
+
+    mod = load_reference_find()
+    if mod is None:
+        return None
+    utils = mod.utils
+    pinned = np.round(np.asarray(beads)).astype(np.int32)          # what find_circles returns (utils.py:159)
+    real_find_circles = utils.find_circles
+    utils.find_circles = lambda img, **kwargs: (pinned, np.ones(len(pinned), dtype=np.float32))
+    try:
+        finder = mod.BeadFinder(min_bead_diameter=min_bead_diameter, max_bead_diameter=max_bead_diameter,
+                                low_edge_quantile=0.1, high_edge_quantile=0.9, num_iter=1, min_roundness=0.3,
+                                roi_length=roi_length, search_channel=channels[0], interactive=False)
+        assay = LabelledAssay({"image": (("channel", "time", "im_y", "im_x"), np.asarray(image))},
+                              {"channel": np.asarray(channels)})
+        out = finder(assay)
+    finally:
+        utils.find_circles = real_find_circles
+    return {k: np.asarray(getattr(out, k).values) for k in ("roi", "fg", "bg", "x", "y", "valid")}
+
+
+def reference_button_finder(image, channels, tag, coarse_x, coarse_y, refine, roi_length=None,
+                            min_button_diameter=16, max_button_diameter=30, chamber_diameter=60,
+                            search_timestep=0):
+    """Run the reference's own ButtonFinder.__call__ (find.py:55-203 incl. find_rois :308-402 and the
+    copy-forward loop :143-181) with its two stochastic pieces pinned: `find_centers` returns the
+    coarse grid (coarse_x, coarse_y: rows x cols), and `utils.find_circles` returns, for the
+    k-th non-blank button in row-major order, `refine[k]` = (y, x, r) in ROI coordinates or None.
+    image (C,T,H,W).  Returns dict(roi, fg, bg, x, y, valid) with the stacked `mark` dimension first."""
+    import numpy as np
+
+    mod = load_reference_find()
+    if mod is None:
+        return None
+    utils = mod.utils
+    calls = {"n": 0}
+
+    def fake_find_circles(img, **kwargs):
+        r = refine[calls["n"]]
+        calls["n"] += 1
+        if r is None:
+            return np.empty((0, 3), dtype=np.int32), np.empty(0, dtype=np.float32)
+        return np.asarray([r], dtype=np.int32), np.ones(1, dtype=np.float32)
+
+    real_find_circles = utils.find_circles
+    utils.find_circles = fake_find_circles
+    try:
+        finder = mod.ButtonFinder(row_dist=100.0, col_dist=100.0, min_button_diameter=min_button_diameter,
+                                  max_button_diameter=max_button_diameter, chamber_diameter=chamber_diameter,
+                                  top_chamber=None, left_chamber=None, low_edge_quantile=0.1, high_edge_quantile=0.9,
+                                  num_iter=1000, min_roundness=0.2, cluster_penalty=10, roi_length=roi_length,
+                                  progress_bar=False, search_timestep=search_timestep, search_channel=channels[0],
+                                  interactive=False)
+        finder.find_centers = lambda images, assay: (np.array(coarse_x, dtype=float), np.array(coarse_y, dtype=float))
+        image = np.asarray(image)
+        c, t, h, w = image.shape
+        rows, cols = np.asarray(tag).shape
+        assay = LabelledAssay(
+            {"image": (("channel", "time", "im_y", "im_x"), image),
+             "tag": (("mark_row", "mark_col"), np.asarray(tag)),
+             "valid": (("mark_row", "mark_col", "time"), np.ones((rows, cols, t), dtype=bool))},
+            {"channel": np.asarray(channels), "time": np.arange(t)})
+        out = finder(assay)
+    finally:
+        utils.find_circles = real_find_circles
+    return {k: np.asarray(getattr(out, k).values) for k in ("roi", "fg", "bg", "x", "y", "valid")}

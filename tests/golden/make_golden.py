@@ -96,6 +96,15 @@ def golden_beads():
         for j in range(m):
             top, bottom, left, right = boxes[j]
             roi[j, ch] = im[..., top:bottom, left:right]  # :601
+    # the reference's OWN BeadFinder.__call__ (find.py:471-605) with the centre finder pinned to
+    # `beads` must give exactly the arrays replayed above
+    from oracle._refload import reference_bead_finder
+
+    ref = reference_bead_finder(image, ["a", "b"], beads, length)
+    assert ref is not None
+    assert np.array_equal(ref["roi"], roi)
+    assert np.array_equal(ref["fg"], np.repeat(fg[:, None], t, 1)) and np.array_equal(ref["bg"], np.repeat(bg[:, None], t, 1))
+    assert np.array_equal(ref["x"][:, 0], beads[:, 1]) and np.array_equal(ref["y"][:, 0], beads[:, 0]) and ref["valid"].all()
     np.savez_compressed(
         os.path.join(HERE, "beads.npz"),
         image_salt=1, image_shape=np.array([c, t, h, w]), roi_length=length, beads=beads,
@@ -146,13 +155,48 @@ def golden_chip():
                 roi[i, j, :, tt] = image[:, tt, top:bottom, left:right]
         fg[:, :, tt] = fg[:, :, tt - 1]
         bg[:, :, tt] = bg[:, :, tt - 1]
+    # the reference's OWN ButtonFinder.__call__ (find.py:55-203, find_rois :308-402, copy-forward
+    # :143-181, stack :182) with find_centers / find_circles pinned must give the same arrays
+    from oracle._refload import reference_button_finder
+
+    refine = [found.get((i, j)) for i in range(rows) for j in range(cols)]
+    ref = reference_button_finder(image, ["a", "b"], np.full((rows, cols), "default"), gx, gy, refine)
+    assert ref is not None
+    assert np.array_equal(ref["roi"], roi.reshape((rows * cols,) + roi.shape[2:]))
+    assert np.array_equal(ref["fg"], fg.reshape((rows * cols,) + fg.shape[2:]))
+    assert np.array_equal(ref["bg"], bg.reshape((rows * cols,) + bg.shape[2:]))
+    assert np.array_equal(ref["x"][:, 0], x.reshape(-1)) and np.array_equal(ref["y"][:, 0], y.reshape(-1))
     np.savez_compressed(
         os.path.join(HERE, "chip.npz"),
         image_salt=2, image_shape=np.array([c, t, h, w]), roi_length=length, chamber_radius=chamber_r,
         max_button_radius=max_r, coarse_x=gx, coarse_y=gy, x=x, y=y, fg_radius=rad,
+        refine=np.array([(-1, -1, -1) if r is None else r for r in refine]),
         roi=roi.reshape((rows * cols,) + roi.shape[2:]),
         fg=fg.reshape((rows * cols,) + fg.shape[2:]), bg=bg.reshape((rows * cols,) + bg.shape[2:]),
     )
+
+
+def golden_chip_multi():
+    """Two search timesteps with different refinement outcomes + copy-forward in between
+    (find.py:119-181): produced directly by the reference's own ButtonFinder.__call__."""
+    from oracle._refload import reference_button_finder
+
+    c, t, h, w, length = 2, 5, 220, 260, 40
+    image = pattern_image(c, t, h, w, salt=3)
+    gx = np.array([[30.5, 128.2, 240.0], [41.0, 130.5, 255.5]])
+    gy = np.array([[25.0, 30.5, 18.5], [190.5, 200.0, 215.49]])
+    rows, cols = gx.shape
+    # refinement results in call order: search timestep 1 (row-major), then search timestep 3
+    refine = [(20, 22, 7), None, (18, 25, 9), None, (21, 19, 6), (30, 33, 8),
+              None, (19, 20, 5), (20, 20, 9), (22, 18, 8), None, (10, 12, 6)]
+    ref = reference_button_finder(image, ["a", "b"], np.full((rows, cols), "default"), gx, gy, refine, roi_length=length,
+                                  min_button_diameter=8, max_button_diameter=18, chamber_diameter=34,
+                                  search_timestep=[1, 3])
+    assert ref is not None
+    np.savez_compressed(os.path.join(HERE, "chip_multi.npz"), image_salt=3, image_shape=np.array([c, t, h, w]),
+                        roi_length=length, chamber_radius=17, max_button_radius=9, search_timesteps=np.array([1, 3]),
+                        refine=np.array([(-1, -1, -1) if r is None else r for r in refine]), coarse_x=gx, coarse_y=gy,
+                        **ref)
 
 
 def golden_masks_cv():
@@ -236,6 +280,7 @@ if __name__ == "__main__":
     golden_stitch()
     golden_beads()
     golden_chip()
+    golden_chip_multi()
     golden_masks_cv()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

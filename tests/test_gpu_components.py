@@ -160,6 +160,38 @@ def test_button_finder_schema_and_values(cuda_device, golden, make_pattern_image
         ButtonFinder(100, 100, 30, 10, 60)                                          # find.py:34-35
 
 
+def test_button_finder_multi_search_matches_reference_call(cuda_device, golden, make_pattern_image):
+    """tests/golden/chip_multi.npz is the output of the reference's own ButtonFinder.__call__ with
+    search_timestep=[1, 3] (executed in place, centre search pinned): the component must give the
+    same roi / fg / bg / x / y, including the copy-forward of find.py:143-181."""
+    from magnify_b200.components import ButtonFinder
+    from magnify_b200.dataset import Assay
+
+    g = golden("chip_multi")
+    c, t, h, w = (int(v) for v in g["image_shape"])
+    image = make_pattern_image(c, t, h, w, salt=int(g["image_salt"]))
+    rows, cols = g["coarse_x"].shape
+    search = [int(v) for v in g["search_timesteps"]]
+    refine = g["refine"].reshape(len(search), rows, cols, 3)
+    radius = np.where(refine[..., 2] >= 0, refine[..., 2], int(g["max_button_radius"]))
+    assay = Assay({"image": (("channel", "time", "im_y", "im_x"), image)},
+                  coords={"tag": (("mark_row", "mark_col"), np.full((rows, cols), "default")),
+                          "valid": (("mark_row", "mark_col", "time"), np.ones((rows, cols, t), bool))})
+
+    def centers(assay, ts):
+        k = search.index(ts)
+        return g["x"][:, ts].reshape(rows, cols), g["y"][:, ts].reshape(rows, cols), radius[k]
+
+    finder = ButtonFinder(row_dist=100, col_dist=150, min_button_diameter=8, max_button_diameter=18,
+                          chamber_diameter=34, roi_length=int(g["roi_length"]), search_timestep=search, centers=centers)
+    out = finder(assay)
+    np.testing.assert_array_equal(out.roi.values, g["roi"])
+    np.testing.assert_array_equal(out.fg.values, g["fg"])
+    np.testing.assert_array_equal(out.bg.values, g["bg"])
+    np.testing.assert_array_equal(out.x.values, g["x"])
+    np.testing.assert_array_equal(out.y.values, g["y"])
+
+
 def test_filter_expression_and_mrbles_intensities(cuda_device):
     """the consumers of the summaries (filter.py:11-37,
     identify.py:76-80) on GPU medians / means, against the NumPy restatement."""

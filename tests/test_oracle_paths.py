@@ -159,6 +159,66 @@ def test_chip_golden(golden, make_pattern_image):
         np.testing.assert_array_equal(bg, d["bg"][:, ti])
 
 
+def chip_multi_inputs(d):
+    """(x, y, fg_radius) per search timestep of tests/golden/chip_multi.npz, row-major markers."""
+    search = [int(v) for v in d["search_timesteps"]]
+    m = d["x"].shape[0]
+    refine = d["refine"].reshape(len(search), m, 3)
+    radius = np.where(refine[..., 2] >= 0, refine[..., 2], int(d["max_button_radius"]))
+    return search, radius
+
+
+def test_chip_multi_search_golden(golden, make_pattern_image):
+    """chip_multi.npz is the output of the reference's own ButtonFinder.__call__ (two search
+    timesteps, refinement hits and misses, copy-forward before / between / after them)."""
+    d = golden("chip_multi")
+    c, t, h, w = (int(v) for v in d["image_shape"])
+    image = make_pattern_image(c, t, h, w, salt=int(d["image_salt"]))
+    length = int(d["roi_length"])
+    search, radius = chip_multi_inputs(d)
+    src = rois.chip_copy_forward(t, search)
+    np.testing.assert_array_equal(src, [1, 1, 1, 3, 3])
+    for ti in range(t):   # copy-forward of centres, find.py:143-151
+        np.testing.assert_array_equal(d["x"][:, ti], d["x"][:, src[ti]])
+        np.testing.assert_array_equal(d["y"][:, ti], d["y"][:, src[ti]])
+    np.testing.assert_array_equal(rois.gather_rois(image, d["x"], d["y"], length), d["roi"])
+    for k, ts in enumerate(search):
+        fg, bg = rois.chip_masks(d["x"][:, ts], d["y"][:, ts], radius[k], length, int(d["chamber_radius"]),
+                                 int(d["max_button_radius"]), w, h)
+        for ti in np.nonzero(src == ts)[0]:
+            np.testing.assert_array_equal(fg, d["fg"][:, ti])
+            np.testing.assert_array_equal(bg, d["bg"][:, ti])
+
+
+def test_finders_against_reference_source_when_present(golden, make_pattern_image):
+    """The committed bead / chip fixtures equal what the reference's own BeadFinder /
+    ButtonFinder `__call__` (find.py, executed in place with the stochastic centre finder
+    pinned) produce on the same inputs."""
+    from oracle._refload import reference_bead_finder, reference_button_finder
+
+    d = golden("beads")
+    c, t, h, w = (int(v) for v in d["image_shape"])
+    image = make_pattern_image(c, t, h, w, salt=int(d["image_salt"]))
+    ref = reference_bead_finder(image, ["a", "b"], d["beads"], int(d["roi_length"]))
+    if ref is None:
+        pytest.skip("/root/reference not available (GPU box); the golden fixtures cover this")
+    np.testing.assert_array_equal(ref["roi"], d["roi"])
+    for ti in range(t):
+        np.testing.assert_array_equal(ref["fg"][:, ti], d["fg"])
+        np.testing.assert_array_equal(ref["bg"][:, ti], d["bg"])
+
+    d = golden("chip")
+    c, t, h, w = (int(v) for v in d["image_shape"])
+    image = make_pattern_image(c, t, h, w, salt=int(d["image_salt"]))
+    rows, cols = d["x"].shape
+    refine = [None if r[2] < 0 else tuple(int(v) for v in r) for r in d["refine"].reshape(-1, 3)]
+    ref = reference_button_finder(image, ["a", "b"], np.full((rows, cols), "default"), d["coarse_x"], d["coarse_y"], refine)
+    np.testing.assert_array_equal(ref["roi"], d["roi"])
+    np.testing.assert_array_equal(ref["fg"], d["fg"])
+    np.testing.assert_array_equal(ref["bg"], d["bg"])
+    np.testing.assert_array_equal(ref["x"][:, 0], d["x"].reshape(-1))
+
+
 def test_copy_forward_sources():
     np.testing.assert_array_equal(rois.chip_copy_forward(6, [2, 4]), [2, 2, 2, 2, 4, 4])
     np.testing.assert_array_equal(rois.chip_copy_forward(3, 0), [0, 0, 0])
