@@ -550,3 +550,238 @@ def reference_button_finder(image, channels, tag, coarse_x, coarse_y, refine, ro
     finally:
         utils.find_circles = real_find_circles
     return {k: np.asarray(getattr(out, k).values) for k in ("roi", "fg", "bg", "x", "y", "valid")}
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference's own `filter_expression` (src/magnify/filter.py:11-37) executed in place.  The
+# function body -- which variables are reduced over which dims, the pairwise-difference
+# statistic, the threshold, the and/or with `valid` -- is the reference's code; the xarray
+# arithmetic it calls (`where` with NaN fill, skip-NaN `median`) is not in /root/reference and is
+# restated here from xarray's published semantics: `where` on an integer array of <= 16 bits
+# promotes to float32 (xarray.core.dtypes.maybe_promote), wider integers to float64, and
+# `median(dim=...)` skips NaN (nanmedian).  `promote` lets the tests check that the outcome does
+# not depend on that promotion rule (medians of u16 values are exact in float32 and float64).
+# ---------------------------------------------------------------------------------------------
+class ReducibleArray(LabelledArray):
+    promote = None   # None = xarray's rule; or a NumPy float dtype
+
+    def _like(self, values, dims=None):
+        out = ReducibleArray(values, self.dims if dims is None else dims, self.coords)
+        out.promote = self.promote
+        return out
+
+    def _index(self, indexers):
+        base = LabelledArray._index(self, indexers)
+        return self._like(base.values, base.dims)
+
+    def where(self, cond):
+        import numpy as np
+
+        dt = self.values.dtype
+        if self.promote is not None:
+            ft = np.dtype(self.promote)
+        elif np.issubdtype(dt, np.integer):
+            ft = np.dtype(np.float32 if dt.itemsize <= 2 else np.float64)
+        else:
+            ft = dt
+        c = np.asarray(cond.values if isinstance(cond, LabelledArray) else cond, dtype=bool)
+        return self._like(np.where(c, self.values.astype(ft), ft.type(np.nan)))
+
+    def _reduce(self, fn, dim):
+        import warnings
+
+        axes = tuple(self.dims.index(d) for d in dim)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)   # all-NaN slices -> NaN, like xarray
+            out = fn(self.values, axis=axes)
+        return self._like(out, tuple(d for d in self.dims if d not in dim))
+
+    def median(self, dim):
+        import numpy as np
+
+        return self._reduce(np.nanmedian, dim)
+
+    def mean(self, dim):
+        import numpy as np
+
+        return self._reduce(np.nanmean, dim)
+
+    def __sub__(self, other):
+        return self._like(self.values - other.values)
+
+    def __gt__(self, other):
+        return self._like(self.values > other)
+
+
+class ValidArray(LabelledArray):
+    """`assay.valid`: (mark, time) bool; `|=` with a (mark,) array broadcasts by dim name."""
+
+    def __ior__(self, other):
+        self.values |= other.values.reshape((-1,) + (1,) * (self.values.ndim - 1))
+        return self
+
+    def __iand__(self, other):
+        self.values &= other.values
+        return self
+
+
+class FilterAssay:
+    def __init__(self, roi, fg, bg, valid, channels, promote=None):
+        self._coords = {"channel": list(channels)}
+        self._roi, self._fg, self._bg, self._valid = roi, fg, bg, valid
+        self._promote = promote
+        self._sel = {}
+
+    channel = property(lambda self: list(self._coords["channel"]))
+    sizes = property(lambda self: {"mark": self._roi.shape[0]})
+
+    def _view(self, **sel):
+        new = FilterAssay(self._roi, self._fg, self._bg, self._valid, self._coords["channel"], self._promote)
+        new._sel = {**self._sel, **sel}
+        return new
+
+    def isel(self, time):
+        return self._view(time=time)
+
+    def sel(self, channel):
+        return self._view(channel=self._coords["channel"].index(channel))
+
+    @property
+    def roi(self):
+        out = ReducibleArray(self._roi, ("mark", "channel", "time", "roi_y", "roi_x"), self._coords)
+        out.promote = self._promote
+        return out._index(self._sel)
+
+    @property
+    def fg(self):
+        return LabelledArray(self._fg, ("mark", "time", "roi_y", "roi_x"), self._coords)._index(
+            {k: v for k, v in self._sel.items() if k == "time"})
+
+    @property
+    def bg(self):
+        return LabelledArray(self._bg, ("mark", "time", "roi_y", "roi_x"), self._coords)._index(
+            {k: v for k, v in self._sel.items() if k == "time"})
+
+    @property
+    def valid(self):
+        return ValidArray(self._valid, ("mark", "time"), self._coords)
+
+    def __getitem__(self, name):
+        return getattr(self, name)
+
+    def __setitem__(self, name, value):
+        assert name == "valid"
+        self._valid = value.values
+
+
+_cached_filter = None
+
+
+def load_reference_filter():
+    global _cached_filter
+    if _cached_filter is not None:
+        return _cached_filter
+    path = os.path.join(REFERENCE_ROOT, "src", "magnify", "filter.py")
+    utils = load_reference_utils()
+    if not os.path.exists(path) or utils is None:
+        return None
+    import numpy as np
+
+    xr = types.ModuleType("xarray")
+    xr.Dataset = type("Dataset", (), {})
+    xr.zeros_like = lambda a, dtype=None: ValidArray(np.zeros_like(a.values, dtype=dtype), a.dims, a.coords)
+    pkg = types.ModuleType("magnify")
+    pkg.__path__ = []
+    registry = types.ModuleType("magnify.registry")
+    registry.component = lambda name: (lambda f: f)
+    pkg.registry, pkg.utils = registry, utils
+    stubs = {"xarray": xr, "magnify": pkg, "magnify.registry": registry, "magnify.utils": utils}
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        spec = importlib.util.spec_from_file_location("_magnify_reference_filter", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    except Exception:
+        mod = None
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _cached_filter = mod
+    return mod
+
+
+def reference_filter_expression(roi, fg, bg, valid, channels, search_channel=None, min_contrast=None, promote=None):
+    """Run the reference's `filter_expression` on (M,C,T,L,L) roi, (M,T,L,L) fg/bg, (M,T) valid.
+    Returns the new `valid` (M,T), or None when /root/reference is absent."""
+    mod = load_reference_filter()
+    if mod is None:
+        return None
+    assay = FilterAssay(roi, fg, bg, valid.copy(), channels, promote)
+    out = mod.filter_expression(assay, search_channel=search_channel, min_contrast=min_contrast)
+    return out._valid
+
+
+# ---------------------------------------------------------------------------------------------
+# identify.py:76-80 -- the intensities `identify_mrbles` starts from.  The rest of that function
+# (pandas / scipy / sklearn clustering) is out of scope, so only the statement that builds `sel`
+# and `intensities` is executed, read from the reference file at run time (located by its text,
+# not copied), on the same stand-ins as above.
+# ---------------------------------------------------------------------------------------------
+class IntensityArray(ReducibleArray):
+    """`assay.roi` with its fg/bg coordinates attached (DataArray attribute access `sel.fg`)."""
+    masks = None   # {"fg": (dims, values), "bg": (dims, values)}
+
+    def _like(self, values, dims=None):
+        out = IntensityArray(values, self.dims if dims is None else dims, self.coords)
+        out.promote, out.masks = self.promote, self.masks
+        return out
+
+    def _index(self, indexers):
+        import numpy as np
+
+        out = ReducibleArray._index(self, indexers)
+        masks = {}
+        for name, (dims, values) in self.masks.items():
+            sub = LabelledArray(values, dims, self.coords)._index({k: v for k, v in indexers.items() if k in dims})
+            masks[name] = (sub.dims, sub.values)
+        out.masks = masks
+        return out
+
+    def __getattr__(self, name):
+        masks = self.__dict__.get("masks") or {}
+        if name in masks:
+            return LabelledArray(masks[name][1], masks[name][0], self.coords)
+        raise AttributeError(name)
+
+    def where(self, cond):
+        import numpy as np
+
+        # broadcast the condition to self.dims by dimension NAME (xarray alignment)
+        c = np.asarray(cond.values, dtype=bool)
+        shape = [self.values.shape[self.dims.index(d)] if d in cond.dims else 1 for d in self.dims]
+        order = [cond.dims.index(d) for d in self.dims if d in cond.dims]
+        c = np.transpose(c, order).reshape(shape)
+        return ReducibleArray.where(self, np.broadcast_to(c, self.values.shape))
+
+
+def reference_mrbles_intensities(roi, fg, bg, channel_names, channels, promote=None):
+    """(mark, len(channels)) intensities by the reference's own expression, or None."""
+    import textwrap
+
+    path = os.path.join(REFERENCE_ROOT, "src", "magnify", "identify.py")
+    if not os.path.exists(path):
+        return None
+    lines = open(path).read().split("\n")
+    start = next(i for i, l in enumerate(lines) if l.strip().startswith("sel = assay.roi.isel(time=0)"))
+    stop = next(i for i in range(start, len(lines)) if lines[i].strip() == ").to_numpy()")
+    code = compile(textwrap.dedent("\n".join(lines[start:stop + 1])), path, "exec")
+    arr = IntensityArray(roi, ("mark", "channel", "time", "roi_y", "roi_x"), {"channel": list(channel_names)})
+    arr.promote = promote
+    arr.masks = {"fg": (("mark", "time", "roi_y", "roi_x"), fg), "bg": (("mark", "time", "roi_y", "roi_x"), bg)}
+    scope = {"assay": type("A", (), {"roi": arr})(), "channels": list(channels)}
+    exec(code, scope)
+    return scope["intensities"]

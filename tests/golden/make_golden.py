@@ -199,6 +199,44 @@ def golden_chip_multi():
                         **ref)
 
 
+def golden_filter_expression():
+    """`filter_expression` (filter.py:11-37) executed in place on u16 ROIs: the composition is the
+    reference's; the xarray where/median arithmetic is restated in oracle/_refload.py and the
+    outcome is asserted to be independent of the float32-vs-float64 promotion of `where`."""
+    from oracle._refload import reference_filter_expression
+
+    rng = np.random.default_rng(5)
+    m, c, t, length = 48, 3, 2, 20
+    roi = rng.integers(380, 420, (m, c, t, length, length)).astype(np.uint16)
+    yy, xx = np.mgrid[0:length, 0:length]
+    fg0 = (yy - 10) ** 2 + (xx - 10) ** 2 <= 25
+    fg = np.broadcast_to(fg0, (m, t, length, length)).copy()
+    bg = np.broadcast_to((yy - 10) ** 2 + (xx - 10) ** 2 > 64, (m, t, length, length)).copy()
+    for i in range(0, m, 3):
+        roi[i][..., fg0] += np.uint16(50 + i)
+    roi[4, 1][..., fg0] += 3000
+    fg[7] = False          # empty foreground -> NaN median -> comparison False
+    valid = rng.random((m, t)) < 0.9
+    out = {"roi": roi, "fg": fg, "bg": bg, "valid": valid, "channels": np.array(["a", "b", "c"])}
+    cases = [(None, None), (None, 40), ("b", None), ("b", 40), (["a", "c"], None), (["a", "c"], 25)]
+    for k, (sc, mc) in enumerate(cases):
+        got = reference_filter_expression(roi, fg, bg, valid, ["a", "b", "c"], sc, mc)
+        assert got is not None
+        assert np.array_equal(got, reference_filter_expression(roi, fg, bg, valid, ["a", "b", "c"], sc, mc, np.float64))
+        out[f"case{k}__valid"] = got
+        out[f"case{k}__search"] = np.array([] if sc is None else np.atleast_1d(sc))
+        out[f"case{k}__min_contrast"] = np.array(-1 if mc is None else mc)
+    # identify.py:76-80 (mean of fg - median of bg at time 0) by the reference's own expression,
+    # under both promotions xarray's `where` may apply to u16 (float32 by maybe_promote; float64)
+    from oracle._refload import reference_mrbles_intensities
+
+    out["intensity_channels"] = np.array(["c", "a"])
+    out["intensities_f32"] = reference_mrbles_intensities(roi, fg, bg, ["a", "b", "c"], ["c", "a"])
+    out["intensities_f64"] = reference_mrbles_intensities(roi, fg, bg, ["a", "b", "c"], ["c", "a"], np.float64)
+    assert out["intensities_f32"].dtype == np.float32 and out["intensities_f64"].dtype == np.float64
+    np.savez_compressed(os.path.join(HERE, "filter.npz"), **out)
+
+
 def golden_masks_cv():
     """cv.circle rasters through utils.circle / utils.annulus (utils.py:30-52) for clipped and
     unclipped centres -- pins the closed form `dx^2+dy^2 <= r^2` used by oracle and kernel."""
@@ -281,6 +319,7 @@ if __name__ == "__main__":
     golden_beads()
     golden_chip()
     golden_chip_multi()
+    golden_filter_expression()
     golden_masks_cv()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -219,3 +219,43 @@ def test_filter_expression_and_mrbles_intensities(cuda_device):
     np.testing.assert_array_equal(out2.valid.values, o_red.filter_expression_valid(roi, fg, bg, valid, [0, 1, 2], 1000))
     inten = mrbles_intensities(assay, channels=["a", "b"])
     np.testing.assert_allclose(inten, o_red.mrbles_intensities(roi[:, :2], fg, bg), rtol=1e-12)
+
+
+def test_filter_expression_golden_from_reference_source(cuda_device, golden):
+    """GPU medians + the reference's threshold logic against tests/golden/filter.npz (outputs of the
+    reference's own filter_expression source, filter.py:11-37, executed in place)."""
+    from magnify_b200.components import filter_expression
+    from magnify_b200.dataset import Assay
+
+    g = golden("filter")
+    names = [str(v) for v in g["channels"]]
+    k = 0
+    while f"case{k}__valid" in g:
+        search = [str(v) for v in g[f"case{k}__search"]] or None
+        mc = int(g[f"case{k}__min_contrast"])
+        assay = Assay({"roi": (("mark", "channel", "time", "roi_y", "roi_x"), g["roi"])},
+                      coords={"channel": (("channel",), np.array(names)),
+                              "fg": (("mark", "time", "roi_y", "roi_x"), g["fg"]),
+                              "bg": (("mark", "time", "roi_y", "roi_x"), g["bg"]),
+                              "valid": (("mark", "time"), g["valid"])})
+        out = filter_expression(assay, search_channel=search, min_contrast=None if mc < 0 else mc)
+        np.testing.assert_array_equal(out.valid.values, g[f"case{k}__valid"], err_msg=f"case {k}")
+        k += 1
+    assert k == 6
+
+
+def test_mrbles_intensities_golden_from_reference_expression(cuda_device, golden):
+    """identify.py:76-80 run in place -> tests/golden/filter.npz; GPU mean/median must reproduce the
+    float64 result to 1e-12 and the float32-promoted one to 1e-5 of the mean (north_star)."""
+    from magnify_b200.components import mrbles_intensities
+    from magnify_b200.dataset import Assay
+
+    g = golden("filter")
+    assay = Assay({"roi": (("mark", "channel", "time", "roi_y", "roi_x"), g["roi"])},
+                  coords={"channel": (("channel",), np.array([str(v) for v in g["channels"]])),
+                          "fg": (("mark", "time", "roi_y", "roi_x"), g["fg"]),
+                          "bg": (("mark", "time", "roi_y", "roi_x"), g["bg"])})
+    got = mrbles_intensities(assay, channels=[str(v) for v in g["intensity_channels"]])
+    np.testing.assert_allclose(got, g["intensities_f64"], rtol=1e-12, atol=1e-10)
+    np.testing.assert_allclose(got, g["intensities_f32"], rtol=0, atol=1e-5 * 500.0)
+    assert np.isnan(got[7]).all()

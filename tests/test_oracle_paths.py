@@ -238,3 +238,52 @@ def test_masked_stats_and_median():
     assert s[m, c, t, 0] == vals.size and s[m, c, t, 2] == vals.sum() and s[m, c, t, 4] == vals.mean()
     med = red.masked_median(roi, fg)
     assert med[m, c, t] == np.median(vals) and np.isnan(med[1]).all()
+
+
+def filter_cases(g):
+    names = [str(v) for v in g["channels"]]
+    k = 0
+    while f"case{k}__valid" in g:
+        search = [str(v) for v in g[f"case{k}__search"]] or None
+        mc = int(g[f"case{k}__min_contrast"])
+        yield names, search, (None if mc < 0 else mc), g[f"case{k}__valid"]
+        k += 1
+
+
+def test_filter_expression_golden_from_reference_source(golden):
+    """tests/golden/filter.npz = the reference's own filter_expression (filter.py:11-37) run in
+    place (composition pinned; xarray's where/median restated, see oracle/_refload.py)."""
+    g = golden("filter")
+    n = 0
+    for names, search, mc, want in filter_cases(g):
+        idx = list(range(len(names))) if search is None else [names.index(s) for s in search]
+        got = red.filter_expression_valid(g["roi"], g["fg"], g["bg"], g["valid"], idx, mc)
+        np.testing.assert_array_equal(got, want)
+        n += 1
+    assert n == 6
+
+
+def test_filter_expression_against_reference_source_when_present(golden):
+    from oracle._refload import reference_filter_expression
+
+    g = golden("filter")
+    for names, search, mc, want in filter_cases(g):
+        for promote in (None, np.float64):
+            got = reference_filter_expression(g["roi"], g["fg"], g["bg"], g["valid"], names, search, mc, promote)
+            if got is None:
+                pytest.skip("/root/reference not available (GPU box); the golden fixture covers this")
+            np.testing.assert_array_equal(got, want)
+
+
+def test_mrbles_intensities_golden_from_reference_expression(golden):
+    """identify.py:76-80 executed in place: bit-identical to the oracle when xarray's `where`
+    promotes u16 to float64; within float32 rounding of the MEAN (<= 1e-5 relative to it, the
+    north_star tolerance) when it promotes to float32 (xarray.core.dtypes.maybe_promote)."""
+    g = golden("filter")
+    names = [str(v) for v in g["channels"]]
+    idx = [names.index(str(c)) for c in g["intensity_channels"]]
+    got = red.mrbles_intensities(g["roi"][:, idx], g["fg"], g["bg"])
+    np.testing.assert_array_equal(got, g["intensities_f64"])
+    assert np.isnan(got[7]).all()                       # empty foreground
+    mean_scale = float(np.nanmax(red.masked_stats(g["roi"][:, idx, :1], g["fg"][:, :1], g["bg"][:, :1])[..., 4]))
+    np.testing.assert_allclose(got, g["intensities_f32"], rtol=0, atol=1e-5 * mean_scale)
