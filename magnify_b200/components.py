@@ -431,6 +431,33 @@ def filter_expression(assay, search_channel=None, min_contrast=None, device=None
     return assay.assign_coords(valid=(tuple(assay["valid"].dims), valid & expressed))
 
 
+def filter_leaky(assay, search_channel=None, device=None):
+    """`filter_leaky` of the reference (filter.py:65-94) with the masked medians computed on the
+    GPU: tagged markers whose blank neighbour (previous / next mark in stacked order) is not
+    "empty" are invalidated.  Needs the stacked chip schema (`tag`, `mark_row` per mark)."""
+    dev = _device(device)
+    channels = list(_to_numpy(assay["channel"])) if "channel" in assay else list(range(assay["roi"].shape[1]))
+    wanted = channels if search_channel is None else ([search_channel] if isinstance(search_channel, str)
+                                                      or np.isscalar(search_channel) else list(search_channel))
+    tag = _to_numpy(assay["tag"])
+    rows = _to_numpy(assay["mark_row"])
+    valid = _to_numpy(assay["valid"]).astype(bool).copy()
+    top = rows.max() if rows.size else 0
+    for ch in wanted:
+        fgm, bgm = _time0_medians(assay, channels.index(ch), dev)
+        diffs = bgm[:, np.newaxis] - bgm[np.newaxis, :]
+        offdiag = np.ones_like(diffs, dtype=bool) & (~np.eye(len(diffs), dtype=bool))
+        empty = fgm - bgm < 5 * diffs[offdiag].std()
+        for i in range(len(tag)):
+            if tag[i] == "":
+                continue
+            if rows[i] > 0 and tag[i - 1] == "":
+                valid[i] &= empty[i - 1]
+            if rows[i] < top and tag[i + 1] == "":
+                valid[i] &= empty[i + 1]
+    return assay.assign_coords(valid=(tuple(assay["valid"].dims), valid))
+
+
 def mrbles_intensities(assay, channels=None, device=None) -> np.ndarray:
     """The per-bead intensities `identify_mrbles` starts from (identify.py:76-80): mean of the
     foreground minus median of the background at time 0, (mark, channel)."""
@@ -464,6 +491,8 @@ EXTRA_FACTORIES = {
     "quantify": make_quantify,
     "filter_expression_b200": lambda search_channel=None, min_contrast=None, device=None: (
         lambda xp: filter_expression(xp, search_channel=search_channel, min_contrast=min_contrast, device=device)),
+    "filter_leaky_b200": lambda search_channel=None, device=None: (
+        lambda xp: filter_leaky(xp, search_channel=search_channel, device=device)),
 }
 
 

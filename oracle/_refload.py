@@ -612,9 +612,20 @@ class ReducibleArray(LabelledArray):
     def __gt__(self, other):
         return self._like(self.values > other)
 
+    def __lt__(self, other):
+        return self._like(self.values < other)
+
 
 class ValidArray(LabelledArray):
     """`assay.valid`: (mark, time) bool; `|=` with a (mark,) array broadcasts by dim name."""
+
+    @property
+    def data(self):
+        return self.values
+
+    @data.setter
+    def data(self, value):
+        self.values[...] = value
 
     def __ior__(self, other):
         self.values |= other.values.reshape((-1,) + (1,) * (self.values.ndim - 1))
@@ -626,17 +637,22 @@ class ValidArray(LabelledArray):
 
 
 class FilterAssay:
-    def __init__(self, roi, fg, bg, valid, channels, promote=None):
+    def __init__(self, roi, fg, bg, valid, channels, promote=None, tag=None, mark_row=None):
         self._coords = {"channel": list(channels)}
         self._roi, self._fg, self._bg, self._valid = roi, fg, bg, valid
         self._promote = promote
         self._sel = {}
+        self._tag, self._mark_row = tag, mark_row
+
+    tag = property(lambda self: LabelledArray(self._tag, ("mark",), self._coords))
+    mark_row = property(lambda self: LabelledArray(self._mark_row, ("mark",), self._coords))
 
     channel = property(lambda self: list(self._coords["channel"]))
     sizes = property(lambda self: {"mark": self._roi.shape[0]})
 
     def _view(self, **sel):
-        new = FilterAssay(self._roi, self._fg, self._bg, self._valid, self._coords["channel"], self._promote)
+        new = FilterAssay(self._roi, self._fg, self._bg, self._valid, self._coords["channel"], self._promote,
+                          self._tag, self._mark_row)
         new._sel = {**self._sel, **sel}
         return new
 
@@ -648,8 +664,9 @@ class FilterAssay:
 
     @property
     def roi(self):
-        out = ReducibleArray(self._roi, ("mark", "channel", "time", "roi_y", "roi_x"), self._coords)
+        out = IntensityArray(self._roi, ("mark", "channel", "time", "roi_y", "roi_x"), self._coords)
         out.promote = self._promote
+        out.masks = {"fg": (("mark", "time", "roi_y", "roi_x"), self._fg), "bg": (("mark", "time", "roi_y", "roi_x"), self._bg)}
         return out._index(self._sel)
 
     @property
@@ -766,6 +783,16 @@ class IntensityArray(ReducibleArray):
         order = [cond.dims.index(d) for d in self.dims if d in cond.dims]
         c = np.transpose(c, order).reshape(shape)
         return ReducibleArray.where(self, np.broadcast_to(c, self.values.shape))
+
+
+def reference_filter_leaky(roi, fg, bg, valid, channels, tag, mark_row, search_channel=None, promote=None):
+    """Run the reference's `filter_leaky_buttons` (filter.py:65-94); returns the new valid (M,T)."""
+    mod = load_reference_filter()
+    if mod is None:
+        return None
+    assay = FilterAssay(roi, fg, bg, valid.copy(), channels, promote, tag, mark_row)
+    out = mod.filter_leaky_buttons(assay, search_channel=search_channel)
+    return out._valid
 
 
 def reference_mrbles_intensities(roi, fg, bg, channel_names, channels, promote=None):

@@ -67,3 +67,30 @@ def filter_expression_valid(roi: np.ndarray, fg: np.ndarray, bg: np.ndarray, val
             upper = min_contrast
         expressed |= (fgm - bgm > upper)[:, None]                     # :35 (broadcast over time)
     return valid & expressed
+
+
+def filter_leaky_valid(roi: np.ndarray, fg: np.ndarray, bg: np.ndarray, valid: np.ndarray, tag: np.ndarray,
+                       mark_row: np.ndarray, channels) -> np.ndarray:
+    """filter.py:65-94: a tagged marker next (in stacked mark order) to an untagged ("" tag) one
+    stays valid only if that blank neighbour is "empty": its fg-bg median contrast at time 0 is
+    below 5 standard deviations of all pairwise background differences.  Neighbours are i-1 (when
+    the marker's row > 0) and i+1 (when its row < max row), exactly as the reference indexes them.
+    valid (M,T) bool, tag (M,) str, mark_row (M,) int; channels = channel indices."""
+    valid = valid.copy()
+    m = roi.shape[0]
+    for c in channels:
+        r0 = roi[:, c : c + 1, :1]
+        bgm = masked_median(r0, bg[:, :1])[:, 0, 0]
+        fgm = masked_median(r0, fg[:, :1])[:, 0, 0]
+        diffs = bgm[:, np.newaxis] - bgm[np.newaxis, :]              # :76-79
+        offdiag = np.ones_like(diffs, dtype=bool) & (~np.eye(len(diffs), dtype=bool))
+        upper = 5 * diffs[offdiag].std()                              # :82
+        empty = fgm - bgm < upper                                     # :84
+        for i in range(m):                                            # :85-92
+            if tag[i] == "":
+                continue
+            if mark_row[i] > 0 and tag[i - 1] == "":
+                valid[i] &= empty[i - 1]
+            if mark_row[i] < mark_row.max() and tag[i + 1] == "":
+                valid[i] &= empty[i + 1]
+    return valid

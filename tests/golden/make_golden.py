@@ -215,6 +215,7 @@ def golden_filter_expression():
     for i in range(0, m, 3):
         roi[i][..., fg0] += np.uint16(50 + i)
     roi[4, 1][..., fg0] += 3000
+    roi[13, 2][..., fg0] += 2000
     fg[7] = False          # empty foreground -> NaN median -> comparison False
     valid = rng.random((m, t)) < 0.9
     out = {"roi": roi, "fg": fg, "bg": bg, "valid": valid, "channels": np.array(["a", "b", "c"])}
@@ -234,6 +235,18 @@ def golden_filter_expression():
     out["intensities_f32"] = reference_mrbles_intensities(roi, fg, bg, ["a", "b", "c"], ["c", "a"])
     out["intensities_f64"] = reference_mrbles_intensities(roi, fg, bg, ["a", "b", "c"], ["c", "a"], np.float64)
     assert out["intensities_f32"].dtype == np.float32 and out["intensities_f64"].dtype == np.float64
+    # filter_leaky (filter.py:65-94) on the same ROIs laid out as a 12 x 4 chip, every fourth
+    # marker blank (some of them bright, one only in channel c); the reference's own function, both promotions
+    from oracle._refload import reference_filter_leaky
+
+    mark_row = np.repeat(np.arange(12), 4)
+    tag = np.array(["" if i % 4 == 1 else f"m{i}" for i in range(m)])
+    out["tag"], out["mark_row"] = tag, mark_row
+    for k, sc in enumerate([None, "b", ["c", "a"]]):
+        got = reference_filter_leaky(roi, fg, bg, valid, ["a", "b", "c"], tag, mark_row, sc)
+        assert np.array_equal(got, reference_filter_leaky(roi, fg, bg, valid, ["a", "b", "c"], tag, mark_row, sc, np.float64))
+        out[f"leaky{k}__valid"] = got
+        out[f"leaky{k}__search"] = np.array([] if sc is None else np.atleast_1d(sc))
     np.savez_compressed(os.path.join(HERE, "filter.npz"), **out)
 
 

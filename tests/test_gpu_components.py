@@ -259,3 +259,23 @@ def test_mrbles_intensities_golden_from_reference_expression(cuda_device, golden
     np.testing.assert_allclose(got, g["intensities_f64"], rtol=1e-12, atol=1e-10)
     np.testing.assert_allclose(got, g["intensities_f32"], rtol=0, atol=1e-5 * 500.0)
     assert np.isnan(got[7]).all()
+
+
+def test_filter_leaky_golden_from_reference_source(cuda_device, golden):
+    """GPU medians + the reference's neighbour logic against the outputs of the reference's own
+    filter_leaky_buttons (filter.py:65-94) executed in place (tests/golden/filter.npz)."""
+    from magnify_b200.components import filter_leaky
+    from magnify_b200.dataset import Assay
+
+    g = golden("filter")
+    names = [str(v) for v in g["channels"]]
+    for k in range(3):
+        search = [str(v) for v in g[f"leaky{k}__search"]] or None
+        assay = Assay({"roi": (("mark", "channel", "time", "roi_y", "roi_x"), g["roi"])},
+                      coords={"channel": (("channel",), np.array(names)),
+                              "fg": (("mark", "time", "roi_y", "roi_x"), g["fg"]),
+                              "bg": (("mark", "time", "roi_y", "roi_x"), g["bg"]),
+                              "tag": (("mark",), g["tag"]), "mark_row": (("mark",), g["mark_row"]),
+                              "valid": (("mark", "time"), g["valid"])})
+        out = filter_leaky(assay, search_channel=search)
+        np.testing.assert_array_equal(out.valid.values, g[f"leaky{k}__valid"], err_msg=f"case {k}")

@@ -287,3 +287,19 @@ def test_mrbles_intensities_golden_from_reference_expression(golden):
     assert np.isnan(got[7]).all()                       # empty foreground
     mean_scale = float(np.nanmax(red.masked_stats(g["roi"][:, idx, :1], g["fg"][:, :1], g["bg"][:, :1])[..., 4]))
     np.testing.assert_allclose(got, g["intensities_f32"], rtol=0, atol=1e-5 * mean_scale)
+
+
+def test_filter_leaky_golden_from_reference_source(golden):
+    """filter.py:65-94 (`filter_leaky_buttons`) executed in place -> leaky* entries of filter.npz."""
+    from oracle._refload import reference_filter_leaky
+
+    g = golden("filter")
+    names = [str(v) for v in g["channels"]]
+    for k in range(3):
+        search = [str(v) for v in g[f"leaky{k}__search"]] or None
+        idx = list(range(len(names))) if search is None else [names.index(s) for s in search]
+        got = red.filter_leaky_valid(g["roi"], g["fg"], g["bg"], g["valid"], g["tag"], g["mark_row"], idx)
+        np.testing.assert_array_equal(got, g[f"leaky{k}__valid"])
+        ref = reference_filter_leaky(g["roi"], g["fg"], g["bg"], g["valid"], names, g["tag"], g["mark_row"], search)
+        if ref is not None:   # build container: the reference's own function again
+            np.testing.assert_array_equal(ref, g[f"leaky{k}__valid"])
