@@ -33,12 +33,14 @@
 extern "C" {
 #endif
 
-#define MGB_ABI_VERSION 3
+#define MGB_ABI_VERSION 4
 
 #define MGB_OK 0
 #define MGB_EINVAL (-1)      /* bad argument (null pointer, negative size, bad itemsize ...) */
 #define MGB_EALIGN (-2)      /* pointer / pitch does not meet the alignment a fast path needs */
 #define MGB_EUNSUPPORTED (-3) /* shape or dtype outside what this build implements */
+#define MGB_EIO (-4)         /* a file could not be opened or read (tiff staging) */
+#define MGB_EFORMAT (-5)     /* not a TIFF / BigTIFF file, or its directory is inconsistent */
 
 /* dtype codes for the generic (any-dtype) entry points */
 #define MGB_U8 0
@@ -193,6 +195,33 @@ int mgb_bead_labels(const int32_t* beads, int64_t M, int64_t H, int64_t W, const
 /* fg[m] = (labels[box m] == m), bg[m] = (labels[box m] == -1)  (find.py:580-584); boxes (M,2). */
 int mgb_bead_masks(const int32_t* labels, int64_t H, int64_t W, const int32_t* boxes, int64_t M,
                    int L, uint8_t* fg, uint8_t* bg, int32_t* counts, void* stream);
+
+/* ---- S / N2: TIFF page staging, reference src/magnify/reader.py:265-279 ---------------------
+ * HOST-ONLY entry points (no kernel is launched): the reference's lazy tile loader reads one
+ * TIFF page per dask chunk with `tifffile.TiffFile(f).pages[i].asarray()`.  These read the same
+ * page bytes -- classic TIFF and BigTIFF, either byte order, any strip layout, Compression = 1
+ * only -- straight into caller-owned host memory (normally a pinned staging buffer that the next
+ * cudaMemcpyAsync consumes), byte-swapped to host order.  A page is returned as `height` rows of
+ * `width * samples` items in file order, i.e. the (tile_y, tile_x) array `asarray()` gives.
+ *
+ * mgb_tiff_open parses the whole main IFD chain once.  info (12 x int64): width, height,
+ * bits per sample, samples per pixel, SampleFormat (1 uint, 2 int, 3 float), Compression,
+ * page bytes, support status (MGB_OK or the MGB_E* code a read would return), ImageDescription
+ * length in bytes, strip count, 1 if BigTIFF, 1 if big-endian. */
+int mgb_tiff_open(const char* host_path, void** host_handle);
+int mgb_tiff_close(void* host_handle);
+int mgb_tiff_page_count(const void* host_handle, int64_t* host_count);
+int mgb_tiff_page_info(const void* host_handle, int64_t page, int64_t* host_info);
+/* Raw ImageDescription bytes (tag 270: OME-XML / Micro-Manager metadata, reader.py:216-222). */
+int mgb_tiff_description(const void* host_handle, int64_t page, char* host_buf, int64_t capacity);
+/* Pages host_pages[0..n) of one open file into host_dst + i*dst_stride_bytes, `threads` readers. */
+int mgb_tiff_read_pages(const void* host_handle, const int64_t* host_pages, int64_t n_pages, void* host_dst,
+                        int64_t dst_stride_bytes, int threads);
+/* Page `page` of each of n_files files (one file per (channel,time,row,col) index, the layout
+ * reader.py:173-186 assembles from the path pattern) into host_dst + i*dst_stride_bytes.  Every
+ * page must be width x height, single-sample, `bits` wide, else MGB_EFORMAT. */
+int mgb_tiff_read_files(const char* const* host_paths, int64_t n_files, int64_t page, int64_t width, int64_t height,
+                        int bits, void* host_dst, int64_t dst_stride_bytes, int threads);
 
 #ifdef __cplusplus
 }

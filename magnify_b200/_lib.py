@@ -13,7 +13,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libmagnify_b200.so")
 
 MGB_U8, MGB_U16, MGB_F32, MGB_F64 = 0, 1, 2, 3
-MGB_EINVAL, MGB_EALIGN, MGB_EUNSUPPORTED = -1, -2, -3
+MGB_EINVAL, MGB_EALIGN, MGB_EUNSUPPORTED, MGB_EIO, MGB_EFORMAT = -1, -2, -3, -4, -5
 
 
 class MagnifyB200Error(RuntimeError):
@@ -52,6 +52,13 @@ SIGNATURES = {
     "mgb_disc_halfwidths": [c_int, POINTER(ctypes.c_int32)],
     "mgb_bead_labels": [_P, _I64, _I64, _I64, _P, c_int, _P, _P],
     "mgb_bead_masks": [_P, _I64, _I64, _P, _I64, c_int, _P, _P, _P, _P],
+    "mgb_tiff_open": [c_char_p, POINTER(c_void_p)],
+    "mgb_tiff_close": [_P],
+    "mgb_tiff_page_count": [_P, POINTER(c_int64)],
+    "mgb_tiff_page_info": [_P, _I64, POINTER(c_int64)],
+    "mgb_tiff_description": [_P, _I64, c_char_p, _I64],
+    "mgb_tiff_read_pages": [_P, POINTER(c_int64), _I64, _P, _I64, c_int],
+    "mgb_tiff_read_files": [POINTER(c_char_p), _I64, _I64, _I64, _I64, c_int, _P, _I64, c_int],
 }
 _SPECIAL_RESTYPE = {"mgb_error_string": c_char_p, "mgb_launch_count": c_int64}
 _NO_STATUS = {"mgb_abi_version", "mgb_error_string", "mgb_sm_count", "mgb_launch_count", "mgb_set_tma_enabled", "mgb_set_stitch_variant", "mgb_set_gather_loader"}
@@ -74,7 +81,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.argtypes = argtypes
         fn.restype = _SPECIAL_RESTYPE.get(name, c_int)
-    if lib.mgb_abi_version() != 3:
+    if lib.mgb_abi_version() != 4:
         raise ImportError("libmagnify_b200.so ABI version mismatch; rebuild with `python -m magnify_b200.build --force`")
     _lib = lib
     return lib

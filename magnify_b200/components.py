@@ -55,14 +55,22 @@ def _tiles_to_device(assay, dev) -> torch.Tensor:
     tile = assay["tile"]
     if tuple(tile.dims) != TILE_DIMS:
         raise ValueError(f"tile must have dims {TILE_DIMS} (run standardize_format first), got {tuple(tile.dims)}")
+    values = getattr(tile, "values", None)
+    if hasattr(values, "blocks"):
+        # lazily read TIFF tiles (reader.TiffTiles): pages land in a pinned buffer, then HBM
+        host = torch.empty(tuple(values.shape), dtype=getattr(torch, str(values.dtype)), pin_memory=True)
+        values.read((), host.numpy())
+        return host.to(dev, non_blocking=True)
     return torch.from_numpy(np.ascontiguousarray(_to_numpy(tile))).to(dev)
 
 
 def _read_tiff(path) -> np.ndarray:
-    import tifffile  # same dependency the reference uses at preprocess.py:75-81
+    """Flat-field / dark-field image file (preprocess.py:75-81 reads it with tifffile): first page,
+    through the native uncompressed-TIFF reader."""
+    from . import reader
 
-    with tifffile.TiffFile(os.fspath(path)) as tif:
-        return tif.asarray()
+    with reader.TiffFile(os.fspath(path)) as tif:
+        return tif.asarray(0)
 
 
 # ---------------------------------------------------------------------------------------------

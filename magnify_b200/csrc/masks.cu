@@ -205,7 +205,9 @@ const char* mgb_error_string(int code) {
     case MGB_OK: return "ok";
     case MGB_EINVAL: return "invalid argument";
     case MGB_EALIGN: return "pointer or pitch not aligned for the vectorised path";
-    case MGB_EUNSUPPORTED: return "shape or dtype not supported by this build";
+    case MGB_EUNSUPPORTED: return "shape, dtype or file encoding not supported by this build";
+    case MGB_EIO: return "file could not be opened or read";
+    case MGB_EFORMAT: return "not a TIFF/BigTIFF file or inconsistent directory";
     default: break;
   }
   if (code > 0) return cudaGetErrorString((cudaError_t)code);

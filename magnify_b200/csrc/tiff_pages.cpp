@@ -1,0 +1,404 @@
+// Uncompressed TIFF / BigTIFF page reads straight into caller-owned (pinned) host buffers.
+//
+// Replaces the per-page `tifffile.TiffFile(...).pages[i].asarray()` of the reference's lazy tile
+// loader (src/magnify/reader.py:265-279, one dask chunk = one TIFF page) on the staging side of
+// the hot path.  Host code only: the IFD chain is parsed once per
+// file, strips are coalesced into as few pread(2) calls as possible and land directly in the
+// destination (a pinned staging buffer), pages are spread over a small thread pool.  Layout
+// knowledge follows the TIFF 6.0 baseline specification and the BigTIFF extension (magic 43,
+// 8-byte offsets); only Compression = 1 (none) is decoded -- anything else is reported, never
+// silently mis-read.
+#include "magnify_b200.h"
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cerrno>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+struct Page {
+  int64_t width = 0, height = 0;
+  int bits = 1, samples = 1, sample_format = 1, compression = 1, planar = 1, predictor = 1;
+  int photometric = 1;
+  int64_t rows_per_strip = -1;
+  bool tiled = false;
+  int64_t subfile_type = 0;
+  std::vector<uint64_t> offsets, counts;
+  uint64_t desc_offset = 0, desc_len = 0;   // ImageDescription (tag 270) bytes in the file
+  int64_t row_bytes() const { return (width * samples * bits + 7) / 8; }
+  int64_t data_bytes() const { return row_bytes() * height; }
+};
+
+struct TiffFile {
+  int fd = -1;
+  bool big = false, swap = false;   // BigTIFF; file byte order != host byte order
+  uint64_t file_size = 0;
+  std::vector<Page> pages;
+  int error = 0;
+};
+
+bool host_is_little() {
+  const uint16_t one = 1;
+  return *reinterpret_cast<const uint8_t*>(&one) == 1;
+}
+
+bool pread_all(int fd, void* dst, uint64_t n, uint64_t off) {
+  uint8_t* p = static_cast<uint8_t*>(dst);
+  while (n > 0) {
+    ssize_t got = ::pread(fd, p, n, static_cast<off_t>(off));
+    if (got < 0) {
+      if (errno == EINTR) continue;
+      return false;
+    }
+    if (got == 0) return false;   // short file
+    p += got;
+    off += static_cast<uint64_t>(got);
+    n -= static_cast<uint64_t>(got);
+  }
+  return true;
+}
+
+template <typename T>
+T load(const uint8_t* p, bool swap) {
+  T v;
+  std::memcpy(&v, p, sizeof(T));
+  if (swap) {
+    uint8_t* b = reinterpret_cast<uint8_t*>(&v);
+    std::reverse(b, b + sizeof(T));
+  }
+  return v;
+}
+
+int type_size(int type) {
+  switch (type) {
+    case 1: case 2: case 6: case 7: return 1;
+    case 3: case 8: return 2;
+    case 4: case 9: case 11: case 13: return 4;
+    case 5: case 10: case 12: case 16: case 17: case 18: return 8;
+    default: return 0;
+  }
+}
+
+// Integer value `i` of an entry's value array (types BYTE/SHORT/LONG/LONG8 and signed kin).
+uint64_t value_at(const uint8_t* p, int type, uint64_t i, bool swap) {
+  switch (type) {
+    case 1: case 6: case 7: return p[i];
+    case 3: case 8: return load<uint16_t>(p + 2 * i, swap);
+    case 4: case 9: case 13: return load<uint32_t>(p + 4 * i, swap);
+    case 16: case 17: case 18: return load<uint64_t>(p + 8 * i, swap);
+    default: return 0;
+  }
+}
+
+// Parse the IFD at `off`; returns the offset of the next IFD (0 = end) or UINT64_MAX on error.
+uint64_t parse_ifd(TiffFile& f, uint64_t off, Page& page) {
+  const uint64_t bad = UINT64_MAX;
+  const int count_bytes = f.big ? 8 : 2, entry_bytes = f.big ? 20 : 12, next_bytes = f.big ? 8 : 4;
+  uint8_t head[8];
+  if (off + count_bytes > f.file_size || !pread_all(f.fd, head, count_bytes, off)) return bad;
+  const uint64_t n = f.big ? load<uint64_t>(head, f.swap) : load<uint16_t>(head, f.swap);
+  if (n == 0 || n > 65536) return bad;
+  std::vector<uint8_t> buf(n * entry_bytes + next_bytes);
+  if (off + count_bytes + buf.size() > f.file_size ||
+      !pread_all(f.fd, buf.data(), buf.size(), off + count_bytes))
+    return bad;
+  std::vector<uint8_t> ext;
+  for (uint64_t e = 0; e < n; ++e) {
+    const uint8_t* p = buf.data() + e * entry_bytes;
+    const int tag = load<uint16_t>(p, f.swap), type = load<uint16_t>(p + 2, f.swap);
+    const uint64_t count = f.big ? load<uint64_t>(p + 4, f.swap) : load<uint32_t>(p + 4, f.swap);
+    const uint8_t* inl = p + (f.big ? 12 : 8);
+    const uint64_t inline_cap = f.big ? 8 : 4;
+    const int ts = type_size(type);
+    if (ts == 0) continue;   // unknown field type: skip the field (TIFF 6.0 p.16)
+    if (count > (UINT64_MAX >> 4)) return bad;
+    const uint64_t bytes = count * ts;
+    const bool inl_value = bytes <= inline_cap;
+    const uint64_t where = inl_value ? 0 : (f.big ? load<uint64_t>(inl, f.swap) : load<uint32_t>(inl, f.swap));
+    auto fetch = [&]() -> const uint8_t* {
+      if (inl_value) return inl;
+      if (where + bytes > f.file_size) return nullptr;
+      ext.resize(bytes);
+      return pread_all(f.fd, ext.data(), bytes, where) ? ext.data() : nullptr;
+    };
+    auto scalar = [&](uint64_t& out) -> bool {
+      const uint8_t* v = fetch();
+      if (!v || count < 1) return false;
+      out = value_at(v, type, 0, f.swap);
+      return true;
+    };
+    uint64_t v = 0;
+    switch (tag) {
+      case 254: if (!scalar(v)) return bad; page.subfile_type = static_cast<int64_t>(v); break;
+      case 256: if (!scalar(v)) return bad; page.width = static_cast<int64_t>(v); break;
+      case 257: if (!scalar(v)) return bad; page.height = static_cast<int64_t>(v); break;
+      case 258: {   // BitsPerSample: one value per sample, all equal for the pages handled here
+        const uint8_t* a = fetch();
+        if (!a || count < 1) return bad;
+        page.bits = static_cast<int>(value_at(a, type, 0, f.swap));
+        for (uint64_t i = 1; i < count; ++i)
+          if (static_cast<int>(value_at(a, type, i, f.swap)) != page.bits) page.compression = -1;
+        break;
+      }
+      case 259: if (!scalar(v)) return bad; if (page.compression != -1) page.compression = static_cast<int>(v); break;
+      case 262: if (!scalar(v)) return bad; page.photometric = static_cast<int>(v); break;
+      case 270:
+        page.desc_len = bytes;
+        if (inl_value) {   // a description of <= 4 (8) bytes lives inside the entry itself
+          page.desc_offset = off + count_bytes + e * entry_bytes + (f.big ? 12 : 8);
+        } else {
+          page.desc_offset = where;
+        }
+        break;
+      case 273: case 324: case 279: case 325: {
+        const uint8_t* a = fetch();
+        if (!a) return bad;
+        std::vector<uint64_t>& dst = (tag == 273 || tag == 324) ? page.offsets : page.counts;
+        dst.resize(count);
+        for (uint64_t i = 0; i < count; ++i) dst[i] = value_at(a, type, i, f.swap);
+        if (tag == 324 || tag == 325) page.tiled = true;
+        break;
+      }
+      case 277: if (!scalar(v)) return bad; page.samples = static_cast<int>(v); break;
+      case 278: if (!scalar(v)) return bad; page.rows_per_strip = static_cast<int64_t>(v); break;
+      case 284: if (!scalar(v)) return bad; page.planar = static_cast<int>(v); break;
+      case 317: if (!scalar(v)) return bad; page.predictor = static_cast<int>(v); break;
+      case 322: case 323: page.tiled = true; break;
+      case 339: if (!scalar(v)) return bad; page.sample_format = static_cast<int>(v); break;
+      default: break;
+    }
+  }
+  const uint8_t* nx = buf.data() + n * entry_bytes;
+  return f.big ? load<uint64_t>(nx, f.swap) : load<uint32_t>(nx, f.swap);
+}
+
+int open_file(const char* path, TiffFile& f, int64_t max_pages) {
+  f.fd = ::open(path, O_RDONLY | O_CLOEXEC);
+  if (f.fd < 0) return MGB_EIO;
+  struct stat st;
+  if (::fstat(f.fd, &st) != 0) return MGB_EIO;
+  f.file_size = static_cast<uint64_t>(st.st_size);
+  uint8_t h[16];
+  if (f.file_size < 8 || !pread_all(f.fd, h, 8, 0)) return MGB_EFORMAT;
+  bool little;
+  if (h[0] == 'I' && h[1] == 'I') little = true;
+  else if (h[0] == 'M' && h[1] == 'M') little = false;
+  else return MGB_EFORMAT;
+  f.swap = little != host_is_little();
+  const uint16_t magic = load<uint16_t>(h + 2, f.swap);
+  uint64_t off;
+  if (magic == 42) {
+    f.big = false;
+    off = load<uint32_t>(h + 4, f.swap);
+  } else if (magic == 43) {
+    f.big = true;
+    if (f.file_size < 16 || !pread_all(f.fd, h, 16, 0)) return MGB_EFORMAT;
+    if (load<uint16_t>(h + 4, f.swap) != 8 || load<uint16_t>(h + 6, f.swap) != 0) return MGB_EFORMAT;
+    off = load<uint64_t>(h + 8, f.swap);
+  } else {
+    return MGB_EFORMAT;
+  }
+  // walk the main IFD chain (one page per IFD, like tifffile's `pages`); a cycle ends the walk
+  std::vector<uint64_t> seen;
+  while (off != 0 && (max_pages < 0 || static_cast<int64_t>(f.pages.size()) < max_pages)) {
+    if (std::find(seen.begin(), seen.end(), off) != seen.end()) break;
+    seen.push_back(off);
+    Page page;
+    const uint64_t next = parse_ifd(f, off, page);
+    if (next == UINT64_MAX) return MGB_EFORMAT;
+    if (page.rows_per_strip <= 0 || page.rows_per_strip > page.height) page.rows_per_strip = page.height;
+    f.pages.push_back(std::move(page));
+    off = next;
+  }
+  return f.pages.empty() ? MGB_EFORMAT : MGB_OK;
+}
+
+// Why a page cannot be decoded by this reader (MGB_OK when it can).
+int page_supported(const Page& p) {
+  if (p.compression != 1 || p.predictor != 1) return MGB_EUNSUPPORTED;
+  if (p.tiled || p.width <= 0 || p.height <= 0) return MGB_EUNSUPPORTED;
+  if (p.bits != 8 && p.bits != 16 && p.bits != 32 && p.bits != 64) return MGB_EUNSUPPORTED;
+  if (p.samples != 1 && p.planar != 1) return MGB_EUNSUPPORTED;
+  if (p.offsets.empty() || p.offsets.size() != p.counts.size()) return MGB_EFORMAT;
+  const int64_t strips = (p.height + p.rows_per_strip - 1) / p.rows_per_strip;
+  if (static_cast<int64_t>(p.offsets.size()) != strips) return MGB_EFORMAT;
+  return MGB_OK;
+}
+
+void swap_inplace(uint8_t* p, int64_t bytes, int itemsize) {
+  if (itemsize == 2) {
+    uint16_t* q = reinterpret_cast<uint16_t*>(p);
+    for (int64_t i = 0; i < bytes / 2; ++i) q[i] = static_cast<uint16_t>((q[i] >> 8) | (q[i] << 8));
+  } else if (itemsize == 4) {
+    uint32_t* q = reinterpret_cast<uint32_t*>(p);
+    for (int64_t i = 0; i < bytes / 4; ++i) q[i] = __builtin_bswap32(q[i]);
+  } else if (itemsize == 8) {
+    uint64_t* q = reinterpret_cast<uint64_t*>(p);
+    for (int64_t i = 0; i < bytes / 8; ++i) q[i] = __builtin_bswap64(q[i]);
+  }
+}
+
+int read_page(const TiffFile& f, const Page& p, void* dst, int64_t dst_bytes) {
+  const int ok = page_supported(p);
+  if (ok != MGB_OK) return ok;
+  const int64_t row_bytes = p.row_bytes(), total = p.data_bytes();
+  if (dst_bytes < total) return MGB_EINVAL;
+  uint8_t* out = static_cast<uint8_t*>(dst);
+  const int64_t strips = static_cast<int64_t>(p.offsets.size());
+  int64_t s = 0;
+  while (s < strips) {
+    // coalesce strips that are back to back in the file and full-sized into one pread
+    const int64_t first = s;
+    const uint64_t start = p.offsets[s];
+    uint64_t run = 0;
+    while (s < strips) {
+      const int64_t rows = std::min<int64_t>(p.rows_per_strip, p.height - s * p.rows_per_strip);
+      const uint64_t want = static_cast<uint64_t>(rows * row_bytes);
+      if (p.counts[s] < want) return MGB_EFORMAT;   // truncated strip
+      if (p.offsets[s] != start + run) break;
+      run += want;
+      ++s;
+      if (p.counts[s - 1] != want) break;   // padded strip: the next one cannot be contiguous data
+    }
+    if (start + run > f.file_size) return MGB_EFORMAT;
+    if (!pread_all(f.fd, out + first * p.rows_per_strip * row_bytes, run, start)) return MGB_EIO;
+  }
+  if (f.swap && p.bits > 8) swap_inplace(out, total, p.bits / 8);
+  return MGB_OK;
+}
+
+template <typename Fn>
+int parallel_for(int64_t n, int threads, Fn fn) {
+  std::atomic<int64_t> next{0};
+  std::atomic<int> status{MGB_OK};
+  auto worker = [&]() {
+    for (;;) {
+      const int64_t i = next.fetch_add(1);
+      if (i >= n || status.load() != MGB_OK) return;
+      const int rc = fn(i);
+      if (rc != MGB_OK) {
+        int expected = MGB_OK;
+        status.compare_exchange_strong(expected, rc);
+      }
+    }
+  };
+  const int nt = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(threads, n)));
+  if (nt == 1) {
+    worker();
+  } else {
+    std::vector<std::thread> pool;
+    pool.reserve(nt);
+    for (int t = 0; t < nt; ++t) pool.emplace_back(worker);
+    for (auto& t : pool) t.join();
+  }
+  return status.load();
+}
+
+}  // namespace
+
+extern "C" {
+
+int mgb_tiff_open(const char* host_path, void** host_handle) {
+  if (!host_path || !host_handle) return MGB_EINVAL;
+  TiffFile* f = new TiffFile();
+  const int rc = open_file(host_path, *f, -1);
+  if (rc != MGB_OK) {
+    if (f->fd >= 0) ::close(f->fd);
+    delete f;
+    *host_handle = nullptr;
+    return rc;
+  }
+  *host_handle = f;
+  return MGB_OK;
+}
+
+int mgb_tiff_close(void* host_handle) {
+  TiffFile* f = static_cast<TiffFile*>(host_handle);
+  if (!f) return MGB_EINVAL;
+  if (f->fd >= 0) ::close(f->fd);
+  delete f;
+  return MGB_OK;
+}
+
+int mgb_tiff_page_count(const void* host_handle, int64_t* host_count) {
+  const TiffFile* f = static_cast<const TiffFile*>(host_handle);
+  if (!f || !host_count) return MGB_EINVAL;
+  *host_count = static_cast<int64_t>(f->pages.size());
+  return MGB_OK;
+}
+
+int mgb_tiff_page_info(const void* host_handle, int64_t page, int64_t* host_info) {
+  const TiffFile* f = static_cast<const TiffFile*>(host_handle);
+  if (!f || !host_info || page < 0 || page >= static_cast<int64_t>(f->pages.size())) return MGB_EINVAL;
+  const Page& p = f->pages[page];
+  host_info[0] = p.width;
+  host_info[1] = p.height;
+  host_info[2] = p.bits;
+  host_info[3] = p.samples;
+  host_info[4] = p.sample_format;
+  host_info[5] = p.compression;
+  host_info[6] = p.data_bytes();
+  host_info[7] = page_supported(p);
+  host_info[8] = static_cast<int64_t>(p.desc_len);
+  host_info[9] = static_cast<int64_t>(p.offsets.size());
+  host_info[10] = f->big ? 1 : 0;
+  host_info[11] = f->swap == host_is_little() ? 1 : 0;   // 1 = big-endian file
+  return MGB_OK;
+}
+
+int mgb_tiff_description(const void* host_handle, int64_t page, char* host_buf, int64_t capacity) {
+  const TiffFile* f = static_cast<const TiffFile*>(host_handle);
+  if (!f || !host_buf || page < 0 || page >= static_cast<int64_t>(f->pages.size())) return MGB_EINVAL;
+  const Page& p = f->pages[page];
+  if (capacity < static_cast<int64_t>(p.desc_len)) return MGB_EINVAL;
+  if (p.desc_len == 0) return MGB_OK;
+  if (p.desc_offset + p.desc_len > f->file_size) return MGB_EFORMAT;
+  return pread_all(f->fd, host_buf, p.desc_len, p.desc_offset) ? MGB_OK : MGB_EIO;
+}
+
+int mgb_tiff_read_pages(const void* host_handle, const int64_t* host_pages, int64_t n_pages, void* host_dst,
+                        int64_t dst_stride_bytes, int threads) {
+  const TiffFile* f = static_cast<const TiffFile*>(host_handle);
+  if (!f || !host_pages || !host_dst || n_pages < 0 || dst_stride_bytes < 0) return MGB_EINVAL;
+  for (int64_t i = 0; i < n_pages; ++i) {
+    if (host_pages[i] < 0 || host_pages[i] >= static_cast<int64_t>(f->pages.size())) return MGB_EINVAL;
+    if (f->pages[host_pages[i]].data_bytes() > dst_stride_bytes) return MGB_EINVAL;
+  }
+  uint8_t* dst = static_cast<uint8_t*>(host_dst);
+  return parallel_for(n_pages, threads, [&](int64_t i) {
+    return read_page(*f, f->pages[host_pages[i]], dst + i * dst_stride_bytes, dst_stride_bytes);
+  });
+}
+
+int mgb_tiff_read_files(const char* const* host_paths, int64_t n_files, int64_t page, int64_t width, int64_t height,
+                        int bits, void* host_dst, int64_t dst_stride_bytes, int threads) {
+  if (!host_paths || !host_dst || n_files < 0 || page < 0 || dst_stride_bytes < 0) return MGB_EINVAL;
+  uint8_t* dst = static_cast<uint8_t*>(host_dst);
+  return parallel_for(n_files, threads, [&](int64_t i) {
+    TiffFile f;
+    int rc = host_paths[i] ? open_file(host_paths[i], f, page + 1) : MGB_EINVAL;
+    if (rc == MGB_OK) {
+      if (page >= static_cast<int64_t>(f.pages.size())) {
+        rc = MGB_EINVAL;
+      } else {
+        const Page& p = f.pages[page];
+        // every file of one acquisition must hold pages of the announced geometry
+        if (p.width != width || p.height != height || p.bits != bits || p.samples != 1) rc = MGB_EFORMAT;
+        else rc = read_page(f, p, dst + i * dst_stride_bytes, dst_stride_bytes);
+      }
+    }
+    if (f.fd >= 0) ::close(f.fd);
+    return rc;
+  });
+}
+
+}  // extern "C"

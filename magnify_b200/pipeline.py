@@ -280,8 +280,9 @@ class ChunkStager:
     pinned memory (the reference's per-page dask chunks, reader.py:265-292, or any iterable of
     NumPy blocks).
 
-    `chunks` yields `((channel, time), ndarray)` with ndarray shaped (R, Cc, H, W) -- one
-    (channel, timepoint) block of the tile stack, in any order.  Each block is copied into one of
+    `chunks` yields `((channel, time), block)` with block an ndarray shaped (R, Cc, H, W) -- one
+    (channel, timepoint) block of the tile stack, in any order -- or a callable `fill(dst)` that
+    writes the block into the pinned slot itself (`reader.TiffTiles.blocks()`).  Each block is copied into one of
     `depth` pinned staging buffers by a small thread pool (NumPy copies release the GIL, so the
     pageable->pinned memcpy of block k+1 overlaps the PCIe copy of block k) and then sent to its
     slot of the device tile stack on the copy stream; flat-field pass 1 runs on the compute stream
@@ -301,6 +302,11 @@ class ChunkStager:
 
     def _fill(self, slot: int, block) -> None:
         dst = self.staging[slot].numpy()
+        if callable(block):
+            # a reader that writes the block itself (reader.TiffTiles.blocks: native page reads
+            # land in the pinned slot, no pageable intermediate)
+            block(dst)
+            return
         src = np.asarray(block)
         if src.shape != dst.shape:
             raise ValueError(f"chunk has shape {src.shape}, expected {dst.shape}")

@@ -812,3 +812,50 @@ def reference_mrbles_intensities(roi, fg, bg, channel_names, channels, promote=N
     scope = {"assay": type("A", (), {"roi": arr})(), "channels": list(channels)}
     exec(code, scope)
     return scope["intensities"]
+
+
+# ---------------------------------------------------------------------------------------------
+# reader.py:80-160 `extract_paths` -- pure Python (re / glob / fnmatch), loaded in place with stub
+# modules for the imports the function does not use (bs4, dask, tifffile, xarray).
+# ---------------------------------------------------------------------------------------------
+_cached_reader = None
+
+
+def load_reference_reader():
+    global _cached_reader
+    if _cached_reader is not None:
+        return _cached_reader
+    path = os.path.join(REFERENCE_ROOT, "src", "magnify", "reader.py")
+    utils = load_reference_utils()
+    if not os.path.exists(path) or utils is None:
+        return None
+    xr = types.ModuleType("xarray")
+    xr.Dataset = type("Dataset", (), {})
+    xr.DataArray = type("DataArray", (), {})
+    dask = types.ModuleType("dask")
+    da = types.ModuleType("dask.array")
+    dask.array = da
+    pkg = types.ModuleType("magnify")
+    pkg.__path__ = []
+    registry = types.ModuleType("magnify.registry")
+    registry.readers = type("Readers", (), {"register": staticmethod(lambda name: (lambda f: f))})()
+    pkg.registry, pkg.utils = registry, utils
+    stubs = {"xarray": xr, "dask": dask, "dask.array": da, "bs4": types.ModuleType("bs4"),
+             "tifffile": types.ModuleType("tifffile"), "magnify": pkg, "magnify.registry": registry,
+             "magnify.utils": utils}
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        spec = importlib.util.spec_from_file_location("_magnify_reference_reader", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    except Exception:
+        mod = None
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _cached_reader = mod
+    return mod

@@ -137,3 +137,51 @@ def test_chunk_stager_from_pageable_blocks(cuda_device):
     with pytest.raises(ValueError):
         stager2 = pipeline.ChunkStager(runner, depth=1, threads=1)
         stager2.feed(iter([((0, 0), np.zeros((1, 1, 8, 8), np.uint16))]))
+
+
+def test_tiff_tiles_staged_through_pinned_ring(cuda_device, tmp_path):
+    """Reader -> staging: one TIFF file per (channel, time, row, col),
+    pages read natively into the pinned ring slots, then the same flat-field + stitch + gather as
+    the device-resident run; also the `flatfield_correct` / `stitch` components on the lazy stack."""
+    import os
+
+    from magnify_b200 import pipeline, reader, synth
+    from magnify_b200.components import FlatfieldStitcher
+    from tiffgen import write_tiff
+
+    case = synth.chip_case(c=2, t=3, r=2, cc=4, h=256, w=256, overlap=22, rows=3, cols=3, row_dist=126.1,
+                           col_dist=250.0, seed=9, device=cuda_device)
+    tiles_np = case.tiles.cpu().numpy()
+    c, t, r, cc, h, w = tiles_np.shape
+    for idx in np.ndindex(c, t, r, cc):
+        write_tiff(os.path.join(tmp_path, f"chip_ch{idx[0]}_2024010{idx[1] + 1}-000000_{idx[2]}_{idx[3]}.tif"),
+                   [tiles_np[idx]], rows_per_strip=[None, 64, 100][idx[3] % 3], big=bool(idx[2] % 2))
+    (xp,) = list(reader.Reader(threads=4)(os.path.join(tmp_path, "chip_(channel)_(time)_(row)_(col).tif")))
+    tiles = xp["tile"].values
+    assert tiles.shape == tiles_np.shape
+
+    plan = pipeline.QuantifyPlan(case.tiles.shape, case.overlap, case.roi_length, case.flat, case.dark,
+                                 device=cuda_device)
+    plan.set_chip_markers(case.x, case.y, case.fg_radius, case.chamber_radius, case.max_button_radius)
+    ref = plan.run_device(case.tiles)
+    image_ref, roi_ref, stats_ref = ref.image.cpu(), ref.roi.cpu(), ref.stats.cpu()
+    runner = pipeline.HostStagedRunner(plan)
+    stager = pipeline.ChunkStager(runner, depth=2, threads=2)
+    image_h, roi_h, stats_h = runner.alloc_host_outputs()
+    assert stager.feed(tiles.blocks()) == c * t
+    runner.finish(image_h, roi_h, stats_h)
+    runner.synchronize()
+    stager.close()
+    assert torch.equal(image_h.view(torch.int16), image_ref.view(torch.int16))
+    assert torch.equal(roi_h.view(torch.int16), roi_ref.view(torch.int16))
+    assert torch.equal(stats_h, stats_ref)
+
+    # flat / dark given as TIFF files (preprocess.py:75-81), float64 pages
+    flat_np, dark_np = np.asarray(case.flat), np.asarray(case.dark)
+    if flat_np.ndim == 2:
+        flat_arg = write_tiff(os.path.join(tmp_path, "flat.tif"), [flat_np], byteorder=">")
+        dark_arg = write_tiff(os.path.join(tmp_path, "dark.tif"), [dark_np], big=True)
+    else:
+        flat_arg, dark_arg = flat_np, dark_np
+    out = FlatfieldStitcher(flat_arg, dark_arg, case.overlap, device=cuda_device)(xp)
+    np.testing.assert_array_equal(out.image.values, image_ref.numpy())

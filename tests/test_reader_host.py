@@ -1,0 +1,212 @@
+"""Host side of the TIFF staging row: the native page reader against
+the struct-level oracle and OpenCV's libtiff, the path-pattern language against the reference's
+own `extract_paths` run in place, and the assembly of the tile stack (reader.py:163-326).
+File I/O only -- nothing here launches a kernel, so it runs without a GPU."""
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from magnify_b200 import _lib, reader
+from oracle import tiff as ot
+from tiffgen import ome_xml, write_tiff
+
+
+# ---- pages -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("big", [False, True])
+@pytest.mark.parametrize("byteorder", ["<", ">"])
+def test_native_pages_match_oracle(tmp_path, big, byteorder):
+    rng = np.random.default_rng(0)
+    for dtype in (np.uint8, np.uint16, np.int16, np.uint32, np.float32, np.float64):
+        pages = [(rng.random((37, 53)) * 200).astype(dtype) for _ in range(4)]
+        for rps, scatter in ((None, False), (5, False), (16, True), (1, True)):
+            path = write_tiff(os.path.join(tmp_path, "a.tif"), pages, big=big, byteorder=byteorder, rows_per_strip=rps,
+                              scatter=scatter, pad_strips=3 if scatter else 0, description="hello")
+            with reader.TiffFile(path) as tif:
+                assert tif.num_pages == 4
+                info = tif.page_info(2)
+                assert info.dtype == np.dtype(dtype) and info.shape == (37, 53)
+                assert bool(info.bigtiff) == big and bool(info.big_endian) == (byteorder == ">")
+                got = tif.read_pages([3, 0, 2], threads=3)
+                for k, page in enumerate([3, 0, 2]):
+                    np.testing.assert_array_equal(got[k], ot.read_page(path, page))
+                    np.testing.assert_array_equal(got[k], pages[page])
+                assert tif.description(0) == b"hello" and tif.description(1) == b""
+
+
+def test_native_reads_libtiff_files_and_refuses_compression(tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(1)
+    pages = [rng.integers(0, 65535, (64, 96), dtype=np.uint16) for _ in range(3)]
+    multi = os.path.join(tmp_path, "m.tif")
+    assert cv2.imwritemulti(multi, pages, [cv2.IMWRITE_TIFF_COMPRESSION, 1])
+    with reader.TiffFile(multi) as tif:
+        np.testing.assert_array_equal(tif.read_pages([0, 1, 2]), np.stack(pages))
+    lzw = os.path.join(tmp_path, "lzw.tif")
+    assert cv2.imwrite(lzw, pages[0])
+    with reader.TiffFile(lzw) as tif:
+        assert tif.page_info(0).compression == 5 and tif.page_info(0).status == _lib.MGB_EUNSUPPORTED
+        with pytest.raises(_lib.MagnifyB200Error) as err:
+            tif.asarray(0)
+        assert err.value.code == _lib.MGB_EUNSUPPORTED
+
+
+def test_open_errors(tmp_path):
+    bad = os.path.join(tmp_path, "bad.tif")
+    open(bad, "wb").write(b"definitely not a tiff file")
+    with pytest.raises(_lib.MagnifyB200Error) as err:
+        reader.TiffFile(bad)
+    assert err.value.code == _lib.MGB_EFORMAT
+    with pytest.raises(_lib.MagnifyB200Error) as err:
+        reader.TiffFile(os.path.join(tmp_path, "missing.tif"))
+    assert err.value.code == _lib.MGB_EIO
+    # truncated pixel data: the directory is fine, the strip runs past the end of the file
+    page = np.arange(64 * 64, dtype=np.uint16).reshape(64, 64)
+    cut = write_tiff(os.path.join(tmp_path, "cut.tif"), [page])
+    raw = open(cut, "rb").read()
+    ifd = struct.unpack("<I", raw[4:8])[0]
+    # keep header + directory, drop half of the pixel bytes by rewriting them past EOF
+    with open(cut, "wb") as f:
+        f.write(raw[:8] + raw[8 + 4096:])
+    with pytest.raises(_lib.MagnifyB200Error):
+        with reader.TiffFile(cut) as tif:
+            tif.asarray(0)
+    assert ifd > 8
+    with pytest.raises(ValueError):
+        ok = write_tiff(os.path.join(tmp_path, "ok.tif"), [page])
+        with reader.TiffFile(ok) as tif:
+            tif.read_pages([0], out=np.empty((1, 64, 64), np.float32))
+
+
+def test_read_files_checks_geometry(tmp_path):
+    rng = np.random.default_rng(2)
+    pages = [rng.integers(0, 65535, (32, 48), dtype=np.uint16) for _ in range(5)]
+    paths = [write_tiff(os.path.join(tmp_path, f"t{i}.tif"), [p], big=bool(i % 2), byteorder="<>"[i % 2],
+                        rows_per_strip=[None, 3, 32, 7, 1][i]) for i, p in enumerate(pages)]
+    out = np.empty((5, 32, 48), np.uint16)
+    reader.read_files(paths, out, threads=3)
+    np.testing.assert_array_equal(out, np.stack(pages))
+    odd = write_tiff(os.path.join(tmp_path, "odd.tif"), [pages[0][:, :40]])
+    with pytest.raises(_lib.MagnifyB200Error) as err:
+        reader.read_files(paths[:2] + [odd], np.empty((3, 32, 48), np.uint16))
+    assert err.value.code == _lib.MGB_EFORMAT
+
+
+# ---- path patterns ---------------------------------------------------------------------------
+KEYS = dict(assay="str", channel="str", time="time", row="int", col="int")
+
+
+def make_tree(root):
+    for assay in ("xpA", "xpB"):
+        for ch in ("egfp", "Cy5"):
+            os.makedirs(os.path.join(root, assay, ch), exist_ok=True)
+            for t in ("20240101-120000", "20240101-130000"):
+                for r in range(2):
+                    for c in range(3):
+                        open(os.path.join(root, assay, ch, f"img_{t}_{r}_{c}_conc{1.5 * r}.tif"), "w").close()
+    os.makedirs(os.path.join(root, "flat"))
+    for i in range(3):
+        open(os.path.join(root, "flat", f"tile{i}.TIF"), "w").close()
+
+
+def patterns(root):
+    return [f"{root}/(assay)/(channel)/img_(time)_(row)_(col)_conc(conc_row|float).tif",
+            f"{root}/(assay)/(channel)/img_(time|%Y%m%d-%H%M%S)_(row)_(col)_*.tif",
+            f"{root}/xpA/(channel)/img_20240101-120000_(row)_(col)_*.tif",
+            f"{root}/xpB/egfp/img_(time | %Y%m%d-%H%M%S)_1_(col)_conc(amount_col|float).tif",
+            f"{root}/flat/tile(col).TIF",
+            f"{root}/flat/*.TIF",
+            f"{root}/**/img_(time)_0_(col)_conc0.0.tif",
+            f"{root}/nothing/(row).tif"]
+
+
+def outcome(fn, pattern):
+    try:
+        paths, meta = fn(pattern, **KEYS)
+        return paths, {k: dict(v) for k, v in meta.items()}
+    except Exception as e:   # noqa: BLE001 -- the exception type is the outcome
+        return type(e).__name__
+
+
+def test_extract_paths_contract(tmp_path):
+    make_tree(str(tmp_path))
+    import datetime
+
+    paths, meta = reader.extract_paths(patterns(str(tmp_path))[0], **KEYS)
+    assert len(paths) == 48
+    key = ("xpA", "Cy5", datetime.datetime(2024, 1, 1, 13, 0), 1, 2)
+    assert paths[key].endswith("xpA/Cy5/img_20240101-130000_1_2_conc1.5.tif")
+    assert dict(meta["conc", "row"]) == {0: 0.0, 1: 1.5}
+    paths, _ = reader.extract_paths(patterns(str(tmp_path))[2], **KEYS)
+    assert len(paths) == 12 and all(k[0] is None and k[2] is None for k in paths)
+    with pytest.raises(ValueError):
+        reader.extract_paths(patterns(str(tmp_path))[5], **KEYS)
+
+
+def test_extract_paths_against_reference_source_when_present(tmp_path):
+    from oracle._refload import load_reference_reader
+
+    ref = load_reference_reader()
+    if ref is None:
+        pytest.skip("/root/reference not available (GPU box)")
+    make_tree(str(tmp_path))
+    for pattern in patterns(str(tmp_path)):
+        assert outcome(reader.extract_paths, pattern) == outcome(ref.extract_paths, pattern), pattern
+
+
+# ---- tile stack assembly ---------------------------------------------------------------------
+def test_read_tiffs_file_per_index(tmp_path):
+    rng = np.random.default_rng(3)
+    c, t, r, cc, h, w = 2, 3, 2, 2, 24, 32
+    tiles = rng.integers(0, 65535, (c, t, r, cc, h, w), dtype=np.uint16)
+    chs, stamps = ["cy5", "egfp"], ["20240101-120000", "20240101-120100", "20240101-120200"]
+    for idx in np.ndindex(c, t, r, cc):
+        write_tiff(os.path.join(tmp_path, f"xp_{chs[idx[0]]}_{stamps[idx[1]]}_{idx[2]}_{idx[3]}.tif"), [tiles[idx]],
+                   rows_per_strip=7)
+    (xp,) = list(reader.Reader(threads=3)(os.path.join(tmp_path, "xp_(channel)_(time)_(row)_(col).tif")))
+    assert xp["tile"].dims == reader.TILE_ORDER and xp["tile"].values.shape == tiles.shape
+    np.testing.assert_array_equal(np.asarray(xp["tile"]), tiles)
+    np.testing.assert_array_equal(xp["tile"].values.read((1, 2)), tiles[1, 2])
+    assert list(xp.coords["channel"].values) == chs
+    assert np.diff(xp.coords["time"].values).tolist() == [60, 60]
+    blocks = dict(xp["tile"].values.blocks())
+    dst = np.empty((r, cc, h, w), np.uint16)
+    blocks[(0, 1)](dst)
+    np.testing.assert_array_equal(dst, tiles[0, 1])
+    # rows / cols only in the path: standardize_format adds channel and time (preprocess.py:35-40)
+    (xp2,) = list(reader.Reader()(os.path.join(tmp_path, "xp_cy5_20240101-120000_(row)_(col).tif")))
+    assert xp2["tile"].dims == ("tile_row", "tile_col", "tile_y", "tile_x")
+    std = reader.standardize_format(xp2)
+    assert std["tile"].dims == reader.TILE_ORDER and std["tile"].values.shape == (1, 1, r, cc, h, w)
+    assert std.attrs["__original_tile_dims__"] == ["tile_row", "tile_col", "tile_y", "tile_x"]
+    np.testing.assert_array_equal(np.asarray(std["tile"])[0, 0], tiles[0, 0])
+    with pytest.raises(FileNotFoundError):
+        list(reader.Reader()(os.path.join(tmp_path, "nothing_(row).tif")))
+
+
+def test_read_tiffs_ome_series_with_micromanager_summary(tmp_path):
+    rng = np.random.default_rng(4)
+    c, t, h, w = 2, 3, 24, 32
+    planes = rng.integers(0, 65535, (t, c, h, w), dtype=np.uint16)
+    summary = json.dumps({"StartTime": "2024-01-01 12:00:00.000 -0800", "ChNames": ["a", "b"]}).encode()
+    header = struct.pack("<IIIIII", 54773648, 0, 483765892, 0, 99384722, 0) + struct.pack("<II", 2355492, len(summary)) \
+        + summary
+    xml = ome_xml(w, h, c, t, order="XYCZT", delta_t_ms=[1000.0 * i for i in range(c * t)])
+    for row in range(2):
+        pages = [planes[ti, ci] if row == 0 else planes[ti, ci][::-1] for ti in range(t) for ci in range(c)]
+        write_tiff(os.path.join(tmp_path, f"ome_{row}.ome.tif"), pages, description=xml, header_extra=header)
+    (xp,) = list(reader.Reader()(os.path.join(tmp_path, "ome_(row).ome.tif")))
+    assert xp["tile"].dims == ("channel", "time", "tile_row", "tile_y", "tile_x")
+    arr = np.asarray(xp["tile"])
+    np.testing.assert_array_equal(arr[:, :, 0], planes.transpose(1, 0, 2, 3))
+    np.testing.assert_array_equal(arr[:, :, 1], planes.transpose(1, 0, 2, 3)[:, :, ::-1])
+    assert list(xp.coords["channel"].values) == ["a", "b"]
+    assert np.diff(xp.coords["time"].values).tolist() == [2, 2]      # DeltaT of every c-th plane
+    std = reader.standardize_format(xp)
+    np.testing.assert_array_equal(std["tile"].values.read((1, 2)), arr[1, 2][:, None])
+    # a multi-page file without OME-XML has the series axis "I": unmappable, like reader.py:208
+    write_tiff(os.path.join(tmp_path, "plain_0.tif"), [planes[0, 0], planes[0, 1]])
+    with pytest.raises(KeyError):
+        list(reader.Reader()(os.path.join(tmp_path, "plain_(row).tif")))
