@@ -196,6 +196,31 @@ int mgb_bead_labels(const int32_t* beads, int64_t M, int64_t H, int64_t W, const
 int mgb_bead_masks(const int32_t* labels, int64_t H, int64_t W, const int32_t* boxes, int64_t M,
                    int L, uint8_t* fg, uint8_t* bg, int32_t* counts, void* stream);
 
+/* ---- N1 / N4: edge detection of the circle finder, reference utils.py:20-27, 113-139 --------
+ * All of it integer / IEEE-exact, i.e. bit-identical to the NumPy + OpenCV calls of the reference.
+ *
+ * to_uint8 (utils.py:20-27): dst = uint8(255 * (x - min) / (max - min)) in float64, truncated
+ * (all zero when max == min).  dtype is an MGB_* code; minmax (2 doubles, device) is scratch and
+ * holds (min, max) afterwards. */
+int mgb_to_uint8(const void* src, int dtype, int64_t n, uint8_t* dst, double* minmax, void* stream);
+/* cv.GaussianBlur(img, (5,5), 0) on uint8 followed by cv.Scharr(.., CV_32F, 1, 0) / (.., 0, 1)
+ * (utils.py:114-118), BORDER_REFLECT_101.  The gradients are exact integers in [-4080, 4080] and
+ * are stored as int16 (what utils.py:128-129 passes to Canny; float32 dx, dy are the same numbers). */
+int mgb_edge_gradients_u8(const uint8_t* image, int64_t H, int64_t W, uint8_t* blurred, int16_t* dx, int16_t* dy,
+                          void* stream);
+/* Exact order statistics of m = dx^2 + dy^2 over n pixels: host_values[i] = the host_ranks[i]-th
+ * smallest m (0-based), up to 4 ranks per call.  grad = sqrt(float32(m)) (utils.py:119) is monotone
+ * in m, so these are the order statistics np.quantile interpolates between (utils.py:125-126).
+ * SYNCHRONISES the stream (three histogram round trips).  scratch: 4*2048 uint32 on the device. */
+int mgb_gradient_order_stats(const int16_t* dx, const int16_t* dy, int64_t n, const int64_t* host_ranks,
+                             int n_ranks, int64_t* host_values, uint32_t* scratch, void* stream);
+/* cv.Canny(dx, dy, threshold1, threshold2, L2gradient=True) (utils.py:127-133) with the integer
+ * thresholds OpenCV derives (low = floor(min(t1,32767)^2), high likewise): edges (H,W) uint8 0/1.
+ * map (H,W) uint8 and changed (1 int) are device scratch.  Hysteresis is iterated to its fixed
+ * point, SYNCHRONISING the stream once per sweep; host_sweeps (nullable) returns the sweep count. */
+int mgb_canny(const int16_t* dx, const int16_t* dy, int64_t H, int64_t W, int low, int high, uint8_t* map,
+              uint8_t* edges, int* changed, int* host_sweeps, void* stream);
+
 /* ---- S / N2: TIFF page staging, reference src/magnify/reader.py:265-279 ---------------------
  * HOST-ONLY entry points (no kernel is launched): the reference's lazy tile loader reads one
  * TIFF page per dask chunk with `tifffile.TiffFile(f).pages[i].asarray()`.  These read the same

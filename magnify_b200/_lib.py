@@ -52,6 +52,10 @@ SIGNATURES = {
     "mgb_disc_halfwidths": [c_int, POINTER(ctypes.c_int32)],
     "mgb_bead_labels": [_P, _I64, _I64, _I64, _P, c_int, _P, _P],
     "mgb_bead_masks": [_P, _I64, _I64, _P, _I64, c_int, _P, _P, _P, _P],
+    "mgb_to_uint8": [_P, c_int, _I64, _P, _P, _P],
+    "mgb_edge_gradients_u8": [_P, _I64, _I64, _P, _P, _P, _P],
+    "mgb_gradient_order_stats": [_P, _P, _I64, POINTER(c_int64), c_int, POINTER(c_int64), _P, _P],
+    "mgb_canny": [_P, _P, _I64, _I64, c_int, c_int, _P, _P, _P, POINTER(c_int), _P],
     "mgb_tiff_open": [c_char_p, POINTER(c_void_p)],
     "mgb_tiff_close": [_P],
     "mgb_tiff_page_count": [_P, POINTER(c_int64)],

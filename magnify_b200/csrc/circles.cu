@@ -1,0 +1,422 @@
+// Edge-detection front end and circle scoring of the reference's circle finder
+// (src/magnify/utils.py:100-344, used by find.py:476-491 for beads and find.py:339-360 for the
+// per-ROI button refinement).
+//
+// Everything in this file is integer or IEEE-exact, so it reproduces the reference's NumPy /
+// OpenCV results bit for bit:
+//   to_uint8            utils.py:20-27   (x - min) * 255 / (max - min) in float64, truncated
+//   GaussianBlur 5x5    utils.py:114     OpenCV's bit-exact fixed-point path for 8-bit images with
+//                                        sigma 0: weights [1 4 6 4 1]^2 / 256, round half up,
+//                                        BORDER_REFLECT_101
+//   Scharr              utils.py:117-118 [3 10 3] x [-1 0 1] on the blurred image, exact integers
+//   gradient quantiles  utils.py:125-126 exact order statistics of dx^2 + dy^2 by a 3-level radix
+//                                        select (sqrt and the float32 sum are monotone in it)
+//   Canny               utils.py:127-133 cv::Canny(dx, dy, low, high, L2gradient=true): squared
+//                                        magnitudes, the TG22 non-maximum suppression, 8-connected
+//                                        hysteresis (iterated to a fixed point; order independent)
+// The random circle sampling that follows in the reference (utils.py:288-344) is not
+// reproducible by construction (unseeded numba RNG under prange); see circles_sample.cu.
+#include "common.cuh"
+
+namespace {
+
+using mgb::kThreads;
+
+// ---------------------------------------------------------------------------------------------
+// to_uint8
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_min_f64(double* addr, double v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a;
+  while (__longlong_as_double((long long)old) > v) {
+    const unsigned long long prev = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
+    if (prev == old) break;
+    old = prev;
+  }
+}
+__device__ __forceinline__ void atomic_max_f64(double* addr, double v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a;
+  while (__longlong_as_double((long long)old) < v) {
+    const unsigned long long prev = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
+    if (prev == old) break;
+    old = prev;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) minmax_kernel(const T* __restrict__ x, int64_t n,
+                                                          double* __restrict__ mm) {
+  double lo = INFINITY, hi = -INFINITY;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = (double)x[i];
+    lo = fmin(lo, v);
+    hi = fmax(hi, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  __shared__ double slo[kThreads / 32], shi[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) {
+    slo[threadIdx.x >> 5] = lo;
+    shi[threadIdx.x >> 5] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kThreads / 32; ++w) {
+      lo = fmin(lo, slo[w]);
+      hi = fmax(hi, shi[w]);
+    }
+    atomic_min_f64(mm, lo);
+    atomic_max_f64(mm + 1, hi);
+  }
+}
+
+__global__ void minmax_init_kernel(double* mm) {
+  mm[0] = INFINITY;
+  mm[1] = -INFINITY;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) to_uint8_kernel(const T* __restrict__ x, int64_t n,
+                                                            const double* __restrict__ mm,
+                                                            uint8_t* __restrict__ out) {
+  const double lo = mm[0], range = mm[1] - mm[0];   // == max(x - min): the subtraction is monotone
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double v = (double)x[i] - lo;
+    if (range > 0) v = __ddiv_rn(__dmul_rn(255.0, v), range);   // (255 * arr) / max, left to right
+    out[i] = (uint8_t)v;                                        // astype(uint8): truncation
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// blur + Scharr
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int p, int len) {
+  if (len == 1) return 0;
+  while ((unsigned)p >= (unsigned)len) p = p < 0 ? -p : 2 * len - 2 - p;
+  return p;
+}
+
+__global__ void __launch_bounds__(kThreads) blur5_u8_kernel(const uint8_t* __restrict__ img, int H, int W,
+                                                            uint8_t* __restrict__ out) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y0 = blockIdx.y * 32 + (threadIdx.x >> 5) * 4;
+  if (x >= W) return;
+  int xs[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) xs[k] = reflect101(x + k - 2, W);
+  // horizontal [1 4 6 4 1] sums of the 8 rows this thread's 4 outputs need, then the vertical pass
+  int h[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int yy = reflect101(y0 + r - 2, H);
+    const uint8_t* row = img + (int64_t)yy * W;
+    h[r] = row[xs[0]] + 4 * row[xs[1]] + 6 * row[xs[2]] + 4 * row[xs[3]] + row[xs[4]];
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int y = y0 + r;
+    if (y < H) out[(int64_t)y * W + x] = (uint8_t)((h[r] + 4 * h[r + 1] + 6 * h[r + 2] + 4 * h[r + 3] + h[r + 4] + 128) >> 8);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) scharr_kernel(const uint8_t* __restrict__ b, int H, int W,
+                                                          int16_t* __restrict__ dx, int16_t* __restrict__ dy) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y0 = blockIdx.y * 32 + (threadIdx.x >> 5) * 4;
+  if (x >= W) return;
+  const int xl = reflect101(x - 1, W), xr = reflect101(x + 1, W);
+  int l[6], c[6], r[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const uint8_t* row = b + (int64_t)reflect101(y0 + k - 1, H) * W;
+    l[k] = row[xl];
+    c[k] = row[x];
+    r[k] = row[xr];
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int y = y0 + k;
+    if (y >= H) break;
+    const int gx = 3 * (r[k] - l[k]) + 10 * (r[k + 1] - l[k + 1]) + 3 * (r[k + 2] - l[k + 2]);
+    const int gy = 3 * (l[k + 2] - l[k]) + 10 * (c[k + 2] - c[k]) + 3 * (r[k + 2] - r[k]);
+    dx[(int64_t)y * W + x] = (int16_t)gx;
+    dy[(int64_t)y * W + x] = (int16_t)gy;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// radix select on m = dx^2 + dy^2 (31 bits: 11 + 10 + 10)
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxTargets = 4;
+struct SelectLevel {
+  int shift;          // bits below this level's digit
+  int bins;           // 1 << digit bits
+  int prefix_shift;   // m >> prefix_shift must equal the target prefix (32 = no prefix at level 0)
+  int n_targets;
+  uint32_t prefix[kMaxTargets];
+};
+
+__global__ void __launch_bounds__(kThreads) grad_hist_kernel(const int16_t* __restrict__ dx,
+                                                             const int16_t* __restrict__ dy, int64_t n,
+                                                             SelectLevel lv, uint32_t* __restrict__ hist) {
+  extern __shared__ uint32_t sh[];
+  const int total = lv.bins * lv.n_targets;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  // warp-uniform trip count so that the match below can use the full mask
+  for (int64_t b = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x - lane); b < n; b += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = b + lane;
+    const bool valid = i < n;
+    const int gx = valid ? dx[i] : 0, gy = valid ? dy[i] : 0;
+    const uint32_t m = (uint32_t)(gx * gx + gy * gy);
+    const uint32_t digit = (m >> lv.shift) & (uint32_t)(lv.bins - 1);
+    int slot = -1;
+    if (!valid) {
+      slot = -1;
+    } else if (lv.prefix_shift >= 32) {
+      slot = (int)digit;
+    } else {
+      const uint32_t p = m >> lv.prefix_shift;
+      for (int t = 0; t < lv.n_targets; ++t)       // prefixes are distinct: at most one matches
+        if (p == lv.prefix[t]) slot = t * lv.bins + (int)digit;
+    }
+    // Gradient magnitudes are heavily concentrated (flat background): aggregate equal slots
+    // within the warp before touching shared memory.
+    const unsigned peers = __match_any_sync(0xffffffffu, slot);
+    if (slot >= 0 && lane == __ffs(peers) - 1) atomicAdd(&sh[slot], (uint32_t)__popc(peers));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < total; i += blockDim.x)
+    if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Canny
+// ---------------------------------------------------------------------------------------------
+constexpr int kCannyShift = 15;
+constexpr int kTG22 = 13573;   // (int)(0.4142135623730950488016887242097 * (1 << 15) + 0.5)
+
+__device__ __forceinline__ int mag_at(const int16_t* __restrict__ dx, const int16_t* __restrict__ dy, int H, int W,
+                                      int y, int x) {
+  if ((unsigned)y >= (unsigned)H || (unsigned)x >= (unsigned)W) return 0;   // zero magnitude outside
+  const int gx = dx[(int64_t)y * W + x], gy = dy[(int64_t)y * W + x];
+  return gx * gx + gy * gy;
+}
+
+// map: 0 = above low and a local maximum (edge candidate), 1 = not an edge, 2 = strong edge
+__global__ void __launch_bounds__(kThreads) canny_nms_kernel(const int16_t* __restrict__ dx,
+                                                             const int16_t* __restrict__ dy, int H, int W, int low,
+                                                             int high, uint8_t* __restrict__ map) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= H) return;
+  const int64_t at = (int64_t)y * W + x;
+  const int xs = dx[at], ys = dy[at];
+  const int m = xs * xs + ys * ys;
+  uint8_t out = 1;
+  if (m > low) {
+    const int ax = abs(xs), ay = abs(ys) << kCannyShift;
+    const int tg22x = ax * kTG22;
+    bool keep;
+    if (ay < tg22x) {
+      keep = m > mag_at(dx, dy, H, W, y, x - 1) && m >= mag_at(dx, dy, H, W, y, x + 1);
+    } else {
+      const int tg67x = tg22x + (ax << (kCannyShift + 1));
+      if (ay > tg67x) {
+        keep = m > mag_at(dx, dy, H, W, y - 1, x) && m >= mag_at(dx, dy, H, W, y + 1, x);
+      } else {
+        const int s = (xs ^ ys) < 0 ? -1 : 1;
+        keep = m > mag_at(dx, dy, H, W, y - 1, x - s) && m > mag_at(dx, dy, H, W, y + 1, x + s);
+      }
+    }
+    if (keep) out = m > high ? 2 : 0;
+  }
+  map[at] = out;
+}
+
+// One sweep of hysteresis: every 32x32 tile is flooded to its own fixed point in shared memory
+// (strong pixels recruit 8-connected candidates); `changed` counts tiles that recruited anything,
+// the host repeats sweeps until a sweep changes nothing.
+__global__ void __launch_bounds__(kThreads) canny_hysteresis_kernel(uint8_t* __restrict__ map, int H, int W,
+                                                                    int* __restrict__ changed) {
+  __shared__ uint8_t t[34][36];
+  __shared__ int again, any;
+  const int x0 = blockIdx.x * 32 - 1, y0 = blockIdx.y * 32 - 1;
+  for (int i = threadIdx.x; i < 34 * 34; i += blockDim.x) {
+    const int ly = i / 34, lx = i - ly * 34;
+    const int y = y0 + ly, x = x0 + lx;
+    t[ly][lx] = ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) ? map[(int64_t)y * W + x] : 1;
+  }
+  if (threadIdx.x == 0) any = 0;
+  __syncthreads();
+  const int lx = (threadIdx.x & 31) + 1, lyb = (threadIdx.x >> 5) * 4 + 1;
+  for (;;) {
+    if (threadIdx.x == 0) again = 0;
+    __syncthreads();
+    bool grew = false;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int ly = lyb + r;
+      if (t[ly][lx] == 0) {
+        const bool near = t[ly - 1][lx - 1] == 2 || t[ly - 1][lx] == 2 || t[ly - 1][lx + 1] == 2 ||
+                          t[ly][lx - 1] == 2 || t[ly][lx + 1] == 2 || t[ly + 1][lx - 1] == 2 ||
+                          t[ly + 1][lx] == 2 || t[ly + 1][lx + 1] == 2;
+        if (near) {
+          t[ly][lx] = 2;   // monotone 0 -> 2: racing readers only see it earlier or later
+          grew = true;
+        }
+      }
+    }
+    if (grew) again = 1;
+    __syncthreads();
+    if (!again) break;
+    if (threadIdx.x == 0) any = 1;
+    __syncthreads();
+  }
+  if (any) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int y = y0 + lyb + r, x = x0 + lx;
+      if (y < H && x < W && t[lyb + r][lx] == 2) map[(int64_t)y * W + x] = 2;
+    }
+    if (threadIdx.x == 0) atomicAdd(changed, 1);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) canny_edges_kernel(const uint8_t* __restrict__ map, int64_t n,
+                                                               uint8_t* __restrict__ edges) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    edges[i] = map[i] == 2 ? 1 : 0;   // utils.py:139 (`edges[edges != 0] = 1`)
+}
+
+int grid_for(int64_t n) {
+  const int64_t blocks = mgb::ceil_div(n, kThreads);
+  const int64_t cap = (int64_t)mgb_sm_count() * 16;
+  return (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+
+template <typename T>
+int to_uint8_launch(const void* src, int64_t n, uint8_t* dst, double* mm, cudaStream_t s) {
+  minmax_init_kernel<<<1, 1, 0, s>>>(mm);
+  MGB_CUDA_LAUNCH_CHECK();
+  minmax_kernel<T><<<grid_for(n), kThreads, 0, s>>>(static_cast<const T*>(src), n, mm);
+  MGB_CUDA_LAUNCH_CHECK();
+  to_uint8_kernel<T><<<grid_for(n), kThreads, 0, s>>>(static_cast<const T*>(src), n, mm, dst);
+  MGB_CUDA_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mgb_to_uint8(const void* src, int dtype, int64_t n, uint8_t* dst, double* minmax, void* stream) {
+  if (n < 0 || (n > 0 && (!src || !dst)) || !minmax) return MGB_EINVAL;
+  if (n == 0) return MGB_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case MGB_U8: return to_uint8_launch<uint8_t>(src, n, dst, minmax, s);
+    case MGB_U16: return to_uint8_launch<uint16_t>(src, n, dst, minmax, s);
+    case MGB_F32: return to_uint8_launch<float>(src, n, dst, minmax, s);
+    case MGB_F64: return to_uint8_launch<double>(src, n, dst, minmax, s);
+    default: return MGB_EUNSUPPORTED;
+  }
+}
+
+int mgb_edge_gradients_u8(const uint8_t* image, int64_t H, int64_t W, uint8_t* blurred, int16_t* dx, int16_t* dy,
+                          void* stream) {
+  if (!image || !blurred || !dx || !dy || H <= 0 || W <= 0 || H > (1 << 30) || W > (1 << 30)) return MGB_EINVAL;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const dim3 grid((unsigned)mgb::ceil_div(W, 32), (unsigned)mgb::ceil_div(H, 32));
+  blur5_u8_kernel<<<grid, kThreads, 0, s>>>(image, (int)H, (int)W, blurred);
+  MGB_CUDA_LAUNCH_CHECK();
+  scharr_kernel<<<grid, kThreads, 0, s>>>(blurred, (int)H, (int)W, dx, dy);
+  MGB_CUDA_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+int mgb_gradient_order_stats(const int16_t* dx, const int16_t* dy, int64_t n, const int64_t* host_ranks,
+                             int n_ranks, int64_t* host_values, uint32_t* scratch, void* stream) {
+  if (!dx || !dy || !host_ranks || !host_values || !scratch || n <= 0 || n_ranks < 1 || n_ranks > kMaxTargets)
+    return MGB_EINVAL;
+  for (int t = 0; t < n_ranks; ++t)
+    if (host_ranks[t] < 0 || host_ranks[t] >= n) return MGB_EINVAL;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int shifts[3] = {20, 10, 0}, bins[3] = {2048, 1024, 1024};
+  uint32_t prefix[kMaxTargets] = {0, 0, 0, 0};
+  int64_t rank[kMaxTargets];
+  for (int t = 0; t < n_ranks; ++t) rank[t] = host_ranks[t];
+  static thread_local uint32_t host_hist[kMaxTargets * 2048];
+  for (int level = 0; level < 3; ++level) {
+    // distinct prefixes of this level (ranks that fell into the same bin share a histogram)
+    SelectLevel lv;
+    lv.shift = shifts[level];
+    lv.bins = bins[level];
+    lv.prefix_shift = level == 0 ? 32 : shifts[level - 1];
+    lv.n_targets = 0;
+    int slot_of[kMaxTargets];
+    for (int t = 0; t < n_ranks; ++t) {
+      int found = -1;
+      for (int u = 0; u < lv.n_targets; ++u)
+        if (level == 0 || lv.prefix[u] == prefix[t]) found = u;
+      if (found < 0) {
+        found = lv.n_targets++;
+        lv.prefix[found] = prefix[t];
+      }
+      slot_of[t] = found;
+    }
+    for (int u = lv.n_targets; u < kMaxTargets; ++u) lv.prefix[u] = 0xffffffffu;
+    const size_t bytes = (size_t)lv.bins * lv.n_targets * sizeof(uint32_t);
+    MGB_CUDA_TRY(cudaMemsetAsync(scratch, 0, bytes, s));
+    grad_hist_kernel<<<grid_for(n), kThreads, bytes, s>>>(dx, dy, n, lv, scratch);
+    MGB_CUDA_LAUNCH_CHECK();
+    MGB_CUDA_TRY(cudaMemcpyAsync(host_hist, scratch, bytes, cudaMemcpyDeviceToHost, s));
+    MGB_CUDA_TRY(cudaStreamSynchronize(s));
+    for (int t = 0; t < n_ranks; ++t) {
+      const uint32_t* h = host_hist + slot_of[t] * lv.bins;
+      int64_t acc = 0;
+      int d = 0;
+      for (; d < lv.bins; ++d) {
+        if (acc + h[d] > rank[t]) break;
+        acc += h[d];
+      }
+      if (d == lv.bins) return MGB_EINVAL;   // rank beyond the counted elements: cannot happen
+      rank[t] -= acc;
+      prefix[t] = level == 0 ? (uint32_t)d : ((prefix[t] << 10) | (uint32_t)d);
+    }
+  }
+  for (int t = 0; t < n_ranks; ++t) host_values[t] = (int64_t)prefix[t];
+  return MGB_OK;
+}
+
+int mgb_canny(const int16_t* dx, const int16_t* dy, int64_t H, int64_t W, int low, int high, uint8_t* map,
+              uint8_t* edges, int* changed, int* host_sweeps, void* stream) {
+  if (!dx || !dy || !map || !edges || !changed || H <= 0 || W <= 0 || H > (1 << 30) || W > (1 << 30))
+    return MGB_EINVAL;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  canny_nms_kernel<<<dim3((unsigned)mgb::ceil_div(W, 32), (unsigned)mgb::ceil_div(H, 8)), kThreads, 0, s>>>(
+      dx, dy, (int)H, (int)W, low, high, map);
+  MGB_CUDA_LAUNCH_CHECK();
+  const dim3 grid((unsigned)mgb::ceil_div(W, 32), (unsigned)mgb::ceil_div(H, 32));
+  int sweeps = 0;
+  for (;;) {
+    MGB_CUDA_TRY(cudaMemsetAsync(changed, 0, sizeof(int), s));
+    canny_hysteresis_kernel<<<grid, kThreads, 0, s>>>(map, (int)H, (int)W, changed);
+    MGB_CUDA_LAUNCH_CHECK();
+    ++sweeps;
+    int host_changed = 0;
+    MGB_CUDA_TRY(cudaMemcpyAsync(&host_changed, changed, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MGB_CUDA_TRY(cudaStreamSynchronize(s));
+    if (host_changed == 0) break;
+  }
+  canny_edges_kernel<<<grid_for(H * W), kThreads, 0, s>>>(map, H * W, edges);
+  MGB_CUDA_LAUNCH_CHECK();
+  if (host_sweeps) *host_sweeps = sweeps;
+  return MGB_OK;
+}
+
+}  // extern "C"

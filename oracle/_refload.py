@@ -859,3 +859,32 @@ def load_reference_reader():
                 sys.modules[k] = v
     _cached_reader = mod
     return mod
+
+
+# ---------------------------------------------------------------------------------------------
+# utils.find_circles (utils.py:100-218) itself, run with a capturing stand-in for the napari GUI:
+# `gui.run_widget(fn, ...)` is how the function obtains `edges` and the filtered circles when a
+# GUI is present (:135-136, :211-212), so a stand-in that just calls `fn()` exposes both stages.
+# ---------------------------------------------------------------------------------------------
+class CapturingGui:
+    def __init__(self):
+        self.stages = []
+
+    def run_widget(self, fn, auto_call=True, last=False):
+        out = fn()
+        self.stages.append(out)
+        return out
+
+
+def reference_find_circles_stages(img, low_edge_quantile, high_edge_quantile, grid_length, num_iter, min_radius,
+                                  max_radius, min_roundness, min_dist):
+    """(edges 0/1 uint8, circles, scores) from the reference's own find_circles, or None."""
+    utils = load_reference_utils()
+    if utils is None:
+        return None
+    gui = CapturingGui()
+    circles, scores = utils.find_circles(img, low_edge_quantile=low_edge_quantile, high_edge_quantile=high_edge_quantile,
+                                         grid_length=grid_length, num_iter=num_iter, min_radius=min_radius,
+                                         max_radius=max_radius, min_roundness=min_roundness, min_dist=min_dist, gui=gui)
+    edges = gui.stages[0][1][0]
+    return edges, circles, scores
