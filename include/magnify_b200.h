@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MGB_ABI_VERSION 4
+#define MGB_ABI_VERSION 5
 
 #define MGB_OK 0
 #define MGB_EINVAL (-1)      /* bad argument (null pointer, negative size, bad itemsize ...) */
@@ -198,28 +198,69 @@ int mgb_bead_masks(const int32_t* labels, int64_t H, int64_t W, const int32_t* b
 
 /* ---- N1 / N4: edge detection of the circle finder, reference utils.py:20-27, 113-139 --------
  * All of it integer / IEEE-exact, i.e. bit-identical to the NumPy + OpenCV calls of the reference.
+ * Every entry point works on a BATCH of B independent images (B, H, W) (B <= 65535): one full
+ * image for bead detection (find.py:476-491), thousands of 72 x 72 crops for the per-ROI button
+ * refinement (find.py:339-360).
  *
- * to_uint8 (utils.py:20-27): dst = uint8(255 * (x - min) / (max - min)) in float64, truncated
- * (all zero when max == min).  dtype is an MGB_* code; minmax (2 doubles, device) is scratch and
- * holds (min, max) afterwards. */
-int mgb_to_uint8(const void* src, int dtype, int64_t n, uint8_t* dst, double* minmax, void* stream);
+ * to_uint8 (utils.py:20-27), per image: dst = uint8(255 * (x - min) / (max - min)) in float64,
+ * truncated (all zero when max == min).  dtype is an MGB_* code; n = pixels per image; minmax
+ * (B, 2) doubles on the device is scratch and holds (min, max) per image afterwards. */
+int mgb_to_uint8(const void* src, int dtype, int64_t B, int64_t n, uint8_t* dst, double* minmax, void* stream);
 /* cv.GaussianBlur(img, (5,5), 0) on uint8 followed by cv.Scharr(.., CV_32F, 1, 0) / (.., 0, 1)
  * (utils.py:114-118), BORDER_REFLECT_101.  The gradients are exact integers in [-4080, 4080] and
  * are stored as int16 (what utils.py:128-129 passes to Canny; float32 dx, dy are the same numbers). */
-int mgb_edge_gradients_u8(const uint8_t* image, int64_t H, int64_t W, uint8_t* blurred, int16_t* dx, int16_t* dy,
-                          void* stream);
-/* Exact order statistics of m = dx^2 + dy^2 over n pixels: host_values[i] = the host_ranks[i]-th
- * smallest m (0-based), up to 4 ranks per call.  grad = sqrt(float32(m)) (utils.py:119) is monotone
- * in m, so these are the order statistics np.quantile interpolates between (utils.py:125-126).
- * SYNCHRONISES the stream (three histogram round trips).  scratch: 4*2048 uint32 on the device. */
-int mgb_gradient_order_stats(const int16_t* dx, const int16_t* dy, int64_t n, const int64_t* host_ranks,
+int mgb_edge_gradients_u8(const uint8_t* image, int64_t B, int64_t H, int64_t W, uint8_t* blurred, int16_t* dx,
+                          int16_t* dy, void* stream);
+/* Exact order statistics of m = dx^2 + dy^2 over the n pixels of every image:
+ * host_values[b, i] = the host_ranks[i]-th smallest m (0-based) of image b, up to 4 ranks per
+ * call.  grad = sqrt(float32(m)) (utils.py:119) is monotone in m, so these are the order
+ * statistics np.quantile interpolates between (utils.py:125-126).  SYNCHRONISES the stream (three
+ * histogram round trips).  scratch: B * 4 * (1 + 2048) uint32 on the device. */
+int mgb_gradient_order_stats(const int16_t* dx, const int16_t* dy, int64_t B, int64_t n, const int64_t* host_ranks,
                              int n_ranks, int64_t* host_values, uint32_t* scratch, void* stream);
-/* cv.Canny(dx, dy, threshold1, threshold2, L2gradient=True) (utils.py:127-133) with the integer
- * thresholds OpenCV derives (low = floor(min(t1,32767)^2), high likewise): edges (H,W) uint8 0/1.
- * map (H,W) uint8 and changed (1 int) are device scratch.  Hysteresis is iterated to its fixed
- * point, SYNCHRONISING the stream once per sweep; host_sweeps (nullable) returns the sweep count. */
-int mgb_canny(const int16_t* dx, const int16_t* dy, int64_t H, int64_t W, int low, int high, uint8_t* map,
-              uint8_t* edges, int* changed, int* host_sweeps, void* stream);
+/* cv.Canny(dx, dy, threshold1, threshold2, L2gradient=True) (utils.py:127-133): edges (B,H,W)
+ * uint8 0/1.  thresholds (B, 2) int32 on the device = the integer (low, high) OpenCV derives
+ * (low = floor(min(t1,32767)^2), high likewise).  map (B,H,W) uint8 and changed (1 int) are device
+ * scratch.  Hysteresis is iterated to its fixed point, SYNCHRONISING the stream once per sweep;
+ * host_sweeps (nullable) returns the sweep count. */
+int mgb_canny(const int16_t* dx, const int16_t* dy, int64_t B, int64_t H, int64_t W, const int32_t* thresholds,
+              uint8_t* map, uint8_t* edges, int* changed, int* host_sweeps, void* stream);
+
+/* ---- N1 / N4: candidate circles and their scores, reference utils.py:141-189, 221-377 --------
+ * Edge pixels grouped by grid cell (utils.py:347-377): counts / starts (B * cells + 1 int64 each,
+ * cells = ceil(H/g) * ceil(W/g), cell-major per image) and coords (total uint32, row << 16 | col,
+ * row-major inside a cell).  Call once with coords = NULL to learn the total (host_total), then
+ * again with a buffer of that capacity.  H, W <= 65535.  SYNCHRONISES the stream. */
+int mgb_edge_cell_lists(const uint8_t* edges, int64_t B, int64_t H, int64_t W, int grid_length, int64_t* counts,
+                        int64_t* starts, uint32_t* coords, int64_t coords_capacity, int64_t* host_total, void* stream);
+/* num_iter circumcircles per image from three random edge pixels of one grid cell
+ * (utils.py:288-344; arithmetic bit-identical to the reference's numba code, draws from a
+ * counter-based generator keyed by `seed`, or from `randoms` (B, num_iter, 3) uint32 when given).
+ * raw (B, num_iter, 3) float32 (nullable) receives (row, col, radius) of every draw.  When `table`
+ * (table_capacity uint64, a power of two >= 2 * B * num_iter) is given, draws are filtered to
+ * min_radius <= radius <= max_radius, rounded half-to-even, tested against the image
+ * (utils.py:157-165) and de-duplicated: circles (<= B * num_iter, 4) int32 = (image, row, col,
+ * radius), *host_n_unique of them, in no particular order.  counter: one uint64 of device scratch.
+ * SYNCHRONISES the stream when `table` is given. */
+int mgb_sample_circles(const uint32_t* coords, const int64_t* starts, const int64_t* counts, int64_t B, int64_t H,
+                       int64_t W, int grid_length, int64_t num_iter, float min_radius, float max_radius,
+                       uint64_t seed, const uint32_t* randoms, float* raw, uint64_t* table, int64_t table_capacity,
+                       int32_t* circles, int64_t* host_n_unique, unsigned long long* counter, void* stream);
+/* angle = float32(atan2(dy, dx)) per pixel (utils.py:169). */
+int mgb_gradient_angles(const int16_t* dx, const int16_t* dy, int64_t n, float* angle, void* stream);
+/* HOST: perimeter of the reference's circle raster (utils.py:433-465) in the reference's order,
+ * (drow, dcol) pairs; capacity >= 20 * r points. */
+int mgb_circle_perimeter(int r, int four_connected, int32_t* host_points, int capacity, int* host_n);
+/* scores[i] = mean_grad(...)[i] / len(perimeter) of utils.py:181-183, 221-249 for circles (N, 4)
+ * int32 (image, row, col, radius) with rmin <= radius <= rmax (NaN otherwise).  perim_offsets
+ * (rmax - rmin + 2), perim_points (P, 2) int16, perim_expected (P) float64 = arctan2(drow, dcol)
+ * concatenate the perimeters of radius rmin..rmax. */
+int mgb_score_circles(const int32_t* circles, int64_t N, int64_t H, int64_t W, const uint8_t* edges,
+                      const float* angle, int rmin, int rmax, const int32_t* perim_offsets,
+                      const int16_t* perim_points, const double* perim_expected, float* scores, void* stream);
+/* HOST: utils.py:252-285 on circles (n, 3) int32 (row, col, radius) sorted best first:
+ * host_valid[i] = 1 when circle i survives. */
+int mgb_filter_neighbors(const int32_t* host_circles, int64_t n, int min_dist, uint8_t* host_valid);
 
 /* ---- S / N2: TIFF page staging, reference src/magnify/reader.py:265-279 ---------------------
  * HOST-ONLY entry points (no kernel is launched): the reference's lazy tile loader reads one

@@ -14,7 +14,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libmagnify_b200.so")
-SOURCES = ("flatfield_stitch.cu", "roi.cu", "roi_tma.cu", "masks.cu", "circles.cu", "tiff_pages.cpp")
+SOURCES = ("flatfield_stitch.cu", "roi.cu", "roi_tma.cu", "masks.cu", "circles.cu", "circles_sample.cu", "circles_host.cpp", "tiff_pages.cpp")
 NVCC_FLAGS = (
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -20,9 +20,18 @@ from . import _lib
 from .ops import _DTYPE_CODE, _check, _ptr, _stream
 
 
-def to_uint8(x: torch.Tensor) -> torch.Tensor:
+def _batched(t: torch.Tensor, name: str, dtype) -> Tuple[torch.Tensor, bool]:
+    """View a (H, W) or (B, H, W) tensor as (B, H, W); second value: whether a batch dim was added."""
+    if t.ndim not in (2, 3):
+        raise ValueError(f"{name} must be (H, W) or (B, H, W), got {tuple(t.shape)}")
+    _check(t, name, dtype, t.ndim)
+    return (t.unsqueeze(0), True) if t.ndim == 2 else (t, False)
+
+
+def to_uint8(x: torch.Tensor, batched: bool = False) -> torch.Tensor:
     """utils.py:20-27: uint8(255 * (x - min) / (max - min)) in float64, truncated; zeros when the
-    array is constant; an empty array stays empty."""
+    array is constant; an empty array stays empty.  With batched=True the leading dim indexes
+    independent images, each scaled by its own min / max (find.py:343 per ROI and channel)."""
     if not x.is_cuda or not x.is_contiguous():
         raise ValueError("to_uint8 needs a contiguous CUDA tensor")
     if x.dtype not in _DTYPE_CODE:
@@ -30,21 +39,22 @@ def to_uint8(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
     if x.numel() == 0:
         return out
-    minmax = torch.empty(2, dtype=torch.float64, device=x.device)
-    _lib.call("mgb_to_uint8", _ptr(x), _DTYPE_CODE[x.dtype], x.numel(), _ptr(out), _ptr(minmax), _stream())
+    b = x.shape[0] if batched else 1
+    minmax = torch.empty((b, 2), dtype=torch.float64, device=x.device)
+    _lib.call("mgb_to_uint8", _ptr(x), _DTYPE_CODE[x.dtype], b, x.numel() // b, _ptr(out), _ptr(minmax), _stream())
     return out
 
 
 def edge_gradients(image: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """utils.py:114-118 on a (H, W) uint8 image: Scharr dx, dy of the 5x5-Gaussian-blurred image as
-    int16 (the float32 arrays of the reference hold exactly these integers)."""
-    _check(image, "image", torch.uint8, 2)
-    h, w = image.shape
-    blurred = torch.empty_like(image)
-    dx = torch.empty((h, w), dtype=torch.int16, device=image.device)
+    """utils.py:114-118 on (H, W) or (B, H, W) uint8 images: Scharr dx, dy of the 5x5-Gaussian-
+    blurred image as int16 (the float32 arrays of the reference hold exactly these integers)."""
+    img, squeeze = _batched(image, "image", torch.uint8)
+    b, h, w = img.shape
+    blurred = torch.empty_like(img)
+    dx = torch.empty((b, h, w), dtype=torch.int16, device=image.device)
     dy = torch.empty_like(dx)
-    _lib.call("mgb_edge_gradients_u8", _ptr(image), h, w, _ptr(blurred), _ptr(dx), _ptr(dy), _stream())
-    return dx, dy
+    _lib.call("mgb_edge_gradients_u8", _ptr(img), b, h, w, _ptr(blurred), _ptr(dx), _ptr(dy), _stream())
+    return (dx[0], dy[0]) if squeeze else (dx, dy)
 
 
 def linear_quantile(n: int, q, lower: np.float32, upper: np.float32, last: np.float32) -> np.float32:
@@ -80,28 +90,34 @@ def _quantile_indexes(n: int, q):
     return v, prev, nxt
 
 
-def gradient_quantiles(dx: torch.Tensor, dy: torch.Tensor, quantiles: Sequence[float]) -> list:
+def gradient_quantiles(dx: torch.Tensor, dy: torch.Tensor, quantiles: Sequence[float]):
     """np.quantile(sqrt(dx**2 + dy**2), q) for every q (utils.py:119, 125-126), float32 results
-    identical to NumPy's.  Needs |dx|, |dy| <= 4095 (true for Scharr of an 8-bit image) so that
+    identical to NumPy's: a list over q for one image, a list over images of such lists for a
+    batch.  Needs |dx|, |dy| <= 4095 (true for Scharr of an 8-bit image) so that
     float32(dx^2 + dy^2) equals the reference's float32 sum of squares."""
-    _check(dx, "dx", torch.int16, 2)
-    _check(dy, "dy", torch.int16, 2)
-    n = dx.numel()
+    gx, squeeze = _batched(dx, "dx", torch.int16)
+    gy, _ = _batched(dy, "dy", torch.int16)
+    b, h, w = gx.shape
+    n = h * w
     wanted = []          # ranks whose order statistic is needed, per quantile
     for q in quantiles:
         _, prev, nxt = _quantile_indexes(n, q)
         wanted.append((n - 1, n - 1) if prev == -1 else (prev, min(nxt, n - 1)))
     ranks = sorted({r for pair in wanted for r in pair} | {n - 1})
-    values = {}
-    scratch = torch.empty(4 * 2048, dtype=torch.int32, device=dx.device)
+    values = [dict() for _ in range(b)]
+    scratch = torch.empty(b * 4 * (1 + 2048), dtype=torch.int32, device=dx.device)
     for i in range(0, len(ranks), 4):
         chunk = ranks[i: i + 4]
         arr = (ctypes.c_int64 * len(chunk))(*chunk)
-        out = (ctypes.c_int64 * len(chunk))()
-        _lib.call("mgb_gradient_order_stats", _ptr(dx), _ptr(dy), n, arr, len(chunk), out, _ptr(scratch), _stream())
-        for r, m in zip(chunk, out):
-            values[r] = np.sqrt(np.float32(m))      # sqrt(float32 sum of exact squares)
-    return [linear_quantile(n, q, values[lo], values[hi], values[n - 1]) for q, (lo, hi) in zip(quantiles, wanted)]
+        out = (ctypes.c_int64 * (b * len(chunk)))()
+        _lib.call("mgb_gradient_order_stats", _ptr(gx), _ptr(gy), b, n, arr, len(chunk), out, _ptr(scratch), _stream())
+        m = np.sqrt(np.ctypeslib.as_array(out).reshape(b, len(chunk)).astype(np.float32))   # sqrt(float32 sum of squares)
+        for k in range(b):
+            for r, v in zip(chunk, m[k]):
+                values[k][r] = v
+    result = [[linear_quantile(n, q, values[k][lo], values[k][hi], values[k][n - 1])
+               for q, (lo, hi) in zip(quantiles, wanted)] for k in range(b)]
+    return result[0] if squeeze else result
 
 
 def canny_thresholds(threshold1: float, threshold2: float) -> Tuple[int, int]:
@@ -118,24 +134,184 @@ def canny_thresholds(threshold1: float, threshold2: float) -> Tuple[int, int]:
     return math.floor(lo), math.floor(hi)
 
 
-def canny(dx: torch.Tensor, dy: torch.Tensor, threshold1: float, threshold2: float, return_sweeps: bool = False):
-    """cv.Canny(dx, dy, threshold1, threshold2, L2gradient=True) != 0 as a (H, W) uint8 0/1 map
-    (utils.py:127-139)."""
-    _check(dx, "dx", torch.int16, 2)
-    _check(dy, "dy", torch.int16, 2)
-    h, w = dx.shape
-    low, high = canny_thresholds(threshold1, threshold2)
-    work = torch.empty((h, w), dtype=torch.uint8, device=dx.device)
+def canny(dx: torch.Tensor, dy: torch.Tensor, threshold1, threshold2, return_sweeps: bool = False):
+    """cv.Canny(dx, dy, threshold1, threshold2, L2gradient=True) != 0 as uint8 0/1 maps
+    (utils.py:127-139).  For a batch, threshold1 / threshold2 are sequences (one pair per image)."""
+    gx, squeeze = _batched(dx, "dx", torch.int16)
+    gy, _ = _batched(dy, "dy", torch.int16)
+    b, h, w = gx.shape
+    t1 = [threshold1] * b if np.ndim(threshold1) == 0 else list(threshold1)
+    t2 = [threshold2] * b if np.ndim(threshold2) == 0 else list(threshold2)
+    if len(t1) != b or len(t2) != b:
+        raise ValueError("one threshold pair per image")
+    thr = np.array([canny_thresholds(a, c) for a, c in zip(t1, t2)], dtype=np.int32).reshape(b, 2)
+    thresholds = torch.from_numpy(thr).to(dx.device)
+    work = torch.empty((b, h, w), dtype=torch.uint8, device=dx.device)
     edges = torch.empty_like(work)
     changed = torch.empty(1, dtype=torch.int32, device=dx.device)
     sweeps = ctypes.c_int()
-    _lib.call("mgb_canny", _ptr(dx), _ptr(dy), h, w, low, high, _ptr(work), _ptr(edges), _ptr(changed),
+    _lib.call("mgb_canny", _ptr(gx), _ptr(gy), b, h, w, _ptr(thresholds), _ptr(work), _ptr(edges), _ptr(changed),
               ctypes.byref(sweeps), _stream())
+    edges = edges[0] if squeeze else edges
     return (edges, sweeps.value) if return_sweeps else edges
 
 
 def find_edges(image: torch.Tensor, low_edge_quantile: float, high_edge_quantile: float):
-    """Steps 1-2 of find_circles (utils.py:113-139) for a (H, W) uint8 image: (edges 0/1, dx, dy)."""
+    """Steps 1-2 of find_circles (utils.py:113-139) for (H, W) or (B, H, W) uint8 images:
+    (edges 0/1, dx, dy)."""
     dx, dy = edge_gradients(image)
-    low, high = gradient_quantiles(dx, dy, (low_edge_quantile, high_edge_quantile))
-    return canny(dx, dy, low, high), dx, dy
+    q = gradient_quantiles(dx, dy, (low_edge_quantile, high_edge_quantile))
+    if image.ndim == 2:
+        return canny(dx, dy, q[0], q[1]), dx, dy
+    return canny(dx, dy, [v[0] for v in q], [v[1] for v in q]), dx, dy
+
+
+# ---------------------------------------------------------------------------------------------
+# candidates, scores, suppression  (utils.py:141-218, 221-377)
+# ---------------------------------------------------------------------------------------------
+def circle_perimeter(r: int, four_connected: bool = False) -> np.ndarray:
+    """utils.py:433-465 `circle_points`: (n, 2) int32 (drow, dcol) in the reference's order."""
+    pts = (ctypes.c_int32 * (40 * r))()
+    n = ctypes.c_int()
+    _lib.call("mgb_circle_perimeter", int(r), int(bool(four_connected)), pts, 20 * r, ctypes.byref(n))
+    return np.ctypeslib.as_array(pts)[: 2 * n.value].reshape(-1, 2).copy()
+
+
+def perimeter_tables(rmin: int, rmax: int):
+    """Concatenated perimeters of radius rmin..rmax for the scoring kernel: offsets (rmax-rmin+2)
+    int32, points (P, 2) int16, expected angles (P) float64 = arctan2(drow, dcol) (utils.py:230)."""
+    pts = [circle_perimeter(r) for r in range(rmin, rmax + 1)]
+    offsets = np.zeros(len(pts) + 1, dtype=np.int32)
+    offsets[1:] = np.cumsum([len(p) for p in pts])
+    points = np.concatenate(pts).astype(np.int32)
+    expected = np.arctan2(points[:, 0], points[:, 1])
+    return offsets, points.astype(np.int16), expected.astype(np.float64)
+
+
+def filter_neighbors(circles: np.ndarray, min_dist: int) -> np.ndarray:
+    """utils.py:252-285 on (n, 3) int32 circles sorted best first: boolean keep mask."""
+    circles = np.ascontiguousarray(circles, dtype=np.int32)
+    valid = np.ones(len(circles), dtype=np.uint8)
+    if len(circles):
+        _lib.call("mgb_filter_neighbors", circles.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), len(circles),
+                  int(min_dist), valid.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+    return valid.astype(bool)
+
+
+class EdgeLists:
+    """Edge pixels of a batch of edge maps grouped by grid cell (utils.py:347-377)."""
+
+    def __init__(self, edges: torch.Tensor, grid_length: int):
+        e, _ = _batched(edges, "edges", torch.uint8)
+        self.b, self.h, self.w = e.shape
+        self.grid_length = int(grid_length)
+        cells = self.b * math.ceil(self.h / grid_length) * math.ceil(self.w / grid_length)
+        self.counts = torch.empty(cells + 1, dtype=torch.int64, device=e.device)
+        self.starts = torch.empty(cells + 1, dtype=torch.int64, device=e.device)
+        total = ctypes.c_int64()
+        args = (_ptr(e), self.b, self.h, self.w, self.grid_length, _ptr(self.counts), _ptr(self.starts))
+        _lib.call("mgb_edge_cell_lists", *args, None, 0, ctypes.byref(total), _stream())
+        self.total = int(total.value)
+        self.coords = torch.empty(max(self.total, 1), dtype=torch.int32, device=e.device)
+        if self.total:
+            _lib.call("mgb_edge_cell_lists", *args, _ptr(self.coords), self.total, ctypes.byref(total), _stream())
+
+    def grid_coords(self) -> np.ndarray:
+        """(total, 2) int32 (row, col) -- `grid_coords` of utils.py:362-375, images concatenated."""
+        packed = self.coords[: self.total].cpu().numpy().view(np.uint32)
+        return np.stack([packed >> 16, packed & 0xFFFF], axis=1).astype(np.int32)
+
+
+def sample_circles(lists: EdgeLists, num_iter: int, min_radius=None, max_radius=None, seed: int = 0,
+                   randoms: torch.Tensor = None, want_raw: bool = False):
+    """utils.py:288-344 (+ :155-165 when a radius window is given).  Returns (raw, circles):
+    raw (B, num_iter, 3) float32 draws (None unless want_raw), circles (U, 4) int32 unique rounded
+    (image, row, col, radius) (None without a radius window)."""
+    dev = lists.coords.device
+    total = lists.b * int(num_iter)
+    raw = torch.empty((lists.b, num_iter, 3), dtype=torch.float32, device=dev) if want_raw else None
+    if randoms is not None:
+        if randoms.dtype != torch.int32 or tuple(randoms.shape) != (lists.b, num_iter, 3) or not randoms.is_contiguous():
+            raise ValueError("randoms must be a contiguous (B, num_iter, 3) int32 tensor holding uint32 bit patterns")
+    window = min_radius is not None
+    table = circles = counter = None
+    n_unique = ctypes.c_int64()
+    cap = 0
+    if window and total:
+        cap = 1 << max(1, (2 * total - 1).bit_length())
+        table = torch.empty(cap, dtype=torch.int64, device=dev)
+        circles = torch.empty((total, 4), dtype=torch.int32, device=dev)
+        counter = torch.empty(1, dtype=torch.int64, device=dev)
+    _lib.call("mgb_sample_circles", _ptr(lists.coords), _ptr(lists.starts), _ptr(lists.counts), lists.b, lists.h, lists.w,
+              lists.grid_length, int(num_iter), float(min_radius if window else 0.0), float(max_radius if window else 0.0),
+              int(seed) & (2**64 - 1), _ptr(randoms), _ptr(raw), _ptr(table), cap, _ptr(circles),
+              ctypes.byref(n_unique), _ptr(counter), _stream())
+    if window:
+        circles = circles[: n_unique.value] if circles is not None else torch.empty((0, 4), dtype=torch.int32, device=dev)
+    return raw, circles
+
+
+def gradient_angles(dx: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    """float32 arctan2(dy, dx) per pixel (utils.py:169), computed in float64 and rounded once."""
+    angle = torch.empty(dx.shape, dtype=torch.float32, device=dx.device)
+    _lib.call("mgb_gradient_angles", _ptr(dx), _ptr(dy), dx.numel(), _ptr(angle), _stream())
+    return angle
+
+
+def score_circles(circles: torch.Tensor, edges: torch.Tensor, angle: torch.Tensor, min_radius: int,
+                  max_radius: int) -> torch.Tensor:
+    """utils.py:181-183 + mean_grad (:221-249): alignment score / perimeter length, float32, for
+    (N, 4) int32 circles (image, row, col, radius)."""
+    e, _ = _batched(edges, "edges", torch.uint8)
+    _check(circles, "circles", torch.int32, 2)
+    b, h, w = e.shape
+    offsets, points, expected = perimeter_tables(int(min_radius), int(max_radius))
+    dev = e.device
+    scores = torch.empty(circles.shape[0], dtype=torch.float32, device=dev)
+    if circles.shape[0]:
+        # keep the uploaded tables referenced until the launch is queued (the caching allocator
+        # would hand a released block to the next upload)
+        tables = [torch.from_numpy(a).to(dev) for a in (offsets, points, expected)]
+        _lib.call("mgb_score_circles", _ptr(circles), circles.shape[0], h, w, _ptr(e), _ptr(angle), int(min_radius),
+                  int(max_radius), _ptr(tables[0]), _ptr(tables[1]), _ptr(tables[2]), _ptr(scores), _stream())
+    return scores
+
+
+def select_circles(circles: np.ndarray, scores: np.ndarray, min_roundness: float, min_dist: int):
+    """utils.py:187-197 on one image's unique circles (n, 3) int32 and float32 scores: keep
+    score >= min_roundness, order best first, suppress neighbours.  Equal scores are ordered by
+    (row, col, radius) -- the reference leaves that order to an unstable sort."""
+    keep = scores >= min_roundness                     # float32 array vs Python float: NumPy casts the scalar
+    circles, scores = circles[keep], scores[keep]
+    order = np.lexsort((circles[:, 2], circles[:, 1], circles[:, 0], -scores))
+    circles, scores = circles[order], scores[order]
+    if min_dist > 0 and len(circles):
+        valid = filter_neighbors(circles, min_dist)
+        circles, scores = circles[valid], scores[valid]
+    return circles, scores
+
+
+def find_circles(image: torch.Tensor, low_edge_quantile: float, high_edge_quantile: float, grid_length: int,
+                 num_iter: int, min_radius: int, max_radius: int, min_roundness: float, min_dist: int, seed: int = 0):
+    """`utils.find_circles` (utils.py:100-218) for a (H, W) uint8 image -> (circles (n,3) int32
+    [row, col, radius], scores (n,) float32), best first; for a (B, H, W) batch a list of such
+    pairs.  Deterministic for a given seed.  Differences from the reference, both outside what it
+    can reproduce itself: the random draws (see csrc/circles_sample.cu) and duplicates -- the
+    reference returns a rounded circle once per draw that produced it when min_dist == 0, here
+    every circle appears once."""
+    edges, dx, dy = find_edges(image, low_edge_quantile, high_edge_quantile)
+    e, squeeze = _batched(edges, "edges", torch.uint8)
+    b = e.shape[0]
+    empty = (np.empty((0, 3), np.int32), np.empty(0, np.float32))
+    lists = EdgeLists(e, grid_length)
+    results = [empty] * b
+    if lists.total and num_iter > 0:
+        _, circles = sample_circles(lists, num_iter, min_radius, max_radius, seed)
+        if circles.shape[0]:
+            angle = gradient_angles(dx, dy)
+            scores = score_circles(circles, e, angle, min_radius, max_radius).cpu().numpy()
+            found = circles.cpu().numpy()
+            for k in range(b):
+                mine = found[:, 0] == k
+                results[k] = select_circles(found[mine, 1:], scores[mine], min_roundness, min_dist)
+    return results[0] if squeeze else results

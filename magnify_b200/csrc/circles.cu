@@ -18,6 +18,9 @@
 // reproducible by construction (unseeded numba RNG under prange); see circles_sample.cu.
 #include "common.cuh"
 
+#include <algorithm>
+#include <vector>
+
 namespace {
 
 using mgb::kThreads;
@@ -44,9 +47,12 @@ __device__ __forceinline__ void atomic_max_f64(double* addr, double v) {
   }
 }
 
+// images are (B, n) / (B, H, W); blockIdx.y (or .z for the 2-D kernels) selects the image
 template <typename T>
 __global__ void __launch_bounds__(kThreads) minmax_kernel(const T* __restrict__ x, int64_t n,
                                                           double* __restrict__ mm) {
+  x += (int64_t)blockIdx.y * n;
+  mm += 2 * blockIdx.y;
   double lo = INFINITY, hi = -INFINITY;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double v = (double)x[i];
@@ -73,15 +79,21 @@ __global__ void __launch_bounds__(kThreads) minmax_kernel(const T* __restrict__ 
   }
 }
 
-__global__ void minmax_init_kernel(double* mm) {
-  mm[0] = INFINITY;
-  mm[1] = -INFINITY;
+__global__ void minmax_init_kernel(double* mm, int64_t B) {
+  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (b < B) {
+    mm[2 * b] = INFINITY;
+    mm[2 * b + 1] = -INFINITY;
+  }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads) to_uint8_kernel(const T* __restrict__ x, int64_t n,
                                                             const double* __restrict__ mm,
                                                             uint8_t* __restrict__ out) {
+  x += (int64_t)blockIdx.y * n;
+  out += (int64_t)blockIdx.y * n;
+  mm += 2 * blockIdx.y;
   const double lo = mm[0], range = mm[1] - mm[0];   // == max(x - min): the subtraction is monotone
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     double v = (double)x[i] - lo;
@@ -101,6 +113,8 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 
 __global__ void __launch_bounds__(kThreads) blur5_u8_kernel(const uint8_t* __restrict__ img, int H, int W,
                                                             uint8_t* __restrict__ out) {
+  img += (int64_t)blockIdx.z * H * W;
+  out += (int64_t)blockIdx.z * H * W;
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y0 = blockIdx.y * 32 + (threadIdx.x >> 5) * 4;
   if (x >= W) return;
@@ -124,6 +138,9 @@ __global__ void __launch_bounds__(kThreads) blur5_u8_kernel(const uint8_t* __res
 
 __global__ void __launch_bounds__(kThreads) scharr_kernel(const uint8_t* __restrict__ b, int H, int W,
                                                           int16_t* __restrict__ dx, int16_t* __restrict__ dy) {
+  b += (int64_t)blockIdx.z * H * W;
+  dx += (int64_t)blockIdx.z * H * W;
+  dy += (int64_t)blockIdx.z * H * W;
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y0 = blockIdx.y * 32 + (threadIdx.x >> 5) * 4;
   if (x >= W) return;
@@ -154,16 +171,24 @@ constexpr int kMaxTargets = 4;
 struct SelectLevel {
   int shift;          // bits below this level's digit
   int bins;           // 1 << digit bits
-  int prefix_shift;   // m >> prefix_shift must equal the target prefix (32 = no prefix at level 0)
-  int n_targets;
-  uint32_t prefix[kMaxTargets];
+  int prefix_shift;   // m >> prefix_shift must equal a target prefix (32 = no prefix at level 0)
+  int n_targets;      // histograms per image at this level
 };
 
 __global__ void __launch_bounds__(kThreads) grad_hist_kernel(const int16_t* __restrict__ dx,
                                                              const int16_t* __restrict__ dy, int64_t n,
-                                                             SelectLevel lv, uint32_t* __restrict__ hist) {
+                                                             SelectLevel lv,
+                                                             const uint32_t* __restrict__ prefixes,
+                                                             uint32_t* __restrict__ hist) {
   extern __shared__ uint32_t sh[];
   const int total = lv.bins * lv.n_targets;
+  dx += (int64_t)blockIdx.y * n;
+  dy += (int64_t)blockIdx.y * n;
+  hist += (int64_t)blockIdx.y * total;
+  uint32_t prefix[kMaxTargets];
+#pragma unroll
+  for (int t = 0; t < kMaxTargets; ++t)
+    prefix[t] = lv.prefix_shift >= 32 ? 0u : prefixes[blockIdx.y * kMaxTargets + t];
   for (int i = threadIdx.x; i < total; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -182,7 +207,7 @@ __global__ void __launch_bounds__(kThreads) grad_hist_kernel(const int16_t* __re
     } else {
       const uint32_t p = m >> lv.prefix_shift;
       for (int t = 0; t < lv.n_targets; ++t)       // prefixes are distinct: at most one matches
-        if (p == lv.prefix[t]) slot = t * lv.bins + (int)digit;
+        if (p == prefix[t]) slot = t * lv.bins + (int)digit;
     }
     // Gradient magnitudes are heavily concentrated (flat background): aggregate equal slots
     // within the warp before touching shared memory.
@@ -209,8 +234,13 @@ __device__ __forceinline__ int mag_at(const int16_t* __restrict__ dx, const int1
 
 // map: 0 = above low and a local maximum (edge candidate), 1 = not an edge, 2 = strong edge
 __global__ void __launch_bounds__(kThreads) canny_nms_kernel(const int16_t* __restrict__ dx,
-                                                             const int16_t* __restrict__ dy, int H, int W, int low,
-                                                             int high, uint8_t* __restrict__ map) {
+                                                             const int16_t* __restrict__ dy, int H, int W,
+                                                             const int32_t* __restrict__ thresholds,
+                                                             uint8_t* __restrict__ map) {
+  dx += (int64_t)blockIdx.z * H * W;
+  dy += (int64_t)blockIdx.z * H * W;
+  map += (int64_t)blockIdx.z * H * W;
+  const int low = thresholds[2 * blockIdx.z], high = thresholds[2 * blockIdx.z + 1];
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= W || y >= H) return;
@@ -245,6 +275,7 @@ __global__ void __launch_bounds__(kThreads) canny_hysteresis_kernel(uint8_t* __r
                                                                     int* __restrict__ changed) {
   __shared__ uint8_t t[34][36];
   __shared__ int again, any;
+  map += (int64_t)blockIdx.z * H * W;
   const int x0 = blockIdx.x * 32 - 1, y0 = blockIdx.y * 32 - 1;
   for (int i = threadIdx.x; i < 34 * 34; i += blockDim.x) {
     const int ly = i / 34, lx = i - ly * 34;
@@ -300,12 +331,15 @@ int grid_for(int64_t n) {
 }
 
 template <typename T>
-int to_uint8_launch(const void* src, int64_t n, uint8_t* dst, double* mm, cudaStream_t s) {
-  minmax_init_kernel<<<1, 1, 0, s>>>(mm);
+int to_uint8_launch(const void* src, int64_t B, int64_t n, uint8_t* dst, double* mm, cudaStream_t s) {
+  minmax_init_kernel<<<(unsigned)mgb::ceil_div(B, kThreads), kThreads, 0, s>>>(mm, B);
   MGB_CUDA_LAUNCH_CHECK();
-  minmax_kernel<T><<<grid_for(n), kThreads, 0, s>>>(static_cast<const T*>(src), n, mm);
+  int gx = grid_for(n);
+  if (B > 1) gx = (int)std::max<int64_t>(1, std::min<int64_t>(gx, mgb::ceil_div((int64_t)mgb_sm_count() * 16, B)));
+  const dim3 grid((unsigned)gx, (unsigned)B);
+  minmax_kernel<T><<<grid, kThreads, 0, s>>>(static_cast<const T*>(src), n, mm);
   MGB_CUDA_LAUNCH_CHECK();
-  to_uint8_kernel<T><<<grid_for(n), kThreads, 0, s>>>(static_cast<const T*>(src), n, mm, dst);
+  to_uint8_kernel<T><<<grid, kThreads, 0, s>>>(static_cast<const T*>(src), n, mm, dst);
   MGB_CUDA_LAUNCH_CHECK();
   return MGB_OK;
 }
@@ -314,24 +348,25 @@ int to_uint8_launch(const void* src, int64_t n, uint8_t* dst, double* mm, cudaSt
 
 extern "C" {
 
-int mgb_to_uint8(const void* src, int dtype, int64_t n, uint8_t* dst, double* minmax, void* stream) {
-  if (n < 0 || (n > 0 && (!src || !dst)) || !minmax) return MGB_EINVAL;
-  if (n == 0) return MGB_OK;
+int mgb_to_uint8(const void* src, int dtype, int64_t B, int64_t n, uint8_t* dst, double* minmax, void* stream) {
+  if (B < 0 || n < 0 || B > 65535 || (B * n > 0 && (!src || !dst)) || !minmax) return MGB_EINVAL;
+  if (B == 0 || n == 0) return MGB_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (dtype) {
-    case MGB_U8: return to_uint8_launch<uint8_t>(src, n, dst, minmax, s);
-    case MGB_U16: return to_uint8_launch<uint16_t>(src, n, dst, minmax, s);
-    case MGB_F32: return to_uint8_launch<float>(src, n, dst, minmax, s);
-    case MGB_F64: return to_uint8_launch<double>(src, n, dst, minmax, s);
+    case MGB_U8: return to_uint8_launch<uint8_t>(src, B, n, dst, minmax, s);
+    case MGB_U16: return to_uint8_launch<uint16_t>(src, B, n, dst, minmax, s);
+    case MGB_F32: return to_uint8_launch<float>(src, B, n, dst, minmax, s);
+    case MGB_F64: return to_uint8_launch<double>(src, B, n, dst, minmax, s);
     default: return MGB_EUNSUPPORTED;
   }
 }
 
-int mgb_edge_gradients_u8(const uint8_t* image, int64_t H, int64_t W, uint8_t* blurred, int16_t* dx, int16_t* dy,
-                          void* stream) {
-  if (!image || !blurred || !dx || !dy || H <= 0 || W <= 0 || H > (1 << 30) || W > (1 << 30)) return MGB_EINVAL;
+int mgb_edge_gradients_u8(const uint8_t* image, int64_t B, int64_t H, int64_t W, uint8_t* blurred, int16_t* dx,
+                          int16_t* dy, void* stream) {
+  if (!image || !blurred || !dx || !dy || B <= 0 || B > 65535 || H <= 0 || W <= 0 || H > (1 << 30) || W > (1 << 30))
+    return MGB_EINVAL;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const dim3 grid((unsigned)mgb::ceil_div(W, 32), (unsigned)mgb::ceil_div(H, 32));
+  const dim3 grid((unsigned)mgb::ceil_div(W, 32), (unsigned)mgb::ceil_div(H, 32), (unsigned)B);
   blur5_u8_kernel<<<grid, kThreads, 0, s>>>(image, (int)H, (int)W, blurred);
   MGB_CUDA_LAUNCH_CHECK();
   scharr_kernel<<<grid, kThreads, 0, s>>>(blurred, (int)H, (int)W, dx, dy);
@@ -339,69 +374,90 @@ int mgb_edge_gradients_u8(const uint8_t* image, int64_t H, int64_t W, uint8_t* b
   return MGB_OK;
 }
 
-int mgb_gradient_order_stats(const int16_t* dx, const int16_t* dy, int64_t n, const int64_t* host_ranks,
+int mgb_gradient_order_stats(const int16_t* dx, const int16_t* dy, int64_t B, int64_t n, const int64_t* host_ranks,
                              int n_ranks, int64_t* host_values, uint32_t* scratch, void* stream) {
-  if (!dx || !dy || !host_ranks || !host_values || !scratch || n <= 0 || n_ranks < 1 || n_ranks > kMaxTargets)
+  if (!dx || !dy || !host_ranks || !host_values || !scratch || B <= 0 || B > 65535 || n <= 0 || n_ranks < 1 ||
+      n_ranks > kMaxTargets)
     return MGB_EINVAL;
   for (int t = 0; t < n_ranks; ++t)
     if (host_ranks[t] < 0 || host_ranks[t] >= n) return MGB_EINVAL;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int shifts[3] = {20, 10, 0}, bins[3] = {2048, 1024, 1024};
-  uint32_t prefix[kMaxTargets] = {0, 0, 0, 0};
-  int64_t rank[kMaxTargets];
-  for (int t = 0; t < n_ranks; ++t) rank[t] = host_ranks[t];
-  static thread_local uint32_t host_hist[kMaxTargets * 2048];
+  // scratch layout: [B * 4] prefixes, then [B * 4 * 2048] histogram words
+  uint32_t* d_prefix = scratch;
+  uint32_t* d_hist = scratch + (size_t)B * kMaxTargets;
+  std::vector<uint32_t> prefix((size_t)B * kMaxTargets, 0u), slot_prefix((size_t)B * kMaxTargets, 0xffffffffu);
+  std::vector<int> slot_of((size_t)B * kMaxTargets, 0);
+  std::vector<int64_t> rank((size_t)B * kMaxTargets);
+  for (int64_t b = 0; b < B; ++b)
+    for (int t = 0; t < n_ranks; ++t) rank[b * kMaxTargets + t] = host_ranks[t];
+  std::vector<uint32_t> host_hist;
+  int gx = grid_for(n);
+  if (B > 1) gx = (int)std::max<int64_t>(1, std::min<int64_t>(gx, mgb::ceil_div((int64_t)mgb_sm_count() * 16, B)));
   for (int level = 0; level < 3; ++level) {
-    // distinct prefixes of this level (ranks that fell into the same bin share a histogram)
     SelectLevel lv;
     lv.shift = shifts[level];
     lv.bins = bins[level];
     lv.prefix_shift = level == 0 ? 32 : shifts[level - 1];
-    lv.n_targets = 0;
-    int slot_of[kMaxTargets];
-    for (int t = 0; t < n_ranks; ++t) {
-      int found = -1;
-      for (int u = 0; u < lv.n_targets; ++u)
-        if (level == 0 || lv.prefix[u] == prefix[t]) found = u;
-      if (found < 0) {
-        found = lv.n_targets++;
-        lv.prefix[found] = prefix[t];
+    // ranks of one image that fell into the same bin share a histogram slot
+    int max_slots = 1;
+    for (int64_t b = 0; b < B; ++b) {
+      int used = 0;
+      for (int t = 0; t < n_ranks; ++t) {
+        int found = -1;
+        for (int u = 0; u < used; ++u)
+          if (level == 0 || slot_prefix[b * kMaxTargets + u] == prefix[b * kMaxTargets + t]) found = u;
+        if (found < 0) {
+          found = used++;
+          slot_prefix[b * kMaxTargets + found] = prefix[b * kMaxTargets + t];
+        }
+        slot_of[b * kMaxTargets + t] = found;
       }
-      slot_of[t] = found;
+      for (int u = used; u < kMaxTargets; ++u) slot_prefix[b * kMaxTargets + u] = 0xffffffffu;
+      max_slots = std::max(max_slots, used);
     }
-    for (int u = lv.n_targets; u < kMaxTargets; ++u) lv.prefix[u] = 0xffffffffu;
-    const size_t bytes = (size_t)lv.bins * lv.n_targets * sizeof(uint32_t);
-    MGB_CUDA_TRY(cudaMemsetAsync(scratch, 0, bytes, s));
-    grad_hist_kernel<<<grid_for(n), kThreads, bytes, s>>>(dx, dy, n, lv, scratch);
+    lv.n_targets = level == 0 ? 1 : max_slots;
+    const size_t words = (size_t)B * lv.bins * lv.n_targets;
+    MGB_CUDA_TRY(cudaMemcpyAsync(d_prefix, slot_prefix.data(), (size_t)B * kMaxTargets * sizeof(uint32_t),
+                                 cudaMemcpyHostToDevice, s));
+    MGB_CUDA_TRY(cudaMemsetAsync(d_hist, 0, words * sizeof(uint32_t), s));
+    grad_hist_kernel<<<dim3((unsigned)gx, (unsigned)B), kThreads, (size_t)lv.bins * lv.n_targets * sizeof(uint32_t), s>>>(
+        dx, dy, n, lv, d_prefix, d_hist);
     MGB_CUDA_LAUNCH_CHECK();
-    MGB_CUDA_TRY(cudaMemcpyAsync(host_hist, scratch, bytes, cudaMemcpyDeviceToHost, s));
+    host_hist.resize(words);
+    MGB_CUDA_TRY(cudaMemcpyAsync(host_hist.data(), d_hist, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     MGB_CUDA_TRY(cudaStreamSynchronize(s));
-    for (int t = 0; t < n_ranks; ++t) {
-      const uint32_t* h = host_hist + slot_of[t] * lv.bins;
-      int64_t acc = 0;
-      int d = 0;
-      for (; d < lv.bins; ++d) {
-        if (acc + h[d] > rank[t]) break;
-        acc += h[d];
+    for (int64_t b = 0; b < B; ++b) {
+      for (int t = 0; t < n_ranks; ++t) {
+        const uint32_t* h = host_hist.data() + ((size_t)b * lv.n_targets + slot_of[b * kMaxTargets + t]) * lv.bins;
+        int64_t acc = 0;
+        int d = 0;
+        for (; d < lv.bins; ++d) {
+          if (acc + h[d] > rank[b * kMaxTargets + t]) break;
+          acc += h[d];
+        }
+        if (d == lv.bins) return MGB_EINVAL;   // rank beyond the counted elements: cannot happen
+        rank[b * kMaxTargets + t] -= acc;
+        uint32_t& p = prefix[b * kMaxTargets + t];
+        p = level == 0 ? (uint32_t)d : ((p << 10) | (uint32_t)d);
       }
-      if (d == lv.bins) return MGB_EINVAL;   // rank beyond the counted elements: cannot happen
-      rank[t] -= acc;
-      prefix[t] = level == 0 ? (uint32_t)d : ((prefix[t] << 10) | (uint32_t)d);
     }
   }
-  for (int t = 0; t < n_ranks; ++t) host_values[t] = (int64_t)prefix[t];
+  for (int64_t b = 0; b < B; ++b)
+    for (int t = 0; t < n_ranks; ++t) host_values[b * n_ranks + t] = (int64_t)prefix[b * kMaxTargets + t];
   return MGB_OK;
 }
 
-int mgb_canny(const int16_t* dx, const int16_t* dy, int64_t H, int64_t W, int low, int high, uint8_t* map,
-              uint8_t* edges, int* changed, int* host_sweeps, void* stream) {
-  if (!dx || !dy || !map || !edges || !changed || H <= 0 || W <= 0 || H > (1 << 30) || W > (1 << 30))
+int mgb_canny(const int16_t* dx, const int16_t* dy, int64_t B, int64_t H, int64_t W, const int32_t* thresholds,
+              uint8_t* map, uint8_t* edges, int* changed, int* host_sweeps, void* stream) {
+  if (!dx || !dy || !thresholds || !map || !edges || !changed || B <= 0 || B > 65535 || H <= 0 || W <= 0 ||
+      H > (1 << 30) || W > (1 << 30))
     return MGB_EINVAL;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  canny_nms_kernel<<<dim3((unsigned)mgb::ceil_div(W, 32), (unsigned)mgb::ceil_div(H, 8)), kThreads, 0, s>>>(
-      dx, dy, (int)H, (int)W, low, high, map);
+  canny_nms_kernel<<<dim3((unsigned)mgb::ceil_div(W, 32), (unsigned)mgb::ceil_div(H, 8), (unsigned)B), kThreads, 0, s>>>(
+      dx, dy, (int)H, (int)W, thresholds, map);
   MGB_CUDA_LAUNCH_CHECK();
-  const dim3 grid((unsigned)mgb::ceil_div(W, 32), (unsigned)mgb::ceil_div(H, 32));
+  const dim3 grid((unsigned)mgb::ceil_div(W, 32), (unsigned)mgb::ceil_div(H, 32), (unsigned)B);
   int sweeps = 0;
   for (;;) {
     MGB_CUDA_TRY(cudaMemsetAsync(changed, 0, sizeof(int), s));
@@ -413,7 +469,7 @@ int mgb_canny(const int16_t* dx, const int16_t* dy, int64_t H, int64_t W, int lo
     MGB_CUDA_TRY(cudaStreamSynchronize(s));
     if (host_changed == 0) break;
   }
-  canny_edges_kernel<<<grid_for(H * W), kThreads, 0, s>>>(map, H * W, edges);
+  canny_edges_kernel<<<grid_for(B * H * W), kThreads, 0, s>>>(map, B * H * W, edges);
   MGB_CUDA_LAUNCH_CHECK();
   if (host_sweeps) *host_sweeps = sweeps;
   return MGB_OK;

@@ -1,0 +1,335 @@
+// Candidate circles and their scores: steps 3-5 of the reference's circle finder
+// (src/magnify/utils.py:141-189, 221-249, 288-377), for a batch of B images.
+//
+//   grid lists     utils.py:347-377  edge pixels grouped by grid cell (cell-major, row-major inside
+//                                    a cell, exactly the order of `grid_coords`)
+//   sampling       utils.py:288-344  three edge pixels -> circumcircle.  The arithmetic reproduces
+//                                    numba's typing of those lines bit for bit (float64 everywhere
+//                                    except the radius, which is sqrt(c0*c0 + c1*c1) in float32;
+//                                    pinned against the reference's own function on 3-pixel images
+//                                    in tests/test_circles_host.py).  Which pixels are drawn is NOT
+//                                    reproducible: the reference uses numba's unseeded per-thread
+//                                    RNG under prange.  Here the draws come from a counter-based
+//                                    generator (seed, image, iteration) or from a caller-supplied
+//                                    table, and p0 is drawn from the cell-major list (a uniform
+//                                    draw over all edge pixels either way).
+//   filter + round utils.py:155-165  radius window, round-half-even to int32, off-image test
+//   dedupe                           identical rounded circles are kept once (an open-addressing
+//                                    table); the reference scores every duplicate again
+//   scoring        utils.py:169-189, 221-249  gradient alignment along the Bresenham perimeter,
+//                                    summed in float64 in perimeter order, stored as float32,
+//                                    divided by the perimeter length in float32
+#include "common.cuh"
+
+#include <algorithm>
+
+#include <cub/device/device_scan.cuh>
+
+namespace {
+
+using mgb::kThreads;
+
+// ---------------------------------------------------------------------------------------------
+// grid lists
+// ---------------------------------------------------------------------------------------------
+struct GridDims {
+  int H, W, g, rows, cols;   // rows = ceil(H / g), cols = ceil(W / g)
+};
+
+// One thread per (image, cell): count (fill == false) or write (fill == true) its edge pixels in
+// row-major order.  coords holds (row << 16 | col); H, W <= 65535.
+template <bool kFill>
+__global__ void __launch_bounds__(kThreads) cell_lists_kernel(const uint8_t* __restrict__ edges, GridDims d,
+                                                              int64_t n_cells_total, int64_t* __restrict__ counts,
+                                                              const int64_t* __restrict__ starts,
+                                                              uint32_t* __restrict__ coords) {
+  const int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (id >= n_cells_total) return;
+  const int64_t per_image = (int64_t)d.rows * d.cols;
+  const int64_t b = id / per_image;
+  const int cell = (int)(id - b * per_image);
+  const int cr = cell / d.cols, cc = cell - cr * d.cols;
+  const uint8_t* img = edges + b * (int64_t)d.H * d.W;
+  const int r1 = min(d.H, (cr + 1) * d.g), c1 = min(d.W, (cc + 1) * d.g);
+  int64_t n = kFill ? starts[id] : 0;
+  for (int r = cr * d.g; r < r1; ++r)
+    for (int c = cc * d.g; c < c1; ++c)
+      if (img[(int64_t)r * d.W + c]) {
+        if (kFill) coords[n] = ((uint32_t)r << 16) | (uint32_t)c;
+        ++n;
+      }
+  if (!kFill) counts[id] = n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sampling
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+struct SampleParams {
+  GridDims d;
+  int64_t B, num_iter;
+  float min_radius, max_radius;
+  uint64_t seed;
+  uint64_t table_mask;   // capacity - 1 (power of two)
+};
+
+constexpr uint64_t kEmpty = ~0ull;
+constexpr int kCoordBias = 1 << 15;   // rounded centres lie within max_radius of the image
+
+__device__ __forceinline__ uint64_t pack_circle(int64_t b, int row, int col, int r) {
+  return ((uint64_t)b << 48) | ((uint64_t)(row + kCoordBias) << 32) | ((uint64_t)(col + kCoordBias) << 16) | (uint64_t)r;
+}
+
+// The circumcircle of p0, p0 + q1, p0 + q2 exactly as numba evaluates utils.py:317-342.
+__device__ __forceinline__ void circumcircle(int p0r, int p0c, int q1r, int q1c, int q2r, int q2c, float* out) {
+  const double eps = (double)1e-20f;
+  const double mid1r = 0.5 * q1r, mid1c = 0.5 * q1c, mid2r = 0.5 * q2r, mid2c = 0.5 * q2c;
+  const double m1 = __ddiv_rn((double)(-q1c), __dadd_rn((double)q1r, eps));
+  const double m2 = __ddiv_rn((double)(-q2c), __dadd_rn((double)q2r, eps));
+  const double b1 = __dsub_rn(mid1r, __dmul_rn(m1, mid1c));
+  const double b2 = __dsub_rn(mid2r, __dmul_rn(m2, mid2c));
+  const float c1 = (float)__ddiv_rn(__dsub_rn(b1, b2), __dadd_rn(__dsub_rn(m2, m1), eps));
+  const float c0 = (float)__dadd_rn(__dmul_rn(m1, (double)c1), b1);
+  const float rad = __fsqrt_rn(__fadd_rn(__fmul_rn(c0, c0), __fmul_rn(c1, c1)));
+  out[0] = (float)__dadd_rn((double)c0, (double)p0r);
+  out[1] = (float)__dadd_rn((double)c1, (double)p0c);
+  out[2] = rad;
+}
+
+__global__ void __launch_bounds__(kThreads) sample_circles_kernel(
+    SampleParams p, const uint32_t* __restrict__ coords, const int64_t* __restrict__ starts,
+    const int64_t* __restrict__ counts, const int64_t* __restrict__ image_starts, const uint32_t* __restrict__ randoms,
+    float* __restrict__ raw, uint64_t* __restrict__ table, uint64_t* __restrict__ unique, unsigned long long* n_unique) {
+  const int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (id >= p.B * p.num_iter) return;
+  const int64_t b = id / p.num_iter;
+  const int64_t base = image_starts[b], n_edges = image_starts[b + 1] - base;
+  float c[3] = {NAN, NAN, NAN};
+  if (n_edges > 0) {
+    uint32_t u0, u1, u2;
+    if (randoms) {
+      u0 = randoms[3 * id];
+      u1 = randoms[3 * id + 1];
+      u2 = randoms[3 * id + 2];
+    } else {
+      const uint64_t a = splitmix64(p.seed ^ (uint64_t)id * 0xD1342543DE82EF95ull);
+      const uint64_t e = splitmix64(a);
+      u0 = (uint32_t)(a >> 32);
+      u1 = (uint32_t)(e >> 32);
+      u2 = (uint32_t)e;
+    }
+    // index = floor(u * n / 2^32): uniform up to 2^-32 * n
+    const uint32_t w0 = coords[base + (int64_t)(((uint64_t)u0 * (uint64_t)n_edges) >> 32)];
+    const int p0r = (int)(w0 >> 16), p0c = (int)(w0 & 0xffff);
+    const int64_t cell = b * (int64_t)p.d.rows * p.d.cols + (int64_t)(p0r / p.d.g) * p.d.cols + p0c / p.d.g;
+    const int64_t st = starts[cell], cnt = counts[cell];
+    const uint32_t w1 = coords[st + (int64_t)(((uint64_t)u1 * (uint64_t)cnt) >> 32)];
+    const uint32_t w2 = coords[st + (int64_t)(((uint64_t)u2 * (uint64_t)cnt) >> 32)];
+    circumcircle(p0r, p0c, (int)(w1 >> 16) - p0r, (int)(w1 & 0xffff) - p0c, (int)(w2 >> 16) - p0r,
+                 (int)(w2 & 0xffff) - p0c, c);
+  }
+  if (raw) {
+    raw[3 * id] = c[0];
+    raw[3 * id + 1] = c[1];
+    raw[3 * id + 2] = c[2];
+  }
+  if (!table) return;
+  // utils.py:157-165: radius window on the float radius, round half to even, off-image test
+  if (!(c[2] >= p.min_radius && c[2] <= p.max_radius)) return;
+  const int row = (int)rintf(c[0]), col = (int)rintf(c[1]), r = (int)rintf(c[2]);
+  if (!(row + r >= 0 && col + r >= 0 && row - r < p.d.H && col - r < p.d.W)) return;
+  if (row <= -kCoordBias || row >= kCoordBias || col <= -kCoordBias || col >= kCoordBias) return;
+  const uint64_t key = pack_circle(b, row, col, r);
+  uint64_t slot = splitmix64(key) & p.table_mask;
+  for (;;) {
+    const uint64_t prev = atomicCAS((unsigned long long*)&table[slot], (unsigned long long)kEmpty, (unsigned long long)key);
+    if (prev == kEmpty) {
+      unique[atomicAdd(n_unique, 1ull)] = key;
+      return;
+    }
+    if (prev == key) return;
+    slot = (slot + 1) & p.table_mask;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scoring
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) grad_angle_kernel(const int16_t* __restrict__ dx,
+                                                              const int16_t* __restrict__ dy, int64_t n,
+                                                              float* __restrict__ angle) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    angle[i] = (float)atan2((double)dy[i], (double)dx[i]);   // np.arctan2(dy, dx) of float32 inputs
+}
+
+// circles (N, 4) int32: image, row, col, radius.  perim_offsets[r - rmin] .. [r - rmin + 1] delimit
+// radius r's perimeter points (drow, dcol) and expected angles.
+__global__ void __launch_bounds__(kThreads) score_circles_kernel(
+    const int32_t* __restrict__ circles, int64_t N, int H, int W, const uint8_t* __restrict__ edges,
+    const float* __restrict__ angle, int rmin, int rmax, const int32_t* __restrict__ perim_offsets,
+    const int16_t* __restrict__ perim_points, const double* __restrict__ perim_expected, float* __restrict__ scores) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int b = circles[4 * i], row = circles[4 * i + 1], col = circles[4 * i + 2], r = circles[4 * i + 3];
+  if (r < rmin || r > rmax) {
+    scores[i] = NAN;
+    return;
+  }
+  const int p0 = perim_offsets[r - rmin], p1 = perim_offsets[r - rmin + 1];
+  const uint8_t* e = edges + (int64_t)b * H * W;
+  const float* a = angle + (int64_t)b * H * W;
+  const double pi = 3.141592653589793, half_pi = 1.5707963267948966;
+  double sum = 0.0;
+  for (int j = p0; j < p1; ++j) {
+    const int y = row + perim_points[2 * j], x = col + perim_points[2 * j + 1];
+    if ((unsigned)y >= (unsigned)H || (unsigned)x >= (unsigned)W) continue;   // zero padding: not an edge
+    const int64_t at = (int64_t)y * W + x;
+    if (e[at]) {
+      double diff = fabs(__dsub_rn((double)a[at], perim_expected[j]));
+      if (diff > pi) diff = __dsub_rn(diff, pi);
+      // 4 * |diff - pi/2| / pi - 1, evaluated left to right without contraction
+      sum = __dadd_rn(sum, __dsub_rn(__ddiv_rn(__dmul_rn(4.0, fabs(__dsub_rn(diff, half_pi))), pi), 1.0));
+    }
+  }
+  scores[i] = __fdiv_rn((float)sum, (float)(p1 - p0));
+}
+
+__global__ void __launch_bounds__(kThreads) unpack_circles_kernel(const uint64_t* __restrict__ unique, int64_t N,
+                                                                  int32_t* __restrict__ circles) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const uint64_t k = unique[i];
+  circles[4 * i] = (int32_t)(k >> 48);
+  circles[4 * i + 1] = (int32_t)((k >> 32) & 0xffff) - kCoordBias;
+  circles[4 * i + 2] = (int32_t)((k >> 16) & 0xffff) - kCoordBias;
+  circles[4 * i + 3] = (int32_t)(k & 0xffff);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mgb_edge_cell_lists(const uint8_t* edges, int64_t B, int64_t H, int64_t W, int grid_length, int64_t* counts,
+                        int64_t* starts, uint32_t* coords, int64_t coords_capacity, int64_t* host_total, void* stream) {
+  if (!edges || !counts || !starts || !host_total || B <= 0 || B > 65535 || H <= 0 || W <= 0 || H > 65535 ||
+      W > 65535 || grid_length <= 0)
+    return MGB_EINVAL;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GridDims d{(int)H, (int)W, grid_length, (int)mgb::ceil_div(H, grid_length), (int)mgb::ceil_div(W, grid_length)};
+  const int64_t cells = B * (int64_t)d.rows * d.cols;
+  const unsigned blocks = (unsigned)mgb::ceil_div(cells, kThreads);
+  cell_lists_kernel<false><<<blocks, kThreads, 0, s>>>(edges, d, cells, counts, nullptr, nullptr);
+  MGB_CUDA_LAUNCH_CHECK();
+  // starts[0 .. cells] = exclusive prefix sum of counts (starts[cells] = total): scan cells + 1
+  // entries with a zero appended to counts by the caller's layout (counts has cells + 1 slots).
+  MGB_CUDA_TRY(cudaMemsetAsync(counts + cells, 0, sizeof(int64_t), s));
+  size_t temp_bytes = 0;
+  MGB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, counts, starts, cells + 1, s));
+  void* temp = nullptr;
+  MGB_CUDA_TRY(cudaMallocAsync(&temp, temp_bytes, s));
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(temp, temp_bytes, counts, starts, cells + 1, s);
+  mgb_count_launch_();
+  cudaFreeAsync(temp, s);
+  if (e != cudaSuccess) return (int)e;
+  int64_t total = 0;
+  MGB_CUDA_TRY(cudaMemcpyAsync(&total, starts + cells, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  MGB_CUDA_TRY(cudaStreamSynchronize(s));
+  *host_total = total;
+  if (!coords) return MGB_OK;                       // size query
+  if (coords_capacity < total) return MGB_EINVAL;
+  if (total > 0) {
+    cell_lists_kernel<true><<<blocks, kThreads, 0, s>>>(edges, d, cells, nullptr, starts, coords);
+    MGB_CUDA_LAUNCH_CHECK();
+  }
+  return MGB_OK;
+}
+
+int mgb_sample_circles(const uint32_t* coords, const int64_t* starts, const int64_t* counts, int64_t B, int64_t H,
+                       int64_t W, int grid_length, int64_t num_iter, float min_radius, float max_radius,
+                       uint64_t seed, const uint32_t* randoms, float* raw, uint64_t* table, int64_t table_capacity,
+                       int32_t* circles, int64_t* host_n_unique, unsigned long long* counter, void* stream) {
+  if (!coords || !starts || !counts || B <= 0 || B > 65535 || H <= 0 || W <= 0 || H > 65535 || W > 65535 ||
+      grid_length <= 0 || num_iter < 0)
+    return MGB_EINVAL;
+  if (table && (!circles || !host_n_unique || !counter || table_capacity < 2 ||
+                (table_capacity & (table_capacity - 1)) != 0 || table_capacity < 2 * B * num_iter))
+    return MGB_EINVAL;
+  if (host_n_unique) *host_n_unique = 0;
+  if (num_iter == 0) return MGB_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SampleParams p;
+  p.d = GridDims{(int)H, (int)W, grid_length, (int)mgb::ceil_div(H, grid_length), (int)mgb::ceil_div(W, grid_length)};
+  p.B = B;
+  p.num_iter = num_iter;
+  p.min_radius = min_radius;
+  p.max_radius = max_radius;
+  p.seed = seed;
+  p.table_mask = table ? (uint64_t)table_capacity - 1 : 0;
+  // image b's edges are coords[starts[b * cells_per_image] .. starts[(b + 1) * cells_per_image])
+  const int64_t per_image = (int64_t)p.d.rows * p.d.cols;
+  int64_t* image_starts = nullptr;
+  MGB_CUDA_TRY(cudaMallocAsync((void**)&image_starts, (size_t)(B + 1) * sizeof(int64_t), s));
+  cudaError_t e = cudaMemcpy2DAsync(image_starts, sizeof(int64_t), starts, (size_t)per_image * sizeof(int64_t),
+                                    sizeof(int64_t), (size_t)(B + 1), cudaMemcpyDeviceToDevice, s);
+  uint64_t* unique = nullptr;
+  if (e == cudaSuccess && table) {
+    e = cudaMemsetAsync(table, 0xff, (size_t)table_capacity * sizeof(uint64_t), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s);
+    if (e == cudaSuccess) e = cudaMallocAsync((void**)&unique, (size_t)(B * num_iter) * sizeof(uint64_t), s);
+  }
+  if (e != cudaSuccess) {
+    cudaFreeAsync(image_starts, s);
+    if (unique) cudaFreeAsync(unique, s);
+    return (int)e;
+  }
+  sample_circles_kernel<<<(unsigned)mgb::ceil_div(B * num_iter, kThreads), kThreads, 0, s>>>(
+      p, coords, starts, counts, image_starts, randoms, raw, table, unique, counter);
+  mgb_count_launch_();
+  e = cudaGetLastError();
+  int64_t n = 0;
+  if (e == cudaSuccess && table) {
+    unsigned long long host_n = 0;
+    e = cudaMemcpyAsync(&host_n, counter, sizeof(host_n), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    n = (int64_t)host_n;
+    if (e == cudaSuccess && n > 0) {
+      unpack_circles_kernel<<<(unsigned)mgb::ceil_div(n, kThreads), kThreads, 0, s>>>(unique, n, circles);
+      mgb_count_launch_();
+      e = cudaGetLastError();
+    }
+  }
+  cudaFreeAsync(image_starts, s);
+  if (unique) cudaFreeAsync(unique, s);
+  if (e != cudaSuccess) return (int)e;
+  if (host_n_unique) *host_n_unique = n;
+  return MGB_OK;
+}
+
+int mgb_gradient_angles(const int16_t* dx, const int16_t* dy, int64_t n, float* angle, void* stream) {
+  if (!dx || !dy || !angle || n < 0) return MGB_EINVAL;
+  if (n == 0) return MGB_OK;
+  const int64_t blocks = std::min<int64_t>(mgb::ceil_div(n, kThreads), (int64_t)mgb_sm_count() * 16);
+  grad_angle_kernel<<<(unsigned)blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(dx, dy, n, angle);
+  MGB_CUDA_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+int mgb_score_circles(const int32_t* circles, int64_t N, int64_t H, int64_t W, const uint8_t* edges,
+                      const float* angle, int rmin, int rmax, const int32_t* perim_offsets,
+                      const int16_t* perim_points, const double* perim_expected, float* scores, void* stream) {
+  if (N < 0 || H <= 0 || W <= 0 || rmin < 1 || rmax < rmin) return MGB_EINVAL;
+  if (N == 0) return MGB_OK;
+  if (!circles || !edges || !angle || !perim_offsets || !perim_points || !perim_expected || !scores) return MGB_EINVAL;
+  score_circles_kernel<<<(unsigned)mgb::ceil_div(N, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      circles, N, (int)H, (int)W, edges, angle, rmin, rmax, perim_offsets, perim_points, perim_expected, scores);
+  MGB_CUDA_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+}  // extern "C"

@@ -250,6 +250,33 @@ def golden_filter_expression():
     np.savez_compressed(os.path.join(HERE, "filter.npz"), **out)
 
 
+def golden_circles():
+    """The reference's own utils.find_circles (utils.py:100-218; unseeded RANSAC) on a fixture with
+    six planted discs and clean edges: with 200000 draws the best-scoring rounded circle of every
+    disc is found on every run, so circles and scores are reproducible."""
+    from oracle import circles as oc
+    from oracle._refload import reference_find_circles_stages
+
+    rng = np.random.default_rng(12)
+    h, w = 260, 300
+    img = (rng.random((h, w)) * 3).astype(np.float64) * 20
+    yy, xx = np.mgrid[0:h, 0:w]
+    discs = [(50, 60, 18), (60, 200, 12), (150, 130, 25), (200, 40, 9), (210, 240, 15), (120, 260, 10)]
+    for cy, cx, r in discs:
+        img[(yy - cy) ** 2 + (xx - cx) ** 2 <= r * r] += 3000
+    image = oc.to_uint8(img.astype(np.uint16))
+    kw = dict(low_edge_quantile=0.85, high_edge_quantile=0.97, grid_length=20, num_iter=200000, min_radius=6,
+              max_radius=30, min_roundness=0.3, min_dist=6)
+    edges, circles, scores = reference_find_circles_stages(image, **kw)
+    found = {tuple(d) for d in discs if any(abs(c[0] - d[0]) <= 2 and abs(c[1] - d[1]) <= 2 and abs(c[2] - d[2]) <= 2
+                                           for c in circles)}
+    assert len(found) == len(discs) == len(circles), (found, circles)
+    again = reference_find_circles_stages(image, **kw)      # the optimum is found every time on this fixture
+    assert {tuple(c) for c in again[1]} == {tuple(c) for c in circles}
+    np.savez_compressed(os.path.join(HERE, "circles.npz"), image=image, discs=np.array(discs), edges=edges,
+                        circles=circles, scores=scores, **{k: np.array(v) for k, v in kw.items()})
+
+
 def golden_masks_cv():
     """cv.circle rasters through utils.circle / utils.annulus (utils.py:30-52) for clipped and
     unclipped centres -- pins the closed form `dx^2+dy^2 <= r^2` used by oracle and kernel."""
@@ -333,6 +360,7 @@ if __name__ == "__main__":
     golden_chip()
     golden_chip_multi()
     golden_filter_expression()
+    golden_circles()
     golden_masks_cv()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -58,3 +58,72 @@ def test_oracle_edges_are_the_reference_functions_edges():
     for arr in (synthetic_discs(20, 30, [(10, 10, 5)]), np.full((4, 4), 7, np.uint16), np.zeros((0, 3), np.float32),
                 synthetic_discs(20, 30, [(10, 10, 5)], dtype=np.float32) - 50):
         np.testing.assert_array_equal(oc.to_uint8(arr), utils_to_uint8(arr))
+
+
+def reference_utils():
+    from oracle._refload import load_reference_utils
+
+    utils = load_reference_utils()
+    if utils is None:
+        pytest.skip("/root/reference not available (GPU box)")
+    return utils
+
+
+def test_perimeter_and_suppression_match_reference_numba():
+    utils = reference_utils()
+    for r in list(range(1, 40)) + [60, 100, 255]:
+        for four in (False, True):
+            np.testing.assert_array_equal(mc.circle_perimeter(r, four), utils.circle_points(r, four))
+    rng = np.random.default_rng(0)
+    for trial in range(120):
+        n, min_dist = int(rng.integers(1, 300)), int(rng.integers(1, 12))
+        c = np.stack([rng.integers(-5, 120, n), rng.integers(-5, 150, n), rng.integers(3, 20, n)], 1).astype(np.int32)
+        if trial % 3 == 0:
+            c[:, :2] = np.abs(c[:, :2])
+        np.testing.assert_array_equal(mc.filter_neighbors(c, min_dist), utils.filter_neighbors(c, min_dist))
+    assert mc.filter_neighbors(np.empty((0, 3), np.int32), 3).shape == (0,)
+
+
+def test_oracle_circumcircle_is_numbas_arithmetic():
+    """Three edge pixels in one grid cell: the reference's candidate_circles can only produce the
+    27 ordered draws of them, so the SET of its float32 outputs pins the arithmetic bit for bit."""
+    from oracle import circles as oc
+
+    utils = reference_utils()
+    rng = np.random.default_rng(0)
+    for trial in range(25):
+        pts = set()
+        while len(pts) < 3:
+            pts.add((int(rng.integers(20, 40)), int(rng.integers(40, 60))))
+        pts = sorted(pts)
+        edges = np.zeros((100, 100), np.uint8)
+        for r, c in pts:
+            edges[r, c] = 1
+        got = {tuple(row.view(np.uint32).tolist()) for row in utils.candidate_circles(edges, 20, 3000)}
+        want = {tuple(oc.circumcircle(a, b, c).view(np.uint32).tolist()) for a in pts for b in pts for c in pts}
+        assert got == want, trial
+
+
+def test_oracle_grid_lists_and_scores_match_reference_numba():
+    from oracle import circles as oc
+
+    utils = reference_utils()
+    img = oc.to_uint8(synthetic_discs(120, 150, [(40, 50, 14), (80, 100, 20), (30, 120, 9)], noise=6))
+    st = oc.edge_stages(img, 0.3, 0.95)
+    coords, starts, counts = oc.grid_lists(st["edges"], 20)
+    rc, rs, rn = utils.grid_array(st["edges"], 20)
+    np.testing.assert_array_equal(coords, rc)
+    np.testing.assert_array_equal(starts, rs)
+    np.testing.assert_array_equal(counts, rn)
+    # scores: the reference's own mean_grad on the same circles
+    rng = np.random.default_rng(1)
+    raw = oc.sampled_circles(st["edges"], 20, rng.integers(0, 2**32, (400, 3), dtype=np.uint64))
+    circles = oc.filter_round(raw, 6, 24, img.shape)
+    assert len(circles) > 20
+    mine = oc.perimeter_scores(circles, st["edges"], st["dx"], st["dy"], 24)
+    pad = 2 * 24
+    angles, padded = np.pad(np.arctan2(st["dy"], st["dx"]), pad), np.pad(st["edges"], pad)
+    for k, (row, col, radius) in enumerate(circles):
+        pts = utils.circle_points(int(radius))
+        want = utils.mean_grad(angles, padded, np.array([[row + pad, col + pad]], np.int32), pts)[0] / len(pts)
+        assert mine[k] == np.float32(want), (k, mine[k], want)

@@ -85,3 +85,132 @@ def test_full_size_tile(cuda_device):
     want = oc.edge_stages(oc.to_uint8(raw), 0.1, 0.9)
     edges, dx, dy = mc.find_edges(u8, 0.1, 0.9)
     np.testing.assert_array_equal(edges.cpu().numpy(), want["edges"])
+
+
+def test_batched_rois_match_per_image_opencv(cuda_device):
+    """A batch of 72 x 72 crops (the per-ROI refinement of find.py:339-360): every image scaled,
+    thresholded and edge-detected on its own, in one set of launches."""
+    from magnify_b200 import circles as mc
+
+    rng = np.random.default_rng(11)
+    b, length = 37, 72
+    raw = np.stack([synthetic_discs(length, length, [(int(rng.integers(20, 52)), int(rng.integers(20, 52)),
+                                                       int(rng.integers(6, 16)))], seed=k, noise=8 + k % 5,
+                                    level=500 + 300 * (k % 7)) for k in range(b)])
+    raw[5] = 1234                                                     # a constant crop -> all zeros
+    u8 = mc.to_uint8(dev(raw, cuda_device), batched=True)
+    want_u8 = np.stack([oc.to_uint8(r) for r in raw])
+    np.testing.assert_array_equal(u8.cpu().numpy(), want_u8)
+    high_q = np.float64(1 - np.pi * 8 / length**2)                    # find.py:345-347
+    edges, dx, dy = mc.find_edges(u8, 0.1, high_q)
+    lows_highs = mc.gradient_quantiles(dx, dy, (0.1, high_q))
+    for k in range(b):
+        want = oc.edge_stages(want_u8[k], 0.1, high_q)
+        np.testing.assert_array_equal(dx[k].cpu().numpy(), want["dx"])
+        assert lows_highs[k][0] == want["low"] and lows_highs[k][1] == want["high"], k
+        np.testing.assert_array_equal(edges[k].cpu().numpy(), want["edges"], err_msg=str(k))
+
+
+# ---- candidates, scores, full finder ---------------------------------------------------------
+def disc_image(seed=0):
+    discs = [(40, 50, 14), (80, 100, 20), (30, 120, 9), (100, 30, 11)]
+    return discs, oc.to_uint8(synthetic_discs(130, 150, discs, seed=seed, noise=5))
+
+
+def test_cell_lists_and_draws_match_oracle_bit_for_bit(cuda_device):
+    from magnify_b200 import circles as mc
+
+    _, img = disc_image()
+    other = oc.to_uint8(synthetic_discs(130, 150, [(60, 70, 25)], seed=4, noise=5))
+    batch = np.stack([img, other, np.zeros_like(img)])               # third image: no edges at all
+    edges, dx, dy = mc.find_edges(dev(batch, cuda_device), 0.3, 0.95)
+    lists = mc.EdgeLists(edges, 20)
+    want = [oc.grid_lists(oc.edge_stages(b, 0.3, 0.95)["edges"], 20) for b in batch[:2]]
+    np.testing.assert_array_equal(lists.grid_coords(), np.concatenate([w[0] for w in want]))
+    assert lists.total == sum(len(w[0]) for w in want)
+    rng = np.random.default_rng(2)
+    num_iter = 700
+    randoms = rng.integers(0, 2**32, (3, num_iter, 3), dtype=np.uint64)
+    raw, circles = mc.sample_circles(lists, num_iter, 6, 26, randoms=dev(randoms.astype(np.uint32).view(np.int32), cuda_device),
+                                     want_raw=True)
+    raw = raw.cpu().numpy()
+    found = circles.cpu().numpy()
+    for k in range(2):
+        e = oc.edge_stages(batch[k], 0.3, 0.95)["edges"]
+        want_raw = oc.sampled_circles(e, 20, randoms[k])
+        np.testing.assert_array_equal(raw[k].view(np.uint32), want_raw.view(np.uint32))      # bits, NaNs included
+        want_set = {tuple(c) for c in oc.filter_round(want_raw, 6, 26, e.shape)}
+        got_set = {tuple(c[1:]) for c in found if c[0] == k}
+        assert got_set == want_set and len(got_set) > 10
+        assert sum(c[0] == k for c in found) == len(got_set)                                  # de-duplicated
+    assert np.isnan(raw[2]).all() and not (found[:, 0] == 2).any()
+
+
+def test_scores_match_oracle(cuda_device):
+    from magnify_b200 import circles as mc
+
+    _, img = disc_image(1)
+    st = oc.edge_stages(img, 0.3, 0.95)
+    edges, dx, dy = mc.find_edges(dev(img, cuda_device), 0.3, 0.95)
+    lists = mc.EdgeLists(edges, 20)
+    _, circles = mc.sample_circles(lists, 3000, 6, 26, seed=5)
+    found = circles.cpu().numpy()
+    assert len(found) > 100
+    scores = mc.score_circles(circles, edges, mc.gradient_angles(dx, dy), 6, 26).cpu().numpy()
+    want = oc.perimeter_scores(found[:, 1:], st["edges"], st["dx"], st["dy"], 26)
+    # float32 arctan2 of NumPy vs float64 arctan2 rounded once: a few ulp of the angle per term
+    np.testing.assert_allclose(scores, want, rtol=0, atol=2e-6)
+    assert scores.max() > 0.5
+
+
+def match(found, truth, tol=2):
+    return all(any(abs(f[0] - t[0]) <= tol and abs(f[1] - t[1]) <= tol and abs(f[2] - t[2]) <= tol for f in found)
+               for t in truth)
+
+
+def test_find_circles_recovers_planted_discs(cuda_device):
+    """The contract of the reference's own tests (tests/test_beads.py:62-66,93-96: centres and radii
+    within tolerance): every planted disc is found, best first, deterministically for a seed."""
+    from magnify_b200 import circles as mc
+
+    discs, img = disc_image(2)
+    args = dict(low_edge_quantile=0.1, high_edge_quantile=0.9, grid_length=20, num_iter=20000, min_radius=6,
+                max_radius=26, min_roundness=0.3, min_dist=6)
+    circles, scores = mc.find_circles(dev(img, cuda_device), seed=7, **args)
+    assert circles.dtype == np.int32 and scores.dtype == np.float32
+    assert match(circles, discs) and (np.diff(scores) <= 0).all()
+    again, scores2 = mc.find_circles(dev(img, cuda_device), seed=7, **args)
+    np.testing.assert_array_equal(circles, again)
+    np.testing.assert_array_equal(scores, scores2)
+    # survivors do not overlap (utils.py:252-285)
+    for i in range(len(circles)):
+        for j in range(i):
+            assert np.hypot(*(circles[i, :2] - circles[j, :2])) > 6
+    # batch: the same image twice plus a blank one
+    batch = dev(np.stack([img, np.zeros_like(img), img]), cuda_device)
+    res = mc.find_circles(batch, seed=7, **args)
+    assert len(res) == 3 and len(res[1][0]) == 0 and match(res[0][0], discs) and match(res[2][0], discs)
+    # min_dist = 0 (the chip refinement, find.py:341-356): best circle = one of the discs
+    best, s = mc.find_circles(dev(img, cuda_device), seed=3, **dict(args, min_dist=0))
+    assert len(best) and match(discs, [best[int(np.argmax(s))]], tol=2)
+
+
+def test_find_circles_agrees_with_reference_run(cuda_device, golden):
+    """tests/golden/circles.npz: the reference's own find_circles on a fixture where its random
+    search converges (same circles on every run).  The GPU finder must report exactly those
+    circles, with the reference's scores up to the float32 arctan2 difference."""
+    from magnify_b200 import circles as mc
+
+    g = golden("circles")
+    kw = {k: g[k].item() for k in ("low_edge_quantile", "high_edge_quantile", "grid_length", "num_iter", "min_radius",
+                                    "max_radius", "min_roundness", "min_dist")}
+    image = dev(g["image"], cuda_device)
+    edges, _, _ = mc.find_edges(image, kw["low_edge_quantile"], kw["high_edge_quantile"])
+    np.testing.assert_array_equal(edges.cpu().numpy(), g["edges"])
+    want = {tuple(c): s for c, s in zip(g["circles"], g["scores"])}
+    for seed in (1, 2, 3):
+        circles, scores = mc.find_circles(image, seed=seed, **kw)
+        got = {tuple(c): s for c, s in zip(circles, scores)}
+        assert set(got) == set(want), (seed, sorted(got), sorted(want))
+        for c in want:
+            assert abs(got[c] - want[c]) <= 2e-6, (c, got[c], want[c])
