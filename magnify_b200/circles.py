@@ -311,7 +311,11 @@ def find_circles(image: torch.Tensor, low_edge_quantile: float, high_edge_quanti
             angle = gradient_angles(dx, dy)
             scores = score_circles(circles, e, angle, min_radius, max_radius).cpu().numpy()
             found = circles.cpu().numpy()
+            by_image = np.argsort(found[:, 0], kind="stable")
+            found, scores = found[by_image], scores[by_image]
+            bounds = np.searchsorted(found[:, 0], np.arange(b + 1))
             for k in range(b):
-                mine = found[:, 0] == k
-                results[k] = select_circles(found[mine, 1:], scores[mine], min_roundness, min_dist)
+                lo, hi = bounds[k], bounds[k + 1]
+                if hi > lo:
+                    results[k] = select_circles(found[lo:hi, 1:], scores[lo:hi], min_roundness, min_dist)
     return results[0] if squeeze else results

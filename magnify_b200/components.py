@@ -8,10 +8,10 @@ is installed, or `magnify_b200.dataset.Assay` (a minimal stand-in with the same 
 names so that `mg.mrbles`, `mg.beads` and `mg.microfluidic_chip` pick them up unchanged
 (INTEGRATION.md).
 
-Centre finding is NOT part of this package (stochastic CPU RANSAC):
-`BeadFinder` / `ButtonFinder` take a `centers` hook, and fall back to the reference's own
-finder (`magnify.utils.find_circles`, `magnify.find.ButtonFinder.find_centers`) when the
-reference package is importable.
+Centre finding (`utils.find_circles`, a random search the reference cannot reproduce from run to
+run) runs on the GPU with a seeded sampler (`magnify_b200.circles`,
+SURVEY.md section 8f rows N1 / N4); `BeadFinder` / `ButtonFinder` also take a `centers` hook that
+pins the centres, which is what the bit-exact ROI / mask parity tests use.
 """
 from __future__ import annotations
 
@@ -22,7 +22,7 @@ from typing import Callable, Optional
 import numpy as np
 import torch
 
-from . import ops, pipeline
+from . import chipgrid, circles, ops, pipeline
 from .dataset import Assay  # noqa: F401  (re-exported: the stand-in Dataset type of this module)
 
 TILE_DIMS = ("channel", "time", "tile_row", "tile_col", "tile_y", "tile_x")
@@ -146,25 +146,17 @@ class FlatfieldStitcher:
 # ---------------------------------------------------------------------------------------------
 # find_beads  (find.py:445-629)
 # ---------------------------------------------------------------------------------------------
-def _reference_utils():
-    try:
-        import magnify.utils as mu  # the reference package, when installed
-
-        return mu
-    except Exception:
-        return None
-
-
 class BeadFinder:
     """ROI/mask half of the reference BeadFinder on the GPU (find.py:503-605).
 
-    centers: ndarray (M,3) of (row, col, radius) or a callable `assay -> ndarray`; when omitted
-    the reference's CPU finder is used (find.py:476-501), which needs `magnify` importable."""
+    centers: ndarray (M,3) of (row, col, radius) or a callable `assay -> ndarray` pins the bead
+    centres; when omitted they are found on the GPU (`magnify_b200.circles.find_circles`, the
+    reference's `utils.find_circles` with a seeded sampler; find.py:476-501)."""
 
     def __init__(self, min_bead_diameter: int, max_bead_diameter: int, low_edge_quantile: float = 0.1,
                  high_edge_quantile: float = 0.9, num_iter: int = 5000000, min_roundness: float = 0.3,
                  roi_length: Optional[int] = None, search_channel=None, interactive: bool = False,
-                 centers=None, device=None):
+                 centers=None, device=None, seed: int = 0):
         if min_bead_diameter > max_bead_diameter:
             raise ValueError("min_bead_diameter must be <= max_bead_diameter.")  # find.py:458-459
         self.min_bead_radius = math.floor(min_bead_diameter / 2)
@@ -177,37 +169,37 @@ class BeadFinder:
         self.interactive = interactive
         self.centers = centers
         self.device = device
+        self.seed = seed
 
-    def find_centers(self, assay) -> np.ndarray:
+    def find_centers(self, assay, image: Optional[torch.Tensor] = None) -> np.ndarray:
+        """(M, 3) float64 (row, col, radius): the pinned `centers`, or the GPU circle finder run on
+        time 0 of every search channel with the reference's parameters (find.py:476-501)."""
         if self.centers is not None:
             beads = self.centers(assay) if callable(self.centers) else self.centers
             return np.asarray(beads, dtype=np.float64).reshape(-1, 3)
-        mu = _reference_utils()
-        if mu is None:
-            raise ImportError("bead centre finding is delegated to the reference (magnify.utils.find_circles); "
-                              "magnify is not importable here -- pass centers=(M,3) array or callable")
-        import scipy.spatial
+        from scipy.spatial import cKDTree
 
-        channels = self.search_channels or list(_to_numpy(assay["channel"]))
-        chan_index = list(_to_numpy(assay["channel"]))
-        image = _to_numpy(assay["image"])
+        dev = _device(self.device)
+        if image is None:
+            image = _image_to_device(assay, dev)
+        names = list(_to_numpy(assay["channel"])) if "channel" in assay else list(range(image.shape[0]))
+        channels = self.search_channels or names
         beads = np.empty((0, 3))
-        for ch in channels:  # find.py:476-501
-            img = mu.to_uint8(image[chan_index.index(ch), 0])
-            b = mu.find_circles(img, low_edge_quantile=self.low_edge_quantile,
-                                high_edge_quantile=self.high_edge_quantile, grid_length=20, num_iter=self.num_iter,
-                                min_radius=self.min_bead_radius, max_radius=self.max_bead_radius,
-                                min_dist=self.min_bead_radius, min_roundness=self.min_roundness, gui=None)[0]
-            if len(beads) > 0 and len(b) > 0:
-                near = scipy.spatial.KDTree(beads[:, :2]).query_ball_point(b[:, :2], 2 * self.min_bead_radius)
-                b = b[~np.array([len(n) > 0 for n in near])]
-            beads = np.concatenate([beads, b])
+        for k, ch in enumerate(channels):
+            img = circles.to_uint8(image[names.index(ch), 0].contiguous())
+            found = circles.find_circles(img, self.low_edge_quantile, self.high_edge_quantile, 20, self.num_iter,
+                                         self.min_bead_radius, self.max_bead_radius, self.min_roundness,
+                                         self.min_bead_radius, seed=self.seed + k)[0].astype(np.float64)
+            if len(beads) > 0 and len(found) > 0:   # drop beads already seen in another channel, find.py:491-500
+                near = cKDTree(beads[:, :2]).query_ball_point(found[:, :2], 2 * self.min_bead_radius)
+                found = found[~np.array([len(n) > 0 for n in near], dtype=bool)]
+            beads = np.concatenate([beads, found])
         return beads
 
     def __call__(self, assay):
         dev = _device(self.device)
-        beads = self.find_centers(assay)
         image = _image_to_device(assay, dev)
+        beads = self.find_centers(assay, image)
         c, t, him, wim = image.shape
         length = self.roi_length
         m = len(beads)
@@ -236,11 +228,11 @@ class BeadFinder:
 
 def make_find_beads(min_bead_diameter: int, max_bead_diameter: int, low_edge_quantile: float,
                     high_edge_quantile: float, num_iter: int, min_roundness: float, roi_length: int,
-                    search_channel, interactive: bool, centers=None, device=None):
+                    search_channel, interactive: bool, centers=None, device=None, seed: int = 0):
     return BeadFinder(min_bead_diameter=min_bead_diameter, max_bead_diameter=max_bead_diameter,
                       low_edge_quantile=low_edge_quantile, high_edge_quantile=high_edge_quantile, num_iter=num_iter,
                       min_roundness=min_roundness, roi_length=roi_length, search_channel=search_channel,
-                      interactive=interactive, centers=centers, device=device)
+                      interactive=interactive, centers=centers, device=device, seed=seed)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -252,15 +244,16 @@ class ButtonFinder:
     centers: callable `(assay, t) -> (x, y, fg_radius)` giving, for a search timestep t, the final
     button centres in image coordinates (rows x cols float64 each) and the foreground radii
     (rows x cols int; max_button_radius where refinement found nothing, find.py:363,378).  When
-    omitted, the reference's own `find_centers` + per-ROI refinement run on the CPU (needs
-    `magnify`), with the refinement crops gathered by the GPU."""
+    omitted, centres are found here: full-image circle finding on the GPU, the reference's grid
+    clustering on the host (`chipgrid`), and the per-chamber refinement as one GPU batch
+    (find.py:205-306, 336-378; seeded, unlike the reference)."""
 
     def __init__(self, row_dist: float, col_dist: float, min_button_diameter: int, max_button_diameter: int,
                  chamber_diameter: int, top_chamber=None, left_chamber=None, low_edge_quantile: float = 0.1,
                  high_edge_quantile: float = 0.9, num_iter: int = 5000000, min_roundness: float = 0.20,
                  cluster_penalty: float = 10, roi_length: Optional[int] = None, progress_bar: bool = False,
                  search_timestep=0, search_channel=None, interactive: bool = False, centers: Optional[Callable] = None,
-                 device=None):
+                 device=None, seed: int = 0):
         if min_button_diameter > max_button_diameter:
             raise ValueError("min_button_diameter must be <= max_button_diameter.")  # find.py:34-35
         self.row_dist, self.col_dist = row_dist, col_dist
@@ -277,24 +270,74 @@ class ButtonFinder:
                            search_timestep=search_timestep, search_channel=search_channel, interactive=interactive)
         self.centers = centers
         self.device = device
+        self.seed = seed
 
-    def _reference_centers(self, assay, t):
-        try:
-            from magnify.find import ButtonFinder as RefFinder
-        except Exception as e:
-            raise ImportError("button centre finding is delegated to the reference (magnify.find.ButtonFinder); "
-                              "magnify is not importable here -- pass centers=callable") from e
-        ref = RefFinder(**self.kwargs)
-        if not ref.search_channels:
-            ref.search_channels = assay.channel
-        images = assay.image.isel(time=t).compute()
-        x, y = ref.find_centers(images.sel(channel=ref.search_channels), assay)
-        assay.x[..., t], assay.y[..., t] = x, y
-        # reference refinement loop (find.py:324-402): returns refined x, y and the fg masks, from
-        # which the per-button radius is recovered as the fg disc's row extent.
-        _, fg, _, x, y, _ = ref.find_rois(images, t, assay)
-        radius = (fg.any(axis=-1).sum(axis=-1) - 1) // 2
-        return np.asarray(x), np.asarray(y), radius.astype(np.int32)
+    def _search_channel_indexes(self, assay, n_channels: int):
+        names = list(_to_numpy(assay["channel"])) if "channel" in assay else list(range(n_channels))
+        wanted = self.kwargs["search_channel"]
+        if wanted is None:
+            return list(range(n_channels))
+        wanted = [wanted] if isinstance(wanted, str) or np.isscalar(wanted) else list(wanted)
+        return [names.index(ch) for ch in wanted]
+
+    def find_centers(self, assay, image: torch.Tensor, t: int):
+        """find.py:205-306: circles of every search channel's full image at time t (GPU), merged
+        across channels, clustered into the chip grid and intersected (host) -> (mark_x, mark_y)."""
+        kw = self.kwargs
+        tag = _to_numpy(assay["tag"])
+        points = np.empty((0, 2))
+        for k, ch in enumerate(self._search_channel_indexes(assay, image.shape[0])):
+            img = circles.to_uint8(image[ch, t].contiguous())
+            found = circles.find_circles(img, kw["low_edge_quantile"], kw["high_edge_quantile"], 20, kw["num_iter"],
+                                         self.min_button_radius, self.max_button_radius, kw["min_roundness"],
+                                         self.chamber_radius, seed=self.seed + 1000 * t + k)[0]
+            points = chipgrid.merge_channel_points(points, found[:, :2].astype(np.float64), self.chamber_radius)
+        return chipgrid.grid_centers(points, tag, tuple(image.shape[-2:]), self.row_dist, self.col_dist,
+                                     self.chamber_radius, kw["top_chamber"], kw["left_chamber"], kw["cluster_penalty"])
+
+    def refine(self, assay, image: torch.Tensor, t: int, x: np.ndarray, y: np.ndarray):
+        """find.py:324-378: crop every chamber at its grid position, look for the best circle in
+        the crop of each search channel (batched on the GPU) and recentre on it.  Returns refined
+        x, y (rows, cols) and the foreground radius per chamber (max_button_radius when nothing
+        was found or the chamber is blank)."""
+        kw = self.kwargs
+        dev = image.device
+        rows, cols = x.shape
+        m, length = rows * cols, self.roi_length
+        him, wim = image.shape[-2:]
+        tag = _to_numpy(assay["tag"]).reshape(m)
+        chans = self._search_channel_indexes(assay, image.shape[0])
+        planes = ops.alloc_image((len(chans), 1, him, wim), image.dtype, dev)
+        for k, ch in enumerate(chans):
+            planes[k, 0].copy_(image[ch, t])
+        xd = torch.from_numpy(np.ascontiguousarray(x.reshape(m, 1))).to(dev)
+        yd = torch.from_numpy(np.ascontiguousarray(y.reshape(m, 1))).to(dev)
+        boxes = ops.bounding_boxes(xd, yd, length, wim, him)
+        crops = ops.roi_gather(planes, boxes, length)                           # (m, channels, 1, L, L)
+        batch = circles.to_uint8(crops.reshape(m * len(chans), length, length), batched=True)   # find.py:343
+        high_q = 1 - np.pi * self.min_button_radius / length**2                 # find.py:345-347
+        found = circles.find_circles(batch, kw["low_edge_quantile"], high_q, 20, kw["num_iter"] // (rows * cols),
+                                     self.min_button_radius, self.max_button_radius, kw["min_roundness"], 0,
+                                     seed=self.seed + 1000 * t + 500)
+        top_left = boxes[:, 0].cpu().numpy()
+        x, y = x.reshape(m).copy(), y.reshape(m).copy()
+        radius = np.full(m, self.max_button_radius, dtype=np.int32)
+        for i in range(m):
+            if tag[i] == "":
+                continue
+            best, best_score = None, -np.inf
+            for k in range(len(chans)):
+                cand, scores = found[i * len(chans) + k]
+                if len(cand) > 0 and scores[0] > best_score:                    # best first: [0] is the argmax
+                    best, best_score = cand[0], scores[0]
+            if best is not None:
+                y[i], x[i] = best[0] + top_left[i, 0], best[1] + top_left[i, 1]
+                radius[i] = best[2]
+        return x.reshape(rows, cols), y.reshape(rows, cols), radius
+
+    def _gpu_centers(self, assay, image: torch.Tensor, t: int):
+        x, y = self.find_centers(assay, image, t)
+        return self.refine(assay, image, t, np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64))
 
     def __call__(self, assay):
         dev = _device(self.device)
@@ -308,11 +351,8 @@ class ButtonFinder:
         x = np.empty((rows, cols, t))
         y = np.empty((rows, cols, t))
         radius = np.empty((m, len(search)), dtype=np.int32)
-        if self.centers is None:
-            assay = assay.assign_coords(x=(("mark_row", "mark_col", "time"), x.copy()),
-                                        y=(("mark_row", "mark_col", "time"), y.copy()))
         for k, ts in enumerate(search):
-            xs, ys, rs = self.centers(assay, ts) if self.centers is not None else self._reference_centers(assay, ts)
+            xs, ys, rs = self.centers(assay, ts) if self.centers is not None else self._gpu_centers(assay, image, ts)
             x[..., ts], y[..., ts], radius[:, k] = xs, ys, np.asarray(rs).reshape(m)
         for ti in range(t):  # copy-forward of the centres, find.py:156-157,174-175
             x[..., ti], y[..., ti] = x[..., src[ti]], y[..., src[ti]]
