@@ -309,8 +309,11 @@ def find_circles(image: torch.Tensor, low_edge_quantile: float, high_edge_quanti
         _, circles = sample_circles(lists, num_iter, min_radius, max_radius, seed)
         if circles.shape[0]:
             angle = gradient_angles(dx, dy)
-            scores = score_circles(circles, e, angle, min_radius, max_radius).cpu().numpy()
-            found = circles.cpu().numpy()
+            scores = score_circles(circles, e, angle, min_radius, max_radius)
+            # utils.py:187-188 on the device, so that only survivors travel to the host; a float32
+            # tensor compared with a Python float casts the scalar to float32, like NumPy does
+            keep = scores >= min_roundness
+            found, scores = circles[keep].cpu().numpy(), scores[keep].cpu().numpy()
             by_image = np.argsort(found[:, 0], kind="stable")
             found, scores = found[by_image], scores[by_image]
             bounds = np.searchsorted(found[:, 0], np.arange(b + 1))
