@@ -1,0 +1,79 @@
+"""Config-5 sized bead detection: one 20480^2 image, 1e5 beads (radius 8-12), 5e7 draws.
+GPU stage times by default; --reference times the reference's utils.find_circles on the local CPU
+(build container only)."""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+SIDE, N_BEADS, NUM_ITER = 20480, 100_000, 50_000_000
+ARGS = dict(low_edge_quantile=0.1, high_edge_quantile=0.9, grid_length=20, num_iter=NUM_ITER, min_radius=6, max_radius=14,
+            min_roundness=0.3, min_dist=6)
+
+
+def image():
+    """Beads on a jittered lattice (no overlaps), uint8, background noise 0..7."""
+    rng = np.random.default_rng(0)
+    per_side = int(np.ceil(np.sqrt(N_BEADS)))
+    pitch = SIDE / per_side
+    img = rng.integers(0, 8, (SIDE, SIDE), dtype=np.uint8)
+    yy, xx = np.mgrid[-12:13, -12:13]
+    k = 0
+    for i in range(per_side):
+        for j in range(per_side):
+            if k >= N_BEADS:
+                break
+            r = int(rng.integers(8, 13))
+            cy = int((i + 0.5) * pitch + rng.integers(-15, 16))
+            cx = int((j + 0.5) * pitch + rng.integers(-15, 16))
+            if 14 <= cy < SIDE - 14 and 14 <= cx < SIDE - 14:
+                img[cy - 12:cy + 13, cx - 12:cx + 13][yy * yy + xx * xx <= r * r] = 200
+            k += 1
+    return img
+
+
+out = {"side": SIDE, "beads": N_BEADS, "num_iter": NUM_ITER}
+img = image()
+if "--reference" in sys.argv:
+    from oracle._refload import load_reference_utils
+
+    utils = load_reference_utils()
+    utils.find_circles(img[:512, :512], **dict(ARGS, num_iter=1000), gui=None)
+    t0 = time.perf_counter()
+    c, s = utils.find_circles(img, **ARGS, gui=None)
+    out["reference_s"] = time.perf_counter() - t0
+    out["reference_found"] = len(c)
+    out["cores"] = os.cpu_count()
+else:
+    import torch
+
+    from magnify_b200 import circles as mc
+
+    dev = torch.device("cuda:0")
+    u8 = torch.from_numpy(img).to(dev)
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, r
+
+    stages = {}
+    mc.find_edges(u8[:2048, :2048].contiguous(), 0.1, 0.9)
+    stages["edges"], (edges, dx, dy) = timed(lambda: mc.find_edges(u8, 0.1, 0.9))
+    stages["cell_lists"], lists = timed(lambda: mc.EdgeLists(edges, 20))
+    stages["sample_dedupe"], (_, circles) = timed(lambda: mc.sample_circles(lists, NUM_ITER, 6, 14, seed=1))
+    stages["angles"], angle = timed(lambda: mc.gradient_angles(dx, dy))
+    stages["score"], scores = timed(lambda: mc.score_circles(circles, edges, angle, 6, 14))
+    out["stages_s"] = stages
+    out["edge_pixels"] = lists.total
+    out["unique_candidates"] = int(circles.shape[0])
+    del angle, scores, circles, lists, edges, dx, dy
+    torch.cuda.empty_cache()
+    out["total_s"], res = timed(lambda: mc.find_circles(u8, seed=1, **ARGS))
+    out["found"] = len(res[0])
+print(json.dumps(out))
