@@ -229,8 +229,9 @@ int mgb_canny(const int16_t* dx, const int16_t* dy, int64_t B, int64_t H, int64_
 /* ---- N1 / N4: candidate circles and their scores, reference utils.py:141-189, 221-377 --------
  * Edge pixels grouped by grid cell (utils.py:347-377): counts / starts (B * cells + 1 int64 each,
  * cells = ceil(H/g) * ceil(W/g), cell-major per image) and coords (total uint32, row << 16 | col,
- * row-major inside a cell).  Call once with coords = NULL to learn the total (host_total), then
- * again with a buffer of that capacity.  H, W <= 65535.  SYNCHRONISES the stream. */
+ * row-major inside a cell).  Call once with coords = NULL: counts and starts are computed and the
+ * total is returned in *host_total (SYNCHRONISES the stream); then again, same arguments, with a
+ * coords buffer of that capacity, which only fills the lists.  H, W <= 65535. */
 int mgb_edge_cell_lists(const uint8_t* edges, int64_t B, int64_t H, int64_t W, int grid_length, int64_t* counts,
                         int64_t* starts, uint32_t* coords, int64_t coords_capacity, int64_t* host_total, void* stream);
 /* num_iter circumcircles per image from three random edge pixels of one grid cell

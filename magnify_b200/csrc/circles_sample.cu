@@ -224,10 +224,19 @@ int mgb_edge_cell_lists(const uint8_t* edges, int64_t B, int64_t H, int64_t W, i
   GridDims d{(int)H, (int)W, grid_length, (int)mgb::ceil_div(H, grid_length), (int)mgb::ceil_div(W, grid_length)};
   const int64_t cells = B * (int64_t)d.rows * d.cols;
   const unsigned blocks = (unsigned)mgb::ceil_div(cells, kThreads);
+  if (coords) {
+    // second call: counts / starts / *host_total come from the size query on the same edges
+    if (coords_capacity < *host_total || *host_total < 0) return MGB_EINVAL;
+    if (*host_total > 0) {
+      cell_lists_kernel<true><<<blocks, kThreads, 0, s>>>(edges, d, cells, nullptr, starts, coords);
+      MGB_CUDA_LAUNCH_CHECK();
+    }
+    return MGB_OK;
+  }
   cell_lists_kernel<false><<<blocks, kThreads, 0, s>>>(edges, d, cells, counts, nullptr, nullptr);
   MGB_CUDA_LAUNCH_CHECK();
-  // starts[0 .. cells] = exclusive prefix sum of counts (starts[cells] = total): scan cells + 1
-  // entries with a zero appended to counts by the caller's layout (counts has cells + 1 slots).
+  // starts[0 .. cells] = exclusive prefix sum of counts (starts[cells] = total): counts has one
+  // extra slot that is zeroed here so that cells + 1 entries can be scanned.
   MGB_CUDA_TRY(cudaMemsetAsync(counts + cells, 0, sizeof(int64_t), s));
   size_t temp_bytes = 0;
   MGB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, counts, starts, cells + 1, s));
@@ -241,12 +250,6 @@ int mgb_edge_cell_lists(const uint8_t* edges, int64_t B, int64_t H, int64_t W, i
   MGB_CUDA_TRY(cudaMemcpyAsync(&total, starts + cells, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
   MGB_CUDA_TRY(cudaStreamSynchronize(s));
   *host_total = total;
-  if (!coords) return MGB_OK;                       // size query
-  if (coords_capacity < total) return MGB_EINVAL;
-  if (total > 0) {
-    cell_lists_kernel<true><<<blocks, kThreads, 0, s>>>(edges, d, cells, nullptr, starts, coords);
-    MGB_CUDA_LAUNCH_CHECK();
-  }
   return MGB_OK;
 }
 
