@@ -132,3 +132,32 @@ def test_ten_by_ten_chip_with_blanks_and_copy_forward(cuda_device):             
     for ti in (1, 2):                                                                # copy-forward
         np.testing.assert_array_equal(x[..., ti], x[..., 0])
         np.testing.assert_array_equal(out.fg.values[:, ti], out.fg.values[:, 0])
+
+
+def test_full_size_chip_all_buttons_found(cuda_device):
+    """Config-2 geometry (7784^2 image, 56 x 32 buttons at the 'pc' spacing, radii 10-15) with the
+    reference's `microfluidic_chip` defaults (registry.py:205-235): every button is located exactly
+    and its refined radius reproduces the disc area.  Background constant, like the reference's own
+    fixtures (on a noisy background the reference's finder itself reports mostly noise circles)."""
+    from magnify_b200.components import ButtonFinder
+
+    rows, cols, side = 56, 32, 7784
+    rng = np.random.default_rng(0)
+    row_dist, col_dist = 406 / 3.22, 750 / 3.22
+    cy = np.round((side - (rows - 1) * row_dist) / 2 + np.arange(rows)[:, None] * row_dist + rng.uniform(-2, 2, (rows, cols)))
+    cx = np.round((side - (cols - 1) * col_dist) / 2 + np.arange(cols)[None, :] * col_dist + rng.uniform(-2, 2, (rows, cols)))
+    radius = 10 + (np.add.outer(np.arange(rows), np.arange(cols)) % 6)
+    image = np.full((side, side), 400, dtype=np.uint16)
+    yy, xx = np.mgrid[-16:17, -16:17]
+    for i in range(rows):
+        for j in range(cols):
+            y, x = int(cy[i, j]), int(cx[i, j])
+            image[y - 16:y + 17, x - 16:x + 17][yy * yy + xx * xx <= radius[i, j] ** 2] = 3000 + 37 * ((i * cols + j) % 50)
+    out = ButtonFinder(row_dist=row_dist, col_dist=col_dist, min_button_diameter=8, max_button_diameter=30,
+                       chamber_diameter=60, num_iter=5_000_000, min_roundness=0.2, cluster_penalty=50,
+                       device=cuda_device)(chip_assay(image, (rows, cols)))
+    assert out.sizes["mark"] == rows * cols
+    np.testing.assert_array_equal(out.x.values[:, 0], cx.reshape(-1))
+    np.testing.assert_array_equal(out.y.values[:, 0], cy.reshape(-1))
+    found_radius = np.sqrt(out.fg.values[:, 0].sum(axis=(1, 2)) / np.pi)
+    assert np.abs(found_radius - radius.reshape(-1)).max() < 0.5
