@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MGB_ABI_VERSION 5
+#define MGB_ABI_VERSION 6
 
 #define MGB_OK 0
 #define MGB_EINVAL (-1)      /* bad argument (null pointer, negative size, bad itemsize ...) */
@@ -241,14 +241,16 @@ int mgb_edge_cell_lists(const uint8_t* edges, int64_t B, int64_t H, int64_t W, i
  * (table_capacity uint64, a power of two >= 2 * B * num_iter) is given, draws are filtered to
  * min_radius <= radius <= max_radius, rounded half-to-even, tested against the image
  * (utils.py:157-165) and de-duplicated: circles (<= B * num_iter, 4) int32 = (image, row, col,
- * radius), *host_n_unique of them, in no particular order.  counter: one uint64 of device scratch.
+ * radius), *host_n_unique of them, sorted by (image, row, col, radius).  counter: one uint64 of device scratch.
  * SYNCHRONISES the stream when `table` is given. */
 int mgb_sample_circles(const uint32_t* coords, const int64_t* starts, const int64_t* counts, int64_t B, int64_t H,
                        int64_t W, int grid_length, int64_t num_iter, float min_radius, float max_radius,
                        uint64_t seed, const uint32_t* randoms, float* raw, uint64_t* table, int64_t table_capacity,
                        int32_t* circles, int64_t* host_n_unique, unsigned long long* counter, void* stream);
-/* angle = float32(atan2(dy, dx)) per pixel (utils.py:169). */
-int mgb_gradient_angles(const int16_t* dx, const int16_t* dy, int64_t n, float* angle, void* stream);
+/* angle = float32(atan2(dy, dx)) per pixel (utils.py:169); with `edges` (nullable, n uint8) only
+ * at edge pixels, 0 elsewhere -- the score never reads the angle of a non-edge pixel. */
+int mgb_gradient_angles(const int16_t* dx, const int16_t* dy, const uint8_t* edges, int64_t n, float* angle,
+                        void* stream);
 /* HOST: perimeter of the reference's circle raster (utils.py:433-465) in the reference's order,
  * (drow, dcol) pairs; capacity >= 20 * r points. */
 int mgb_circle_perimeter(int r, int four_connected, int32_t* host_points, int capacity, int* host_n);
@@ -259,6 +261,9 @@ int mgb_circle_perimeter(int r, int four_connected, int32_t* host_points, int ca
 int mgb_score_circles(const int32_t* circles, int64_t N, int64_t H, int64_t W, const uint8_t* edges,
                       const float* angle, int rmin, int rmax, const int32_t* perim_offsets,
                       const int16_t* perim_points, const double* perim_expected, float* scores, void* stream);
+/* order (N) int32: the permutation that lists circles (N, 4) image by image, best score first
+ * (utils.py:192-193, `argsort(-scores)`), equal scores in input order (stable). */
+int mgb_order_circles(const int32_t* circles, const float* scores, int64_t N, int32_t* order, void* stream);
 /* HOST: utils.py:252-285 on circles (n, 3) int32 (row, col, radius) sorted best first:
  * host_valid[i] = 1 when circle i survives. */
 int mgb_filter_neighbors(const int32_t* host_circles, int64_t n, int min_dist, uint8_t* host_valid);

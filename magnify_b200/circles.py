@@ -103,7 +103,7 @@ def gradient_quantiles(dx: torch.Tensor, dy: torch.Tensor, quantiles: Sequence[f
     for q in quantiles:
         _, prev, nxt = _quantile_indexes(n, q)
         wanted.append((n - 1, n - 1) if prev == -1 else (prev, min(nxt, n - 1)))
-    ranks = sorted({r for pair in wanted for r in pair} | {n - 1})
+    ranks = sorted({r for pair in wanted for r in pair})          # at most 4 for two quantiles: one call
     values = [dict() for _ in range(b)]
     scratch = torch.empty(b * 4 * (1 + 2048), dtype=torch.int32, device=dx.device)
     for i in range(0, len(ranks), 4):
@@ -115,7 +115,8 @@ def gradient_quantiles(dx: torch.Tensor, dy: torch.Tensor, quantiles: Sequence[f
         for k in range(b):
             for r, v in zip(chunk, m[k]):
                 values[k][r] = v
-    result = [[linear_quantile(n, q, values[k][lo], values[k][hi], values[k][n - 1])
+    # a virtual index at or beyond n - 1 asked for rank n - 1 twice above, so `hi` is the maximum then
+    result = [[linear_quantile(n, q, values[k][lo], values[k][hi], values[k][hi])
                for q, (lo, hi) in zip(quantiles, wanted)] for k in range(b)]
     return result[0] if squeeze else result
 
@@ -251,10 +252,13 @@ def sample_circles(lists: EdgeLists, num_iter: int, min_radius=None, max_radius=
     return raw, circles
 
 
-def gradient_angles(dx: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
-    """float32 arctan2(dy, dx) per pixel (utils.py:169), computed in float64 and rounded once."""
+def gradient_angles(dx: torch.Tensor, dy: torch.Tensor, edges: torch.Tensor = None) -> torch.Tensor:
+    """float32 arctan2(dy, dx) per pixel (utils.py:169), computed in float64 and rounded once; with
+    an edge map only at its edge pixels (0 elsewhere), which is all the score reads."""
     angle = torch.empty(dx.shape, dtype=torch.float32, device=dx.device)
-    _lib.call("mgb_gradient_angles", _ptr(dx), _ptr(dy), dx.numel(), _ptr(angle), _stream())
+    if edges is not None and (edges.dtype != torch.uint8 or edges.numel() != dx.numel() or not edges.is_contiguous()):
+        raise ValueError("edges must be a contiguous uint8 map of the gradients' shape")
+    _lib.call("mgb_gradient_angles", _ptr(dx), _ptr(dy), _ptr(edges), dx.numel(), _ptr(angle), _stream())
     return angle
 
 
@@ -291,6 +295,14 @@ def select_circles(circles: np.ndarray, scores: np.ndarray, min_roundness: float
     return circles, scores
 
 
+def order_circles(circles: torch.Tensor, scores: torch.Tensor) -> torch.Tensor:
+    """Device permutation: image by image, best score first, ties in input order (the input of
+    `sample_circles` is sorted by (image, row, col, radius))."""
+    order = torch.empty(circles.shape[0], dtype=torch.int32, device=circles.device)
+    _lib.call("mgb_order_circles", _ptr(circles), _ptr(scores), circles.shape[0], _ptr(order), _stream())
+    return order
+
+
 def find_circles(image: torch.Tensor, low_edge_quantile: float, high_edge_quantile: float, grid_length: int,
                  num_iter: int, min_radius: int, max_radius: int, min_roundness: float, min_dist: int, seed: int = 0):
     """`utils.find_circles` (utils.py:100-218) for a (H, W) uint8 image -> (circles (n,3) int32
@@ -308,17 +320,22 @@ def find_circles(image: torch.Tensor, low_edge_quantile: float, high_edge_quanti
     if lists.total and num_iter > 0:
         _, circles = sample_circles(lists, num_iter, min_radius, max_radius, seed)
         if circles.shape[0]:
-            angle = gradient_angles(dx, dy)
+            angle = gradient_angles(dx, dy, edges)
             scores = score_circles(circles, e, angle, min_radius, max_radius)
             # utils.py:187-188 on the device, so that only survivors travel to the host; a float32
             # tensor compared with a Python float casts the scalar to float32, like NumPy does
             keep = scores >= min_roundness
-            found, scores = circles[keep].cpu().numpy(), scores[keep].cpu().numpy()
-            by_image = np.argsort(found[:, 0], kind="stable")
-            found, scores = found[by_image], scores[by_image]
-            bounds = np.searchsorted(found[:, 0], np.arange(b + 1))
-            for k in range(b):
-                lo, hi = bounds[k], bounds[k + 1]
-                if hi > lo:
-                    results[k] = select_circles(found[lo:hi, 1:], scores[lo:hi], min_roundness, min_dist)
+            circles, scores = circles[keep].contiguous(), scores[keep].contiguous()
+            if circles.shape[0]:
+                order = order_circles(circles, scores).long()                 # utils.py:192-193
+                found, scores = circles[order].cpu().numpy(), scores[order].cpu().numpy()
+                bounds = np.searchsorted(found[:, 0], np.arange(b + 1))
+                for k in range(b):
+                    lo, hi = bounds[k], bounds[k + 1]
+                    if hi > lo:
+                        mine, sc = found[lo:hi, 1:], scores[lo:hi]
+                        if min_dist > 0:                                      # utils.py:194-196
+                            valid = filter_neighbors(mine, min_dist)
+                            mine, sc = mine[valid], sc[valid]
+                        results[k] = (np.ascontiguousarray(mine), sc)
     return results[0] if squeeze else results

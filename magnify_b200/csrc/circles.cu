@@ -269,12 +269,28 @@ __global__ void __launch_bounds__(kThreads) canny_nms_kernel(const int16_t* __re
 }
 
 // One sweep of hysteresis: every 32x32 tile is flooded to its own fixed point in shared memory
-// (strong pixels recruit 8-connected candidates); `changed` counts tiles that recruited anything,
-// the host repeats sweeps until a sweep changes nothing.
+// (strong pixels recruit 8-connected candidates).  A tile only has work when it or one of its
+// eight neighbours recruited something in the previous sweep (`active_in`, one byte per tile; NULL
+// on the first sweep = every tile); tiles that recruit set `active_out` and bump `changed`.  The
+// host repeats sweeps until a sweep changes nothing.
 __global__ void __launch_bounds__(kThreads) canny_hysteresis_kernel(uint8_t* __restrict__ map, int H, int W,
+                                                                    const uint8_t* __restrict__ active_in,
+                                                                    uint8_t* __restrict__ active_out,
                                                                     int* __restrict__ changed) {
   __shared__ uint8_t t[34][36];
   __shared__ int again, any;
+  const int tiles_x = gridDim.x, tiles_y = gridDim.y;
+  const int64_t tile_base = (int64_t)blockIdx.z * tiles_x * tiles_y;
+  if (active_in) {
+    bool work = false;
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int ty = (int)blockIdx.y + dy, tx = (int)blockIdx.x + dx;
+        if (ty >= 0 && ty < tiles_y && tx >= 0 && tx < tiles_x && active_in[tile_base + (int64_t)ty * tiles_x + tx])
+          work = true;
+      }
+    if (!work) return;   // uniform over the block
+  }
   map += (int64_t)blockIdx.z * H * W;
   const int x0 = blockIdx.x * 32 - 1, y0 = blockIdx.y * 32 - 1;
   for (int i = threadIdx.x; i < 34 * 34; i += blockDim.x) {
@@ -314,7 +330,10 @@ __global__ void __launch_bounds__(kThreads) canny_hysteresis_kernel(uint8_t* __r
       const int y = y0 + lyb + r, x = x0 + lx;
       if (y < H && x < W && t[lyb + r][lx] == 2) map[(int64_t)y * W + x] = 2;
     }
-    if (threadIdx.x == 0) atomicAdd(changed, 1);
+    if (threadIdx.x == 0) {
+      active_out[tile_base + (int64_t)blockIdx.y * tiles_x + blockIdx.x] = 1;
+      atomicAdd(changed, 1);
+    }
   }
 }
 
@@ -458,17 +477,28 @@ int mgb_canny(const int16_t* dx, const int16_t* dy, int64_t B, int64_t H, int64_
       dx, dy, (int)H, (int)W, thresholds, map);
   MGB_CUDA_LAUNCH_CHECK();
   const dim3 grid((unsigned)mgb::ceil_div(W, 32), (unsigned)mgb::ceil_div(H, 32), (unsigned)B);
+  // two byte-per-tile activity maps, ping-ponged between sweeps
+  const size_t n_tiles = (size_t)grid.x * grid.y * grid.z;
+  uint8_t* active = nullptr;
+  MGB_CUDA_TRY(cudaMallocAsync((void**)&active, 2 * n_tiles, s));
   int sweeps = 0;
+  cudaError_t e = cudaSuccess;
   for (;;) {
-    MGB_CUDA_TRY(cudaMemsetAsync(changed, 0, sizeof(int), s));
-    canny_hysteresis_kernel<<<grid, kThreads, 0, s>>>(map, (int)H, (int)W, changed);
-    MGB_CUDA_LAUNCH_CHECK();
+    uint8_t* out = active + (size_t)(sweeps & 1) * n_tiles;
+    const uint8_t* in = sweeps == 0 ? nullptr : active + (size_t)((sweeps + 1) & 1) * n_tiles;
+    if ((e = cudaMemsetAsync(changed, 0, sizeof(int), s)) != cudaSuccess) break;
+    if ((e = cudaMemsetAsync(out, 0, n_tiles, s)) != cudaSuccess) break;
+    canny_hysteresis_kernel<<<grid, kThreads, 0, s>>>(map, (int)H, (int)W, in, out, changed);
+    mgb_count_launch_();
+    if ((e = cudaGetLastError()) != cudaSuccess) break;
     ++sweeps;
     int host_changed = 0;
-    MGB_CUDA_TRY(cudaMemcpyAsync(&host_changed, changed, sizeof(int), cudaMemcpyDeviceToHost, s));
-    MGB_CUDA_TRY(cudaStreamSynchronize(s));
+    if ((e = cudaMemcpyAsync(&host_changed, changed, sizeof(int), cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) break;
     if (host_changed == 0) break;
   }
+  cudaFreeAsync(active, s);
+  if (e != cudaSuccess) return (int)e;
   canny_edges_kernel<<<grid_for(B * H * W), kThreads, 0, s>>>(map, B * H * W, edges);
   MGB_CUDA_LAUNCH_CHECK();
   if (host_sweeps) *host_sweeps = sweeps;

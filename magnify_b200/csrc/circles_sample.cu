@@ -23,6 +23,7 @@
 
 #include <algorithm>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 namespace {
@@ -161,11 +162,14 @@ __global__ void __launch_bounds__(kThreads) sample_circles_kernel(
 // ---------------------------------------------------------------------------------------------
 // scoring
 // ---------------------------------------------------------------------------------------------
+// The score only reads the angle at edge pixels (utils.py:241-243), so only those are computed
+// when an edge map is given (the float64 atan2 is the expensive part of this kernel).
 __global__ void __launch_bounds__(kThreads) grad_angle_kernel(const int16_t* __restrict__ dx,
-                                                              const int16_t* __restrict__ dy, int64_t n,
+                                                              const int16_t* __restrict__ dy,
+                                                              const uint8_t* __restrict__ edges, int64_t n,
                                                               float* __restrict__ angle) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    angle[i] = (float)atan2((double)dy[i], (double)dx[i]);   // np.arctan2(dy, dx) of float32 inputs
+    angle[i] = (!edges || edges[i]) ? (float)atan2((double)dy[i], (double)dx[i]) : 0.0f;   // np.arctan2(dy, dx)
 }
 
 // circles (N, 4) int32: image, row, col, radius.  perim_offsets[r - rmin] .. [r - rmin + 1] delimit
@@ -211,9 +215,54 @@ __global__ void __launch_bounds__(kThreads) unpack_circles_kernel(const uint64_t
   circles[4 * i + 3] = (int32_t)(k & 0xffff);
 }
 
+// key = (image << 32) | (0xffffffff - ordered(score)): ascending keys = image ascending, score
+// descending; NaN scores sort last within their image.
+__global__ void __launch_bounds__(kThreads) order_keys_kernel(const int32_t* __restrict__ circles,
+                                                              const float* __restrict__ scores, int64_t N,
+                                                              uint64_t* __restrict__ keys, int32_t* __restrict__ index) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float sc = scores[i];
+  uint32_t u = __float_as_uint(sc);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);          // total order of finite floats
+  if (sc != sc) u = 0;                                     // NaN: lowest score
+  keys[i] = ((uint64_t)(uint32_t)circles[4 * i] << 32) | (uint64_t)(0xffffffffu - u);
+  index[i] = (int32_t)i;
+}
+
 }  // namespace
 
 extern "C" {
+
+int mgb_order_circles(const int32_t* circles, const float* scores, int64_t N, int32_t* order, void* stream) {
+  if (N < 0 || N > INT32_MAX) return MGB_EINVAL;
+  if (N == 0) return MGB_OK;
+  if (!circles || !scores || !order) return MGB_EINVAL;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint64_t* keys = nullptr;
+  int32_t* index = nullptr;
+  void* temp = nullptr;
+  size_t temp_bytes = 0;
+  // keys in, keys out (2 N x 8 bytes) + the identity permutation (N x 4 bytes)
+  cudaError_t e = cudaMallocAsync((void**)&keys, (size_t)N * 2 * sizeof(uint64_t), s);
+  if (e == cudaSuccess) e = cudaMallocAsync((void**)&index, (size_t)N * sizeof(int32_t), s);
+  if (e == cudaSuccess) {
+    order_keys_kernel<<<(unsigned)mgb::ceil_div(N, kThreads), kThreads, 0, s>>>(circles, scores, N, keys, index);
+    mgb_count_launch_();
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys, keys + N, index, order, N, 0, 64, s);
+  if (e == cudaSuccess) e = cudaMallocAsync(&temp, temp_bytes, s);
+  if (e == cudaSuccess) {
+    // LSD radix sort: stable, so equal (image, score) keep the (row, col, radius) order of the input
+    e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys + N, index, order, N, 0, 64, s);
+    mgb_count_launch_();
+  }
+  if (temp) cudaFreeAsync(temp, s);
+  if (index) cudaFreeAsync(index, s);
+  if (keys) cudaFreeAsync(keys, s);
+  return e == cudaSuccess ? MGB_OK : (int)e;
+}
 
 int mgb_edge_cell_lists(const uint8_t* edges, int64_t B, int64_t H, int64_t W, int grid_length, int64_t* counts,
                         int64_t* starts, uint32_t* coords, int64_t coords_capacity, int64_t* host_total, void* stream) {
@@ -302,9 +351,26 @@ int mgb_sample_circles(const uint32_t* coords, const int64_t* starts, const int6
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     n = (int64_t)host_n;
     if (e == cudaSuccess && n > 0) {
-      unpack_circles_kernel<<<(unsigned)mgb::ceil_div(n, kThreads), kThreads, 0, s>>>(unique, n, circles);
-      mgb_count_launch_();
-      e = cudaGetLastError();
+      // Order the unique circles by (image, row, col, radius): the scoring kernel's threads then
+      // walk neighbouring perimeters (its edge / angle reads hit in L1/L2 instead of fetching a
+      // sector per byte), and the output no longer depends on the order of the atomics above.
+      uint64_t* sorted = nullptr;
+      void* temp = nullptr;
+      size_t temp_bytes = 0;
+      e = cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, unique, sorted, n, 0, 64, s);
+      if (e == cudaSuccess) e = cudaMallocAsync((void**)&sorted, (size_t)n * sizeof(uint64_t), s);
+      if (e == cudaSuccess) e = cudaMallocAsync(&temp, temp_bytes, s);
+      if (e == cudaSuccess) {
+        e = cub::DeviceRadixSort::SortKeys(temp, temp_bytes, unique, sorted, n, 0, 64, s);
+        mgb_count_launch_();
+      }
+      if (e == cudaSuccess) {
+        unpack_circles_kernel<<<(unsigned)mgb::ceil_div(n, kThreads), kThreads, 0, s>>>(sorted, n, circles);
+        mgb_count_launch_();
+        e = cudaGetLastError();
+      }
+      if (temp) cudaFreeAsync(temp, s);
+      if (sorted) cudaFreeAsync(sorted, s);
     }
   }
   cudaFreeAsync(image_starts, s);
@@ -314,11 +380,12 @@ int mgb_sample_circles(const uint32_t* coords, const int64_t* starts, const int6
   return MGB_OK;
 }
 
-int mgb_gradient_angles(const int16_t* dx, const int16_t* dy, int64_t n, float* angle, void* stream) {
+int mgb_gradient_angles(const int16_t* dx, const int16_t* dy, const uint8_t* edges, int64_t n, float* angle,
+                        void* stream) {
   if (!dx || !dy || !angle || n < 0) return MGB_EINVAL;
   if (n == 0) return MGB_OK;
   const int64_t blocks = std::min<int64_t>(mgb::ceil_div(n, kThreads), (int64_t)mgb_sm_count() * 16);
-  grad_angle_kernel<<<(unsigned)blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(dx, dy, n, angle);
+  grad_angle_kernel<<<(unsigned)blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(dx, dy, edges, n, angle);
   MGB_CUDA_LAUNCH_CHECK();
   return MGB_OK;
 }
