@@ -81,10 +81,14 @@ struct SampleParams {
 };
 
 constexpr uint64_t kEmpty = ~0ull;
-constexpr int kCoordBias = 1 << 15;   // rounded centres lie within max_radius of the image
+// 64-bit circle key: image (16 bits) | row + bias (18) | col + bias (18) | radius (12); ascending
+// keys = ascending (image, row, col, radius).  Rounded centres lie within max_radius of an image of
+// at most 65535 pixels a side, so 18 bits with a bias of 2^16 always suffice.
+constexpr int kCoordBias = 1 << 16;
+constexpr int kMaxKeyRadius = 4095;
 
 __device__ __forceinline__ uint64_t pack_circle(int64_t b, int row, int col, int r) {
-  return ((uint64_t)b << 48) | ((uint64_t)(row + kCoordBias) << 32) | ((uint64_t)(col + kCoordBias) << 16) | (uint64_t)r;
+  return ((uint64_t)b << 48) | ((uint64_t)(row + kCoordBias) << 30) | ((uint64_t)(col + kCoordBias) << 12) | (uint64_t)r;
 }
 
 // The circumcircle of p0, p0 + q1, p0 + q2 exactly as numba evaluates utils.py:317-342.
@@ -145,7 +149,8 @@ __global__ void __launch_bounds__(kThreads) sample_circles_kernel(
   if (!(c[2] >= p.min_radius && c[2] <= p.max_radius)) return;
   const int row = (int)rintf(c[0]), col = (int)rintf(c[1]), r = (int)rintf(c[2]);
   if (!(row + r >= 0 && col + r >= 0 && row - r < p.d.H && col - r < p.d.W)) return;
-  if (row <= -kCoordBias || row >= kCoordBias || col <= -kCoordBias || col >= kCoordBias) return;
+  if (row <= -kCoordBias || row >= 3 * kCoordBias || col <= -kCoordBias || col >= 3 * kCoordBias || r > kMaxKeyRadius)
+    return;   // cannot happen for max_radius <= 4095 (checked by the launcher)
   const uint64_t key = pack_circle(b, row, col, r);
   uint64_t slot = splitmix64(key) & p.table_mask;
   for (;;) {
@@ -210,9 +215,9 @@ __global__ void __launch_bounds__(kThreads) unpack_circles_kernel(const uint64_t
   if (i >= N) return;
   const uint64_t k = unique[i];
   circles[4 * i] = (int32_t)(k >> 48);
-  circles[4 * i + 1] = (int32_t)((k >> 32) & 0xffff) - kCoordBias;
-  circles[4 * i + 2] = (int32_t)((k >> 16) & 0xffff) - kCoordBias;
-  circles[4 * i + 3] = (int32_t)(k & 0xffff);
+  circles[4 * i + 1] = (int32_t)((k >> 30) & 0x3ffff) - kCoordBias;
+  circles[4 * i + 2] = (int32_t)((k >> 12) & 0x3ffff) - kCoordBias;
+  circles[4 * i + 3] = (int32_t)(k & 0xfff);
 }
 
 // key = (image << 32) | (0xffffffff - ordered(score)): ascending keys = image ascending, score
@@ -309,7 +314,7 @@ int mgb_sample_circles(const uint32_t* coords, const int64_t* starts, const int6
   if (!coords || !starts || !counts || B <= 0 || B > 65535 || H <= 0 || W <= 0 || H > 65535 || W > 65535 ||
       grid_length <= 0 || num_iter < 0)
     return MGB_EINVAL;
-  if (table && (!circles || !host_n_unique || !counter || table_capacity < 2 ||
+  if (table && (max_radius > (float)kMaxKeyRadius || !circles || !host_n_unique || !counter || table_capacity < 2 ||
                 (table_capacity & (table_capacity - 1)) != 0 || table_capacity < 2 * B * num_iter))
     return MGB_EINVAL;
   if (host_n_unique) *host_n_unique = 0;
