@@ -132,14 +132,65 @@ class QuantifyPlan:
         return self
 
     # -- device-resident run ------------------------------------------------------------------
+    # -- markers found on the device-resident image -----------------------------------------------
+    def stitched(self, tiles: torch.Tensor, image_out=None) -> torch.Tensor:
+        """Flat-field + stitch only (the first two stages of run_device): the image the finders
+        search, (C, T, Him, Wim) in HBM.  Pass it back to run_device(image=...) to skip the
+        recomputation."""
+        ff = self.ff
+        maxima = None
+        if not ff.identity:
+            maxima = ops.flatfield_maxima(tiles, ff)
+            if self.group is not None:
+                import torch.distributed as dist
+
+                dist.all_reduce(maxima, op=dist.ReduceOp.MAX, group=self.group)
+        return ops.flatfield_stitch(tiles, overlap=self.overlap, plan=ff, maxima=maxima, out=image_out)
+
+    def locate_chip_markers(self, image: torch.Tensor, finder, tag, channels=None):
+        """Button centres found on the device image by a `components.ButtonFinder` (GPU circle
+        finder + host grid fit + batched refinement, find.py:205-378) at its search timesteps,
+        copied forward to the others (find.py:143-157), then `set_chip_markers`.  No image bytes
+        leave the GPU.  tag: (rows, cols) array of chamber names ("" = blank)."""
+        from .dataset import Assay
+
+        c, t = self.tile_shape[:2]
+        tag = np.asarray(tag)
+        names = np.asarray(channels if channels is not None else [f"c{k}" for k in range(c)])
+        assay = Assay(coords={"tag": (("mark_row", "mark_col"), tag), "channel": (("channel",), names)})
+        rows, cols = tag.shape
+        src = copy_forward_sources(t, finder.search_timesteps)
+        search = sorted(set(src.tolist()))
+        x = np.empty((rows * cols, t))
+        y = np.empty((rows * cols, t))
+        radius = np.empty((rows * cols, len(search)), dtype=np.int32)
+        for k, ts in enumerate(search):
+            xs, ys, rs = finder._gpu_centers(assay, image, ts)
+            x[:, ts], y[:, ts], radius[:, k] = xs.reshape(-1), ys.reshape(-1), rs
+        for ti in range(t):
+            x[:, ti], y[:, ti] = x[:, src[ti]], y[:, src[ti]]
+        return self.set_chip_markers(x, y, radius, finder.chamber_radius, finder.max_button_radius,
+                                     finder.search_timesteps)
+
+    def locate_bead_markers(self, image: torch.Tensor, finder, channels=None):
+        """Bead centres found on the device image by a `components.BeadFinder` (find.py:476-501),
+        then `set_bead_markers`."""
+        from .dataset import Assay
+
+        names = np.asarray(channels if channels is not None else [f"c{k}" for k in range(self.tile_shape[0])])
+        beads = finder.find_centers(Assay(coords={"channel": (("channel",), names)}), image)
+        return self.set_bead_markers(beads)
+
     def run_device(self, tiles: torch.Tensor, want_roi: bool = True, image_out=None, roi_out=None,
-                   stats_out=None, record: Optional[list] = None, peer_stats=None) -> QuantifyResult:
+                   stats_out=None, record: Optional[list] = None, peer_stats=None,
+                   image: Optional[torch.Tensor] = None) -> QuantifyResult:
         """Whole hot path on tiles already in HBM (all launches on the current stream).
 
         record: optional list that receives (stage, start_event, end_event) CUDA-event triples
         recorded on the launching stream (bench.py's per-kernel timing).
         peer_stats: `SymmetricSummaries.peer_blocks` -- the gather kernel then writes the summaries
-        into every rank's gathered buffer over NVLink instead of `stats_out` (result.stats is None)."""
+        into every rank's gathered buffer over NVLink instead of `stats_out` (result.stats is None).
+        image: the output of `stitched(tiles)` when it was already computed to locate the markers."""
         if self.boxes is None:
             raise RuntimeError("set_chip_markers / set_bead_markers must be called first")
         if tuple(tiles.shape) != self.tile_shape:
@@ -158,14 +209,17 @@ class QuantifyPlan:
 
         ff = self.ff
         maxima = None
-        if not ff.identity:
-            maxima = stage("flatfield_max", lambda: ops.flatfield_maxima(tiles, ff))
-            if self.group is not None:
-                import torch.distributed as dist
+        if image is None:
+            if not ff.identity:
+                maxima = stage("flatfield_max", lambda: ops.flatfield_maxima(tiles, ff))
+                if self.group is not None:
+                    import torch.distributed as dist
 
-                stage("allreduce_max", lambda: dist.all_reduce(maxima, op=dist.ReduceOp.MAX, group=self.group))
-        image = stage("flatfield_stitch", lambda: ops.flatfield_stitch(tiles, overlap=self.overlap, plan=ff,
-                                                                       maxima=maxima, out=image_out))
+                    stage("allreduce_max", lambda: dist.all_reduce(maxima, op=dist.ReduceOp.MAX, group=self.group))
+            image = stage("flatfield_stitch", lambda: ops.flatfield_stitch(tiles, overlap=self.overlap, plan=ff,
+                                                                           maxima=maxima, out=image_out))
+        elif tuple(image.shape) != tuple(self.image_shape):
+            raise ValueError(f"image has shape {tuple(image.shape)}, plan expects {tuple(self.image_shape)}")
         roi, stats = stage("roi_gather_stats", lambda: ops.roi_gather_stats(
             image, self.boxes, self.fg, self.bg, self.roi_length, mask_t=self.mask_t, want_roi=want_roi,
             out_roi=roi_out, out_stats=stats_out, order=self.order, peer_stats=peer_stats))

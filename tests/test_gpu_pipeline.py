@@ -185,3 +185,45 @@ def test_tiff_tiles_staged_through_pinned_ring(cuda_device, tmp_path):
         flat_arg, dark_arg = flat_np, dark_np
     out = FlatfieldStitcher(flat_arg, dark_arg, case.overlap, device=cuda_device)(xp)
     np.testing.assert_array_equal(out.image.values, image_ref.numpy())
+
+
+def test_markers_located_on_device_image(cuda_device):
+    """tiles in HBM -> flat-field + stitch -> buttons found on the device image -> gather + stats,
+    without the image leaving the GPU; equals the component path (image through the host)."""
+    from magnify_b200 import pipeline
+    from magnify_b200.components import BeadFinder, ButtonFinder
+    from magnify_b200.dataset import Assay
+    from test_gpu_finders import draw_beads, draw_chip
+    from test_gpu_end_to_end import split_into_tiles
+
+    shape, overlap, t = (5, 4), 8, 3
+    chip = draw_chip(shape, 20, row_dist=100, col_dist=100) + 50                         # (600, 500)
+    frames = np.stack([chip + 3 * k for k in range(t)])
+    tiles = np.stack([split_into_tiles(f, 2, 2, overlap) for f in frames])[None]          # (1, T, 2, 2, h, w)
+    tiles_d = torch.from_numpy(np.ascontiguousarray(tiles)).to(cuda_device)
+    tag = np.full(shape, "default", dtype="<U200")
+    kw = dict(row_dist=100, col_dist=100, min_button_diameter=16, max_button_diameter=32, chamber_diameter=60,
+              num_iter=20000, min_roundness=0.2, cluster_penalty=50, search_timestep=[0, 2], device=cuda_device, seed=4)
+    plan = pipeline.QuantifyPlan(tiles_d.shape, overlap, ButtonFinder(**kw).roi_length, device=cuda_device)
+    image = plan.stitched(tiles_d)
+    plan.locate_chip_markers(image, ButtonFinder(**kw), tag)
+    res = plan.run_device(tiles_d, image=image)
+    np.testing.assert_array_equal(res.image.cpu().numpy()[0], frames)
+    assay = Assay({"image": (("channel", "time", "im_y", "im_x"), frames[None])},
+                  coords={"channel": (("channel",), np.array(["c0"])), "tag": (("mark_row", "mark_col"), tag),
+                          "valid": (("mark_row", "mark_col", "time"), np.ones(shape + (t,), bool))})
+    out = ButtonFinder(**kw)(assay)
+    np.testing.assert_array_equal(plan.x.cpu().numpy(), out.x.values)
+    np.testing.assert_array_equal(res.roi.cpu().numpy(), out.roi.values)
+    fg = res.fg.cpu().numpy().astype(bool)[:, res.mask_t.cpu().numpy()]
+    np.testing.assert_array_equal(fg, out.fg.values)
+    assert (res.stats[:, 0, :, 4].cpu().numpy() > 900).all()                              # fg means on the buttons
+    # beads
+    beads_img = draw_beads((600, 500), [[100, 100], [300, 250], [500, 400]]) + 20
+    tiles_b = torch.from_numpy(np.ascontiguousarray(split_into_tiles(beads_img, 2, 2, overlap)[None, None])).to(cuda_device)
+    finder = BeadFinder(16, 24, num_iter=5000, device=cuda_device)
+    bplan = pipeline.QuantifyPlan(tiles_b.shape, overlap, finder.roi_length, device=cuda_device)
+    bimage = bplan.stitched(tiles_b)
+    bplan.locate_bead_markers(bimage, finder)
+    bres = bplan.run_device(tiles_b, image=bimage)
+    assert bres.roi.shape[0] == 3 and (bres.stats[:, 0, 0, 4].cpu().numpy() > 900).all()
