@@ -268,70 +268,69 @@ __global__ void __launch_bounds__(kThreads) canny_nms_kernel(const int16_t* __re
   map[at] = out;
 }
 
-// One sweep of hysteresis: every 32x32 tile is flooded to its own fixed point in shared memory
-// (strong pixels recruit 8-connected candidates).  A tile only has work when it or one of its
-// eight neighbours recruited something in the previous sweep (`active_in`, one byte per tile; NULL
-// on the first sweep = every tile); tiles that recruit set `active_out` and bump `changed`.  The
-// host repeats sweeps until a sweep changes nothing.
+// One sweep of hysteresis, one WARP per 32x32 tile, bit-parallel: lane l holds column l of the
+// tile as two 64-bit row masks (bit r = row r of a 34-row window with a one-pixel halo): `strong`
+// (map == 2) and `cand` (map == 0, interior rows only).  A flood step is
+//     reach = strong | left lane's strong | right lane's strong;  reach |= reach << 1 | reach >> 1;
+//     newly = cand & reach;  strong |= newly;  cand &= ~newly
+// -- two shuffles and a few logic ops for the whole tile -- repeated until no lane recruits.
+// Lanes 0 and 31 take their outer neighbour from the halo columns, which (like the halo rows) are
+// read once and not updated inside a sweep.  A tile only has work when it or one of its eight
+// neighbours recruited something in the previous sweep (`active_in`, one byte per tile; NULL on
+// the first sweep = every tile); tiles that recruit set `active_out` and bump `changed`.  The host
+// repeats sweeps until a sweep changes nothing.
 __global__ void __launch_bounds__(kThreads) canny_hysteresis_kernel(uint8_t* __restrict__ map, int H, int W,
+                                                                    int tiles_x, int tiles_y,
                                                                     const uint8_t* __restrict__ active_in,
                                                                     uint8_t* __restrict__ active_out,
                                                                     int* __restrict__ changed) {
-  __shared__ uint8_t t[34][36];
-  __shared__ int again, any;
-  const int tiles_x = gridDim.x, tiles_y = gridDim.y;
+  const int lane = threadIdx.x & 31;
+  const int64_t tile = blockIdx.x * (int64_t)(kThreads / 32) + (threadIdx.x >> 5);
+  if (tile >= (int64_t)tiles_x * tiles_y) return;   // whole warp
+  const int ty = (int)(tile / tiles_x), tx = (int)(tile - (int64_t)ty * tiles_x);
   const int64_t tile_base = (int64_t)blockIdx.z * tiles_x * tiles_y;
   if (active_in) {
-    bool work = false;
-    for (int dy = -1; dy <= 1; ++dy)
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int ty = (int)blockIdx.y + dy, tx = (int)blockIdx.x + dx;
-        if (ty >= 0 && ty < tiles_y && tx >= 0 && tx < tiles_x && active_in[tile_base + (int64_t)ty * tiles_x + tx])
-          work = true;
-      }
-    if (!work) return;   // uniform over the block
+    bool mine = false;
+    if (lane < 9) {
+      const int ny = ty + lane / 3 - 1, nx = tx + lane % 3 - 1;
+      mine = ny >= 0 && ny < tiles_y && nx >= 0 && nx < tiles_x && active_in[tile_base + (int64_t)ny * tiles_x + nx];
+    }
+    if (!__any_sync(0xffffffffu, mine)) return;
   }
   map += (int64_t)blockIdx.z * H * W;
-  const int x0 = blockIdx.x * 32 - 1, y0 = blockIdx.y * 32 - 1;
-  for (int i = threadIdx.x; i < 34 * 34; i += blockDim.x) {
-    const int ly = i / 34, lx = i - ly * 34;
-    const int y = y0 + ly, x = x0 + lx;
-    t[ly][lx] = ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) ? map[(int64_t)y * W + x] : 1;
+  const int x = tx * 32 + lane, y0 = ty * 32 - 1;
+  const int xh = lane == 0 ? tx * 32 - 1 : tx * 32 + 32;   // halo column read by lanes 0 and 31
+  uint64_t strong = 0, cand = 0, halo = 0;
+  for (int r = 0; r < 34; ++r) {
+    const int y = y0 + r;
+    if ((unsigned)y >= (unsigned)H) continue;
+    const uint8_t* row = map + (int64_t)y * W;
+    if (x < W) {
+      const uint8_t v = row[x];
+      strong |= (uint64_t)(v == 2) << r;
+      if (r >= 1 && r <= 32) cand |= (uint64_t)(v == 0) << r;
+    }
+    if ((lane == 0 || lane == 31) && (unsigned)xh < (unsigned)W) halo |= (uint64_t)(row[xh] == 2) << r;
   }
-  if (threadIdx.x == 0) any = 0;
-  __syncthreads();
-  const int lx = (threadIdx.x & 31) + 1, lyb = (threadIdx.x >> 5) * 4 + 1;
+  const uint64_t before = strong;
   for (;;) {
-    if (threadIdx.x == 0) again = 0;
-    __syncthreads();
-    bool grew = false;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int ly = lyb + r;
-      if (t[ly][lx] == 0) {
-        const bool near = t[ly - 1][lx - 1] == 2 || t[ly - 1][lx] == 2 || t[ly - 1][lx + 1] == 2 ||
-                          t[ly][lx - 1] == 2 || t[ly][lx + 1] == 2 || t[ly + 1][lx - 1] == 2 ||
-                          t[ly + 1][lx] == 2 || t[ly + 1][lx + 1] == 2;
-        if (near) {
-          t[ly][lx] = 2;   // monotone 0 -> 2: racing readers only see it earlier or later
-          grew = true;
-        }
-      }
-    }
-    if (grew) again = 1;
-    __syncthreads();
-    if (!again) break;
-    if (threadIdx.x == 0) any = 1;
-    __syncthreads();
+    uint64_t left = __shfl_up_sync(0xffffffffu, strong, 1), right = __shfl_down_sync(0xffffffffu, strong, 1);
+    if (lane == 0) left = halo;
+    if (lane == 31) right = halo;
+    uint64_t reach = strong | left | right;
+    reach |= (reach << 1) | (reach >> 1);
+    const uint64_t newly = cand & reach;
+    strong |= newly;
+    cand &= ~newly;
+    if (!__any_sync(0xffffffffu, newly != 0)) break;
   }
-  if (any) {
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int y = y0 + lyb + r, x = x0 + lx;
-      if (y < H && x < W && t[lyb + r][lx] == 2) map[(int64_t)y * W + x] = 2;
-    }
-    if (threadIdx.x == 0) {
-      active_out[tile_base + (int64_t)blockIdx.y * tiles_x + blockIdx.x] = 1;
+  const uint64_t grew = strong & ~before;
+  if (__any_sync(0xffffffffu, grew != 0)) {
+    if (grew)
+      for (int r = 1; r <= 32; ++r)
+        if ((grew >> r) & 1) map[(int64_t)(y0 + r) * W + x] = 2;
+    if (lane == 0) {
+      active_out[tile_base + tile] = 1;
       atomicAdd(changed, 1);
     }
   }
@@ -480,7 +479,7 @@ int mgb_canny(const int16_t* dx, const int16_t* dy, int64_t B, int64_t H, int64_
   // two byte-per-tile activity maps, ping-ponged between sweeps
   const size_t n_tiles = (size_t)grid.x * grid.y * grid.z;
   uint8_t* active = nullptr;
-  MGB_CUDA_TRY(cudaMallocAsync((void**)&active, 2 * n_tiles, s));
+  MGB_CUDA_TRY(mgb::scratch_alloc((void**)&active, 2 * n_tiles, s));
   int sweeps = 0;
   cudaError_t e = cudaSuccess;
   for (;;) {
@@ -488,7 +487,8 @@ int mgb_canny(const int16_t* dx, const int16_t* dy, int64_t B, int64_t H, int64_
     const uint8_t* in = sweeps == 0 ? nullptr : active + (size_t)((sweeps + 1) & 1) * n_tiles;
     if ((e = cudaMemsetAsync(changed, 0, sizeof(int), s)) != cudaSuccess) break;
     if ((e = cudaMemsetAsync(out, 0, n_tiles, s)) != cudaSuccess) break;
-    canny_hysteresis_kernel<<<grid, kThreads, 0, s>>>(map, (int)H, (int)W, in, out, changed);
+    canny_hysteresis_kernel<<<dim3((unsigned)mgb::ceil_div((int64_t)grid.x * grid.y, kThreads / 32), 1, (unsigned)B),
+                              kThreads, 0, s>>>(map, (int)H, (int)W, (int)grid.x, (int)grid.y, in, out, changed);
     mgb_count_launch_();
     if ((e = cudaGetLastError()) != cudaSuccess) break;
     ++sweeps;

@@ -249,15 +249,15 @@ int mgb_order_circles(const int32_t* circles, const float* scores, int64_t N, in
   void* temp = nullptr;
   size_t temp_bytes = 0;
   // keys in, keys out (2 N x 8 bytes) + the identity permutation (N x 4 bytes)
-  cudaError_t e = cudaMallocAsync((void**)&keys, (size_t)N * 2 * sizeof(uint64_t), s);
-  if (e == cudaSuccess) e = cudaMallocAsync((void**)&index, (size_t)N * sizeof(int32_t), s);
+  cudaError_t e = mgb::scratch_alloc((void**)&keys, (size_t)N * 2 * sizeof(uint64_t), s);
+  if (e == cudaSuccess) e = mgb::scratch_alloc((void**)&index, (size_t)N * sizeof(int32_t), s);
   if (e == cudaSuccess) {
     order_keys_kernel<<<(unsigned)mgb::ceil_div(N, kThreads), kThreads, 0, s>>>(circles, scores, N, keys, index);
     mgb_count_launch_();
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys, keys + N, index, order, N, 0, 64, s);
-  if (e == cudaSuccess) e = cudaMallocAsync(&temp, temp_bytes, s);
+  if (e == cudaSuccess) e = mgb::scratch_alloc(&temp, temp_bytes, s);
   if (e == cudaSuccess) {
     // LSD radix sort: stable, so equal (image, score) keep the (row, col, radius) order of the input
     e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys + N, index, order, N, 0, 64, s);
@@ -295,7 +295,7 @@ int mgb_edge_cell_lists(const uint8_t* edges, int64_t B, int64_t H, int64_t W, i
   size_t temp_bytes = 0;
   MGB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, counts, starts, cells + 1, s));
   void* temp = nullptr;
-  MGB_CUDA_TRY(cudaMallocAsync(&temp, temp_bytes, s));
+  MGB_CUDA_TRY(mgb::scratch_alloc(&temp, temp_bytes, s));
   cudaError_t e = cub::DeviceScan::ExclusiveSum(temp, temp_bytes, counts, starts, cells + 1, s);
   mgb_count_launch_();
   cudaFreeAsync(temp, s);
@@ -331,14 +331,14 @@ int mgb_sample_circles(const uint32_t* coords, const int64_t* starts, const int6
   // image b's edges are coords[starts[b * cells_per_image] .. starts[(b + 1) * cells_per_image])
   const int64_t per_image = (int64_t)p.d.rows * p.d.cols;
   int64_t* image_starts = nullptr;
-  MGB_CUDA_TRY(cudaMallocAsync((void**)&image_starts, (size_t)(B + 1) * sizeof(int64_t), s));
+  MGB_CUDA_TRY(mgb::scratch_alloc((void**)&image_starts, (size_t)(B + 1) * sizeof(int64_t), s));
   cudaError_t e = cudaMemcpy2DAsync(image_starts, sizeof(int64_t), starts, (size_t)per_image * sizeof(int64_t),
                                     sizeof(int64_t), (size_t)(B + 1), cudaMemcpyDeviceToDevice, s);
   uint64_t* unique = nullptr;
   if (e == cudaSuccess && table) {
     e = cudaMemsetAsync(table, 0xff, (size_t)table_capacity * sizeof(uint64_t), s);
     if (e == cudaSuccess) e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s);
-    if (e == cudaSuccess) e = cudaMallocAsync((void**)&unique, (size_t)(B * num_iter) * sizeof(uint64_t), s);
+    if (e == cudaSuccess) e = mgb::scratch_alloc((void**)&unique, (size_t)(B * num_iter) * sizeof(uint64_t), s);
   }
   if (e != cudaSuccess) {
     cudaFreeAsync(image_starts, s);
@@ -363,8 +363,8 @@ int mgb_sample_circles(const uint32_t* coords, const int64_t* starts, const int6
       void* temp = nullptr;
       size_t temp_bytes = 0;
       e = cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, unique, sorted, n, 0, 64, s);
-      if (e == cudaSuccess) e = cudaMallocAsync((void**)&sorted, (size_t)n * sizeof(uint64_t), s);
-      if (e == cudaSuccess) e = cudaMallocAsync(&temp, temp_bytes, s);
+      if (e == cudaSuccess) e = mgb::scratch_alloc((void**)&sorted, (size_t)n * sizeof(uint64_t), s);
+      if (e == cudaSuccess) e = mgb::scratch_alloc(&temp, temp_bytes, s);
       if (e == cudaSuccess) {
         e = cub::DeviceRadixSort::SortKeys(temp, temp_bytes, unique, sorted, n, 0, 64, s);
         mgb_count_launch_();

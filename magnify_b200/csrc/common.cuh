@@ -31,6 +31,26 @@ __host__ __device__ inline bool aligned16(const void* p) {
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Stream-ordered scratch for the few entry points whose temporary sizes are only known inside the
+// call (CUB temp storage, the unique-circle list).  The device's default memory pool is told once
+// to keep freed blocks instead of returning them to the driver at every synchronisation, so
+// repeated calls do not pay an allocation from the OS each time.
+inline cudaError_t scratch_alloc(void** ptr, size_t bytes, cudaStream_t stream) {
+  static thread_local int tuned_device = -1;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (tuned_device != dev) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    tuned_device = dev;
+  }
+  return cudaMallocAsync(ptr, bytes, stream);
+}
+
 // Streaming 128-bit global accesses: every tile / image / roi byte is touched once per pass,
 // so keep them out of L1 (the coefficient tables and masks are what should stay cached).
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {

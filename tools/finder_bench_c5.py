@@ -69,6 +69,13 @@ else:
     stages["sample_dedupe"], (_, circles) = timed(lambda: mc.sample_circles(lists, NUM_ITER, 6, 14, seed=1))
     stages["angles"], angle = timed(lambda: mc.gradient_angles(dx, dy))
     stages["score"], scores = timed(lambda: mc.score_circles(circles, edges, angle, 6, 14))
+    keep = scores >= 0.3
+    stages["threshold_order"], (sc_c, sc_s) = timed(lambda: (lambda c, s2: (lambda o: (c[o], s2[o]))(mc.order_circles(c, s2).long()))(circles[keep].contiguous(), scores[keep].contiguous()))
+    stages["d2h_survivors"], (host_c, host_s) = timed(lambda: (sc_c.cpu().numpy(), sc_s.cpu().numpy()))
+    t0 = time.perf_counter()
+    valid = mc.filter_neighbors(host_c[:, 1:], 6)
+    stages["host_nms"] = time.perf_counter() - t0
+    out["survivors"] = int(len(host_c))
     out["stages_s"] = stages
     out["edge_pixels"] = lists.total
     out["unique_candidates"] = int(circles.shape[0])
