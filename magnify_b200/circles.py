@@ -69,7 +69,7 @@ def linear_quantile(n: int, q, lower: np.float32, upper: np.float32, last: np.fl
     if prev == -1:
         lower = upper = last
     gamma = np.asanyarray(np.asanyarray(v - np.asanyarray(np.intp(prev))), dtype=v.dtype)
-    a, b = np.asanyarray(lower, dtype=np.float32), np.asanyarray(upper, dtype=np.float32)
+    a, b = np.asanyarray(lower, dtype=np.float32), np.asanyarray(upper, dtype=np.float32)   # scalars or (B,) arrays
     diff = np.subtract(b, a)
     out = np.asanyarray(np.add(a, diff * gamma))
     np.subtract(b, diff * (1 - gamma), out=out, where=gamma >= 0.5, casting="unsafe", dtype=type(out.dtype))
@@ -104,7 +104,7 @@ def gradient_quantiles(dx: torch.Tensor, dy: torch.Tensor, quantiles: Sequence[f
         _, prev, nxt = _quantile_indexes(n, q)
         wanted.append((n - 1, n - 1) if prev == -1 else (prev, min(nxt, n - 1)))
     ranks = sorted({r for pair in wanted for r in pair})          # at most 4 for two quantiles: one call
-    values = [dict() for _ in range(b)]
+    values = {}                                                   # rank -> (b,) float32 order statistics
     scratch = torch.empty(b * 4 * (1 + 2048), dtype=torch.int32, device=dx.device)
     for i in range(0, len(ranks), 4):
         chunk = ranks[i: i + 4]
@@ -112,12 +112,12 @@ def gradient_quantiles(dx: torch.Tensor, dy: torch.Tensor, quantiles: Sequence[f
         out = (ctypes.c_int64 * (b * len(chunk)))()
         _lib.call("mgb_gradient_order_stats", _ptr(gx), _ptr(gy), b, n, arr, len(chunk), out, _ptr(scratch), _stream())
         m = np.sqrt(np.ctypeslib.as_array(out).reshape(b, len(chunk)).astype(np.float32))   # sqrt(float32 sum of squares)
-        for k in range(b):
-            for r, v in zip(chunk, m[k]):
-                values[k][r] = v
-    # a virtual index at or beyond n - 1 asked for rank n - 1 twice above, so `hi` is the maximum then
-    result = [[linear_quantile(n, q, values[k][lo], values[k][hi], values[k][hi])
-               for q, (lo, hi) in zip(quantiles, wanted)] for k in range(b)]
+        for j, r in enumerate(chunk):
+            values[r] = m[:, j].copy()
+    # a virtual index at or beyond n - 1 asked for rank n - 1 twice above, so `hi` is the maximum then;
+    # linear_quantile is elementwise, so whole batches go through it at once
+    per_q = [np.atleast_1d(linear_quantile(n, q, values[lo], values[hi], values[hi])) for q, (lo, hi) in zip(quantiles, wanted)]
+    result = [[col[k] for col in per_q] for k in range(b)]
     return result[0] if squeeze else result
 
 
