@@ -1,8 +1,7 @@
 """Circle finder timing.  On the GPU box: stage times of the GPU
 finder for (a) a 2048^2 bead image with the reference's default 5e6 draws and (b) the per-chamber
-refinement batch of config 2 (1792 crops of 72^2, 5e6 // 1792 draws each).  With --reference (build
-container only, needs /root/reference) the reference's own utils.find_circles is timed on the same
-images on the local CPU cores."""
+refinement batch of config 2 (1792 crops of 72^2, 5e6 // 1792 draws each).  The reference's own
+utils.find_circles is timed on the same images by tests/reference_finder_timing.py (build container)."""
 import json
 import os
 import sys
@@ -32,28 +31,10 @@ BEADS = dict(low_edge_quantile=0.1, high_edge_quantile=0.9, grid_length=20, num_
 ROIS = dict(low_edge_quantile=0.1, high_edge_quantile=1 - np.pi * 8 / 72**2, grid_length=20, num_iter=5_000_000 // 1792,
             min_radius=8, max_radius=15, min_roundness=0.2, min_dist=0)
 
-out = {}
-if "--reference" in sys.argv:
-    from oracle import circles as oc
-    from oracle._refload import load_reference_utils
 
-    utils = load_reference_utils()
-    img = oc.to_uint8(bead_image())
-    utils.find_circles(img[:256, :256], **dict(BEADS, num_iter=1000), gui=None)          # numba warm-up
-    t0 = time.perf_counter()
-    c, s = utils.find_circles(img, **BEADS, gui=None)
-    out["reference_beads_s"] = time.perf_counter() - t0
-    out["reference_beads_found"] = len(c)
-    rois = roi_batch()
-    t0 = time.perf_counter()
-    hits = 0
-    for r in rois[:256]:
-        c, s = utils.find_circles(oc.to_uint8(r), **ROIS, gui=None)
-        hits += len(c) > 0
-    out["reference_rois_s_extrapolated_1792"] = (time.perf_counter() - t0) * 1792 / 256
-    out["reference_rois_hit_fraction"] = hits / 256
-    out["cores"] = os.cpu_count()
-else:
+
+def main():
+    out = {}
     import torch
 
     from magnify_b200 import circles as mc
@@ -90,4 +71,8 @@ else:
     rois = torch.from_numpy(roi_batch()).to(dev)
     out["gpu_rois_total_s"], res = timed(lambda: mc.find_circles(mc.to_uint8(rois, batched=True), seed=2, **ROIS))
     out["gpu_rois_hit_fraction"] = float(np.mean([len(r[0]) > 0 for r in res]))
-print(json.dumps(out))
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,6 +1,6 @@
 """Config-5 sized bead detection: one 20480^2 image, 1e5 beads (radius 8-12), 5e7 draws.
-GPU stage times by default; --reference times the reference's utils.find_circles on the local CPU
-(build container only)."""
+GPU stage times; the reference's utils.find_circles is timed on the same image by
+tests/reference_finder_timing.py c5 (build container only)."""
 import json
 import os
 import sys
@@ -35,19 +35,9 @@ def image():
     return img
 
 
-out = {"side": SIDE, "beads": N_BEADS, "num_iter": NUM_ITER}
-img = image()
-if "--reference" in sys.argv:
-    from oracle._refload import load_reference_utils
-
-    utils = load_reference_utils()
-    utils.find_circles(img[:512, :512], **dict(ARGS, num_iter=1000), gui=None)
-    t0 = time.perf_counter()
-    c, s = utils.find_circles(img, **ARGS, gui=None)
-    out["reference_s"] = time.perf_counter() - t0
-    out["reference_found"] = len(c)
-    out["cores"] = os.cpu_count()
-else:
+def main():
+    out = {"side": SIDE, "beads": N_BEADS, "num_iter": NUM_ITER}
+    img = image()
     import torch
 
     from magnify_b200 import circles as mc
@@ -70,7 +60,13 @@ else:
     stages["angles"], angle = timed(lambda: mc.gradient_angles(dx, dy))
     stages["score"], scores = timed(lambda: mc.score_circles(circles, edges, angle, 6, 14))
     keep = scores >= 0.3
-    stages["threshold_order"], (sc_c, sc_s) = timed(lambda: (lambda c, s2: (lambda o: (c[o], s2[o]))(mc.order_circles(c, s2).long()))(circles[keep].contiguous(), scores[keep].contiguous()))
+
+    def threshold_order():
+        c, sc = circles[keep].contiguous(), scores[keep].contiguous()
+        order = mc.order_circles(c, sc).long()
+        return c[order], sc[order]
+
+    stages["threshold_order"], (sc_c, sc_s) = timed(threshold_order)
     stages["d2h_survivors"], (host_c, host_s) = timed(lambda: (sc_c.cpu().numpy(), sc_s.cpu().numpy()))
     t0 = time.perf_counter()
     valid = mc.filter_neighbors(host_c[:, 1:], 6)
@@ -83,4 +79,8 @@ else:
     torch.cuda.empty_cache()
     out["total_s"], res = timed(lambda: mc.find_circles(u8, seed=1, **ARGS))
     out["found"] = len(res[0])
-print(json.dumps(out))
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

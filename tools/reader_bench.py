@@ -1,8 +1,7 @@
 """TIFF staging throughput, run on the GPU box:
   1. native page reads (mgb_tiff_read_files) of 2048x2048 u16 single-page files from the page
      cache into PINNED memory, by thread count;
-  2. the same files decoded by libtiff through cv2.imread (what a per-page Python reader costs)
-     and by the struct-level oracle;
+  2. the same files decoded by libtiff through cv2.imread (what a per-page Python reader costs);
   3. files -> pinned ring -> HBM -> flat-field max + fused flat-field/stitch + gather/stats
      (pipeline.ChunkStager fed by reader.TiffTiles.blocks), end to end.
 Writes one JSON object to stdout."""
@@ -59,12 +58,6 @@ try:
         img = cv2.imread(p, cv2.IMREAD_UNCHANGED)
     out["cv2_libtiff_GBps_1thread"] = n_cv * h * w * 2 / (time.perf_counter() - t0) / 1e9
     assert np.array_equal(img, flat[n_cv - 1])
-    from oracle import tiff as ot
-
-    t0 = time.perf_counter()
-    for p in paths[:16]:
-        img = ot.read_page(p, 0)
-    out["oracle_struct_GBps_1thread"] = 16 * h * w * 2 / (time.perf_counter() - t0) / 1e9
 
     # end to end: files -> pinned ring -> HBM -> kernels -> host outputs
     plan = pipeline.QuantifyPlan(case.tiles.shape, case.overlap, case.roi_length, case.flat, case.dark, device=dev)
