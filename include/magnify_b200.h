@@ -227,6 +227,10 @@ int mgb_canny(const int16_t* dx, const int16_t* dy, int64_t B, int64_t H, int64_
               uint8_t* map, uint8_t* edges, int* changed, int* host_sweeps, void* stream);
 
 /* ---- N1 / N4: candidate circles and their scores, reference utils.py:141-189, 221-377 --------
+ * Temporaries whose size is only known inside a call (CUB scan / sort storage, the unique-circle
+ * list, the hysteresis activity maps) are taken from the device's default stream-ordered memory
+ * pool (cudaMallocAsync); the library sets that pool's release threshold so that freed blocks are
+ * kept for the next call instead of going back to the driver at every synchronisation.
  * Edge pixels grouped by grid cell (utils.py:347-377): counts / starts (B * cells + 1 int64 each,
  * cells = ceil(H/g) * ceil(W/g), cell-major per image) and coords (total uint32, row << 16 | col,
  * row-major inside a cell).  Call once with coords = NULL: counts and starts are computed and the
