@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MGB_ABI_VERSION 6
+#define MGB_ABI_VERSION 7
 
 #define MGB_OK 0
 #define MGB_EINVAL (-1)      /* bad argument (null pointer, negative size, bad itemsize ...) */
@@ -268,6 +268,18 @@ int mgb_score_circles(const int32_t* circles, int64_t N, int64_t H, int64_t W, c
 /* order (N) int32: the permutation that lists circles (N, 4) image by image, best score first
  * (utils.py:192-193, `argsort(-scores)`), equal scores in input order (stable). */
 int mgb_order_circles(const int32_t* circles, const float* scores, int64_t N, int32_t* order, void* stream);
+/* utils.py:252-285 on the device for circles (N, 4) int32 (image, row, col, radius) listed image by
+ * image, best first (the output order of mgb_order_circles), centres within max_radius of a
+ * B x H x W batch: state[i] = 1 when circle i survives, 2 when it is suppressed.  Two circles
+ * conflict when the rings of radius min_dist around their centres share a pixel, which depends
+ * only on the centre offset: conflict is that relation as a (4 min_dist + 1)^2 byte map on the
+ * device (index (drow + 2 min_dist) * (4 min_dist + 1) + dcol + 2 min_dist).  The sequential
+ * best-first pass is reproduced by rounds of "rejected once a higher-ranked conflicting circle is
+ * kept, kept once all of them are rejected"; SYNCHRONISES the stream once per round.  Callers must
+ * use the host version when a centre lies more than min_dist + 1 pixels outside the image (there
+ * the reference's raster indices wrap around). */
+int mgb_filter_neighbors_device(const int32_t* circles, int64_t N, int64_t B, int64_t H, int64_t W, int max_radius,
+                                int min_dist, const uint8_t* conflict, uint8_t* state, int* host_rounds, void* stream);
 /* HOST: utils.py:252-285 on circles (n, 3) int32 (row, col, radius) sorted best first:
  * host_valid[i] = 1 when circle i survives. */
 int mgb_filter_neighbors(const int32_t* host_circles, int64_t n, int min_dist, uint8_t* host_valid);

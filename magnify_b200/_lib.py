@@ -63,6 +63,7 @@ SIGNATURES = {
     "mgb_circle_perimeter": [c_int, c_int, POINTER(ctypes.c_int32), c_int, POINTER(c_int)],
     "mgb_score_circles": [_P, _I64, _I64, _I64, _P, _P, c_int, c_int, _P, _P, _P, _P, _P],
     "mgb_order_circles": [_P, _P, _I64, _P, _P],
+    "mgb_filter_neighbors_device": [_P, _I64, _I64, _I64, _I64, c_int, c_int, _P, _P, POINTER(c_int), _P],
     "mgb_filter_neighbors": [POINTER(ctypes.c_int32), _I64, c_int, POINTER(ctypes.c_uint8)],
     "mgb_tiff_open": [c_char_p, POINTER(c_void_p)],
     "mgb_tiff_close": [_P],
@@ -93,7 +94,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.argtypes = argtypes
         fn.restype = _SPECIAL_RESTYPE.get(name, c_int)
-    if lib.mgb_abi_version() != 6:
+    if lib.mgb_abi_version() != 7:
         raise ImportError("libmagnify_b200.so ABI version mismatch; rebuild with `python -m magnify_b200.build --force`")
     _lib = lib
     return lib

@@ -199,6 +199,43 @@ def filter_neighbors(circles: np.ndarray, min_dist: int) -> np.ndarray:
     return valid.astype(bool)
 
 
+def conflict_map(min_dist: int) -> np.ndarray:
+    """(4 min_dist + 1)^2 uint8: entry (drow + 2 min_dist, dcol + 2 min_dist) is 1 when the rings
+    of radius min_dist (utils.py:262, 4-connected raster) around two centres (drow, dcol) apart
+    share a pixel -- the pairs utils.py:252-285 treats as neighbours."""
+    ring = circle_perimeter(min_dist, four_connected=True)
+    reach = 2 * min_dist
+    out = np.zeros((2 * reach + 1, 2 * reach + 1), dtype=np.uint8)
+    diff = (ring[:, None, :] - ring[None, :, :]).reshape(-1, 2)
+    out[diff[:, 0] + reach, diff[:, 1] + reach] = 1
+    return out
+
+
+def filter_neighbors_device(circles: torch.Tensor, batch: int, height: int, width: int, max_radius: int,
+                            min_dist: int, return_rounds: bool = False):
+    """utils.py:252-285 on the device: boolean keep mask for (N, 4) int32 circles (image, row, col,
+    radius) listed image by image, best first.  Only valid when no centre lies more than
+    min_dist + 1 pixels above / left of the image (`needs_host_suppression`)."""
+    _check(circles, "circles", torch.int32, 2)
+    n = circles.shape[0]
+    state = torch.empty(n, dtype=torch.uint8, device=circles.device)
+    conflict = torch.from_numpy(conflict_map(min_dist)).to(circles.device)
+    rounds = ctypes.c_int()
+    _lib.call("mgb_filter_neighbors_device", _ptr(circles), n, int(batch), int(height), int(width), int(max_radius),
+              int(min_dist), _ptr(conflict), _ptr(state), ctypes.byref(rounds), _stream())
+    keep = state == 1
+    return (keep, rounds.value) if return_rounds else keep
+
+
+def needs_host_suppression(circles: torch.Tensor, min_dist: int) -> bool:
+    """True when some centre is so far outside the image that the reference's claim raster is
+    indexed below zero (utils.py:270-271 then wrap around like NumPy's negative indices); only the
+    host implementation reproduces that."""
+    if circles.shape[0] == 0:
+        return False
+    return bool((circles[:, 1:3] < -(min_dist + 1)).any().item())
+
+
 class EdgeLists:
     """Edge pixels of a batch of edge maps grouped by grid cell (utils.py:347-377)."""
 
@@ -328,13 +365,18 @@ def find_circles(image: torch.Tensor, low_edge_quantile: float, high_edge_quanti
             circles, scores = circles[keep].contiguous(), scores[keep].contiguous()
             if circles.shape[0]:
                 order = order_circles(circles, scores).long()                 # utils.py:192-193
-                found, scores = circles[order].cpu().numpy(), scores[order].cpu().numpy()
+                circles, scores = circles[order].contiguous(), scores[order]
+                on_device = min_dist > 0 and not needs_host_suppression(circles, min_dist)
+                if on_device:                                                 # utils.py:194-196
+                    valid = filter_neighbors_device(circles, b, e.shape[1], e.shape[2], max_radius, min_dist)
+                    circles, scores = circles[valid], scores[valid]
+                found, scores = circles.cpu().numpy(), scores.cpu().numpy()
                 bounds = np.searchsorted(found[:, 0], np.arange(b + 1))
                 for k in range(b):
                     lo, hi = bounds[k], bounds[k + 1]
                     if hi > lo:
                         mine, sc = found[lo:hi, 1:], scores[lo:hi]
-                        if min_dist > 0:                                      # utils.py:194-196
+                        if min_dist > 0 and not on_device:                    # raster wrap-around case: host
                             valid = filter_neighbors(mine, min_dist)
                             mine, sc = mine[valid], sc[valid]
                         results[k] = (np.ascontiguousarray(mine), sc)

@@ -408,3 +408,143 @@ int mgb_score_circles(const int32_t* circles, int64_t N, int64_t H, int64_t W, c
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Neighbour suppression on the device (utils.py:252-285).  The reference walks the circles best
+// first; each accepted circle claims the raster ring of radius min_dist around its centre and a
+// circle is rejected when its own ring touches a claimed pixel.  Whether two circles conflict
+// depends only on the offset of their centres (ring and shifted ring share a pixel), so the greedy
+// pass is a fixed-priority independent-set problem: a circle is REJECTED as soon as a conflicting
+// circle of higher rank is KEPT, and KEPT once every conflicting circle of higher rank is
+// REJECTED.  Rounds of that rule reach the sequential result (each decision is final when made).
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr uint8_t kUndecided = 0, kKept = 1, kRejected = 2;
+
+struct NmsGrid {
+  int cell, cells_y, cells_x, origin;   // cell edge; cells per image; coordinate offset (centres >= -origin)
+  int reach;                            // conflicts need |drow|, |dcol| <= reach
+};
+
+__device__ __forceinline__ int64_t nms_cell_of(const NmsGrid& g, int b, int row, int col) {
+  return ((int64_t)b * g.cells_y + (row + g.origin) / g.cell) * g.cells_x + (col + g.origin) / g.cell;
+}
+
+__global__ void __launch_bounds__(kThreads) nms_count_kernel(const int32_t* __restrict__ circles, int64_t N, NmsGrid g,
+                                                             int32_t* __restrict__ counts) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < N) atomicAdd(&counts[nms_cell_of(g, circles[4 * i], circles[4 * i + 1], circles[4 * i + 2])], 1);
+}
+
+__global__ void __launch_bounds__(kThreads) nms_fill_kernel(const int32_t* __restrict__ circles, int64_t N, NmsGrid g,
+                                                            const int32_t* __restrict__ starts, int32_t* __restrict__ cursor,
+                                                            int32_t* __restrict__ members) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int64_t c = nms_cell_of(g, circles[4 * i], circles[4 * i + 1], circles[4 * i + 2]);
+  members[starts[c] + atomicAdd(&cursor[c], 1)] = (int32_t)i;
+}
+
+// conflict bitmap: (2 reach + 1)^2 bytes, index (drow + reach) * (2 reach + 1) + dcol + reach
+__global__ void __launch_bounds__(kThreads) nms_round_kernel(const int32_t* __restrict__ circles, int64_t N, NmsGrid g,
+                                                             const int32_t* __restrict__ starts,
+                                                             const int32_t* __restrict__ members,
+                                                             const uint8_t* __restrict__ conflict,
+                                                             volatile uint8_t* __restrict__ state, int* __restrict__ undecided) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= N || state[i] != kUndecided) return;
+  const int b = circles[4 * i], row = circles[4 * i + 1], col = circles[4 * i + 2];
+  const int cy = (row + g.origin) / g.cell, cx = (col + g.origin) / g.cell;
+  const int span = 2 * g.reach + 1;
+  bool pending = false;
+  for (int ny = max(cy - 1, 0); ny <= min(cy + 1, g.cells_y - 1); ++ny)
+    for (int nx = max(cx - 1, 0); nx <= min(cx + 1, g.cells_x - 1); ++nx) {
+      const int64_t c = ((int64_t)b * g.cells_y + ny) * g.cells_x + nx;
+      for (int k = starts[c]; k < starts[c + 1]; ++k) {
+        const int j = members[k];
+        if (j >= i) continue;   // only circles of higher rank matter (the list is best first per image)
+        const int dr = circles[4 * j + 1] - row, dc = circles[4 * j + 2] - col;
+        if (abs(dr) > g.reach || abs(dc) > g.reach || !conflict[(dr + g.reach) * span + dc + g.reach]) continue;
+        const uint8_t s = state[j];
+        if (s == kKept) {
+          state[i] = kRejected;
+          return;
+        }
+        if (s == kUndecided) pending = true;
+      }
+    }
+  if (pending) {
+    atomicAdd(undecided, 1);
+  } else {
+    state[i] = kKept;
+  }
+}
+
+}  // namespace
+
+extern "C" int mgb_filter_neighbors_device(const int32_t* circles, int64_t N, int64_t B, int64_t H, int64_t W,
+                                           int max_radius, int min_dist, const uint8_t* conflict, uint8_t* state,
+                                           int* host_rounds, void* stream) {
+  if (N < 0 || N > INT32_MAX || B <= 0 || H <= 0 || W <= 0 || min_dist < 1 || max_radius < 0) return MGB_EINVAL;
+  if (host_rounds) *host_rounds = 0;
+  if (N == 0) return MGB_OK;
+  if (!circles || !conflict || !state) return MGB_EINVAL;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  NmsGrid g;
+  g.reach = 2 * min_dist;
+  g.cell = g.reach + 1;
+  g.origin = max_radius + 1;   // centres lie within max_radius of the image (utils.py:160-165)
+  g.cells_y = (int)mgb::ceil_div(H + 2 * (int64_t)g.origin, g.cell);
+  g.cells_x = (int)mgb::ceil_div(W + 2 * (int64_t)g.origin, g.cell);
+  const int64_t cells = B * (int64_t)g.cells_y * g.cells_x;
+  if (cells + 1 > INT32_MAX) return MGB_EUNSUPPORTED;
+  int32_t *counts = nullptr, *starts = nullptr, *members = nullptr;
+  int* undecided = nullptr;
+  void* temp = nullptr;
+  size_t temp_bytes = 0;
+  const unsigned blocks = (unsigned)mgb::ceil_div(N, kThreads);
+  cudaError_t e = mgb::scratch_alloc((void**)&counts, (size_t)(cells + 1) * sizeof(int32_t), s);
+  if (e == cudaSuccess) e = mgb::scratch_alloc((void**)&starts, (size_t)(cells + 1) * sizeof(int32_t), s);
+  if (e == cudaSuccess) e = mgb::scratch_alloc((void**)&members, (size_t)N * sizeof(int32_t), s);
+  if (e == cudaSuccess) e = mgb::scratch_alloc((void**)&undecided, sizeof(int), s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(counts, 0, (size_t)(cells + 1) * sizeof(int32_t), s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(state, 0, (size_t)N, s);
+  if (e == cudaSuccess) {
+    nms_count_kernel<<<blocks, kThreads, 0, s>>>(circles, N, g, counts);
+    mgb_count_launch_();
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, counts, starts, cells + 1, s);
+  if (e == cudaSuccess) e = mgb::scratch_alloc(&temp, temp_bytes, s);
+  if (e == cudaSuccess) {
+    e = cub::DeviceScan::ExclusiveSum(temp, temp_bytes, counts, starts, cells + 1, s);
+    mgb_count_launch_();
+  }
+  if (e == cudaSuccess) e = cudaMemsetAsync(counts, 0, (size_t)(cells + 1) * sizeof(int32_t), s);   // reused as cursors
+  if (e == cudaSuccess) {
+    nms_fill_kernel<<<blocks, kThreads, 0, s>>>(circles, N, g, starts, counts, members);
+    mgb_count_launch_();
+    e = cudaGetLastError();
+  }
+  int rounds = 0;
+  while (e == cudaSuccess) {
+    e = cudaMemsetAsync(undecided, 0, sizeof(int), s);
+    if (e != cudaSuccess) break;
+    nms_round_kernel<<<blocks, kThreads, 0, s>>>(circles, N, g, starts, members, conflict, state, undecided);
+    mgb_count_launch_();
+    if ((e = cudaGetLastError()) != cudaSuccess) break;
+    ++rounds;
+    int left = 0;
+    if ((e = cudaMemcpyAsync(&left, undecided, sizeof(int), cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) break;
+    if (left == 0) break;
+  }
+  if (temp) cudaFreeAsync(temp, s);
+  if (undecided) cudaFreeAsync(undecided, s);
+  if (members) cudaFreeAsync(members, s);
+  if (starts) cudaFreeAsync(starts, s);
+  if (counts) cudaFreeAsync(counts, s);
+  if (host_rounds) *host_rounds = rounds;
+  return e == cudaSuccess ? MGB_OK : (int)e;
+}

@@ -214,3 +214,34 @@ def test_find_circles_agrees_with_reference_run(cuda_device, golden):
         assert set(got) == set(want), (seed, sorted(got), sorted(want))
         for c in want:
             assert abs(got[c] - want[c]) <= 2e-6, (c, got[c], want[c])
+
+
+def test_device_neighbour_suppression_equals_sequential_pass(cuda_device):
+    """mgb_filter_neighbors_device (rounds of the fixed-priority rule) == the sequential ring-claim
+    pass of utils.py:252-285 (host version, itself equal to the reference's numba function)."""
+    from magnify_b200 import circles as mc
+
+    rng = np.random.default_rng(0)
+    for trial in range(40):
+        b = int(rng.integers(1, 4))
+        h, w = int(rng.integers(40, 300)), int(rng.integers(40, 300))
+        min_dist, max_radius = int(rng.integers(1, 12)), int(rng.integers(12, 25))
+        lo = -min(min_dist + 1, max_radius)                       # stay out of the raster wrap-around regime
+        per_image = []
+        for k in range(b):
+            n = int(rng.integers(0, 400))
+            c = np.stack([np.full(n, k), rng.integers(lo, h + max_radius, n), rng.integers(lo, w + max_radius, n),
+                          rng.integers(3, max_radius + 1, n)], 1).astype(np.int32)
+            if trial % 4 == 0 and n:                              # dense clusters: long dependency chains
+                c[:, 1] = rng.integers(10, 30, n)
+                c[:, 2] = np.sort(rng.integers(0, w, n))
+            per_image.append(c)
+        circles = np.concatenate(per_image)
+        keep, rounds = mc.filter_neighbors_device(dev(circles, cuda_device), b, h, w, max_radius, min_dist, return_rounds=True)
+        want = np.concatenate([mc.filter_neighbors(c[:, 1:], min_dist) for c in per_image]) if len(circles) else np.zeros(0, bool)
+        np.testing.assert_array_equal(keep.cpu().numpy(), want, err_msg=f"trial {trial}")
+        assert rounds >= (1 if len(circles) else 0)
+    far = dev(np.array([[0, -9, 5, 12], [0, 4, 4, 6]], np.int32), cuda_device)
+    assert mc.needs_host_suppression(far, 3) and not mc.needs_host_suppression(far, 8)
+    cm = mc.conflict_map(2)
+    assert cm.shape == (9, 9) and cm[4, 4] == 1 and (cm == cm[::-1, ::-1]).all()
