@@ -161,3 +161,91 @@ def test_full_size_chip_all_buttons_found(cuda_device):
     np.testing.assert_array_equal(out.y.values[:, 0], cy.reshape(-1))
     found_radius = np.sqrt(out.fg.values[:, 0].sum(axis=(1, 2)) / np.pi)
     assert np.abs(found_radius - radius.reshape(-1)).max() < 0.5
+
+
+# ---- more of tests/test_chip.py ---------------------------------------------------------------
+@pytest.mark.parametrize("shape,button,row_dist,col_dist,kw,num_iter", [
+    ((3, 5), 20, 100, 100, {}, 5000),                                                     # :135-159
+    ((5, 3), 20, 100, 100, {}, 5000),                                                     # :162-186
+    ((4, 4), 40, 150, 150, dict(min_button_diameter=30, max_button_diameter=50, chamber_diameter=100), 5000),   # :194-221
+    ((4, 4), 20, 80, 120, {}, 5000),                                                      # :224-252
+    ((2, 2), 20, 100, 100, {}, 1000),                                                     # :260-283
+])
+def test_chip_geometries(cuda_device, shape, button, row_dist, col_dist, kw, num_iter):
+    from magnify_b200.components import ButtonFinder
+
+    params = dict(CHIP, row_dist=row_dist, col_dist=col_dist)
+    params.update(kw)
+    out = ButtonFinder(num_iter=num_iter, **params)(chip_assay(draw_chip(shape, button, row_dist, col_dist), shape))
+    assert out.sizes["mark"] == shape[0] * shape[1]
+    x, y = out.x.values.reshape(shape), out.y.values.reshape(shape)
+    for i in range(shape[0]):
+        for j in range(shape[1]):
+            assert abs(x[i, j] - (j + 1) * col_dist) < 5 and abs(y[i, j] - (i + 1) * row_dist) < 5
+    radii = np.sqrt(out.fg.values[:, 0].sum(axis=(1, 2)) / np.pi)
+    assert 0.85 * button / 2 < radii.min() and radii.max() < 1.15 * button / 2
+
+
+def test_chip_blank_positions_with_default_tags(cuda_device):                          # :286-311
+    from magnify_b200.components import ButtonFinder
+
+    blanks = [(0, 0), (1, 2), (2, 1), (3, 3)]
+    out = ButtonFinder(num_iter=5000, **CHIP)(chip_assay(draw_chip((4, 4), 20, blanks=blanks), (4, 4)))
+    assert out.sizes["mark"] == 16
+    assert (out.fg.values[:, 0].sum(axis=(1, 2)) > 100).sum() >= 12
+
+
+def test_chip_refinding_follows_shifted_buttons(cuda_device):                          # :487-546, :549-597
+    from magnify_b200.components import ButtonFinder
+
+    t0 = draw_chip((2, 2), 20)
+    t1 = np.zeros_like(t0)
+    t1[10:, 10:] = t0[:-10, :-10]
+    assay = chip_assay(t0, (2, 2), t=2)
+    assay["image"] = (("channel", "time", "im_y", "im_x"), np.stack([t0, t1])[None])
+    out = ButtonFinder(num_iter=5000, search_timestep=[0, 1], **CHIP)(assay)
+    x, y = out.x.values.reshape(2, 2, 2), out.y.values.reshape(2, 2, 2)
+    for i in range(2):
+        for j in range(2):
+            assert abs(x[i, j, 0] - (j + 1) * 100) < 5 and abs(x[i, j, 1] - ((j + 1) * 100 + 10)) < 5
+            assert abs(y[i, j, 0] - (i + 1) * 100) < 5 and abs(y[i, j, 1] - ((i + 1) * 100 + 10)) < 5
+    # searched only at t = 0: t = 1 copies the t = 0 positions although the buttons moved
+    out = ButtonFinder(num_iter=5000, search_timestep=0, **CHIP)(assay.copy())
+    np.testing.assert_array_equal(out.x.values[:, 0], out.x.values[:, 1])
+    assert np.abs(out.x.values[:, 0].reshape(2, 2)[0] - np.array([100, 200])).max() < 5
+
+
+def test_chip_search_channel(cuda_device):                                             # :655-697
+    from magnify_b200.components import ButtonFinder
+    from magnify_b200.dataset import Assay
+
+    chip = draw_chip((3, 3), 20)
+    image = np.stack([chip, np.zeros_like(chip)])[:, None]
+    tag = np.full((3, 3), "default", dtype="<U200")
+    assay = Assay({"image": (("channel", "time", "im_y", "im_x"), image)},
+                  coords={"channel": (("channel",), np.array(["bf", "gfp"])), "tag": (("mark_row", "mark_col"), tag),
+                          "valid": (("mark_row", "mark_col", "time"), np.ones((3, 3, 1), bool))})
+    out = ButtonFinder(num_iter=5000, search_channel="bf", **CHIP)(assay)
+    x, y = out.x.values.reshape(3, 3), out.y.values.reshape(3, 3)
+    for i in range(3):
+        for j in range(3):
+            assert abs(x[i, j] - (j + 1) * 100) < 5 and abs(y[i, j] - (i + 1) * 100) < 5
+    radii = np.sqrt(out.fg.values[:, 0].sum(axis=(1, 2)) / np.pi)
+    assert 8 < radii.min() and radii.max() < 12 and out.roi.shape[1] == 2
+
+
+# ---- more of tests/test_beads.py ---------------------------------------------------------------
+def test_beads_sizes_spacing_intensity(cuda_device):                                   # :121-216
+    from magnify_b200.components import BeadFinder
+
+    out = BeadFinder(14, 32, num_iter=10000)(bead_assay(draw_beads((1024, 1024), [[300, 300], [300, 700], [700, 300], [700, 700]],
+                                                                   diameters=[16, 20, 24, 28])))
+    areas = out.fg.values[:, 0].sum(axis=(1, 2))
+    assert out.sizes["mark"] == 4 and areas.max() / areas.min() > 1.5
+    out = BeadFinder(16, 24, num_iter=10000)(bead_assay(draw_beads((1024, 1024), [[500, 500], [500, 540], [540, 500]])))
+    assert out.sizes["mark"] == 3
+    pos = np.stack([out.x.values[:, 0], out.y.values[:, 0]], 1)
+    assert min(np.linalg.norm(pos[i] - pos[j]) for i in range(3) for j in range(i)) > 20
+    out = BeadFinder(16, 24, num_iter=10000)(bead_assay(draw_beads((1024, 1024), [[300, 500], [500, 500], [700, 500]],
+                                                                   value=[500, 1000, 2000])))
+    assert out.sizes["mark"] == 3 and (radii_from_fg(out) > 8.5).all()
