@@ -411,3 +411,131 @@ def iter_blocks(tiles):
             if hasattr(block, "compute"):       # dask: materialise this block only
                 block = block.compute()
             yield (ci, ti), block
+
+
+class StreamingRunner:
+    """Two passes over a block source for stacks that fit neither HBM nor host RAM (config 5 as a
+    whole is 335 GB): only `depth` timepoints are resident at any time.
+
+    Pass 1 streams every (channel, timepoint) block through a pinned slot into HBM and accumulates
+    the two global flat-field maxima (preprocess.py:84,86 need them before any pixel can be
+    corrected; skipped for the identity flat-field).  Pass 2 streams the blocks again, one
+    timepoint at a time: flat-field + stitch, gather + reductions, and the results of that
+    timepoint go back through pinned buffers to `sink`.  The reference does the same two sweeps
+    implicitly: its lazy dask graph re-reads every TIFF page for `tiles.max()` and again for the
+    corrected tiles (preprocess.py:83-87 on the page-per-chunk array of reader.py:265-292).
+
+    source(c, t, dst): fill the C-contiguous (R, Cc, H, W) array `dst` (a pinned slot) with block
+    (c, t) -- e.g. `lambda c, t, dst: tiles.read((c, t), dst)` for a `reader.TiffTiles`.
+    sink(t, image, roi, stats): called once per timepoint, in order, with NumPy views of pinned
+    buffers that are only valid during the call: image (C, Him, Wim) or None, roi (M, C, L, L) or
+    None, stats (M, C, 6)."""
+
+    def __init__(self, plan: QuantifyPlan, depth: int = 2, want_image: bool = True, want_roi: bool = True,
+                 threads: int = 4):
+        from concurrent.futures import ThreadPoolExecutor
+
+        if plan.boxes is None:
+            raise RuntimeError("set_chip_markers / set_bead_markers must be called first")
+        self.pool = ThreadPoolExecutor(max_workers=max(1, threads))   # the channels of a timepoint are filled concurrently
+        if depth < 2:
+            raise ValueError("depth must be at least 2 (one timepoint in flight, one being filled)")
+        self.plan, self.depth, self.want_image, self.want_roi = plan, depth, want_image, want_roi
+        c, t, r, cc, h, w = plan.tile_shape
+        dev = plan.device
+        m, length = plan.boxes.shape[0], plan.roi_length
+        him, wim = plan.image_shape[-2:]
+        pin = dict(pin_memory=True)
+        self.tiles_pin = [torch.empty((c, r, cc, h, w), dtype=torch.uint16, **pin) for _ in range(depth)]
+        self.tiles_dev = [torch.empty((c, 1, r, cc, h, w), dtype=torch.uint16, device=dev) for _ in range(depth)]
+        self.image_dev = [ops.alloc_image((c, 1, him, wim), torch.uint16, dev) for _ in range(depth)]
+        self.roi_dev = [torch.empty((m, c, 1, length, length), dtype=torch.uint16, device=dev) if want_roi else None
+                        for _ in range(depth)]
+        self.stats_dev = [torch.empty((m, c, 1, 6), dtype=torch.float64, device=dev) for _ in range(depth)]
+        self.image_pin = [torch.empty((c, 1, him, wim), dtype=torch.uint16, **pin) if want_image else None
+                          for _ in range(depth)]
+        self.roi_pin = [torch.empty((m, c, 1, length, length), dtype=torch.uint16, **pin) if want_roi else None
+                        for _ in range(depth)]
+        self.stats_pin = [torch.empty((m, c, 1, 6), dtype=torch.float64, **pin) for _ in range(depth)]
+        self.h2d = torch.cuda.Stream(device=dev)
+        self.d2h = torch.cuda.Stream(device=dev)
+        self.boxes_t = [plan.boxes[:, ti:ti + 1].contiguous() for ti in range(t)]
+        self.mask_t = [plan.mask_t[ti:ti + 1].contiguous() if plan.mask_t is not None else None for ti in range(t)]
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def _stage_in(self, source, ti: int, slot: int, consumed) -> "torch.cuda.Event":
+        """Fill the slot's pinned tiles from the source and queue their upload."""
+        c = self.plan.tile_shape[0]
+        if consumed[slot] is not None:
+            consumed[slot].synchronize()              # the slot's previous upload has been read by the kernels
+        dst = self.tiles_pin[slot].numpy()
+        list(self.pool.map(lambda ci: source(ci, ti, dst[ci]), range(c)))   # NumPy copies / native reads drop the GIL
+        with torch.cuda.stream(self.h2d):
+            self.tiles_dev[slot][:, 0].copy_(self.tiles_pin[slot], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.h2d)
+        self.h2d_bytes += self.tiles_pin[slot].numel() * 2
+        return ev
+
+    def run(self, source, sink) -> None:
+        plan, ff = self.plan, self.plan.ff
+        c, t = plan.tile_shape[:2]
+        compute = torch.cuda.current_stream(plan.device)
+        consumed = [None] * self.depth               # per slot: kernels done reading tiles_dev / tiles_pin uploaded
+        self.h2d_bytes = self.d2h_bytes = 0
+        # ---- pass 1: global maxima
+        if not ff.identity:
+            ff.maxima.zero_()
+            for ti in range(t):
+                slot = ti % self.depth
+                up = self._stage_in(source, ti, slot, consumed)
+                compute.wait_event(up)
+                for ci in range(c):
+                    ops.flatfield_maxima_accumulate(self.tiles_dev[slot][ci, 0], ff, ci)
+                ev = torch.cuda.Event()
+                ev.record(compute)
+                consumed[slot] = ev
+            if plan.group is not None:
+                import torch.distributed as dist
+
+                dist.all_reduce(ff.maxima, op=dist.ReduceOp.MAX, group=plan.group)
+        # ---- pass 2: correct + stitch + gather per timepoint, results drained behind the kernels
+        drained = [None] * self.depth                # per slot: (timepoint, event after its D2H copies)
+
+        def deliver(slot):
+            ti, ev = drained[slot]
+            ev.synchronize()
+            sink(ti, self.image_pin[slot].numpy()[:, 0] if self.want_image else None,
+                 self.roi_pin[slot].numpy()[:, :, 0] if self.want_roi else None, self.stats_pin[slot].numpy()[:, :, 0])
+            drained[slot] = None
+
+        for ti in range(t):
+            slot = ti % self.depth
+            if drained[slot] is not None:
+                deliver(slot)                         # frees the slot's device and pinned output buffers
+            up = self._stage_in(source, ti, slot, consumed)
+            compute.wait_event(up)
+            image = ops.flatfield_stitch(self.tiles_dev[slot], overlap=plan.overlap, plan=ff,
+                                         maxima=None if ff.identity else ff.maxima, out=self.image_dev[slot])
+            roi, stats = ops.roi_gather_stats(image, self.boxes_t[ti], plan.fg, plan.bg, plan.roi_length,
+                                              mask_t=self.mask_t[ti], want_roi=self.want_roi,
+                                              out_roi=self.roi_dev[slot], out_stats=self.stats_dev[slot], order=plan.order)
+            done = torch.cuda.Event()
+            done.record(compute)
+            consumed[slot] = done
+            with torch.cuda.stream(self.d2h):
+                self.d2h.wait_event(done)
+                if self.want_image:
+                    ops.to_host_dense(image, out=self.image_pin[slot])
+                    self.d2h_bytes += self.image_pin[slot].numel() * 2
+                if self.want_roi:
+                    self.roi_pin[slot].copy_(roi, non_blocking=True)
+                    self.d2h_bytes += self.roi_pin[slot].numel() * 2
+                self.stats_pin[slot].copy_(stats, non_blocking=True)
+                self.d2h_bytes += self.stats_pin[slot].numel() * 8
+                ev = torch.cuda.Event()
+                ev.record(self.d2h)
+            drained[slot] = (ti, ev)
+        for ti in range(max(0, t - self.depth), t):   # remaining timepoints, in order
+            if drained[ti % self.depth] is not None and drained[ti % self.depth][0] == ti:
+                deliver(ti % self.depth)

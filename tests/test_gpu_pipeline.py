@@ -227,3 +227,50 @@ def test_markers_located_on_device_image(cuda_device):
     bplan.locate_bead_markers(bimage, finder)
     bres = bplan.run_device(tiles_b, image=bimage)
     assert bres.roi.shape[0] == 3 and (bres.stats[:, 0, 0, 4].cpu().numpy() > 900).all()
+
+
+@pytest.mark.parametrize("identity", [False, True])
+def test_streaming_runner_two_passes(cuda_device, tmp_path, identity):
+    """Stacks larger than HBM: two sweeps over the block source with `depth` timepoints resident;
+    per-timepoint results equal the all-resident run (from NumPy blocks and from TIFF pages)."""
+    import os
+
+    from magnify_b200 import pipeline, reader, synth
+    from tiffgen import write_tiff
+
+    case = synth.chip_case(c=2, t=5, r=2, cc=2, h=256, w=256, overlap=22, rows=3, cols=2, row_dist=126.1,
+                           col_dist=200.0, seed=13, device=cuda_device)
+    flat, dark = (1.0, 0.0) if identity else (case.flat, case.dark)
+    plan = pipeline.QuantifyPlan(case.tiles.shape, case.overlap, case.roi_length, flat, dark, device=cuda_device)
+    radius = np.repeat(case.fg_radius, 2, axis=1)
+    plan.set_chip_markers(case.x, case.y, radius, case.chamber_radius, case.max_button_radius, search_timesteps=[0, 3])
+    ref = plan.run_device(case.tiles)
+    image_ref, roi_ref, stats_ref = ref.image.cpu().numpy(), ref.roi.cpu().numpy(), ref.stats.cpu().numpy()
+    tiles_np = case.tiles.cpu().numpy()
+    c, t = tiles_np.shape[:2]
+
+    def check(source, depth):
+        seen = []
+
+        def sink(ti, image, roi, stats):
+            seen.append(ti)
+            np.testing.assert_array_equal(image, image_ref[:, ti])
+            np.testing.assert_array_equal(roi, roi_ref[:, :, ti])
+            np.testing.assert_array_equal(stats, stats_ref[:, :, ti])
+
+        runner = pipeline.StreamingRunner(plan, depth=depth)
+        runner.run(source, sink)
+        assert seen == list(range(t))
+        passes = 1 if identity else 2
+        assert runner.h2d_bytes == passes * tiles_np.nbytes
+
+    check(lambda ci, ti, dst: np.copyto(dst, tiles_np[ci, ti]), depth=2)
+    check(lambda ci, ti, dst: np.copyto(dst, tiles_np[ci, ti]), depth=3)
+    if not identity:
+        for idx in np.ndindex(*tiles_np.shape[:4]):
+            write_tiff(os.path.join(tmp_path, f"s_ch{idx[0]}_2024010{idx[1] + 1}-000000_{idx[2]}_{idx[3]}.tif"), [tiles_np[idx]])
+        (xp,) = list(reader.Reader(threads=4)(os.path.join(tmp_path, "s_(channel)_(time)_(row)_(col).tif")))
+        lazy = xp["tile"].values
+        check(lambda ci, ti, dst: lazy.read((ci, ti), dst), depth=2)
+    with pytest.raises(ValueError):
+        pipeline.StreamingRunner(plan, depth=1)
