@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MGB_ABI_VERSION 7
+#define MGB_ABI_VERSION 8
 
 #define MGB_OK 0
 #define MGB_EINVAL (-1)      /* bad argument (null pointer, negative size, bad itemsize ...) */
@@ -184,6 +184,14 @@ int mgb_roi_median_u16(const uint16_t* roi, int64_t M, int64_t C, int64_t T, int
  * (nullable) receives the fg/bg pixel counts. */
 int mgb_chip_masks(const int32_t* rel, const int32_t* r_fg, int r_inner, int r_outer, int64_t M,
                    int L, uint8_t* fg, uint8_t* bg, int32_t* counts, void* stream);
+
+/* ---- filter_nonround, reference filter.py:40-62 -------------------------------------------
+ * perimeter[m] = sum over cv.findContours(mask m, RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) of
+ * cv.arcLength(contour, closed=True) for masks (M, L, L) uint8 (non-zero = foreground), L <= 180:
+ * Suzuki-Abe border following, 8-connected, only outer borders whose parent is the frame; the
+ * length is the sum of the chain steps (1 or sqrt 2) in float64 (OpenCV rounds each polygon
+ * segment to float32: <= 6e-8 relative difference). */
+int mgb_mask_perimeters(const uint8_t* masks, int64_t M, int L, double* perimeter, void* stream);
 
 /* ---- F5-F7: bead masks, reference utils.py:380-465 and find.py:561-586 ---------------------
  * HOST helper: hw[0..r] = row half-widths of filled_circle_points(r) (utils.py:398-430). */

@@ -52,6 +52,7 @@ SIGNATURES = {
     "mgb_disc_halfwidths": [c_int, POINTER(ctypes.c_int32)],
     "mgb_bead_labels": [_P, _I64, _I64, _I64, _P, c_int, _P, _P],
     "mgb_bead_masks": [_P, _I64, _I64, _P, _I64, c_int, _P, _P, _P, _P],
+    "mgb_mask_perimeters": [_P, _I64, c_int, _P, _P],
     "mgb_to_uint8": [_P, c_int, _I64, _I64, _P, _P, _P],
     "mgb_edge_gradients_u8": [_P, _I64, _I64, _I64, _P, _P, _P, _P],
     "mgb_gradient_order_stats": [_P, _P, _I64, _I64, POINTER(c_int64), c_int, POINTER(c_int64), _P, _P],
@@ -94,7 +95,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.argtypes = argtypes
         fn.restype = _SPECIAL_RESTYPE.get(name, c_int)
-    if lib.mgb_abi_version() != 7:
+    if lib.mgb_abi_version() != 8:
         raise ImportError("libmagnify_b200.so ABI version mismatch; rebuild with `python -m magnify_b200.build --force`")
     _lib = lib
     return lib

@@ -506,6 +506,25 @@ def filter_leaky(assay, search_channel=None, device=None):
     return assay.assign_coords(valid=(tuple(assay["valid"].dims), valid))
 
 
+def filter_nonround(assay, min_roundness: float = 0.75, search_channel=None, device=None):
+    """`filter_nonround` of the reference (filter.py:40-62): markers whose time-0 foreground has a
+    roundness 4 pi area / perimeter^2 not above `min_roundness` (or no contour at all) are
+    invalidated.  Perimeters come from the GPU border-following kernel (`ops.mask_perimeters`).  The
+    reference repeats the same test once per search channel although `fg` has no channel axis; the
+    outcome is that of a single pass."""
+    dev = _device(device)
+    fg0 = np.ascontiguousarray(_to_numpy(assay["fg"])[:, 0])
+    valid = _to_numpy(assay["valid"]).astype(bool).copy()
+    if fg0.shape[0]:
+        perimeter = ops.mask_perimeters(torch.from_numpy(fg0.view(np.uint8)).to(dev)).cpu().numpy()
+        areas = fg0.sum(axis=(1, 2))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            roundness = 4 * np.pi * areas.astype(np.float64) / perimeter**2
+        keep = (perimeter != 0) & (roundness > min_roundness)
+        valid &= keep.reshape((-1,) + (1,) * (valid.ndim - 1))
+    return assay.assign_coords(valid=(tuple(assay["valid"].dims), valid))
+
+
 def mrbles_intensities(assay, channels=None, device=None) -> np.ndarray:
     """The per-bead intensities `identify_mrbles` starts from (identify.py:76-80): mean of the
     foreground minus median of the background at time 0, (mark, channel)."""
@@ -539,6 +558,8 @@ EXTRA_FACTORIES = {
     "quantify": make_quantify,
     "filter_expression_b200": lambda search_channel=None, min_contrast=None, device=None: (
         lambda xp: filter_expression(xp, search_channel=search_channel, min_contrast=min_contrast, device=device)),
+    "filter_nonround_b200": lambda min_roundness=0.75, search_channel=None, device=None: (
+        lambda xp: filter_nonround(xp, min_roundness=min_roundness, search_channel=search_channel, device=device)),
     "filter_leaky_b200": lambda search_channel=None, device=None: (
         lambda xp: filter_leaky(xp, search_channel=search_channel, device=device)),
 }

@@ -591,3 +591,21 @@ def bead_masks(labels: torch.Tensor, boxes: torch.Tensor, roi_length: int, want_
         _lib.call("mgb_bead_masks", _ptr(labels), h, w, _ptr(boxes), m, int(roi_length), _ptr(fg), _ptr(bg),
                   _ptr(counts), _stream())
     return (fg, bg, counts) if want_counts else (fg, bg)
+
+
+# ---------------------------------------------------------------------------------------------
+# filter_nonround  (reference src/magnify/filter.py:40-62)
+# ---------------------------------------------------------------------------------------------
+def mask_perimeters(masks: torch.Tensor) -> torch.Tensor:
+    """Perimeter of every (L, L) mask of a (M, L, L) uint8 / bool stack as
+    `sum(cv.arcLength(c, True) for c in cv.findContours(mask, RETR_EXTERNAL, CHAIN_APPROX_SIMPLE)[0])`
+    measures it (filter.py:54-55); float64 (M,)."""
+    masks = masks.view(torch.uint8) if masks.dtype == torch.bool else masks
+    _check(masks, "masks", dtype=torch.uint8, ndim=3)
+    m, length, width = masks.shape
+    if length != width:
+        raise ValueError("masks must be square (M, L, L)")
+    out = torch.empty(m, dtype=torch.float64, device=masks.device)
+    with torch.cuda.device(masks.device):
+        _lib.call("mgb_mask_perimeters", _ptr(masks), m, length, _ptr(out), _stream())
+    return out

@@ -320,6 +320,12 @@ class LabelledArray:
     def max(self):
         return self.values.max()
 
+    def sum(self, dim=None):
+        if dim is None:
+            return self.values.sum()
+        axes = tuple(self.dims.index(d) for d in dim)
+        return LabelledArray(self.values.sum(axis=axes), tuple(d for d in self.dims if d not in dim), self.coords)
+
     def _index(self, indexers):
         import numpy as np
 
@@ -792,6 +798,20 @@ def reference_filter_leaky(roi, fg, bg, valid, channels, tag, mark_row, search_c
         return None
     assay = FilterAssay(roi, fg, bg, valid.copy(), channels, promote, tag, mark_row)
     out = mod.filter_leaky_buttons(assay, search_channel=search_channel)
+    return out._valid
+
+
+def reference_filter_nonround(fg, valid, channels, min_roundness=0.75, search_channel=None):
+    """Run the reference's `filter_nonround` (filter.py:40-62; real cv2) -> new valid (M,T)."""
+    import numpy as np
+
+    mod = load_reference_filter()
+    if mod is None:
+        return None
+    m, t, length = fg.shape[0], fg.shape[1], fg.shape[-1]
+    roi = np.zeros((m, len(channels), t, length, length), np.uint16)
+    assay = FilterAssay(roi, fg, fg, valid.copy(), channels)
+    out = mod.filter_nonround(assay, min_roundness=min_roundness, search_channel=search_channel)
     return out._valid
 
 

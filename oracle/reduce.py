@@ -94,3 +94,22 @@ def filter_leaky_valid(roi: np.ndarray, fg: np.ndarray, bg: np.ndarray, valid: n
             if mark_row[i] < mark_row.max() and tag[i + 1] == "":
                 valid[i] &= empty[i + 1]
     return valid
+
+
+def filter_nonround_valid(fg: np.ndarray, valid: np.ndarray, min_roundness: float = 0.75) -> np.ndarray:
+    """filter.py:40-62 with the reference's own OpenCV calls (cv2 is in the image): per marker,
+    external contours of the time-0 foreground, perimeter = sum of closed arc lengths, invalid
+    when there is no contour or 4 pi area / perimeter^2 <= min_roundness.  fg (M,T,L,L), valid (M,T)."""
+    import cv2 as cv
+
+    valid = valid.copy()
+    masks = (fg[:, 0] != 0).astype(np.uint8) * 255                  # utils.to_uint8 of a boolean stack
+    areas = fg[:, 0].sum(axis=(1, 2))
+    for i in range(len(masks)):
+        contours, _ = cv.findContours(masks[i], cv.RETR_EXTERNAL, cv.CHAIN_APPROX_SIMPLE)   # :54
+        perimeter = sum(cv.arcLength(c, True) for c in contours)                             # :55
+        if perimeter == 0:
+            valid[i] = False                                                                  # :56-58
+            continue
+        valid[i] &= 4 * np.pi * float(areas[i]) / perimeter**2 > min_roundness               # :59-60
+    return valid

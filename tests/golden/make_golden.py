@@ -277,6 +277,34 @@ def golden_circles():
                         circles=circles, scores=scores, **{k: np.array(v) for k, v in kw.items()})
 
 
+def golden_nonround():
+    """`filter_nonround` (filter.py:40-62) executed in place with the real cv2 on elliptical, empty,
+    single-pixel and two-component foregrounds."""
+    from oracle._refload import reference_filter_nonround
+
+    rng = np.random.default_rng(0)
+    m, t, length = 40, 2, 48
+    yy, xx = np.mgrid[0:length, 0:length]
+    fg = np.zeros((m, t, length, length), bool)
+    for i in range(m):
+        a, b = rng.uniform(4, 18), rng.uniform(4, 18)
+        if i % 5 == 0:
+            b = a
+        fg[i, :] = ((yy - 24) / a) ** 2 + ((xx - 24) / b) ** 2 <= 1
+    fg[3] = False                                          # no contour at all
+    fg[7] = False
+    fg[7, :, 10, 10] = True                                # one pixel: a contour of length 0
+    fg[9, :] |= (np.abs(yy - 5) <= 1) & (xx > 3) & (xx < 40)   # a second component
+    fg[11, :] &= ~(((yy - 24) ** 2 + (xx - 24) ** 2) <= 9)     # a hole (ignored by RETR_EXTERNAL)
+    valid = rng.random((m, t)) < 0.9
+    out = {"fg": fg, "valid": valid}
+    for k, mr in enumerate((0.75, 0.5, 0.9)):
+        got = reference_filter_nonround(fg, valid, ["a", "b"], mr)
+        assert got is not None
+        out[f"case{k}__valid"], out[f"case{k}__min_roundness"] = got, np.array(mr)
+    np.savez_compressed(os.path.join(HERE, "nonround.npz"), **out)
+
+
 def golden_masks_cv():
     """cv.circle rasters through utils.circle / utils.annulus (utils.py:30-52) for clipped and
     unclipped centres -- pins the closed form `dx^2+dy^2 <= r^2` used by oracle and kernel."""
@@ -361,6 +389,7 @@ if __name__ == "__main__":
     golden_chip_multi()
     golden_filter_expression()
     golden_circles()
+    golden_nonround()
     golden_masks_cv()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -3,6 +3,7 @@ arguments, exceptions and dataset schema as the reference's Stitcher / flatfield
 BeadFinder / ButtonFinder, pixel values against the oracle and the golden fixtures."""
 import numpy as np
 import pytest
+import torch
 
 from oracle import flatfield as o_ff
 from oracle import reduce as o_red
@@ -279,3 +280,47 @@ def test_filter_leaky_golden_from_reference_source(cuda_device, golden):
                               "valid": (("mark", "time"), g["valid"])})
         out = filter_leaky(assay, search_channel=search)
         np.testing.assert_array_equal(out.valid.values, g[f"leaky{k}__valid"], err_msg=f"case {k}")
+
+
+def test_mask_perimeters_match_opencv(cuda_device):
+    """ops.mask_perimeters == sum of cv.arcLength over cv.findContours(RETR_EXTERNAL,
+    CHAIN_APPROX_SIMPLE) (filter.py:54-55) on noise, rings with islands, discs and blobs."""
+    cv2 = pytest.importorskip("cv2")
+    from magnify_b200 import ops
+
+    rng = np.random.default_rng(0)
+    for length in (1, 2, 3, 7, 24, 48, 72, 100):
+        masks = []
+        yy, xx = np.mgrid[0:length, 0:length]
+        for trial in range(24):
+            kind = trial % 4
+            if kind == 0:
+                m = rng.random((length, length)) < rng.uniform(0.1, 0.9)
+            elif kind == 1:
+                d2 = (yy - length / 2) ** 2 + (xx - length / 2) ** 2
+                m = (d2 <= (length / 3) ** 2) & ~(d2 <= (length / 6) ** 2) | (d2 <= (length / 12) ** 2)
+            elif kind == 2:
+                m = (yy - rng.uniform(0, length)) ** 2 + (xx - rng.uniform(0, length)) ** 2 <= rng.uniform(1, length / 2 + 1) ** 2
+            else:
+                m = cv2.GaussianBlur(rng.random((length, length)).astype(np.float32), (5, 5), 0) > 0.5
+            masks.append(m)
+        masks = np.stack(masks)
+        masks[-1] = False
+        got = ops.mask_perimeters(torch.from_numpy(masks).to(cuda_device)).cpu().numpy()
+        want = []
+        for m in masks:
+            contours, _ = cv2.findContours(m.astype(np.uint8) * 255, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+            want.append(sum(cv2.arcLength(c, True) for c in contours))
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=0)
+        assert got[-1] == 0
+
+
+def test_filter_nonround_golden_from_reference_source(cuda_device, golden):
+    from magnify_b200.components import filter_nonround
+    from magnify_b200.dataset import Assay
+
+    g = golden("nonround")
+    for k in range(3):
+        assay = Assay(coords={"fg": (("mark", "time", "roi_y", "roi_x"), g["fg"]), "valid": (("mark", "time"), g["valid"])})
+        out = filter_nonround(assay, min_roundness=float(g[f"case{k}__min_roundness"]))
+        np.testing.assert_array_equal(out.valid.values, g[f"case{k}__valid"], err_msg=f"case {k}")

@@ -303,3 +303,17 @@ def test_filter_leaky_golden_from_reference_source(golden):
         ref = reference_filter_leaky(g["roi"], g["fg"], g["bg"], g["valid"], names, g["tag"], g["mark_row"], search)
         if ref is not None:   # build container: the reference's own function again
             np.testing.assert_array_equal(ref, g[f"leaky{k}__valid"])
+
+
+def test_filter_nonround_golden_from_reference_source(golden):
+    """filter.py:40-62 executed in place with the real OpenCV -> tests/golden/nonround.npz."""
+    pytest.importorskip("cv2")
+    from oracle._refload import reference_filter_nonround
+
+    g = golden("nonround")
+    for k in range(3):
+        mr = float(g[f"case{k}__min_roundness"])
+        np.testing.assert_array_equal(red.filter_nonround_valid(g["fg"], g["valid"], mr), g[f"case{k}__valid"])
+        ref = reference_filter_nonround(g["fg"], g["valid"], ["a", "b"], mr)
+        if ref is not None:
+            np.testing.assert_array_equal(ref, g[f"case{k}__valid"])
