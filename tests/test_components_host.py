@@ -46,3 +46,30 @@ def test_install_needs_magnify():
     else:
         names = components.install()
         assert "stitch" in names and "quantify" in names
+
+
+def test_api_standardize_and_restore_shapes():
+    """api._standardized / _restore: the dims bookkeeping of standardize_format / restore_format
+    (preprocess.py:11-42, postprocess.py:20-49) without touching the GPU."""
+    from magnify_b200 import api
+    from magnify_b200.dataset import Var
+
+    arr = np.arange(2 * 3 * 4 * 5, dtype=np.uint16).reshape(3, 2, 4, 5)            # (time, channel, y, x)
+    (xp,) = api._standardized(arr, ("time", "channel", "y", "x"), {"channel": ["a", "b"]})
+    assert xp["tile"].dims == ("channel", "time", "tile_row", "tile_col", "tile_y", "tile_x")
+    assert xp["tile"].values.shape == (2, 3, 1, 1, 4, 5)
+    np.testing.assert_array_equal(xp["tile"].values[1, 2, 0, 0], arr[2, 1])
+    assert xp.attrs["__original_tile_dims__"] == ["time", "channel", "tile_y", "tile_x"]
+    with pytest.raises(ValueError):
+        api._standardized(arr, None, None)
+    with pytest.raises(NotImplementedError):
+        api._standardized(arr, ("time", "depth", "y", "x"), None)
+    # restore: un-stack marks, squeeze the added channel axis, keep the original time axis
+    (xp,) = api._standardized(arr[:, 0], ("time", "y", "x"), None)
+    xp.data_vars["roi"] = Var(("mark", "channel", "time", "roi_y", "roi_x"), np.zeros((6, 1, 3, 8, 8), np.uint16))
+    xp.coords["x"] = Var(("mark", "time"), np.zeros((6, 3)))
+    xp.coords["mark_row"] = Var(("mark",), np.repeat(np.arange(2), 3))
+    out = api._restore(xp, (2, 3))
+    assert out.roi.dims == ("mark_row", "mark_col", "time", "roi_y", "roi_x") and out.roi.shape == (2, 3, 3, 8, 8)
+    assert out.x.dims == ("mark_row", "mark_col", "time") and "tile" not in out and "mark_row" not in out
+    assert "__original_tile_dims__" not in out.attrs
