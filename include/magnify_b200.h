@@ -187,7 +187,7 @@ int mgb_chip_masks(const int32_t* rel, const int32_t* r_fg, int r_inner, int r_o
 
 /* ---- filter_nonround, reference filter.py:40-62 -------------------------------------------
  * perimeter[m] = sum over cv.findContours(mask m, RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) of
- * cv.arcLength(contour, closed=True) for masks (M, L, L) uint8 (non-zero = foreground), L <= 180:
+ * cv.arcLength(contour, closed=True) for masks (M, L, L) uint8 (non-zero = foreground), L <= 160:
  * Suzuki-Abe border following, 8-connected, only outer borders whose parent is the frame; the
  * length is the sum of the chain steps (1 or sqrt 2) in float64 (OpenCV rounds each polygon
  * segment to float32: <= 6e-8 relative difference). */

@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(32) mask_perimeter_kernel(const uint8_t* __res
   const int P = L + 2;                       // framed side
   int16_t* f = sm;                           // P * P labels
   int16_t* parent = sm + P * P;              // per border
-  uint8_t* is_hole = reinterpret_cast<uint8_t*>(parent + (L * L / 2 + 4));
+  uint8_t* is_hole = reinterpret_cast<uint8_t*>(parent + (L * L + 4));   // every pixel starts at most one border
   const uint8_t* mask = masks + (int64_t)blockIdx.x * L * L;
   for (int i = threadIdx.x; i < P * P; i += 32) {
     const int y = i / P - 1, x = i % P - 1;
@@ -321,11 +321,11 @@ __global__ void __launch_bounds__(32) mask_perimeter_kernel(const uint8_t* __res
 }  // namespace mgb
 
 extern "C" int mgb_mask_perimeters(const uint8_t* masks, int64_t M, int L, double* perimeter, void* stream) {
-  if (M < 0 || L <= 0 || L > 180) return MGB_EINVAL;
+  if (M < 0 || L <= 0 || L > 160) return MGB_EINVAL;   // labels are int16 and the tables must fit shared memory
   if (M == 0) return MGB_OK;
   if (!masks || !perimeter) return MGB_EINVAL;
   if (M > INT32_MAX) return MGB_EUNSUPPORTED;
-  const int P = L + 2, borders = L * L / 2 + 4;
+  const int P = L + 2, borders = L * L + 4;
   const size_t bytes = (size_t)P * P * 2 + (size_t)borders * 2 + (size_t)borders + 16;
   if (bytes > 48 * 1024)
     MGB_CUDA_TRY(cudaFuncSetAttribute(mgb::mask_perimeter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
