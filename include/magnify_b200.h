@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MGB_ABI_VERSION 8
+#define MGB_ABI_VERSION 9
 
 #define MGB_OK 0
 #define MGB_EINVAL (-1)      /* bad argument (null pointer, negative size, bad itemsize ...) */
@@ -228,11 +228,12 @@ int mgb_gradient_order_stats(const int16_t* dx, const int16_t* dy, int64_t B, in
                              int n_ranks, int64_t* host_values, uint32_t* scratch, void* stream);
 /* cv.Canny(dx, dy, threshold1, threshold2, L2gradient=True) (utils.py:127-133): edges (B,H,W)
  * uint8 0/1.  thresholds (B, 2) int32 on the device = the integer (low, high) OpenCV derives
- * (low = floor(min(t1,32767)^2), high likewise).  map (B,H,W) uint8 and changed (1 int) are device
- * scratch.  Hysteresis is iterated to its fixed point, SYNCHRONISING the stream once per sweep;
- * host_sweeps (nullable) returns the sweep count. */
+ * (low = floor(min(t1,32767)^2), high likewise).  changed (1 int) is device scratch.  Non-maximum
+ * suppression writes two bit planes (strong / candidate, one word per row and 32 pixels); the
+ * hysteresis floods them one warp per 32x32 tile and is iterated to its fixed point,
+ * SYNCHRONISING the stream once per sweep; host_sweeps (nullable) returns the sweep count. */
 int mgb_canny(const int16_t* dx, const int16_t* dy, int64_t B, int64_t H, int64_t W, const int32_t* thresholds,
-              uint8_t* map, uint8_t* edges, int* changed, int* host_sweeps, void* stream);
+              uint8_t* edges, int* changed, int* host_sweeps, void* stream);
 
 /* ---- N1 / N4: candidate circles and their scores, reference utils.py:141-189, 221-377 --------
  * Temporaries whose size is only known inside a call (CUB scan / sort storage, the unique-circle

@@ -56,7 +56,7 @@ SIGNATURES = {
     "mgb_to_uint8": [_P, c_int, _I64, _I64, _P, _P, _P],
     "mgb_edge_gradients_u8": [_P, _I64, _I64, _I64, _P, _P, _P, _P],
     "mgb_gradient_order_stats": [_P, _P, _I64, _I64, POINTER(c_int64), c_int, POINTER(c_int64), _P, _P],
-    "mgb_canny": [_P, _P, _I64, _I64, _I64, _P, _P, _P, _P, POINTER(c_int), _P],
+    "mgb_canny": [_P, _P, _I64, _I64, _I64, _P, _P, _P, POINTER(c_int), _P],
     "mgb_edge_cell_lists": [_P, _I64, _I64, _I64, c_int, _P, _P, _P, _I64, POINTER(c_int64), _P],
     "mgb_sample_circles": [_P, _P, _P, _I64, _I64, _I64, c_int, _I64, ctypes.c_float, ctypes.c_float, ctypes.c_uint64,
                            _P, _P, _P, _I64, _P, POINTER(c_int64), _P, _P],
@@ -95,7 +95,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.argtypes = argtypes
         fn.restype = _SPECIAL_RESTYPE.get(name, c_int)
-    if lib.mgb_abi_version() != 8:
+    if lib.mgb_abi_version() != 9:
         raise ImportError("libmagnify_b200.so ABI version mismatch; rebuild with `python -m magnify_b200.build --force`")
     _lib = lib
     return lib

@@ -147,11 +147,10 @@ def canny(dx: torch.Tensor, dy: torch.Tensor, threshold1, threshold2, return_swe
         raise ValueError("one threshold pair per image")
     thr = np.array([canny_thresholds(a, c) for a, c in zip(t1, t2)], dtype=np.int32).reshape(b, 2)
     thresholds = torch.from_numpy(thr).to(dx.device)
-    work = torch.empty((b, h, w), dtype=torch.uint8, device=dx.device)
-    edges = torch.empty_like(work)
+    edges = torch.empty((b, h, w), dtype=torch.uint8, device=dx.device)
     changed = torch.empty(1, dtype=torch.int32, device=dx.device)
     sweeps = ctypes.c_int()
-    _lib.call("mgb_canny", _ptr(gx), _ptr(gy), b, h, w, _ptr(thresholds), _ptr(work), _ptr(edges), _ptr(changed),
+    _lib.call("mgb_canny", _ptr(gx), _ptr(gy), b, h, w, _ptr(thresholds), _ptr(edges), _ptr(changed),
               ctypes.byref(sweeps), _stream())
     edges = edges[0] if squeeze else edges
     return (edges, sweeps.value) if return_sweeps else edges

@@ -13,7 +13,7 @@
 //                                        select (sqrt and the float32 sum are monotone in it)
 //   Canny               utils.py:127-133 cv::Canny(dx, dy, low, high, L2gradient=true): squared
 //                                        magnitudes, the TG22 non-maximum suppression, 8-connected
-//                                        hysteresis (iterated to a fixed point; order independent)
+//                                        hysteresis on bit planes (iterated to a fixed point; order independent)
 // The random circle sampling that follows in the reference (utils.py:288-344) is not
 // reproducible by construction (unseeded numba RNG under prange); see circles_sample.cu.
 #include "common.cuh"
@@ -232,59 +232,70 @@ __device__ __forceinline__ int mag_at(const int16_t* __restrict__ dx, const int1
   return gx * gx + gy * gy;
 }
 
-// map: 0 = above low and a local maximum (edge candidate), 1 = not an edge, 2 = strong edge
+// Non-maximum suppression + double threshold.  The result is stored as two bit planes, one 32-bit
+// word per image row and 32-pixel column block (bit i = pixel x = 32 * block + i): `strong` (above
+// the high threshold: edge) and `cand` (a local maximum above the low threshold: edge if connected
+// to a strong pixel).  planes = [strong (B, H, words)] [cand (B, H, words)].
 __global__ void __launch_bounds__(kThreads) canny_nms_kernel(const int16_t* __restrict__ dx,
-                                                             const int16_t* __restrict__ dy, int H, int W,
+                                                             const int16_t* __restrict__ dy, int H, int W, int words,
                                                              const int32_t* __restrict__ thresholds,
-                                                             uint8_t* __restrict__ map) {
+                                                             uint32_t* __restrict__ strong, uint32_t* __restrict__ cand) {
   dx += (int64_t)blockIdx.z * H * W;
   dy += (int64_t)blockIdx.z * H * W;
-  map += (int64_t)blockIdx.z * H * W;
   const int low = thresholds[2 * blockIdx.z], high = thresholds[2 * blockIdx.z + 1];
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x >= W || y >= H) return;
-  const int64_t at = (int64_t)y * W + x;
-  const int xs = dx[at], ys = dy[at];
-  const int m = xs * xs + ys * ys;
-  uint8_t out = 1;
-  if (m > low) {
-    const int ax = abs(xs), ay = abs(ys) << kCannyShift;
-    const int tg22x = ax * kTG22;
-    bool keep;
-    if (ay < tg22x) {
-      keep = m > mag_at(dx, dy, H, W, y, x - 1) && m >= mag_at(dx, dy, H, W, y, x + 1);
-    } else {
-      const int tg67x = tg22x + (ax << (kCannyShift + 1));
-      if (ay > tg67x) {
-        keep = m > mag_at(dx, dy, H, W, y - 1, x) && m >= mag_at(dx, dy, H, W, y + 1, x);
+  if (y >= H) return;                       // whole warp
+  int out = 1;                              // 0 = candidate, 1 = not an edge, 2 = strong edge
+  if (x < W) {
+    const int64_t at = (int64_t)y * W + x;
+    const int xs = dx[at], ys = dy[at];
+    const int m = xs * xs + ys * ys;
+    if (m > low) {
+      const int ax = abs(xs), ay = abs(ys) << kCannyShift;
+      const int tg22x = ax * kTG22;
+      bool keep;
+      if (ay < tg22x) {
+        keep = m > mag_at(dx, dy, H, W, y, x - 1) && m >= mag_at(dx, dy, H, W, y, x + 1);
       } else {
-        const int s = (xs ^ ys) < 0 ? -1 : 1;
-        keep = m > mag_at(dx, dy, H, W, y - 1, x - s) && m > mag_at(dx, dy, H, W, y + 1, x + s);
+        const int tg67x = tg22x + (ax << (kCannyShift + 1));
+        if (ay > tg67x) {
+          keep = m > mag_at(dx, dy, H, W, y - 1, x) && m >= mag_at(dx, dy, H, W, y + 1, x);
+        } else {
+          const int s = (xs ^ ys) < 0 ? -1 : 1;
+          keep = m > mag_at(dx, dy, H, W, y - 1, x - s) && m > mag_at(dx, dy, H, W, y + 1, x + s);
+        }
       }
+      if (keep) out = m > high ? 2 : 0;
     }
-    if (keep) out = m > high ? 2 : 0;
   }
-  map[at] = out;
+  const uint32_t sbits = __ballot_sync(0xffffffffu, out == 2), cbits = __ballot_sync(0xffffffffu, out == 0);
+  if ((threadIdx.x & 31) == 0) {
+    const int64_t at = ((int64_t)blockIdx.z * H + y) * words + blockIdx.x;
+    strong[at] = sbits;
+    cand[at] = cbits;
+  }
 }
 
-// One sweep of hysteresis, one WARP per 32x32 tile, bit-parallel: lane l holds column l of the
-// tile as two 64-bit row masks (bit r = row r of a 34-row window with a one-pixel halo): `strong`
-// (map == 2) and `cand` (map == 0, interior rows only).  A flood step is
-//     reach = strong | left lane's strong | right lane's strong;  reach |= reach << 1 | reach >> 1;
+// One sweep of hysteresis, one WARP per 32x32 tile, bit-parallel on the planes above: lane r holds
+// row r of the tile as 34-bit column masks (bit 0 / bit 33 = the halo pixels left / right of the
+// tile, taken from the neighbouring words), lanes 0 and 31 also hold the halo rows above / below.
+// A flood step is
+//     h = strong | strong << 1 | strong >> 1;  reach = h | row above's h | row below's h;
 //     newly = cand & reach;  strong |= newly;  cand &= ~newly
-// -- two shuffles and a few logic ops for the whole tile -- repeated until no lane recruits.
-// Lanes 0 and 31 take their outer neighbour from the halo columns, which (like the halo rows) are
-// read once and not updated inside a sweep.  A tile only has work when it or one of its eight
-// neighbours recruited something in the previous sweep (`active_in`, one byte per tile; NULL on
-// the first sweep = every tile); tiles that recruit set `active_out` and bump `changed`.  The host
-// repeats sweeps until a sweep changes nothing.
-__global__ void __launch_bounds__(kThreads) canny_hysteresis_kernel(uint8_t* __restrict__ map, int H, int W,
-                                                                    int tiles_x, int tiles_y,
-                                                                    const uint8_t* __restrict__ active_in,
+// -- two shuffles and a few logic ops for the whole tile -- repeated until no lane recruits.  Halo
+// bits are read once per sweep and not updated inside it.  Each (row, block) word belongs to
+// exactly one tile, so the updated strong words are stored without atomics.  A tile only has work
+// when it or one of its eight neighbours recruited something in the previous sweep (`active_in`,
+// one byte per tile; NULL on the first sweep = every tile); tiles that recruit set `active_out` and
+// bump `changed`.  The host repeats sweeps until a sweep changes nothing.
+__global__ void __launch_bounds__(kThreads) canny_hysteresis_kernel(uint32_t* __restrict__ strong_plane,
+                                                                    uint32_t* __restrict__ cand_plane, int H, int words,
+                                                                    int tiles_y, const uint8_t* __restrict__ active_in,
                                                                     uint8_t* __restrict__ active_out,
                                                                     int* __restrict__ changed) {
   const int lane = threadIdx.x & 31;
+  const int tiles_x = words;
   const int64_t tile = blockIdx.x * (int64_t)(kThreads / 32) + (threadIdx.x >> 5);
   if (tile >= (int64_t)tiles_x * tiles_y) return;   // whole warp
   const int ty = (int)(tile / tiles_x), tx = (int)(tile - (int64_t)ty * tiles_x);
@@ -297,38 +308,40 @@ __global__ void __launch_bounds__(kThreads) canny_hysteresis_kernel(uint8_t* __r
     }
     if (!__any_sync(0xffffffffu, mine)) return;
   }
-  map += (int64_t)blockIdx.z * H * W;
-  const int x = tx * 32 + lane, y0 = ty * 32 - 1;
-  const int xh = lane == 0 ? tx * 32 - 1 : tx * 32 + 32;   // halo column read by lanes 0 and 31
-  uint64_t strong = 0, cand = 0, halo = 0;
-  for (int r = 0; r < 34; ++r) {
-    const int y = y0 + r;
-    if ((unsigned)y >= (unsigned)H) continue;
-    const uint8_t* row = map + (int64_t)y * W;
-    if (x < W) {
-      const uint8_t v = row[x];
-      strong |= (uint64_t)(v == 2) << r;
-      if (r >= 1 && r <= 32) cand |= (uint64_t)(v == 0) << r;
-    }
-    if ((lane == 0 || lane == 31) && (unsigned)xh < (unsigned)W) halo |= (uint64_t)(row[xh] == 2) << r;
-  }
+  const uint32_t* sp = strong_plane + (int64_t)blockIdx.z * H * words;
+  uint32_t* cp = cand_plane + (int64_t)blockIdx.z * H * words;
+  auto strong_row = [&](int y) -> uint64_t {          // 34-bit strong mask of image row y around block tx
+    if ((unsigned)y >= (unsigned)H) return 0;
+    const uint32_t* row = sp + (int64_t)y * words;
+    uint64_t m = (uint64_t)row[tx] << 1;
+    if (tx > 0) m |= row[tx - 1] >> 31;
+    if (tx + 1 < words) m |= (uint64_t)(row[tx + 1] & 1u) << 33;
+    return m;
+  };
+  const int y = ty * 32 + lane;
+  uint64_t strong = strong_row(y);
+  uint64_t cand = (y < H) ? (uint64_t)cp[(int64_t)y * words + tx] << 1 : 0;
+  uint64_t halo = 0;                                   // lane 0: the row above the tile, lane 31: the row below
+  if (lane == 0) halo = strong_row(ty * 32 - 1);
+  if (lane == 31) halo = strong_row(ty * 32 + 32);
   const uint64_t before = strong;
+  const uint64_t interior = 0x1fffffffeull;            // bits 1..32
   for (;;) {
-    uint64_t left = __shfl_up_sync(0xffffffffu, strong, 1), right = __shfl_down_sync(0xffffffffu, strong, 1);
-    if (lane == 0) left = halo;
-    if (lane == 31) right = halo;
-    uint64_t reach = strong | left | right;
-    reach |= (reach << 1) | (reach >> 1);
-    const uint64_t newly = cand & reach;
+    const uint64_t h = strong | (strong << 1) | (strong >> 1);
+    uint64_t up = __shfl_up_sync(0xffffffffu, h, 1), down = __shfl_down_sync(0xffffffffu, h, 1);
+    if (lane == 0) up = halo | (halo << 1) | (halo >> 1);
+    if (lane == 31) down = halo | (halo << 1) | (halo >> 1);
+    const uint64_t newly = cand & (h | up | down) & interior;
     strong |= newly;
     cand &= ~newly;
     if (!__any_sync(0xffffffffu, newly != 0)) break;
   }
-  const uint64_t grew = strong & ~before;
+  const uint64_t grew = (strong & ~before) & interior;
   if (__any_sync(0xffffffffu, grew != 0)) {
-    if (grew)
-      for (int r = 1; r <= 32; ++r)
-        if ((grew >> r) & 1) map[(int64_t)(y0 + r) * W + x] = 2;
+    if (grew) {
+      strong_plane[((int64_t)blockIdx.z * H + y) * words + tx] = (uint32_t)(strong >> 1);
+      cp[(int64_t)y * words + tx] = (uint32_t)(cand >> 1);
+    }
     if (lane == 0) {
       active_out[tile_base + tile] = 1;
       atomicAdd(changed, 1);
@@ -336,10 +349,14 @@ __global__ void __launch_bounds__(kThreads) canny_hysteresis_kernel(uint8_t* __r
   }
 }
 
-__global__ void __launch_bounds__(kThreads) canny_edges_kernel(const uint8_t* __restrict__ map, int64_t n,
-                                                               uint8_t* __restrict__ edges) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    edges[i] = map[i] == 2 ? 1 : 0;   // utils.py:139 (`edges[edges != 0] = 1`)
+// edges (B, H, W) uint8 0/1 from the strong plane (utils.py:139 `edges[edges != 0] = 1`)
+__global__ void __launch_bounds__(kThreads) canny_edges_kernel(const uint32_t* __restrict__ strong, int H, int W,
+                                                               int words, uint8_t* __restrict__ edges) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= H) return;
+  const uint32_t word = strong[((int64_t)blockIdx.z * H + y) * words + blockIdx.x];
+  edges[((int64_t)blockIdx.z * H + y) * W + x] = (word >> (threadIdx.x & 31)) & 1u;
 }
 
 int grid_for(int64_t n) {
@@ -467,28 +484,33 @@ int mgb_gradient_order_stats(const int16_t* dx, const int16_t* dy, int64_t B, in
 }
 
 int mgb_canny(const int16_t* dx, const int16_t* dy, int64_t B, int64_t H, int64_t W, const int32_t* thresholds,
-              uint8_t* map, uint8_t* edges, int* changed, int* host_sweeps, void* stream) {
-  if (!dx || !dy || !thresholds || !map || !edges || !changed || B <= 0 || B > 65535 || H <= 0 || W <= 0 ||
-      H > (1 << 30) || W > (1 << 30))
+              uint8_t* edges, int* changed, int* host_sweeps, void* stream) {
+  if (!dx || !dy || !thresholds || !edges || !changed || B <= 0 || B > 65535 || H <= 0 || W <= 0 || H > (1 << 30) ||
+      W > (1 << 30))
     return MGB_EINVAL;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  canny_nms_kernel<<<dim3((unsigned)mgb::ceil_div(W, 32), (unsigned)mgb::ceil_div(H, 8), (unsigned)B), kThreads, 0, s>>>(
-      dx, dy, (int)H, (int)W, thresholds, map);
-  MGB_CUDA_LAUNCH_CHECK();
-  const dim3 grid((unsigned)mgb::ceil_div(W, 32), (unsigned)mgb::ceil_div(H, 32), (unsigned)B);
-  // two byte-per-tile activity maps, ping-ponged between sweeps
-  const size_t n_tiles = (size_t)grid.x * grid.y * grid.z;
-  uint8_t* active = nullptr;
-  MGB_CUDA_TRY(mgb::scratch_alloc((void**)&active, 2 * n_tiles, s));
-  int sweeps = 0;
+  const int words = (int)mgb::ceil_div(W, 32);
+  const dim3 px_grid((unsigned)words, (unsigned)mgb::ceil_div(H, 8), (unsigned)B);
+  const int tiles_y = (int)mgb::ceil_div(H, 32);
+  const size_t plane = (size_t)B * H * words;                 // words per bit plane
+  const size_t n_tiles = (size_t)B * tiles_y * words;
+  // scratch: strong plane, candidate plane, two byte-per-tile activity maps (ping-ponged between sweeps)
+  uint32_t* planes = nullptr;
+  MGB_CUDA_TRY(mgb::scratch_alloc((void**)&planes, 2 * plane * sizeof(uint32_t) + 2 * n_tiles, s));
+  uint32_t *strong = planes, *cand = planes + plane;
+  uint8_t* active = reinterpret_cast<uint8_t*>(planes + 2 * plane);
   cudaError_t e = cudaSuccess;
-  for (;;) {
+  canny_nms_kernel<<<px_grid, kThreads, 0, s>>>(dx, dy, (int)H, (int)W, words, thresholds, strong, cand);
+  mgb_count_launch_();
+  e = cudaGetLastError();
+  int sweeps = 0;
+  while (e == cudaSuccess) {
     uint8_t* out = active + (size_t)(sweeps & 1) * n_tiles;
     const uint8_t* in = sweeps == 0 ? nullptr : active + (size_t)((sweeps + 1) & 1) * n_tiles;
     if ((e = cudaMemsetAsync(changed, 0, sizeof(int), s)) != cudaSuccess) break;
     if ((e = cudaMemsetAsync(out, 0, n_tiles, s)) != cudaSuccess) break;
-    canny_hysteresis_kernel<<<dim3((unsigned)mgb::ceil_div((int64_t)grid.x * grid.y, kThreads / 32), 1, (unsigned)B),
-                              kThreads, 0, s>>>(map, (int)H, (int)W, (int)grid.x, (int)grid.y, in, out, changed);
+    canny_hysteresis_kernel<<<dim3((unsigned)mgb::ceil_div((int64_t)words * tiles_y, kThreads / 32), 1, (unsigned)B),
+                              kThreads, 0, s>>>(strong, cand, (int)H, words, tiles_y, in, out, changed);
     mgb_count_launch_();
     if ((e = cudaGetLastError()) != cudaSuccess) break;
     ++sweeps;
@@ -497,10 +519,13 @@ int mgb_canny(const int16_t* dx, const int16_t* dy, int64_t B, int64_t H, int64_
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) break;
     if (host_changed == 0) break;
   }
-  cudaFreeAsync(active, s);
+  if (e == cudaSuccess) {
+    canny_edges_kernel<<<px_grid, kThreads, 0, s>>>(strong, (int)H, (int)W, words, edges);
+    mgb_count_launch_();
+    e = cudaGetLastError();
+  }
+  cudaFreeAsync(planes, s);
   if (e != cudaSuccess) return (int)e;
-  canny_edges_kernel<<<grid_for(B * H * W), kThreads, 0, s>>>(map, B * H * W, edges);
-  MGB_CUDA_LAUNCH_CHECK();
   if (host_sweeps) *host_sweeps = sweeps;
   return MGB_OK;
 }

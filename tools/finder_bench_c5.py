@@ -77,7 +77,9 @@ def main():
     out["unique_candidates"] = int(circles.shape[0])
     del angle, scores, circles, lists, edges, dx, dy
     torch.cuda.empty_cache()
-    out["total_s"], res = timed(lambda: mc.find_circles(u8, seed=1, **ARGS))
+    runs = [timed(lambda: mc.find_circles(u8, seed=1, **ARGS)) for _ in range(4)]
+    out["total_s_runs"] = [r[0] for r in runs]
+    out["total_s"], res = min(runs, key=lambda r: r[0])
     out["found"] = len(res[0])
     print(json.dumps(out))
 
