@@ -21,6 +21,27 @@ _RENAME = {"x": "tile_x", "y": "tile_y", "row": "tile_row", "col": "tile_col"}  
 CHIP_SPACING = {"minichip": (375 / 1.61, 400 / 1.61), "pc": (406 / 3.22, 750 / 3.22), "ps": (375 / 3.22, 655 / 3.22)}
 
 
+def read_pinlist(pinlist, blank=None) -> np.ndarray:
+    """identify.py:14-29: a pinlist CSV with columns `Indices` ("(col, row)", 1-based) and
+    `MutantID` -> (rows, cols) array of chamber names; names listed in `blank` (default "",
+    "blank", "BLANK") and missing names become "" (an empty chamber)."""
+    import csv
+
+    blank = ["", "blank", "BLANK"] if blank is None else ([blank] if isinstance(blank, str) else list(blank))
+    cells = []
+    with open(pinlist, newline="") as f:
+        for row in csv.DictReader(f):
+            col, r = (int(v) for v in row["Indices"].replace("(", "").replace(")", "").split(","))
+            name = row.get("MutantID") or ""
+            cells.append((r - 1, col - 1, "" if name in blank else name))
+    rows, cols = max(c[0] for c in cells) + 1, max(c[1] for c in cells) + 1
+    width = max(1, max(len(c[2]) for c in cells))
+    tag = np.zeros((rows, cols), dtype=f"<U{width}")
+    for r, col, name in cells:
+        tag[r, col] = name
+    return tag
+
+
 def _standardized(data, dims: Optional[Sequence[str]], coords: Optional[dict]):
     """-> list of standardized assays (tile (channel, time, tile_row, tile_col, tile_y, tile_x)), each
     remembering its original tile dims (preprocess.py:11-42)."""
@@ -88,16 +109,17 @@ def beads(data, dims=None, coords=None, flatfield=1.0, darkfield=0.0, overlap: i
     return results[0] if len(results) == 1 else results
 
 
-def microfluidic_chip(data, dims=None, coords=None, shape=(8, 8), tags=None, overlap: int = 102,
+def microfluidic_chip(data, dims=None, coords=None, shape=(8, 8), pinlist=None, blank=None, tags=None,
+                      overlap: int = 102,
                       row_dist: float = 375 / 1.61, col_dist: float = 400 / 1.61, chip_type: Optional[str] = None,
                       min_button_diameter: int = 8, max_button_diameter: int = 30, chamber_diameter: int = 60,
                       top_chamber=None, left_chamber=None, low_edge_quantile: float = 0.1, high_edge_quantile: float = 0.9,
                       num_iter: int = 5000000, min_roundness: float = 0.2, cluster_penalty: float = 50,
                       roi_length: Optional[int] = None, search_timestep=0, search_channel=None, flatfield=1.0,
                       darkfield=0.0, device=None, seed: int = 0):
-    """`mg.microfluidic_chip` (registry.py:14-203): `shape` (all chambers "default") or `tags`, a
-    (rows, cols) array of chamber names with "" for blanks (what identify.py:14-45 builds from a
-    pinlist).  The reference's chip pipeline has no flat-field step; `flatfield` / `darkfield` are an
+    """`mg.microfluidic_chip` (registry.py:14-203): `pinlist` (CSV, identify.py:18-29), `shape` (all
+    chambers "default", identify.py:30-32) or `tags`, a ready (rows, cols) array of chamber names
+    with "" for blanks.  The reference's chip pipeline has no flat-field step; `flatfield` / `darkfield` are an
     addition (identity by default)."""
     if chip_type is not None:
         if chip_type not in CHIP_SPACING:
@@ -105,7 +127,9 @@ def microfluidic_chip(data, dims=None, coords=None, shape=(8, 8), tags=None, ove
         row_dist, col_dist = CHIP_SPACING[chip_type]
     results = []
     for xp in _standardized(data, dims, coords):
-        if tags is None:
+        if pinlist is not None:
+            tag = read_pinlist(pinlist, blank)                                        # identify.py:18-29
+        elif tags is None:
             tag = np.empty((shape[0], shape[1]), dtype="<U200")
             tag.fill("default")                                                       # identify.py:30-32
         else:

@@ -908,3 +908,58 @@ def reference_find_circles_stages(img, low_edge_quantile, high_edge_quantile, gr
                                          max_radius=max_radius, min_roundness=min_roundness, min_dist=min_dist, gui=gui)
     edges = gui.stages[0][1][0]
     return edges, circles, scores
+
+
+# ---------------------------------------------------------------------------------------------
+# identify.py:13-45 `identify_buttons` (pandas pinlist parsing) loaded in place.
+# ---------------------------------------------------------------------------------------------
+_cached_identify = None
+
+
+def load_reference_identify():
+    global _cached_identify
+    if _cached_identify is not None:
+        return _cached_identify
+    path = os.path.join(REFERENCE_ROOT, "src", "magnify", "identify.py")
+    if not os.path.exists(path):
+        return None
+    try:
+        import numba  # noqa: F401
+        import pandas  # noqa: F401
+        import scipy  # noqa: F401
+    except Exception:
+        return None
+    pkg = types.ModuleType("magnify")
+    pkg.__path__ = []
+    registry = types.ModuleType("magnify.registry")
+    registry.component = lambda name: (lambda f: f)
+    pkg.registry = registry
+    stubs = {"magnify": pkg, "magnify.registry": registry}
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        spec = importlib.util.spec_from_file_location("_magnify_reference_identify", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    except Exception:
+        mod = None
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _cached_identify = mod
+    return mod
+
+
+def reference_identify_buttons(num_times, shape=None, pinlist=None, blank=None):
+    """(tag (rows, cols), valid (rows, cols, T)) from the reference's identify_buttons, or None."""
+    import numpy as np
+
+    mod = load_reference_identify()
+    if mod is None:
+        return None
+    assay = LabelledAssay({"image": (("channel", "time", "im_y", "im_x"), np.zeros((1, num_times, 2, 2), np.uint8))}, {})
+    out = mod.identify_buttons(assay, shape=shape, pinlist=pinlist, blank=blank)
+    return out._vars["tag"][1], out._vars["valid"][1]

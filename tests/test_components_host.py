@@ -73,3 +73,30 @@ def test_api_standardize_and_restore_shapes():
     assert out.roi.dims == ("mark_row", "mark_col", "time", "roi_y", "roi_x") and out.roi.shape == (2, 3, 3, 8, 8)
     assert out.x.dims == ("mark_row", "mark_col", "time") and "tile" not in out and "mark_row" not in out
     assert "__original_tile_dims__" not in out.attrs
+
+
+def test_pinlist_matches_reference_identify_buttons(tmp_path):
+    """api.read_pinlist == the tag array of the reference's identify_buttons (identify.py:13-45, pandas)
+    run in place, for names, listed blanks, missing names and a custom blank list."""
+    import os
+
+    from magnify_b200 import api
+    from oracle._refload import reference_identify_buttons
+
+    path = os.path.join(tmp_path, "pins.csv")
+    with open(path, "w") as f:
+        f.write("Indices,MutantID,Other\n")
+        names = {(1, 1): "wt", (2, 1): "blank", (3, 1): "mutA", (1, 2): "", (2, 2): "BLANK", (3, 2): "a_longer_name_17",
+                 (1, 3): "x", (2, 3): "EMPTY", (3, 3): "y"}
+        for (col, row), name in names.items():
+            f.write(f'"({col},{row})",{name},7\n')
+    for blank in (None, ["EMPTY", "x"]):
+        mine = api.read_pinlist(path, blank)
+        assert mine.shape == (3, 3)
+        ref = reference_identify_buttons(4, pinlist=path, blank=blank)
+        if ref is None:
+            pytest.skip("/root/reference not available (GPU box)")
+        np.testing.assert_array_equal(mine, ref[0].astype(mine.dtype))
+        assert ref[1].shape == (3, 3, 4) and ref[1].all()
+    tag, valid = reference_identify_buttons(2, shape=(2, 5))
+    assert tag.shape == (2, 5) and (tag == "default").all() and tag.dtype == np.dtype("<U200")
