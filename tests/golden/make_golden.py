@@ -305,6 +305,22 @@ def golden_nonround():
     np.savez_compressed(os.path.join(HERE, "nonround.npz"), **out)
 
 
+def golden_bead_field():
+    """The reference's own find_circles (default 5e6 unseeded draws) on the 2048^2 / 300-bead field of
+    tools/finder_bench.py: a realistic-size run to compare detection sets with (not bit-exact: random)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "tools"))
+    import finder_bench as fb
+    from oracle import circles as oc
+    from oracle._refload import load_reference_utils
+
+    utils = load_reference_utils()
+    img = oc.to_uint8(fb.bead_image())
+    circles, scores = utils.find_circles(img, **fb.BEADS, gui=None)
+    assert len(circles) > 250
+    np.savez_compressed(os.path.join(HERE, "bead_field_reference.npz"), circles=circles, scores=scores,
+                        **{k: np.array(v) for k, v in fb.BEADS.items()})
+
+
 def golden_masks_cv():
     """cv.circle rasters through utils.circle / utils.annulus (utils.py:30-52) for clipped and
     unclipped centres -- pins the closed form `dx^2+dy^2 <= r^2` used by oracle and kernel."""
@@ -390,6 +406,7 @@ if __name__ == "__main__":
     golden_filter_expression()
     golden_circles()
     golden_nonround()
+    golden_bead_field()
     golden_masks_cv()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -245,3 +245,29 @@ def test_device_neighbour_suppression_equals_sequential_pass(cuda_device):
     assert mc.needs_host_suppression(far, 3) and not mc.needs_host_suppression(far, 8)
     cm = mc.conflict_map(2)
     assert cm.shape == (9, 9) and cm[4, 4] == 1 and (cm == cm[::-1, ::-1]).all()
+
+
+def test_bead_field_detections_agree_with_reference_run(cuda_device, golden):
+    """2048^2 field with 300 beads, the reference's default 5e6 draws: the reference's own detections
+    (tests/golden/bead_field_reference.npz, one unseeded run) and the GPU finder's agree bead for
+    bead -- at least 98 % of either set has a counterpart within one pixel in row, col and radius."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import finder_bench as fb
+    from magnify_b200 import circles as mc
+
+    g = golden("bead_field_reference")
+    kw = {k: g[k].item() for k in fb.BEADS}
+    assert kw == fb.BEADS
+    img = mc.to_uint8(dev(fb.bead_image(), cuda_device))
+    circles, scores = mc.find_circles(img, seed=0, **kw)
+    ref = g["circles"]
+    assert abs(len(circles) - len(ref)) <= 6
+
+    def covered(a, b):
+        d = np.abs(a[:, None, :].astype(np.int64) - b[None, :, :]).max(axis=2)
+        return (d.min(axis=1) <= 1).mean()
+
+    assert covered(ref, circles) >= 0.98 and covered(circles, ref) >= 0.98
