@@ -72,40 +72,41 @@ def _standardized(data, dims: Optional[Sequence[str]], coords: Optional[dict]):
     return [xp]
 
 
-def _restore(xp: Assay, grid: Optional[tuple]) -> Assay:
-    """drop (tiles) + restore_format (postprocess.py:6-49): un-stack `mark` into (mark_row, mark_col)
-    for chips and squeeze the dims standardize_format had added."""
+def _restore(xp: Assay, grid: Optional[tuple], roi_only: bool = False, drop_tiles: bool = True):
+    """drop + restore_format (postprocess.py:6-49): un-stack `mark` into (mark_row, mark_col) for
+    chips and squeeze the dims standardize_format had added.  roi_only returns the `roi` variable
+    alone (postprocess.py:11-12); drop_tiles=False keeps the tile stack (squeezed like the rest)."""
     original = xp.attrs.get("__original_tile_dims__", list(reader.TILE_ORDER))
-    added = {"channel": "channel" not in original, "time": "time" not in original}
+    added = {d: d not in original for d in reader.TILE_ORDER}                      # postprocess.py:29-33
     out = Assay(attrs={k: v for k, v in xp.attrs.items() if k != "__original_tile_dims__"})
     variables = list(xp.data_vars.items()) + list(xp.coords.items())
     for name, var in variables:
-        if name in ("tile", "mark_row", "mark_col") or name.startswith("tile_"):
+        if name in ("mark_row", "mark_col") or (drop_tiles and (name == "tile" or name.startswith("tile_"))):
             continue
         dims, values = list(var.dims), np.asarray(var.values)
         if grid is not None and dims and dims[0] == "mark":
             values = values.reshape(tuple(grid) + values.shape[1:])
             dims = ["mark_row", "mark_col"] + dims[1:]
-        for d in ("channel", "time"):
+        for d in reader.TILE_ORDER:
             if added[d] and d in dims and values.shape[dims.index(d)] == 1:
                 values = np.squeeze(values, axis=dims.index(d))
                 dims.remove(d)
         target = out.data_vars if name in xp.data_vars else out.coords
         target[name] = Var(tuple(dims), values)
-    return out
+    return out.data_vars["roi"] if roi_only else out
 
 
 def beads(data, dims=None, coords=None, flatfield=1.0, darkfield=0.0, overlap: int = 102, min_bead_diameter: int = 10,
           max_bead_diameter: int = 50, low_edge_quantile: float = 0.1, high_edge_quantile: float = 0.9,
           num_iter: int = 5000000, min_roundness: float = 0.3, roi_length: Optional[int] = None, search_channel=None,
-          device=None, seed: int = 0):
+          roi_only: bool = False, drop_tiles: bool = True, device=None, seed: int = 0):
     """`mg.beads` (registry.py:452-559): one Assay, or a list when the pattern matches several."""
     results = []
     for xp in _standardized(data, dims, coords):
         xp = FlatfieldStitcher(flatfield, darkfield, overlap, device=device)(xp)
         xp = BeadFinder(min_bead_diameter, max_bead_diameter, low_edge_quantile, high_edge_quantile, num_iter,
                         min_roundness, roi_length, search_channel, device=device, seed=seed)(xp)
-        results.append(_restore(xp, None))
+        results.append(_restore(xp, None, roi_only, drop_tiles))
     return results[0] if len(results) == 1 else results
 
 
@@ -115,8 +116,8 @@ def microfluidic_chip(data, dims=None, coords=None, shape=(8, 8), pinlist=None, 
                       min_button_diameter: int = 8, max_button_diameter: int = 30, chamber_diameter: int = 60,
                       top_chamber=None, left_chamber=None, low_edge_quantile: float = 0.1, high_edge_quantile: float = 0.9,
                       num_iter: int = 5000000, min_roundness: float = 0.2, cluster_penalty: float = 50,
-                      roi_length: Optional[int] = None, search_timestep=0, search_channel=None, flatfield=1.0,
-                      darkfield=0.0, device=None, seed: int = 0):
+                      roi_length: Optional[int] = None, search_timestep=0, search_channel=None, roi_only: bool = False,
+                      drop_tiles: bool = True, flatfield=1.0, darkfield=0.0, device=None, seed: int = 0):
     """`mg.microfluidic_chip` (registry.py:14-203): `pinlist` (CSV, identify.py:18-29), `shape` (all
     chambers "default", identify.py:30-32) or `tags`, a ready (rows, cols) array of chamber names
     with "" for blanks.  The reference's chip pipeline has no flat-field step; `flatfield` / `darkfield` are an
@@ -141,5 +142,5 @@ def microfluidic_chip(data, dims=None, coords=None, shape=(8, 8), pinlist=None, 
         xp = ButtonFinder(row_dist, col_dist, min_button_diameter, max_button_diameter, chamber_diameter, top_chamber,
                           left_chamber, low_edge_quantile, high_edge_quantile, num_iter, min_roundness, cluster_penalty,
                           roi_length, False, search_timestep, search_channel, device=device, seed=seed)(xp)
-        results.append(_restore(xp, tag.shape))
+        results.append(_restore(xp, tag.shape, roi_only, drop_tiles))
     return results[0] if len(results) == 1 else results

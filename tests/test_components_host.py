@@ -73,6 +73,10 @@ def test_api_standardize_and_restore_shapes():
     assert out.roi.dims == ("mark_row", "mark_col", "time", "roi_y", "roi_x") and out.roi.shape == (2, 3, 3, 8, 8)
     assert out.x.dims == ("mark_row", "mark_col", "time") and "tile" not in out and "mark_row" not in out
     assert "__original_tile_dims__" not in out.attrs
+    only = api._restore(xp, (2, 3), roi_only=True)
+    assert only.dims == out.roi.dims and only.shape == out.roi.shape
+    kept = api._restore(xp, (2, 3), drop_tiles=False)
+    assert kept.tile.dims == ("time", "tile_y", "tile_x") and kept.tile.shape == (3, 4, 5)
 
 
 def test_pinlist_matches_reference_identify_buttons(tmp_path):
