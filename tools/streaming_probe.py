@@ -55,4 +55,35 @@ for depth in (2, 3):
     roi_px = plan.boxes.shape[0] * 4 * T * case.roi_length ** 2
     out[f"depth{depth}"] = {"s": best, "h2d_GB": runner.h2d_bytes / 1e9, "d2h_GB": runner.d2h_bytes / 1e9,
                             "pcie_GBps": (runner.h2d_bytes + runner.d2h_bytes) / best / 1e9, "roi_px_per_s": roi_px / best}
+if "--tiff" in sys.argv:
+    # the same two sweeps with the blocks read from TIFF files (page cache) by the native reader
+    import shutil
+    import tempfile
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    from magnify_b200 import reader
+    from tiffgen import write_tiff
+
+    root = tempfile.mkdtemp(prefix="mgb_stream_", dir=os.environ.get("MGB_TIFF_DIR", "/tmp"))
+    try:
+        for idx in np.ndindex(*tiles_np.shape[:4]):
+            write_tiff(os.path.join(root, f"s_ch{idx[0]}_2024{idx[1] // 28 + 1:02d}{idx[1] % 28 + 1:02d}-000000_{idx[2]}_{idx[3]}.tif"),
+                       [tiles_np[idx]], rows_per_strip=64)
+        (xp,) = list(reader.Reader(threads=16)(os.path.join(root, "s_(channel)_(time)_(row)_(col).tif")))
+        lazy = xp["tile"].values
+        lazy.threads = 8
+        runner = pipeline.StreamingRunner(plan, depth=3, threads=4)
+        checks = []
+        best = 1e9
+        for _ in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            runner.run(lambda ci, ti, dst: lazy.read((ci, ti), dst), sink)
+            torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        assert all(checks) and len(checks) == 2 * T
+        out["tiff_depth3"] = {"s": best, "file_GB_read": 2 * tiles_np.nbytes / 1e9, "file_GBps": 2 * tiles_np.nbytes / best / 1e9,
+                              "roi_px_per_s": plan.boxes.shape[0] * 4 * T * case.roi_length ** 2 / best}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
 print(json.dumps(out))
