@@ -155,8 +155,10 @@ uint64_t parse_ifd(TiffFile& f, uint64_t off, Page& page) {
         page.desc_len = bytes;
         if (inl_value) {   // a description of <= 4 (8) bytes lives inside the entry itself
           page.desc_offset = off + count_bytes + e * entry_bytes + (f.big ? 12 : 8);
-        } else {
+        } else if (where + bytes <= f.file_size) {
           page.desc_offset = where;
+        } else {
+          page.desc_len = 0;   // points past the end of the file: treat as absent
         }
         break;
       case 273: case 324: case 279: case 325: {

@@ -210,3 +210,39 @@ def test_read_tiffs_ome_series_with_micromanager_summary(tmp_path):
     write_tiff(os.path.join(tmp_path, "plain_0.tif"), [planes[0, 0], planes[0, 1]])
     with pytest.raises(KeyError):
         list(reader.Reader()(os.path.join(tmp_path, "plain_(row).tif")))
+
+
+def test_corrupted_files_never_crash_the_reader(tmp_path):
+    """Byte flips and truncations in the header / directory of valid files: the native parser
+    either reads the file or reports an error code -- no crash, no hang, no huge allocation."""
+    rng = np.random.default_rng(7)
+    page = rng.integers(0, 65535, (40, 48), dtype=np.uint16)
+    outcomes = {"ok": 0, "error": 0}
+    for big in (False, True):
+        for byteorder in "<>":
+            good = write_tiff(os.path.join(tmp_path, "g.tif"), [page, page[::-1]], big=big, byteorder=byteorder,
+                              rows_per_strip=7, description="d" * 40)
+            raw = bytearray(open(good, "rb").read())
+            ifd_region = list(range(0, 16)) + list(range(len(raw) - 700, len(raw)))
+            for trial in range(150):
+                bad = bytearray(raw)
+                if trial % 5 == 0:
+                    bad = bad[: int(rng.integers(1, len(bad)))]
+                else:
+                    for _ in range(int(rng.integers(1, 6))):
+                        pos = int(rng.choice(ifd_region))
+                        if pos < len(bad):
+                            bad[pos] = int(rng.integers(0, 256))
+                path = os.path.join(tmp_path, "b.tif")
+                open(path, "wb").write(bytes(bad))
+                try:
+                    with reader.TiffFile(path) as tif:
+                        for k in range(min(tif.num_pages, 3)):
+                            info = tif.page_info(k)
+                            if info.status == 0 and 0 < info.nbytes < (1 << 24):
+                                tif.read_pages([k], out=np.empty((1,) + info.shape, info.dtype), threads=1)
+                            tif.description(k)
+                    outcomes["ok"] += 1
+                except _lib.MagnifyB200Error:
+                    outcomes["error"] += 1
+    assert outcomes["ok"] > 0 and outcomes["error"] > 0
