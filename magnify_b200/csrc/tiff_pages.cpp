@@ -19,6 +19,7 @@
 #include <cerrno>
 #include <cstdint>
 #include <cstring>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -286,7 +287,12 @@ int parallel_for(int64_t n, int threads, Fn fn) {
     for (;;) {
       const int64_t i = next.fetch_add(1);
       if (i >= n || status.load() != MGB_OK) return;
-      const int rc = fn(i);
+      int rc;
+      try {
+        rc = fn(i);
+      } catch (...) {   // e.g. bad_alloc on a corrupt directory: never let it cross the C ABI / thread
+        rc = MGB_EIO;
+      }
       if (rc != MGB_OK) {
         int expected = MGB_OK;
         status.compare_exchange_strong(expected, rc);
@@ -311,8 +317,14 @@ extern "C" {
 
 int mgb_tiff_open(const char* host_path, void** host_handle) {
   if (!host_path || !host_handle) return MGB_EINVAL;
-  TiffFile* f = new TiffFile();
-  const int rc = open_file(host_path, *f, -1);
+  TiffFile* f = new (std::nothrow) TiffFile();
+  if (!f) return MGB_EIO;
+  int rc;
+  try {
+    rc = open_file(host_path, *f, -1);
+  } catch (...) {
+    rc = MGB_EIO;
+  }
   if (rc != MGB_OK) {
     if (f->fd >= 0) ::close(f->fd);
     delete f;
