@@ -296,8 +296,9 @@ int mgb_filter_neighbors(const int32_t* host_circles, int64_t n, int min_dist, u
 /* ---- S / N2: TIFF page staging, reference src/magnify/reader.py:265-279 ---------------------
  * HOST-ONLY entry points (no kernel is launched): the reference's lazy tile loader reads one
  * TIFF page per dask chunk with `tifffile.TiffFile(f).pages[i].asarray()`.  These read the same
- * page bytes -- classic TIFF and BigTIFF, either byte order, any strip layout, Compression = 1
- * only -- straight into caller-owned host memory (normally a pinned staging buffer that the next
+ * page bytes -- classic TIFF and BigTIFF, either byte order, strips or tiles, Compression 1
+ * (direct pread), 5 (LZW), 8 / 32946 (Deflate) or 32773 (PackBits), Predictor 1 or 2 -- straight
+ * into caller-owned host memory (normally a pinned staging buffer that the next
  * cudaMemcpyAsync consumes), byte-swapped to host order.  A page is returned as `height` rows of
  * `width * samples` items in file order, i.e. the (tile_y, tile_x) array `asarray()` gives.
  *

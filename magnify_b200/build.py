@@ -30,7 +30,7 @@ def find_nvcc() -> str:
 
 
 def _inputs():
-    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".cpp"))]
     files += [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE) if f.endswith(".h")]
     return files
 
@@ -48,7 +48,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     cmd = [find_nvcc(), *NVCC_FLAGS, "-I", INCLUDE]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-lz", "-o", LIB_PATH]   # zlib: Deflate-compressed TIFF pages
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)

@@ -5,12 +5,15 @@
 // the hot path.  Host code only: the IFD chain is parsed once per
 // file, strips are coalesced into as few pread(2) calls as possible and land directly in the
 // destination (a pinned staging buffer), pages are spread over a small thread pool.  Layout
-// knowledge follows the TIFF 6.0 baseline specification and the BigTIFF extension (magic 43,
-// 8-byte offsets); only Compression = 1 (none) is decoded -- anything else is reported, never
-// silently mis-read.
+// knowledge follows the TIFF 6.0 specification and the BigTIFF extension (magic 43, 8-byte
+// offsets).  Uncompressed stripped pages -- what Micro-Manager and most acquisition software write
+// -- take the direct path; LZW, Deflate and PackBits data, horizontal differencing (Predictor 2)
+// and tiled pages are decoded chunk by chunk on the reading thread.  Anything else (JPEG, float
+// predictor, planar multi-sample) is reported, never silently mis-read.
 #include "magnify_b200.h"
 
 #include <fcntl.h>
+#include <zlib.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -32,6 +35,7 @@ struct Page {
   int photometric = 1;
   int64_t rows_per_strip = -1;
   bool tiled = false;
+  int64_t tile_width = 0, tile_length = 0;
   int64_t subfile_type = 0;
   std::vector<uint64_t> offsets, counts;
   uint64_t desc_offset = 0, desc_len = 0;   // ImageDescription (tag 270) bytes in the file
@@ -175,7 +179,8 @@ uint64_t parse_ifd(TiffFile& f, uint64_t off, Page& page) {
       case 278: if (!scalar(v)) return bad; page.rows_per_strip = static_cast<int64_t>(v); break;
       case 284: if (!scalar(v)) return bad; page.planar = static_cast<int>(v); break;
       case 317: if (!scalar(v)) return bad; page.predictor = static_cast<int>(v); break;
-      case 322: case 323: page.tiled = true; break;
+      case 322: if (!scalar(v)) return bad; page.tiled = true; page.tile_width = static_cast<int64_t>(v); break;
+      case 323: if (!scalar(v)) return bad; page.tiled = true; page.tile_length = static_cast<int64_t>(v); break;
       case 339: if (!scalar(v)) return bad; page.sample_format = static_cast<int>(v); break;
       default: break;
     }
@@ -225,15 +230,26 @@ int open_file(const char* path, TiffFile& f, int64_t max_pages) {
   return f.pages.empty() ? MGB_EFORMAT : MGB_OK;
 }
 
+bool plain_strips(const Page& p) { return p.compression == 1 && p.predictor == 1 && !p.tiled; }
+
 // Why a page cannot be decoded by this reader (MGB_OK when it can).
 int page_supported(const Page& p) {
-  if (p.compression != 1 || p.predictor != 1) return MGB_EUNSUPPORTED;
-  if (p.tiled || p.width <= 0 || p.height <= 0) return MGB_EUNSUPPORTED;
+  const bool codec = p.compression == 1 || p.compression == 5 || p.compression == 8 || p.compression == 32946 ||
+                     p.compression == 32773;
+  if (!codec) return MGB_EUNSUPPORTED;
+  if (p.predictor != 1 && !(p.predictor == 2 && p.sample_format != 3)) return MGB_EUNSUPPORTED;
+  if (p.width <= 0 || p.height <= 0) return MGB_EUNSUPPORTED;
   if (p.bits != 8 && p.bits != 16 && p.bits != 32 && p.bits != 64) return MGB_EUNSUPPORTED;
   if (p.samples != 1 && p.planar != 1) return MGB_EUNSUPPORTED;
   if (p.offsets.empty() || p.offsets.size() != p.counts.size()) return MGB_EFORMAT;
-  const int64_t strips = (p.height + p.rows_per_strip - 1) / p.rows_per_strip;
-  if (static_cast<int64_t>(p.offsets.size()) != strips) return MGB_EFORMAT;
+  if (p.tiled) {
+    if (p.tile_width <= 0 || p.tile_length <= 0 || p.tile_width > (1 << 20) || p.tile_length > (1 << 20)) return MGB_EFORMAT;
+    const int64_t across = (p.width + p.tile_width - 1) / p.tile_width, down = (p.height + p.tile_length - 1) / p.tile_length;
+    if (static_cast<int64_t>(p.offsets.size()) != across * down) return MGB_EFORMAT;
+  } else {
+    const int64_t strips = (p.height + p.rows_per_strip - 1) / p.rows_per_strip;
+    if (static_cast<int64_t>(p.offsets.size()) != strips) return MGB_EFORMAT;
+  }
   return MGB_OK;
 }
 
@@ -250,12 +266,187 @@ void swap_inplace(uint8_t* p, int64_t bytes, int itemsize) {
   }
 }
 
+// ---- decoders: each fills exactly `want` bytes of dst (false: corrupt or short data) -----------
+
+// TIFF 6.0 section 13: variable-width codes packed most significant bit first, ClearCode 256,
+// EndOfInformation 257, first free code 258, the width grows one code early (at 511, 1023, 2047).
+bool lzw_decode(const uint8_t* src, size_t n, uint8_t* dst, size_t want) {
+  static thread_local std::vector<uint16_t> prefix(4096);
+  static thread_local std::vector<uint8_t> suffix(4096), first(4096);
+  static thread_local std::vector<uint16_t> length(4096);
+  for (int i = 0; i < 256; ++i) {
+    prefix[i] = 0xffff;
+    suffix[i] = first[i] = static_cast<uint8_t>(i);
+    length[i] = 1;
+  }
+  size_t out = 0, bitpos = 0;
+  const size_t nbits = n * 8;
+  int width = 9, next = 258, prev = -1;
+  while (out < want) {
+    if (bitpos + width > nbits) return false;
+    uint32_t code = 0;
+    {   // up to 12 bits spanning at most 3 bytes
+      const size_t byte = bitpos >> 3;
+      uint32_t window = static_cast<uint32_t>(src[byte]) << 16;
+      if (byte + 1 < n) window |= static_cast<uint32_t>(src[byte + 1]) << 8;
+      if (byte + 2 < n) window |= src[byte + 2];
+      code = (window >> (24 - (bitpos & 7) - width)) & ((1u << width) - 1);
+      bitpos += width;
+    }
+    if (code == 257) break;
+    if (code == 256) {
+      width = 9;
+      next = 258;
+      prev = -1;
+      continue;
+    }
+    int entry;
+    if (prev < 0) {
+      if (code > 255) return false;
+      entry = static_cast<int>(code);
+    } else if (static_cast<int>(code) < next) {
+      if (code > 255 && code < 258) return false;
+      entry = static_cast<int>(code);
+      if (next < 4096) {
+        prefix[next] = static_cast<uint16_t>(prev);
+        suffix[next] = first[entry];
+        first[next] = first[prev];
+        length[next] = static_cast<uint16_t>(length[prev] + 1);
+        ++next;
+      }
+    } else if (static_cast<int>(code) == next && next < 4096) {
+      prefix[next] = static_cast<uint16_t>(prev);
+      suffix[next] = first[prev];
+      first[next] = first[prev];
+      length[next] = static_cast<uint16_t>(length[prev] + 1);
+      entry = next++;
+    } else {
+      return false;
+    }
+    const size_t len = length[entry];
+    const size_t take = std::min(len, want - out);
+    // the string is stored backwards along the prefix chain
+    int c = entry;
+    for (size_t k = len; k-- > 0;) {
+      if (k < take) dst[out + k] = suffix[c];
+      c = prefix[c];
+    }
+    out += take;
+    prev = entry;
+    if (next == (1 << width) - 1 && width < 12) ++width;
+  }
+  return out == want;
+}
+
+bool packbits_decode(const uint8_t* src, size_t n, uint8_t* dst, size_t want) {
+  size_t in = 0, out = 0;
+  while (out < want && in < n) {
+    const int8_t h = static_cast<int8_t>(src[in++]);
+    if (h >= 0) {
+      const size_t run = static_cast<size_t>(h) + 1;
+      if (in + run > n) return false;
+      const size_t take = std::min(run, want - out);
+      std::memcpy(dst + out, src + in, take);
+      in += run;
+      out += take;
+    } else if (h != -128) {
+      if (in >= n) return false;
+      const size_t run = static_cast<size_t>(1 - h), take = std::min(run, want - out);
+      std::memset(dst + out, src[in++], take);
+      out += take;
+    }
+  }
+  return out == want;
+}
+
+bool inflate_decode(const uint8_t* src, size_t n, uint8_t* dst, size_t want) {
+  z_stream z;
+  std::memset(&z, 0, sizeof(z));
+  if (inflateInit(&z) != Z_OK) return false;
+  z.next_in = const_cast<Bytef*>(src);
+  z.avail_in = static_cast<uInt>(n);
+  z.next_out = dst;
+  z.avail_out = static_cast<uInt>(want);
+  const int rc = inflate(&z, Z_FINISH);
+  const bool ok = (rc == Z_STREAM_END || rc == Z_OK || rc == Z_BUF_ERROR) && z.avail_out == 0;
+  inflateEnd(&z);
+  return ok;
+}
+
+// Predictor 2 (TIFF 6.0 section 14): every sample is stored as the difference to the sample
+// `samples` positions earlier in its row; undo it in native byte order.
+template <typename T>
+void undo_differencing(uint8_t* row, int64_t items, int samples) {
+  T* q = reinterpret_cast<T*>(row);
+  for (int64_t i = samples; i < items; ++i) q[i] = static_cast<T>(q[i] + q[i - samples]);
+}
+
+// Decode one strip or tile of `rows` x `cols` pixels into `chunk` (rows * cols * samples items,
+// native byte order, differencing undone).
+int decode_chunk(const TiffFile& f, const Page& p, uint64_t offset, uint64_t count, int64_t rows, int64_t cols,
+                 std::vector<uint8_t>& packed, uint8_t* chunk) {
+  const int item = p.bits / 8;
+  const size_t want = static_cast<size_t>(rows * cols * p.samples * item);
+  if (offset + count > f.file_size || count > (1ull << 31) || want > (1ull << 31)) return MGB_EFORMAT;
+  if (p.compression == 1) {
+    if (count < want) return MGB_EFORMAT;
+    if (!pread_all(f.fd, chunk, want, offset)) return MGB_EIO;
+  } else {
+    packed.resize(count);
+    if (!pread_all(f.fd, packed.data(), count, offset)) return MGB_EIO;
+    bool ok;
+    if (p.compression == 5) ok = lzw_decode(packed.data(), count, chunk, want);
+    else if (p.compression == 32773) ok = packbits_decode(packed.data(), count, chunk, want);
+    else ok = inflate_decode(packed.data(), count, chunk, want);
+    if (!ok) return MGB_EFORMAT;
+  }
+  if (f.swap && item > 1) swap_inplace(chunk, static_cast<int64_t>(want), item);
+  if (p.predictor == 2) {
+    const int64_t items = cols * p.samples;
+    for (int64_t r = 0; r < rows; ++r) {
+      uint8_t* row = chunk + r * items * item;
+      if (item == 1) undo_differencing<uint8_t>(row, items, p.samples);
+      else if (item == 2) undo_differencing<uint16_t>(row, items, p.samples);
+      else if (item == 4) undo_differencing<uint32_t>(row, items, p.samples);
+      else undo_differencing<uint64_t>(row, items, p.samples);
+    }
+  }
+  return MGB_OK;
+}
+
 int read_page(const TiffFile& f, const Page& p, void* dst, int64_t dst_bytes) {
   const int ok = page_supported(p);
   if (ok != MGB_OK) return ok;
   const int64_t row_bytes = p.row_bytes(), total = p.data_bytes();
   if (dst_bytes < total) return MGB_EINVAL;
   uint8_t* out = static_cast<uint8_t*>(dst);
+  if (!plain_strips(p)) {
+    // compressed, differenced or tiled pages: chunk by chunk through a scratch buffer
+    std::vector<uint8_t> packed, chunk;
+    const int item = p.bits / 8;
+    if (p.tiled) {
+      const int64_t across = (p.width + p.tile_width - 1) / p.tile_width;
+      const int64_t tile_row_bytes = p.tile_width * p.samples * item;
+      chunk.resize(static_cast<size_t>(p.tile_length * tile_row_bytes));
+      for (size_t t = 0; t < p.offsets.size(); ++t) {
+        const int rc = decode_chunk(f, p, p.offsets[t], p.counts[t], p.tile_length, p.tile_width, packed, chunk.data());
+        if (rc != MGB_OK) return rc;
+        const int64_t y0 = static_cast<int64_t>(t / across) * p.tile_length, x0 = static_cast<int64_t>(t % across) * p.tile_width;
+        const int64_t rows = std::min(p.tile_length, p.height - y0), cols = std::min(p.tile_width, p.width - x0);
+        for (int64_t r = 0; r < rows; ++r)
+          std::memcpy(out + (y0 + r) * row_bytes + x0 * p.samples * item, chunk.data() + r * tile_row_bytes,
+                      static_cast<size_t>(cols * p.samples * item));
+      }
+    } else {
+      for (size_t s = 0; s < p.offsets.size(); ++s) {
+        const int64_t y0 = static_cast<int64_t>(s) * p.rows_per_strip;
+        const int64_t rows = std::min<int64_t>(p.rows_per_strip, p.height - y0);
+        const int rc = decode_chunk(f, p, p.offsets[s], p.counts[s], rows, p.width, packed, out + y0 * row_bytes);
+        if (rc != MGB_OK) return rc;
+      }
+    }
+    return MGB_OK;
+  }
   const int64_t strips = static_cast<int64_t>(p.offsets.size());
   int64_t s = 0;
   while (s < strips) {

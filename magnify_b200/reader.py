@@ -7,8 +7,10 @@ dimensions into the canonical tile stack of `read_tiffs` (:163-326), and -- inst
 staging buffers (`include/magnify_b200.h`, `mgb_tiff_*`; `csrc/tiff_pages.cpp`).
 
 What is and is not reproduced:
-  * pixels: uncompressed classic TIFF / BigTIFF pages, either byte order (bit-exact; compressed
-    pages raise -- there is no slow path);
+  * pixels: classic TIFF / BigTIFF pages, either byte order, strips or tiles, uncompressed (the
+    direct path: pread into the pinned slot) or LZW / Deflate / PackBits with optional horizontal
+    differencing (decoded on the reading threads); bit-exact.  JPEG, the floating-point predictor
+    and planar multi-sample pages raise;
   * in-file axes: single-page files ("YX") and OME-TIFF series described by the OME-XML `Pixels`
     element of the first page (DimensionOrder / SizeC / SizeT / SizeZ, length-1 axes squeezed, the
     way tifffile presents `series[0]`); a multi-page file without OME-XML has the tifffile axis

@@ -36,7 +36,7 @@ def test_native_pages_match_oracle(tmp_path, big, byteorder):
                 assert tif.description(0) == b"hello" and tif.description(1) == b""
 
 
-def test_native_reads_libtiff_files_and_refuses_compression(tmp_path):
+def test_native_reads_libtiff_files_and_refuses_jpeg(tmp_path):
     cv2 = pytest.importorskip("cv2")
     rng = np.random.default_rng(1)
     pages = [rng.integers(0, 65535, (64, 96), dtype=np.uint16) for _ in range(3)]
@@ -45,9 +45,14 @@ def test_native_reads_libtiff_files_and_refuses_compression(tmp_path):
     with reader.TiffFile(multi) as tif:
         np.testing.assert_array_equal(tif.read_pages([0, 1, 2]), np.stack(pages))
     lzw = os.path.join(tmp_path, "lzw.tif")
-    assert cv2.imwrite(lzw, pages[0])
+    assert cv2.imwrite(lzw, pages[0])                                # libtiff default: LZW + differencing
     with reader.TiffFile(lzw) as tif:
-        assert tif.page_info(0).compression == 5 and tif.page_info(0).status == _lib.MGB_EUNSUPPORTED
+        assert tif.page_info(0).compression == 5 and tif.page_info(0).status == 0
+        np.testing.assert_array_equal(tif.asarray(0), pages[0])
+    jpeg = os.path.join(tmp_path, "jpeg.tif")                        # JPEG-in-TIFF: not decoded here
+    assert cv2.imwrite(jpeg, (pages[0] >> 8).astype(np.uint8), [cv2.IMWRITE_TIFF_COMPRESSION, 7])
+    with reader.TiffFile(jpeg) as tif:
+        assert tif.page_info(0).compression == 7 and tif.page_info(0).status == _lib.MGB_EUNSUPPORTED
         with pytest.raises(_lib.MagnifyB200Error) as err:
             tif.asarray(0)
         assert err.value.code == _lib.MGB_EUNSUPPORTED
@@ -246,3 +251,69 @@ def test_corrupted_files_never_crash_the_reader(tmp_path):
                 except _lib.MagnifyB200Error:
                     outcomes["error"] += 1
     assert outcomes["ok"] > 0 and outcomes["error"] > 0
+
+
+# ---- compressed / differenced / tiled pages ---------------------------------------------------
+def test_libtiff_compressed_files_decode(tmp_path):
+    """Files written by libtiff through cv2.imwrite with LZW (its default, with horizontal
+    differencing), Deflate and PackBits: the native decoders reproduce the pixels."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    smooth = (np.add.outer(np.arange(300), np.arange(257)) * 37 % 60000).astype(np.uint16)
+    images = [smooth, rng.integers(0, 65535, (123, 131), dtype=np.uint16), (smooth >> 8).astype(np.uint8),
+              np.zeros((64, 64), np.uint16), rng.integers(0, 255, (50, 70), dtype=np.uint8)]
+    for k, img in enumerate(images):
+        for comp in (5, 8, 32946, 32773, 1):
+            path = os.path.join(tmp_path, f"c{k}_{comp}.tif")
+            assert cv2.imwrite(path, img, [cv2.IMWRITE_TIFF_COMPRESSION, comp])
+            with reader.TiffFile(path) as tif:
+                info = tif.page_info(0)
+                assert info.status == 0 and info.compression == comp
+                np.testing.assert_array_equal(tif.asarray(0), img, err_msg=f"image {k} compression {comp}")
+            np.testing.assert_array_equal(cv2.imread(path, cv2.IMREAD_UNCHANGED), img)
+    multi = os.path.join(tmp_path, "multi_lzw.tif")
+    assert cv2.imwritemulti(multi, images[:2] and [smooth, smooth[::-1].copy()])
+    with reader.TiffFile(multi) as tif:
+        got = tif.read_pages([1, 0], threads=2)
+        np.testing.assert_array_equal(got[0], smooth[::-1])
+        np.testing.assert_array_equal(got[1], smooth)
+
+
+@pytest.mark.parametrize("big", [False, True])
+@pytest.mark.parametrize("byteorder", ["<", ">"])
+def test_tiled_deflate_and_predictor_pages(tmp_path, big, byteorder):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(6)
+    for dtype in (np.uint8, np.uint16, np.uint32, np.float32):
+        page = (rng.random((70, 90)) * 200).astype(dtype)
+        for kw in (dict(tile=(16, 32)), dict(tile=(64, 64), deflate=True), dict(deflate=True, rows_per_strip=9),
+                   dict(deflate=True, predictor=True, rows_per_strip=16), dict(tile=(32, 16), deflate=True, predictor=True)):
+            if kw.get("predictor") and np.dtype(dtype).kind == "f":
+                continue
+            path = write_tiff(os.path.join(tmp_path, "t.tif"), [page, page.T.copy()], big=big, byteorder=byteorder, **kw)
+            with reader.TiffFile(path) as tif:
+                np.testing.assert_array_equal(tif.asarray(0), page, err_msg=str(kw))
+                np.testing.assert_array_equal(tif.asarray(1), page.T, err_msg=str(kw))
+            if dtype != np.uint32:                                  # libtiff through OpenCV agrees with the writer
+                ok, decoded = cv2.imreadmulti(path, flags=cv2.IMREAD_UNCHANGED)
+                assert ok and np.array_equal(decoded[0], page)
+
+
+def test_corrupt_compressed_data_is_an_error(tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(8)
+    img = rng.integers(0, 65535, (64, 64), dtype=np.uint16)
+    for comp in (5, 8, 32773):
+        path = os.path.join(tmp_path, f"x{comp}.tif")
+        assert cv2.imwrite(path, img, [cv2.IMWRITE_TIFF_COMPRESSION, comp])
+        raw = bytearray(open(path, "rb").read())
+        for trial in range(40):
+            bad = bytearray(raw)
+            for _ in range(4):
+                bad[int(rng.integers(8, len(bad) - 300))] = int(rng.integers(0, 256))
+            open(path, "wb").write(bytes(bad))
+            try:
+                with reader.TiffFile(path) as tif:
+                    tif.asarray(0)                                   # wrong pixels are acceptable, a crash is not
+            except _lib.MagnifyB200Error:
+                pass
