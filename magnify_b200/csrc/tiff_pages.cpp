@@ -270,69 +270,69 @@ void swap_inplace(uint8_t* p, int64_t bytes, int itemsize) {
 
 // TIFF 6.0 section 13: variable-width codes packed most significant bit first, ClearCode 256,
 // EndOfInformation 257, first free code 258, the width grows one code early (at 511, 1023, 2047).
+// Every table string is a substring of what has already been written: string(next) =
+// string(prev) + first byte of the current string, and those bytes sit back to back in the output.
+// So an entry is just (position, length) into the output and emitting a code is a short forward
+// copy (byte-wise, because the "KwKwK" code may overlap its own source).
+struct LzwTable {
+  uint32_t pos[4096];
+  uint16_t len[4096];
+};
+
 bool lzw_decode(const uint8_t* src, size_t n, uint8_t* dst, size_t want) {
-  static thread_local std::vector<uint16_t> prefix(4096);
-  static thread_local std::vector<uint8_t> suffix(4096), first(4096);
-  static thread_local std::vector<uint16_t> length(4096);
-  for (int i = 0; i < 256; ++i) {
-    prefix[i] = 0xffff;
-    suffix[i] = first[i] = static_cast<uint8_t>(i);
-    length[i] = 1;
-  }
-  size_t out = 0, bitpos = 0;
-  const size_t nbits = n * 8;
-  int width = 9, next = 258, prev = -1;
+  static thread_local LzwTable table;
+  LzwTable& t = table;
+  size_t out = 0, in = 0;
+  uint64_t acc = 0;       // bit reservoir, most significant bits first
+  int have = 0;
+  int width = 9, next = 258;
+  bool has_prev = false;
+  size_t prev_pos = 0, prev_len = 0;
   while (out < want) {
-    if (bitpos + width > nbits) return false;
-    uint32_t code = 0;
-    {   // up to 12 bits spanning at most 3 bytes
-      const size_t byte = bitpos >> 3;
-      uint32_t window = static_cast<uint32_t>(src[byte]) << 16;
-      if (byte + 1 < n) window |= static_cast<uint32_t>(src[byte + 1]) << 8;
-      if (byte + 2 < n) window |= src[byte + 2];
-      code = (window >> (24 - (bitpos & 7) - width)) & ((1u << width) - 1);
-      bitpos += width;
+    while (have <= 56 && in < n) {
+      acc |= static_cast<uint64_t>(src[in++]) << (56 - have);
+      have += 8;
     }
+    if (have < width) return false;
+    const int code = static_cast<int>(acc >> (64 - width));
+    acc <<= width;
+    have -= width;
     if (code == 257) break;
     if (code == 256) {
       width = 9;
       next = 258;
-      prev = -1;
+      has_prev = false;
       continue;
     }
-    int entry;
-    if (prev < 0) {
-      if (code > 255) return false;
-      entry = static_cast<int>(code);
-    } else if (static_cast<int>(code) < next) {
-      if (code > 255 && code < 258) return false;
-      entry = static_cast<int>(code);
-      if (next < 4096) {
-        prefix[next] = static_cast<uint16_t>(prev);
-        suffix[next] = first[entry];
-        first[next] = first[prev];
-        length[next] = static_cast<uint16_t>(length[prev] + 1);
-        ++next;
-      }
-    } else if (static_cast<int>(code) == next && next < 4096) {
-      prefix[next] = static_cast<uint16_t>(prev);
-      suffix[next] = first[prev];
-      first[next] = first[prev];
-      length[next] = static_cast<uint16_t>(length[prev] + 1);
-      entry = next++;
+    size_t from, len;
+    const size_t here = out;
+    if (code < 256) {
+      dst[out++] = static_cast<uint8_t>(code);
+      len = 1;
     } else {
-      return false;
+      if (!has_prev) return false;
+      if (code < next) {
+        if (code < 258) return false;
+        from = t.pos[code];
+        len = t.len[code];
+      } else if (code == next) {
+        from = prev_pos;
+        len = prev_len + 1;
+      } else {
+        return false;
+      }
+      const size_t take = std::min(len, want - out);
+      for (size_t k = 0; k < take; ++k) dst[out + k] = dst[from + k];
+      out += take;
     }
-    const size_t len = length[entry];
-    const size_t take = std::min(len, want - out);
-    // the string is stored backwards along the prefix chain
-    int c = entry;
-    for (size_t k = len; k-- > 0;) {
-      if (k < take) dst[out + k] = suffix[c];
-      c = prefix[c];
+    if (has_prev && next < 4096) {
+      t.pos[next] = static_cast<uint32_t>(prev_pos);
+      t.len[next] = static_cast<uint16_t>(prev_len + 1);
+      ++next;
     }
-    out += take;
-    prev = entry;
+    has_prev = true;
+    prev_pos = here;
+    prev_len = len;
     if (next == (1 << width) - 1 && width < 12) ++width;
   }
   return out == want;
