@@ -542,3 +542,34 @@ def test_unaligned_image_width_uses_padded_rows(cuda_device, shape, overlap, gat
     np.testing.assert_allclose(stats.cpu().numpy(), o_red.masked_stats(want_roi, np.repeat(fg, t, 1), np.repeat(bg, t, 1)),
                                rtol=1e-12, equal_nan=True)
     np.testing.assert_array_equal(ops.roi_gather(image, boxes, length).cpu().numpy(), want_roi)
+
+
+def test_random_geometry_sweep(cuda_device):
+    """Random tile grids, tile sizes and overlaps (every alignment class of the kept width, the
+    clip and the image pitch): plain stitch for three dtypes and flat-field + stitch, all bit-exact
+    against the oracle, dense and x-padded output images alike."""
+    from magnify_b200 import ops
+
+    rng = np.random.default_rng(2024)
+    for trial in range(48):
+        c, t, r, cc = (int(v) for v in rng.integers(1, 4, 4))
+        h = int(rng.integers(9, 80))
+        w = int(rng.choice([8, 16, 24, 40, 64, 72, 80])) if trial % 3 else int(rng.integers(9, 80))
+        overlap = int(rng.integers(0, min(h, w) - 1))
+        shape = (c, t, r, cc, h, w)
+        dtype = [np.uint16, np.uint8, np.float32][trial % 3]
+        tiles = (rng.random(shape) * 250).astype(dtype)
+        want = o_st.stitch(tiles, overlap)
+        got = ops.stitch(dev(tiles, cuda_device), overlap)
+        np.testing.assert_array_equal(got.cpu().numpy(), want, err_msg=f"stitch {shape} ov {overlap} {dtype}")
+        padded = ops.alloc_image(want.shape, got.dtype, cuda_device)
+        ops.stitch(dev(tiles, cuda_device), overlap, out=padded)
+        np.testing.assert_array_equal(ops.to_host_dense(padded, non_blocking=False).numpy(), want)
+        if dtype == np.uint16:
+            tiles16, flat, dark = _ff_case(rng, shape, per_channel=bool(trial % 2), scalar_dark=bool(trial % 4 == 0))
+            want_ff = o_st.stitch(o_ff.flatfield_correct(tiles16, flat, dark), overlap)
+            plan = ops.FlatFieldPlan(shape, flat, dark, device=cuda_device)
+            out = ops.alloc_image(want_ff.shape, torch.uint16, cuda_device)
+            ops.flatfield_stitch(dev(tiles16, cuda_device), overlap=overlap, plan=plan, out=out)
+            np.testing.assert_array_equal(ops.to_host_dense(out, non_blocking=False).numpy(), want_ff,
+                                          err_msg=f"flat-field {shape} ov {overlap}")
