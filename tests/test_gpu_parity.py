@@ -573,3 +573,39 @@ def test_random_geometry_sweep(cuda_device):
             ops.flatfield_stitch(dev(tiles16, cuda_device), overlap=overlap, plan=plan, out=out)
             np.testing.assert_array_equal(ops.to_host_dense(out, non_blocking=False).numpy(), want_ff,
                                           err_msg=f"flat-field {shape} ov {overlap}")
+
+
+def test_random_gather_sweep(cuda_device):
+    """Random window lengths (every parity / alignment class), image sizes (dense and x-padded),
+    marker counts, mask timesteps and marker orders: crops bit-exact, masked sums exact, medians
+    exact, for centres anywhere in and slightly beyond the image (boxes shift inwards, utils.py:66-80)."""
+    from magnify_b200 import ops
+
+    rng = np.random.default_rng(77)
+    for trial in range(36):
+        length = int(rng.integers(2, 110))
+        c, t = int(rng.integers(1, 4)), int(rng.integers(1, 5))
+        h, w = int(rng.integers(length, length + 200)), int(rng.integers(length, length + 260))
+        m = int(rng.integers(1, 40))
+        image = rng.integers(0, 65535, (c, t, h, w), dtype=np.uint16, endpoint=True)
+        x = rng.uniform(-5, w + 5, (m, t))
+        y = rng.uniform(-5, h + 5, (m, t))
+        tm = int(rng.integers(1, t + 1))
+        mask_t = np.sort(rng.integers(0, tm, t)).astype(np.int32)
+        fg = rng.random((m, tm, length, length)) < rng.uniform(0, 1)
+        bg = rng.random((m, tm, length, length)) < rng.uniform(0, 1)
+        want_roi = o_rois.gather_rois(image, x, y, length)
+        want = o_red.masked_stats(want_roi, fg[:, mask_t], bg[:, mask_t])
+        img_d = ops.alloc_image(image.shape, torch.uint16, cuda_device) if trial % 2 else dev(image, cuda_device)
+        if trial % 2:
+            img_d.copy_(dev(image, cuda_device))
+        boxes = ops.bounding_boxes(dev(x, cuda_device), dev(y, cuda_device), length, w, h)
+        order = ops.spatial_order(boxes) if trial % 3 == 0 else None
+        roi, stats = ops.roi_gather_stats(img_d, boxes, dev(fg.view(np.uint8), cuda_device), dev(bg.view(np.uint8), cuda_device),
+                                          length, mask_t=dev(mask_t, cuda_device), order=order)
+        msg = f"trial {trial}: L={length} image {(c, t, h, w)} m={m} tm={tm}"
+        np.testing.assert_array_equal(roi.cpu().numpy(), want_roi, err_msg=msg)
+        np.testing.assert_allclose(stats.cpu().numpy(), want, rtol=1e-12, equal_nan=True, err_msg=msg)
+        np.testing.assert_array_equal(ops.roi_gather(img_d, boxes, length).cpu().numpy(), want_roi, err_msg=msg)
+        med = ops.roi_median(roi, dev(fg.view(np.uint8), cuda_device), mask_t=dev(mask_t, cuda_device)).cpu().numpy()
+        np.testing.assert_array_equal(med, o_red.masked_median(want_roi, fg[:, mask_t]), err_msg=msg)
