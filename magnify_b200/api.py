@@ -2,9 +2,10 @@
 over the GPU components: read -> standardize_format -> [identify_buttons] -> flatfield_correct ->
 stitch -> find_beads / find_buttons -> drop -> restore_format, on the `Assay` stand-in.
 
-`data` is a path pattern (reader.py's `(channel)_(time)_(row)_(col)` language), an `Assay`, or a
-NumPy array with `dims` naming its axes the way the reference's DataArrays do ("channel", "time",
-"row", "col", "y", "x" -- or the already standardized "tile_row", ... names).
+`data` is a path pattern (reader.py's `(channel)_(time)_(row)_(col)` language), an `Assay`, a
+labelled array with `.dims` / `.values` / `.coords` (an `xarray.DataArray`), or a NumPy array with
+`dims` naming its axes the way the reference's DataArrays do ("channel", "time", "row", "col",
+"y", "x" -- or the already standardized "tile_row", ... names).
 """
 from __future__ import annotations
 
@@ -47,6 +48,15 @@ def _standardized(data, dims: Optional[Sequence[str]], coords: Optional[dict]):
     remembering its original tile dims (preprocess.py:11-42)."""
     if isinstance(data, (str, os.PathLike)):
         return [reader.standardize_format(xp) for xp in reader.Reader()(data)]
+    if not isinstance(data, Assay) and hasattr(data, "dims") and hasattr(data, "values") and dims is None:
+        # a labelled array such as xarray.DataArray (what the reference's callers pass, tests/test_chip.py:40)
+        dims = tuple(data.dims)
+        labelled = getattr(data, "coords", {})
+        coords = dict(coords or {})
+        for name in ("channel", "time"):
+            if name in dims and name in labelled and name not in coords:
+                coords[name] = np.asarray(labelled[name].values if hasattr(labelled[name], "values") else labelled[name])
+        data = np.asarray(data.values)
     if isinstance(data, Assay):
         tile = data["tile"]
         arr, names = np.asarray(tile.values), [_RENAME.get(d, d) for d in tile.dims]

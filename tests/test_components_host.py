@@ -62,6 +62,14 @@ def test_api_standardize_and_restore_shapes():
     assert xp.attrs["__original_tile_dims__"] == ["time", "channel", "tile_y", "tile_x"]
     with pytest.raises(ValueError):
         api._standardized(arr, None, None)
+
+    class Labelled:                                   # the duck type of xarray.DataArray
+        dims = ("channel", "y", "x")
+        values = arr[0]
+        coords = {"channel": Var(("channel",), np.array(["bf", "gfp"]))}
+
+    (lab,) = api._standardized(Labelled(), None, None)
+    assert lab["tile"].values.shape == (2, 1, 1, 1, 4, 5) and list(lab.coords["channel"].values) == ["bf", "gfp"]
     with pytest.raises(NotImplementedError):
         api._standardized(arr, ("time", "depth", "y", "x"), None)
     # restore: un-stack marks, squeeze the added channel axis, keep the original time axis
