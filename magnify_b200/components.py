@@ -546,22 +546,25 @@ def make_quantify(median: bool = True, device=None):
 # ---------------------------------------------------------------------------------------------
 # registration
 # ---------------------------------------------------------------------------------------------
+def _component(fn):
+    """The reference's `@registry.component` idiom (registry.py:16-29): factory(**kwargs) returns a
+    callable that applies `fn(assay, **kwargs)`."""
+    return lambda **kwargs: (lambda xp: fn(xp, **kwargs))
+
+
 FACTORIES = {
     "flatfield_correct": make_flatfield_correct,
     "stitch": make_stitch,
     "find_beads": make_find_beads,
     "find_buttons": make_find_buttons,
+    "filter_expression": _component(filter_expression),      # filter.py:11-37
+    "filter_nonround": _component(filter_nonround),          # filter.py:40-62
+    "filter_leaky": _component(filter_leaky),                # filter.py:65-94
 }
 EXTRA_FACTORIES = {
     "flatfield_stitch_b200": lambda flatfield=1.0, darkfield=0.0, overlap=102, device=None: FlatfieldStitcher(
         flatfield, darkfield, overlap, device),
     "quantify": make_quantify,
-    "filter_expression_b200": lambda search_channel=None, min_contrast=None, device=None: (
-        lambda xp: filter_expression(xp, search_channel=search_channel, min_contrast=min_contrast, device=device)),
-    "filter_nonround_b200": lambda min_roundness=0.75, search_channel=None, device=None: (
-        lambda xp: filter_nonround(xp, min_roundness=min_roundness, search_channel=search_channel, device=device)),
-    "filter_leaky_b200": lambda search_channel=None, device=None: (
-        lambda xp: filter_leaky(xp, search_channel=search_channel, device=device)),
 }
 
 
