@@ -112,3 +112,18 @@ def test_pinlist_matches_reference_identify_buttons(tmp_path):
         assert ref[1].shape == (3, 3, 4) and ref[1].all()
     tag, valid = reference_identify_buttons(2, shape=(2, 5))
     assert tag.shape == (2, 5) and (tag == "default").all() and tag.dtype == np.dtype("<U200")
+
+
+def test_factories_cover_the_reference_names():
+    """The names the predefined pipelines hard-wire (registry.py:243-269, 431-449, 593-610) plus the
+    three filters, each a factory(**kwargs) -> callable(assay) like the reference's (registry.py:16-29)."""
+    from magnify_b200 import components as comp
+
+    assert set(comp.FACTORIES) == {"flatfield_correct", "stitch", "find_beads", "find_buttons", "filter_expression",
+                                   "filter_nonround", "filter_leaky"}
+    assert set(comp.EXTRA_FACTORIES) == {"flatfield_stitch_b200", "quantify"}
+    assert callable(comp.FACTORIES["stitch"](overlap=10))
+    assert callable(comp.FACTORIES["filter_nonround"](min_roundness=0.5, search_channel="egfp"))
+    assert callable(comp.FACTORIES["filter_expression"](min_contrast=40))
+    with pytest.raises(ValueError):
+        comp.FACTORIES["stitch"](overlap=-1)                                         # stitch.py:8-9
