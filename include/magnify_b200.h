@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MGB_ABI_VERSION 9
+#define MGB_ABI_VERSION 10
 
 #define MGB_OK 0
 #define MGB_EINVAL (-1)      /* bad argument (null pointer, negative size, bad itemsize ...) */
@@ -177,6 +177,14 @@ int mgb_roi_stats_u16(const uint16_t* roi, int64_t M, int64_t C, int64_t T, int 
 int mgb_roi_median_u16(const uint16_t* roi, int64_t M, int64_t C, int64_t T, int L,
                        const int32_t* mask_t, int64_t Tm, const uint8_t* mask, double* median,
                        void* stream);
+
+/* The same two reductions for a float32 roi (the reference accepts float images, tests/test_chip.py:76-96):
+ * float64 accumulation in a fixed order, NaN pixels skipped (nanmean / nanmedian); the median is the
+ * exact middle value (mean of the two middle values for even counts) as float64. */
+int mgb_roi_stats_f32(const float* roi, int64_t M, int64_t C, int64_t T, int L, const int32_t* mask_t, int64_t Tm,
+                      const uint8_t* fg, const uint8_t* bg, double* stats, void* stream);
+int mgb_roi_median_f32(const float* roi, int64_t M, int64_t C, int64_t T, int L, const int32_t* mask_t, int64_t Tm,
+                       const uint8_t* mask, double* median, void* stream);
 
 /* ---- F8: chip masks, reference utils.py:30-52 through find.py:380-400 ----------------------
  * fg[m] = disc(radius r_fg[m]), bg[m] = annulus(r_inner < d <= r_outer) centred on rel[m] =

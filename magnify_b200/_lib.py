@@ -48,6 +48,8 @@ SIGNATURES = {
                                        POINTER(ctypes.c_uint64), c_int, _P],
     "mgb_roi_stats_u16": [_P, _I64, _I64, _I64, c_int, _P, _I64, _P, _P, _P, _P],
     "mgb_roi_median_u16": [_P, _I64, _I64, _I64, c_int, _P, _I64, _P, _P, _P],
+    "mgb_roi_stats_f32": [_P, _I64, _I64, _I64, c_int, _P, _I64, _P, _P, _P, _P],
+    "mgb_roi_median_f32": [_P, _I64, _I64, _I64, c_int, _P, _I64, _P, _P, _P],
     "mgb_chip_masks": [_P, _P, c_int, c_int, _I64, c_int, _P, _P, _P, _P],
     "mgb_disc_halfwidths": [c_int, POINTER(ctypes.c_int32)],
     "mgb_bead_labels": [_P, _I64, _I64, _I64, _P, c_int, _P, _P],
@@ -95,7 +97,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.argtypes = argtypes
         fn.restype = _SPECIAL_RESTYPE.get(name, c_int)
-    if lib.mgb_abi_version() != 9:
+    if lib.mgb_abi_version() != 10:
         raise ImportError("libmagnify_b200.so ABI version mismatch; rebuild with `python -m magnify_b200.build --force`")
     _lib = lib
     return lib

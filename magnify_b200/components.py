@@ -64,6 +64,18 @@ def _tiles_to_device(assay, dev) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(_to_numpy(tile))).to(dev)
 
 
+def _roi_to_device(roi: np.ndarray, dev) -> torch.Tensor:
+    """Upload a roi for the reductions: uint16 as is; any other dtype the reference accepts
+    (float images, tests/test_chip.py:76-96; 8-bit) as float32, which represents uint8 / int16 /
+    float32 values exactly."""
+    roi = np.ascontiguousarray(roi)
+    if roi.dtype == np.uint16:
+        return torch.from_numpy(roi).to(dev)
+    if roi.dtype in (np.float32, np.uint8, np.int8, np.int16):
+        return torch.from_numpy(roi.astype(np.float32)).to(dev)
+    raise TypeError(f"roi dtype {roi.dtype} is not supported by the GPU reductions (uint16, float32, 8/16-bit integers)")
+
+
 def _read_tiff(path) -> np.ndarray:
     """Flat-field / dark-field image file (preprocess.py:75-81 reads it with tifffile): first page,
     through the native uncompressed-TIFF reader."""
@@ -420,9 +432,7 @@ def quantify(assay, median: bool = True, device=None):
     bg_median] (mark,channel,time) computed from roi/fg/bg: `roi.where(fg).mean(["roi_x","roi_y"])`
     etc.  uint16 roi only."""
     dev = _device(device)
-    roi = torch.from_numpy(np.ascontiguousarray(_to_numpy(assay["roi"]))).to(dev)
-    if roi.dtype != torch.uint16:
-        raise TypeError(f"quantify needs a uint16 roi, got {roi.dtype}")
+    roi = _roi_to_device(_to_numpy(assay["roi"]), dev)
     m, c, t, length, _ = roi.shape
     fg = torch.from_numpy(np.ascontiguousarray(_to_numpy(assay["fg"])).view(np.uint8)).to(dev)
     bg = torch.from_numpy(np.ascontiguousarray(_to_numpy(assay["bg"])).view(np.uint8)).to(dev)
@@ -448,9 +458,7 @@ def _time0_medians(assay, channel_index: int, dev):
     roi = np.ascontiguousarray(_to_numpy(assay["roi"])[:, channel_index : channel_index + 1, :1])
     fg = np.ascontiguousarray(_to_numpy(assay["fg"])[:, :1]).view(np.uint8)
     bg = np.ascontiguousarray(_to_numpy(assay["bg"])[:, :1]).view(np.uint8)
-    roi_d = torch.from_numpy(roi).to(dev)
-    if roi_d.dtype != torch.uint16:
-        raise TypeError(f"needs a uint16 roi, got {roi_d.dtype}")
+    roi_d = _roi_to_device(roi, dev)
     fgm = ops.roi_median(roi_d, torch.from_numpy(fg).to(dev)).cpu().numpy()[:, 0, 0]
     bgm = ops.roi_median(roi_d, torch.from_numpy(bg).to(dev)).cpu().numpy()[:, 0, 0]
     return fgm, bgm
@@ -531,7 +539,7 @@ def mrbles_intensities(assay, channels=None, device=None) -> np.ndarray:
     dev = _device(device)
     names = list(_to_numpy(assay["channel"])) if "channel" in assay else list(range(assay["roi"].shape[1]))
     idx = list(range(len(names))) if channels is None else [names.index(c) for c in channels]
-    roi = torch.from_numpy(np.ascontiguousarray(_to_numpy(assay["roi"])[:, idx, :1])).to(dev)
+    roi = _roi_to_device(_to_numpy(assay["roi"])[:, idx, :1], dev)
     fg = torch.from_numpy(np.ascontiguousarray(_to_numpy(assay["fg"])[:, :1]).view(np.uint8)).to(dev)
     bg = torch.from_numpy(np.ascontiguousarray(_to_numpy(assay["bg"])[:, :1]).view(np.uint8)).to(dev)
     mean_fg = ops.roi_stats(roi, fg, bg)[:, :, 0, 4]

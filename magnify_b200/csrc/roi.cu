@@ -179,12 +179,26 @@ roi_gather_scalar_kernel(const U* __restrict__ image, U* __restrict__ roi, int64
 }
 
 // ---- masked median (exact) -----------------------------------------------------------------
+// Pixel <-> 32-bit search key (monotone; 0xffffffff = "not in the mask").  float32: the usual
+// sign-flip order on the bit pattern; NaN pixels are skipped like np.nanmedian skips them.
+__device__ __forceinline__ uint32_t median_key(uint16_t v) { return v; }
+__device__ __forceinline__ uint32_t median_key(float v) {
+  if (v != v) return 0xffffffffu;
+  const uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+template <typename TPix> __device__ __forceinline__ double median_value(uint32_t key);
+template <> __device__ __forceinline__ double median_value<uint16_t>(uint32_t key) { return (double)key; }
+template <> __device__ __forceinline__ double median_value<float>(uint32_t key) {
+  return (double)__uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
+}
+
 // One CTA per ROI.  Every thread keeps its pixels as 32-bit keys (masked-out -> 0xffffffff) in
-// registers; the k-th smallest is found by a 16-step binary search on the value with one block
-// count per step.  NPT = keys per thread.
-template <int NPT>
+// registers; the k-th smallest is found by a binary search on the key with one block count per
+// step.  NPT = keys per thread.
+template <int NPT, typename TPix>
 __global__ void __launch_bounds__(kThreads)
-roi_median_u16_kernel(const uint16_t* __restrict__ roi, int64_t C, int64_t T, int L,
+roi_median_kernel(const TPix* __restrict__ roi, int64_t C, int64_t T, int L,
                       const int32_t* __restrict__ mask_t, int64_t Tm,
                       const uint8_t* __restrict__ mask, double* __restrict__ median) {
   __shared__ uint32_t red[2][kThreads / 32];
@@ -192,7 +206,7 @@ roi_median_u16_kernel(const uint16_t* __restrict__ roi, int64_t C, int64_t T, in
   const int64_t t = n % T;
   const int64_t m = n / (T * C);
   const int total = L * L;
-  const uint16_t* src = roi + n * (int64_t)total;
+  const TPix* src = roi + n * (int64_t)total;
   const uint8_t* mk = mask + (m * Tm + mask_t[t]) * (int64_t)total;
   uint32_t key[NPT];
   uint32_t cnt = 0;
@@ -200,7 +214,10 @@ roi_median_u16_kernel(const uint16_t* __restrict__ roi, int64_t C, int64_t T, in
   for (int i = 0; i < NPT; ++i) {
     const int idx = threadIdx.x + i * kThreads;
     key[i] = 0xffffffffu;
-    if (idx < total && mk[idx]) { key[i] = src[idx]; ++cnt; }
+    if (idx < total && mk[idx]) {
+      key[i] = median_key(src[idx]);
+      if (key[i] != 0xffffffffu) ++cnt;
+    }
   }
   int buf = 0;
   auto block_count = [&](uint32_t c) -> uint32_t {
@@ -239,7 +256,7 @@ roi_median_u16_kernel(const uint16_t* __restrict__ roi, int64_t C, int64_t T, in
     for (int i = 0; i < kThreads / 32; ++i) { lo = min(lo, rng[0][i]); hi = max(hi, rng[1][i]); }
   }
   while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
+    const uint32_t mid = lo + ((hi - lo) >> 1);   // float keys use the full 32 bits: lo + hi would wrap
     uint32_t c = 0;
 #pragma unroll
     for (int i = 0; i < NPT; ++i) c += (key[i] <= mid) ? 1u : 0u;
@@ -265,7 +282,45 @@ roi_median_u16_kernel(const uint16_t* __restrict__ roi, int64_t C, int64_t T, in
     for (int i = 0; i < kThreads / 32; ++i) g = min(g, red[buf][i]);
     if (tot < k1 + 2) v2 = g;
   }
-  if (threadIdx.x == 0) median[n] = 0.5 * ((double)v1 + (double)v2);
+  if (threadIdx.x == 0) median[n] = 0.5 * (median_value<TPix>(v1) + median_value<TPix>(v2));
+}
+
+// Masked sums of a float32 roi: one CTA per (m, c, t), float64 accumulation in a fixed order
+// (thread-strided partial sums, warp shuffles, then the warps in index order), NaN pixels skipped
+// like np.nansum / np.nanmean.  Record layout as for uint16: n_fg, n_bg, sum_fg, sum_bg, mean_fg, mean_bg.
+__global__ void __launch_bounds__(kThreads)
+roi_stats_f32_kernel(const float* __restrict__ roi, int64_t C, int64_t T, int L, const int32_t* __restrict__ mask_t,
+                     int64_t Tm, const uint8_t* __restrict__ fg, const uint8_t* __restrict__ bg,
+                     double* __restrict__ stats) {
+  __shared__ double red[4][kThreads / 32];
+  const int64_t n = blockIdx.x;
+  const int64_t t = n % T;
+  const int64_t m = n / (T * C);
+  const int total = L * L;
+  const float* src = roi + n * (int64_t)total;
+  const int64_t moff = (m * Tm + mask_t[t]) * (int64_t)total;
+  double v[4] = {0.0, 0.0, 0.0, 0.0};   // n_fg, n_bg, sum_fg, sum_bg
+  for (int i = threadIdx.x; i < total; i += kThreads) {
+    const float x = src[i];
+    if (x != x) continue;
+    if (fg[moff + i]) { v[0] += 1.0; v[2] += (double)x; }
+    if (bg[moff + i]) { v[1] += 1.0; v[3] += (double)x; }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int w = 0; w < kThreads / 32; ++w)
+      for (int k = 0; k < 4; ++k) s[k] += red[k][w];
+    double* out = stats + n * 6;
+    out[0] = s[0]; out[1] = s[1]; out[2] = s[2]; out[3] = s[3];
+    out[4] = s[2] / s[0];   // 0 / 0 = NaN for an empty mask, like np.nanmean
+    out[5] = s[3] / s[1];
+  }
 }
 
 static uint32_t magic_for(uint32_t d) { return (uint32_t)((0x100000000ULL + d - 1) / d); }
@@ -284,6 +339,29 @@ static int g_tma_enabled = 1;
 }  // namespace mgb
 
 using namespace mgb;
+
+template <typename TPix>
+static int launch_roi_median(const TPix* roi, int64_t M, int64_t C, int64_t T, int L, const int32_t* mask_t, int64_t Tm,
+                             const uint8_t* mask, double* median, void* stream) {
+  if (M < 0 || C < 0 || T < 0 || L <= 0) return MGB_EINVAL;
+  const int64_t n_roi = M * C * T;
+  if (n_roi == 0) return MGB_OK;
+  if (n_roi > INT32_MAX) return MGB_EUNSUPPORTED;
+  if (!roi || !mask_t || !mask || !median || Tm <= 0) return MGB_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int npt = (int)ceil_div((int64_t)L * L, kThreads);
+#define MGB_MED(N) roi_median_kernel<N, TPix><<<(unsigned)n_roi, kThreads, 0, st>>>(roi, C, T, L, mask_t, Tm, mask, median)
+  if (npt <= 4) MGB_MED(4);
+  else if (npt <= 10) MGB_MED(10);
+  else if (npt <= 21) MGB_MED(21);
+  else if (npt <= 40) MGB_MED(40);
+  else if (npt <= 64) MGB_MED(64);
+  else if (npt <= 100) MGB_MED(100);
+  else return MGB_EUNSUPPORTED;   // L > 160
+#undef MGB_MED
+  MGB_CUDA_LAUNCH_CHECK();
+  return MGB_OK;
+}
 
 extern "C" {
 
@@ -406,22 +484,22 @@ int mgb_roi_stats_u16(const uint16_t* roi, int64_t M, int64_t C, int64_t T, int 
 int mgb_roi_median_u16(const uint16_t* roi, int64_t M, int64_t C, int64_t T, int L,
                        const int32_t* mask_t, int64_t Tm, const uint8_t* mask, double* median,
                        void* stream) {
+  return launch_roi_median<uint16_t>(roi, M, C, T, L, mask_t, Tm, mask, median, stream);
+}
+
+int mgb_roi_median_f32(const float* roi, int64_t M, int64_t C, int64_t T, int L, const int32_t* mask_t, int64_t Tm,
+                       const uint8_t* mask, double* median, void* stream) {
+  return launch_roi_median<float>(roi, M, C, T, L, mask_t, Tm, mask, median, stream);
+}
+
+int mgb_roi_stats_f32(const float* roi, int64_t M, int64_t C, int64_t T, int L, const int32_t* mask_t, int64_t Tm,
+                      const uint8_t* fg, const uint8_t* bg, double* stats, void* stream) {
   if (M < 0 || C < 0 || T < 0 || L <= 0) return MGB_EINVAL;
   const int64_t n_roi = M * C * T;
   if (n_roi == 0) return MGB_OK;
   if (n_roi > INT32_MAX) return MGB_EUNSUPPORTED;
-  if (!roi || !mask_t || !mask || !median || Tm <= 0) return MGB_EINVAL;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int npt = (int)ceil_div((int64_t)L * L, kThreads);
-#define MGB_MED(N) roi_median_u16_kernel<N><<<(unsigned)n_roi, kThreads, 0, st>>>(roi, C, T, L, mask_t, Tm, mask, median)
-  if (npt <= 4) MGB_MED(4);
-  else if (npt <= 10) MGB_MED(10);
-  else if (npt <= 21) MGB_MED(21);
-  else if (npt <= 40) MGB_MED(40);
-  else if (npt <= 64) MGB_MED(64);
-  else if (npt <= 100) MGB_MED(100);
-  else return MGB_EUNSUPPORTED;   // L > 160
-#undef MGB_MED
+  if (!roi || !mask_t || !fg || !bg || !stats || Tm <= 0) return MGB_EINVAL;
+  roi_stats_f32_kernel<<<(unsigned)n_roi, kThreads, 0, (cudaStream_t)stream>>>(roi, C, T, L, mask_t, Tm, fg, bg, stats);
   MGB_CUDA_LAUNCH_CHECK();
   return MGB_OK;
 }

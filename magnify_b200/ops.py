@@ -471,8 +471,11 @@ def roi_gather_stats(
 
 
 def roi_stats(roi: torch.Tensor, fg: torch.Tensor, bg: torch.Tensor, mask_t: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Masked sums / counts / means of an existing roi (M,C,T,L,L) uint16 -> (M,C,T,6) float64."""
-    _check(roi, "roi", dtype=torch.uint16, ndim=5)
+    """Masked sums / counts / means of an existing roi (M,C,T,L,L) uint16 or float32 -> (M,C,T,6)
+    float64 (float32: float64 accumulation, NaN pixels skipped)."""
+    if roi.dtype not in (torch.uint16, torch.float32):
+        raise TypeError(f"roi must be uint16 or float32, got {roi.dtype}")
+    _check(roi, "roi", ndim=5)
     m, c, t, length, _ = roi.shape
     fg = fg.view(torch.uint8) if fg.dtype == torch.bool else fg
     bg = bg.view(torch.uint8) if bg.dtype == torch.bool else bg
@@ -490,15 +493,18 @@ def roi_stats(roi: torch.Tensor, fg: torch.Tensor, bg: torch.Tensor, mask_t: Opt
             raise ValueError("mask_t is required when fg/bg hold neither 1 nor T timesteps")
     stats = torch.empty((m, c, t, 6), dtype=torch.float64, device=roi.device)
     with torch.cuda.device(roi.device):
-        _lib.call("mgb_roi_stats_u16", _ptr(roi), m, c, t, int(length), _ptr(mask_t), tm, _ptr(fg), _ptr(bg),
-                  _ptr(stats), _stream())
+        _lib.call("mgb_roi_stats_u16" if roi.dtype == torch.uint16 else "mgb_roi_stats_f32", _ptr(roi), m, c, t,
+                  int(length), _ptr(mask_t), tm, _ptr(fg), _ptr(bg), _ptr(stats), _stream())
     return stats
 
 
 def roi_median(roi: torch.Tensor, mask: torch.Tensor, mask_t: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Exact masked median per (m,c,t) -> (M,C,T) float64, NaN for an empty mask
-    (`roi.where(mask).median(dim=["roi_x","roi_y"])`, identify.py:79, filter.py:21-22)."""
-    _check(roi, "roi", dtype=torch.uint16, ndim=5)
+    (`roi.where(mask).median(dim=["roi_x","roi_y"])`, identify.py:79, filter.py:21-22); uint16 or
+    float32 roi (NaN pixels skipped)."""
+    if roi.dtype not in (torch.uint16, torch.float32):
+        raise TypeError(f"roi must be uint16 or float32, got {roi.dtype}")
+    _check(roi, "roi", ndim=5)
     m, c, t, length, _ = roi.shape
     mask = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
     _check(mask, "mask", dtype=torch.uint8, ndim=4)
@@ -514,8 +520,8 @@ def roi_median(roi: torch.Tensor, mask: torch.Tensor, mask_t: Optional[torch.Ten
             raise ValueError("mask_t is required when mask holds neither 1 nor T timesteps")
     out = torch.empty((m, c, t), dtype=torch.float64, device=roi.device)
     with torch.cuda.device(roi.device):
-        _lib.call("mgb_roi_median_u16", _ptr(roi), m, c, t, int(length), _ptr(mask_t), tm, _ptr(mask), _ptr(out),
-                  _stream())
+        _lib.call("mgb_roi_median_u16" if roi.dtype == torch.uint16 else "mgb_roi_median_f32", _ptr(roi), m, c, t,
+                  int(length), _ptr(mask_t), tm, _ptr(mask), _ptr(out), _stream())
     return out
 
 

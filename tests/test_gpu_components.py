@@ -324,3 +324,31 @@ def test_filter_nonround_golden_from_reference_source(cuda_device, golden):
         assay = Assay(coords={"fg": (("mark", "time", "roi_y", "roi_x"), g["fg"]), "valid": (("mark", "time"), g["valid"])})
         out = filter_nonround(assay, min_roundness=float(g[f"case{k}__min_roundness"]))
         np.testing.assert_array_equal(out.valid.values, g[f"case{k}__valid"], err_msg=f"case {k}")
+
+
+def test_quantify_and_filters_accept_float_roi(cuda_device):
+    """quantify / filter_expression on a float32 roi equal the uint16 run on the same values."""
+    from magnify_b200.components import filter_expression, quantify
+    from magnify_b200.dataset import Assay
+
+    rng = np.random.default_rng(3)
+    m, c, t, length = 20, 2, 2, 24
+    roi = rng.integers(380, 420, (m, c, t, length, length)).astype(np.uint16)
+    yy, xx = np.mgrid[0:length, 0:length]
+    fg0 = (yy - 12) ** 2 + (xx - 12) ** 2 <= 25
+    roi[::2][..., fg0] += 300
+    fg = np.broadcast_to(fg0, (m, t, length, length)).copy()
+    bg = np.broadcast_to((yy - 12) ** 2 + (xx - 12) ** 2 > 64, (m, t, length, length)).copy()
+
+    def assay(values):
+        return Assay({"roi": (("mark", "channel", "time", "roi_y", "roi_x"), values)},
+                     coords={"channel": (("channel",), np.array(["a", "b"])), "fg": (("mark", "time", "roi_y", "roi_x"), fg),
+                             "bg": (("mark", "time", "roi_y", "roi_x"), bg), "valid": (("mark", "time"), np.ones((m, t), bool))})
+
+    a16, a32 = quantify(assay(roi)), quantify(assay(roi.astype(np.float32)))
+    for name in ("fg_sum", "bg_sum", "fg_mean", "bg_mean", "fg_median", "bg_median", "fg_count"):
+        np.testing.assert_array_equal(a16[name].values, a32[name].values, err_msg=name)
+    v16 = filter_expression(assay(roi)).valid.values
+    v32 = filter_expression(assay(roi.astype(np.float32))).valid.values
+    np.testing.assert_array_equal(v16, v32)
+    assert v16[::2].all() and v16[1::2].sum() < v16[::2].sum()     # the bright half is expressed

@@ -609,3 +609,43 @@ def test_random_gather_sweep(cuda_device):
         np.testing.assert_array_equal(ops.roi_gather(img_d, boxes, length).cpu().numpy(), want_roi, err_msg=msg)
         med = ops.roi_median(roi, dev(fg.view(np.uint8), cuda_device), mask_t=dev(mask_t, cuda_device)).cpu().numpy()
         np.testing.assert_array_equal(med, o_red.masked_median(want_roi, fg[:, mask_t]), err_msg=msg)
+
+
+def test_float32_roi_stats_and_median(cuda_device):
+    """The reductions on a float32 roi (the reference accepts float images): float64 sums in a
+    fixed order (rtol 1e-12 against NumPy's float64 sums), exact medians, NaN pixels and empty
+    masks handled like nanmean / nanmedian."""
+    from magnify_b200 import ops
+
+    rng = np.random.default_rng(31)
+    for length in (5, 24, 72, 101):
+        m, c, t = 7, 2, 3
+        roi = (rng.standard_normal((m, c, t, length, length)) * 500 + 1000).astype(np.float32)
+        roi[1, 0, 0, :2] = np.nan
+        roi[2, 1, 1] = -3.5
+        roi[3, 0, 2, 0, 0] = np.inf
+        fg = rng.random((m, 2, length, length)) < 0.4
+        bg = rng.random((m, 2, length, length)) < 0.6
+        fg[4] = False
+        mask_t = np.array([0, 1, 1], dtype=np.int32)
+        stats = ops.roi_stats(dev(roi, cuda_device), dev(fg.view(np.uint8), cuda_device), dev(bg.view(np.uint8), cuda_device),
+                              mask_t=dev(mask_t, cuda_device)).cpu().numpy()
+        med = ops.roi_median(dev(roi, cuda_device), dev(fg.view(np.uint8), cuda_device), mask_t=dev(mask_t, cuda_device)).cpu().numpy()
+        r64 = roi.astype(np.float64)
+        for mi in range(m):
+            for ci in range(c):
+                for ti in range(t):
+                    f, b = fg[mi, mask_t[ti]], bg[mi, mask_t[ti]]
+                    px = r64[mi, ci, ti]
+                    ok = ~np.isnan(px)
+                    want = [float((f & ok).sum()), float((b & ok).sum()), px[f & ok].sum(), px[b & ok].sum()]
+                    np.testing.assert_allclose(stats[mi, ci, ti, :4], want, rtol=1e-12)
+                    with np.errstate(invalid="ignore", divide="ignore"):
+                        means = [np.float64(want[2]) / want[0], np.float64(want[3]) / want[1]]
+                    np.testing.assert_allclose(stats[mi, ci, ti, 4:], means, rtol=1e-12, equal_nan=True)
+                    vals = np.sort(px[f & ok])
+                    if len(vals) == 0:
+                        assert np.isnan(med[mi, ci, ti])
+                    else:
+                        lo, hi = vals[(len(vals) - 1) // 2], vals[len(vals) // 2]
+                        assert med[mi, ci, ti] == 0.5 * (lo + hi), (length, mi, ci, ti)
