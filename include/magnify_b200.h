@@ -292,7 +292,8 @@ int mgb_order_circles(const int32_t* circles, const float* scores, int64_t N, in
  * only on the centre offset: conflict is that relation as a (4 min_dist + 1)^2 byte map on the
  * device (index (drow + 2 min_dist) * (4 min_dist + 1) + dcol + 2 min_dist).  The sequential
  * best-first pass is reproduced by rounds of "rejected once a higher-ranked conflicting circle is
- * kept, kept once all of them are rejected"; SYNCHRONISES the stream once per round.  Callers must
+ * kept, kept once all of them are rejected"; SYNCHRONISES the stream once per round and returns
+ * MGB_EUNSUPPORTED (state undefined) when 256 rounds did not settle every circle.  Callers must
  * use the host version when a centre lies more than min_dist + 1 pixels outside the image (there
  * the reference's raster indices wrap around). */
 int mgb_filter_neighbors_device(const int32_t* circles, int64_t N, int64_t B, int64_t H, int64_t W, int max_radius,

@@ -198,6 +198,10 @@ def filter_neighbors(circles: np.ndarray, min_dist: int) -> np.ndarray:
     return valid.astype(bool)
 
 
+class SuppressionNotSettled(RuntimeError):
+    """The device suppression met a dependency chain longer than its round limit; use the host pass."""
+
+
 def conflict_map(min_dist: int) -> np.ndarray:
     """(4 min_dist + 1)^2 uint8: entry (drow + 2 min_dist, dcol + 2 min_dist) is 1 when the rings
     of radius min_dist (utils.py:262, 4-connected raster) around two centres (drow, dcol) apart
@@ -220,8 +224,12 @@ def filter_neighbors_device(circles: torch.Tensor, batch: int, height: int, widt
     state = torch.empty(n, dtype=torch.uint8, device=circles.device)
     conflict = torch.from_numpy(conflict_map(min_dist)).to(circles.device)
     rounds = ctypes.c_int()
-    _lib.call("mgb_filter_neighbors_device", _ptr(circles), n, int(batch), int(height), int(width), int(max_radius),
-              int(min_dist), _ptr(conflict), _ptr(state), ctypes.byref(rounds), _stream())
+    rc = _lib.try_call("mgb_filter_neighbors_device", _ptr(circles), n, int(batch), int(height), int(width),
+                       int(max_radius), int(min_dist), _ptr(conflict), _ptr(state), ctypes.byref(rounds), _stream())
+    if rc == _lib.MGB_EUNSUPPORTED:
+        raise SuppressionNotSettled(f"{rounds.value} rounds did not settle every circle")
+    if rc != 0:
+        raise _lib.MagnifyB200Error("mgb_filter_neighbors_device", rc, _lib.error_string(rc))
     keep = state == 1
     return (keep, rounds.value) if return_rounds else keep
 
@@ -367,8 +375,11 @@ def find_circles(image: torch.Tensor, low_edge_quantile: float, high_edge_quanti
                 circles, scores = circles[order].contiguous(), scores[order]
                 on_device = min_dist > 0 and not needs_host_suppression(circles, min_dist)
                 if on_device:                                                 # utils.py:194-196
-                    valid = filter_neighbors_device(circles, b, e.shape[1], e.shape[2], max_radius, min_dist)
-                    circles, scores = circles[valid], scores[valid]
+                    try:
+                        valid = filter_neighbors_device(circles, b, e.shape[1], e.shape[2], max_radius, min_dist)
+                        circles, scores = circles[valid], scores[valid]
+                    except SuppressionNotSettled:
+                        on_device = False                                     # very long chains: sequential host pass
                 found, scores = circles.cpu().numpy(), scores.cpu().numpy()
                 bounds = np.searchsorted(found[:, 0], np.arange(b + 1))
                 for k in range(b):

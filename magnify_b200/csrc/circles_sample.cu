@@ -528,6 +528,7 @@ extern "C" int mgb_filter_neighbors_device(const int32_t* circles, int64_t N, in
     e = cudaGetLastError();
   }
   int rounds = 0;
+  bool gave_up = false;
   while (e == cudaSuccess) {
     e = cudaMemsetAsync(undecided, 0, sizeof(int), s);
     if (e != cudaSuccess) break;
@@ -539,6 +540,10 @@ extern "C" int mgb_filter_neighbors_device(const int32_t* circles, int64_t N, in
     if ((e = cudaMemcpyAsync(&left, undecided, sizeof(int), cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) break;
     if (left == 0) break;
+    if (rounds >= 256) {   // a dependency chain this long is cheaper to walk sequentially on the host
+      gave_up = true;
+      break;
+    }
   }
   if (temp) cudaFreeAsync(temp, s);
   if (undecided) cudaFreeAsync(undecided, s);
@@ -546,5 +551,6 @@ extern "C" int mgb_filter_neighbors_device(const int32_t* circles, int64_t N, in
   if (starts) cudaFreeAsync(starts, s);
   if (counts) cudaFreeAsync(counts, s);
   if (host_rounds) *host_rounds = rounds;
-  return e == cudaSuccess ? MGB_OK : (int)e;
+  if (e != cudaSuccess) return (int)e;
+  return gave_up ? MGB_EUNSUPPORTED : MGB_OK;
 }
