@@ -271,3 +271,20 @@ def test_bead_field_detections_agree_with_reference_run(cuda_device, golden):
         return (d.min(axis=1) <= 1).mean()
 
     assert covered(ref, circles) >= 0.98 and covered(circles, ref) >= 0.98
+
+
+def test_device_suppression_chain_limit(cuda_device):
+    """A line of circles where every one conflicts with its predecessor is the worst case for the
+    round-based rule (one decision per round): short chains settle and equal the sequential pass,
+    a chain beyond the round limit raises so that the finder takes the host pass."""
+    from magnify_b200 import circles as mc
+
+    def chain(n):                      # centres 3 px apart, best first: kept, rejected, kept, ...
+        return np.stack([np.zeros(n), np.full(n, 20), 10 + 3 * np.arange(n), np.full(n, 8)], 1).astype(np.int32)
+
+    short = chain(150)
+    keep, rounds = mc.filter_neighbors_device(dev(short, cuda_device), 1, 64, 1000, 10, 4, return_rounds=True)
+    np.testing.assert_array_equal(keep.cpu().numpy(), mc.filter_neighbors(short[:, 1:], 4))
+    assert 10 < rounds <= 256
+    with pytest.raises(mc.SuppressionNotSettled):
+        mc.filter_neighbors_device(dev(chain(3000), cuda_device), 1, 64, 9100, 10, 4)
