@@ -12,13 +12,12 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np
 
 from magnify_b200 import api
 from magnify_b200.components import filter_expression, quantify
-from tiffgen import write_tiff
+from magnify_b200.reader import write_tiff
 
 
 def synthetic_chip(rows=12, cols=8, row_dist=126, col_dist=233, channels=("bf", "egfp"), times=3, seed=0):
@@ -59,7 +58,7 @@ def main():
             tiles = split_into_tiles(image[c, t, : image.shape[2] // 2 * 2, : image.shape[3] // 2 * 2], 2, 2, overlap)
             for i in range(2):
                 for j in range(2):
-                    write_tiff(os.path.join(workdir, f"chip_{name}_2024010{t + 1}-120000_{i}_{j}.tif"), [tiles[i][j]])
+                    write_tiff(os.path.join(workdir, f"chip_{name}_2024010{t + 1}-120000_{i}_{j}.tif"), tiles[i][j])
     print(f"wrote {len(channels) * image.shape[1] * 4} TIFF tiles to {workdir} in {time.perf_counter() - t0:.2f} s")
 
     tags = np.full((rows, cols), "sample", dtype="<U16")

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MGB_ABI_VERSION 10
+#define MGB_ABI_VERSION 11
 
 #define MGB_OK 0
 #define MGB_EINVAL (-1)      /* bad argument (null pointer, negative size, bad itemsize ...) */
@@ -329,6 +329,14 @@ int mgb_tiff_read_pages(const void* host_handle, const int64_t* host_pages, int6
  * page must be width x height, single-sample, `bits` wide, else MGB_EFORMAT. */
 int mgb_tiff_read_files(const char* const* host_paths, int64_t n_files, int64_t page, int64_t width, int64_t height,
                         int bits, void* host_dst, int64_t dst_stride_bytes, int threads);
+
+/* Results to disk (no counterpart in the reference, which caches to zarr, accessor.py:18-35): n_pages
+ * host pages of height x width items (bits in {8,16,32,64}; sample_format 1 uint, 2 int, 3 float) as
+ * an uncompressed little-endian TIFF, one strip per page, written with `threads` parallel pwrite
+ * calls.  bigtiff: 1 BigTIFF, 0 classic (MGB_EINVAL beyond 4 GB), -1 choose by size.
+ * host_description (nullable) becomes the ImageDescription of the first page. */
+int mgb_tiff_write(const char* host_path, const void* host_pages, int64_t n_pages, int64_t height, int64_t width,
+                   int bits, int sample_format, int bigtiff, const char* host_description, int threads);
 
 #ifdef __cplusplus
 }

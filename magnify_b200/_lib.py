@@ -74,6 +74,7 @@ SIGNATURES = {
     "mgb_tiff_page_info": [_P, _I64, POINTER(c_int64)],
     "mgb_tiff_description": [_P, _I64, c_char_p, _I64],
     "mgb_tiff_read_pages": [_P, POINTER(c_int64), _I64, _P, _I64, c_int],
+    "mgb_tiff_write": [c_char_p, _P, _I64, _I64, _I64, c_int, c_int, c_int, c_char_p, c_int],
     "mgb_tiff_read_files": [POINTER(c_char_p), _I64, _I64, _I64, _I64, c_int, _P, _I64, c_int],
 }
 _SPECIAL_RESTYPE = {"mgb_error_string": c_char_p, "mgb_launch_count": c_int64}
@@ -97,7 +98,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.argtypes = argtypes
         fn.restype = _SPECIAL_RESTYPE.get(name, c_int)
-    if lib.mgb_abi_version() != 10:
+    if lib.mgb_abi_version() != 11:
         raise ImportError("libmagnify_b200.so ABI version mismatch; rebuild with `python -m magnify_b200.build --force`")
     _lib = lib
     return lib

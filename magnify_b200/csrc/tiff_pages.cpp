@@ -607,3 +607,120 @@ int mgb_tiff_read_files(const char* const* host_paths, int64_t n_files, int64_t 
 }
 
 }  // extern "C"
+
+// ---- writer: uncompressed little-endian pages, one strip each, directories after the pixel data ----
+namespace {
+
+bool pwrite_all(int fd, const void* src, uint64_t n, uint64_t off) {
+  const uint8_t* p = static_cast<const uint8_t*>(src);
+  while (n > 0) {
+    const ssize_t put = ::pwrite(fd, p, n, static_cast<off_t>(off));
+    if (put < 0) {
+      if (errno == EINTR) continue;
+      return false;
+    }
+    p += put;
+    off += static_cast<uint64_t>(put);
+    n -= static_cast<uint64_t>(put);
+  }
+  return true;
+}
+
+template <typename T>
+void put(std::vector<uint8_t>& buf, T v) {   // host is little-endian on every platform this library builds for
+  const uint8_t* b = reinterpret_cast<const uint8_t*>(&v);
+  buf.insert(buf.end(), b, b + sizeof(T));
+}
+
+void put_entry(std::vector<uint8_t>& buf, bool big, uint16_t tag, uint16_t type, uint64_t count, uint64_t value) {
+  put<uint16_t>(buf, tag);
+  put<uint16_t>(buf, type);
+  if (big) {
+    put<uint64_t>(buf, count);
+    put<uint64_t>(buf, value);
+  } else {
+    put<uint32_t>(buf, static_cast<uint32_t>(count));
+    put<uint32_t>(buf, static_cast<uint32_t>(value));
+  }
+}
+
+}  // namespace
+
+extern "C" int mgb_tiff_write(const char* host_path, const void* host_pages, int64_t n_pages, int64_t height,
+                              int64_t width, int bits, int sample_format, int bigtiff, const char* host_description,
+                              int threads) {
+  if (!host_path || !host_pages || n_pages <= 0 || height <= 0 || width <= 0) return MGB_EINVAL;
+  if ((bits != 8 && bits != 16 && bits != 32 && bits != 64) || sample_format < 1 || sample_format > 3) return MGB_EINVAL;
+  if (!host_is_little()) return MGB_EUNSUPPORTED;
+  const uint64_t page_bytes = static_cast<uint64_t>(height) * width * (bits / 8);
+  const uint64_t desc_len = host_description ? std::strlen(host_description) + 1 : 0;
+  const uint64_t header = 16;                                   // classic files simply leave 8 bytes unused
+  const uint64_t desc_off = header + page_bytes * n_pages;      // description, then the directories
+  const bool big = bigtiff > 0 || (bigtiff < 0 && desc_off + desc_len + 256ull * n_pages > 0xfff00000ull);
+  if (!big && desc_off + desc_len + 256ull * n_pages > 0xfff00000ull) return MGB_EINVAL;   // needs BigTIFF
+  const int n_entries = host_description ? 11 : 10;
+  const uint64_t ifd_bytes = (big ? 8 : 2) + static_cast<uint64_t>(n_entries) * (big ? 20 : 12) + (big ? 8 : 4);
+  uint64_t ifd0 = desc_off + desc_len;
+  ifd0 += ifd0 & 1;                                             // directories start on an even offset
+  int rc = MGB_OK;
+  const int fd = ::open(host_path, O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0644);
+  if (fd < 0) return MGB_EIO;
+  try {
+    std::vector<uint8_t> head;
+    head.push_back('I');
+    head.push_back('I');
+    if (big) {
+      put<uint16_t>(head, 43);
+      put<uint16_t>(head, 8);
+      put<uint16_t>(head, 0);
+      put<uint64_t>(head, ifd0);
+    } else {
+      put<uint16_t>(head, 42);
+      put<uint32_t>(head, static_cast<uint32_t>(ifd0));
+      head.resize(16, 0);
+    }
+    std::vector<uint8_t> dirs;
+    for (int64_t k = 0; k < n_pages; ++k) {
+      if (big) put<uint64_t>(dirs, static_cast<uint64_t>(n_entries));
+      else put<uint16_t>(dirs, static_cast<uint16_t>(n_entries));
+      const bool with_desc = host_description && k == 0;
+      put_entry(dirs, big, 256, 4, 1, static_cast<uint64_t>(width));
+      put_entry(dirs, big, 257, 4, 1, static_cast<uint64_t>(height));
+      put_entry(dirs, big, 258, 3, 1, static_cast<uint64_t>(bits));
+      put_entry(dirs, big, 259, 3, 1, 1);
+      put_entry(dirs, big, 262, 3, 1, 1);
+      if (host_description) {   // later pages carry a one-byte (empty) description so that every directory has the same size
+        if (with_desc && desc_len > (big ? 8u : 4u)) {
+          put_entry(dirs, big, 270, 2, desc_len, desc_off);
+        } else if (with_desc) {   // short enough to live in the value field itself
+          uint64_t packed = 0;
+          std::memcpy(&packed, host_description, desc_len);
+          put_entry(dirs, big, 270, 2, desc_len, packed);
+        } else {
+          put_entry(dirs, big, 270, 2, 1, 0);
+        }
+      }
+      put_entry(dirs, big, 273, big ? 16 : 4, 1, header + page_bytes * k);
+      put_entry(dirs, big, 277, 3, 1, 1);
+      put_entry(dirs, big, 278, 4, 1, static_cast<uint64_t>(height));
+      put_entry(dirs, big, 279, big ? 16 : 4, 1, page_bytes);
+      put_entry(dirs, big, 339, 3, 1, static_cast<uint64_t>(sample_format));
+      const uint64_t next = k + 1 < n_pages ? ifd0 + ifd_bytes * (k + 1) : 0;
+      if (big) put<uint64_t>(dirs, next);
+      else put<uint32_t>(dirs, static_cast<uint32_t>(next));
+    }
+    if (!pwrite_all(fd, head.data(), head.size(), 0)) rc = MGB_EIO;
+    if (rc == MGB_OK && desc_len && !pwrite_all(fd, host_description, desc_len, desc_off)) rc = MGB_EIO;
+    if (rc == MGB_OK && !pwrite_all(fd, dirs.data(), dirs.size(), ifd0)) rc = MGB_EIO;
+    if (rc == MGB_OK) {
+      const uint8_t* src = static_cast<const uint8_t*>(host_pages);
+      rc = parallel_for(n_pages, threads, [&](int64_t k) {
+        return pwrite_all(fd, src + page_bytes * k, page_bytes, header + page_bytes * k) ? MGB_OK : MGB_EIO;
+      });
+    }
+  } catch (...) {
+    rc = MGB_EIO;
+  }
+  if (::close(fd) != 0 && rc == MGB_OK) rc = MGB_EIO;
+  return rc;
+}

@@ -135,6 +135,25 @@ def read_files(paths: Sequence[str], out: np.ndarray, page: int = 0, threads: in
     return out
 
 
+def write_tiff(path, pages: np.ndarray, description: Optional[str] = None, bigtiff: Optional[bool] = None,
+               threads: int = 8) -> str:
+    """Save (H, W) or (N, H, W) pages as an uncompressed TIFF / BigTIFF (one strip per page, parallel
+    writes) -- e.g. a stitched image or a stack of crops taken from the pinned result buffers.  The
+    reference has no TIFF output (it caches to zarr); this is the inverse of the page reader."""
+    arr = np.ascontiguousarray(pages)
+    if arr.ndim == 2:
+        arr = arr[None]
+    if arr.ndim != 3:
+        raise ValueError(f"pages must be (H, W) or (N, H, W), got {arr.shape}")
+    kind = {"u": 1, "i": 2, "f": 3}.get(arr.dtype.kind)
+    if kind is None or arr.dtype.itemsize not in (1, 2, 4, 8) or arr.dtype.byteorder == ">":
+        raise TypeError(f"unsupported dtype {arr.dtype}")
+    _lib.call("mgb_tiff_write", os.fspath(path).encode(), ctypes.c_void_p(arr.ctypes.data), arr.shape[0], arr.shape[1],
+              arr.shape[2], arr.dtype.itemsize * 8, kind, -1 if bigtiff is None else int(bool(bigtiff)),
+              None if description is None else description.encode(), int(threads))
+    return os.fspath(path)
+
+
 # ---------------------------------------------------------------------------------------------
 # path patterns  (reader.py:80-160)
 # ---------------------------------------------------------------------------------------------

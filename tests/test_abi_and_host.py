@@ -29,7 +29,7 @@ def test_library_exports_header_symbols(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mgb_abi_version() == 10
+    assert lib.mgb_abi_version() == 11
     assert lib.mgb_error_string(-2).decode().startswith("pointer")
 
 

@@ -317,3 +317,29 @@ def test_corrupt_compressed_data_is_an_error(tmp_path):
                     tif.asarray(0)                                   # wrong pixels are acceptable, a crash is not
             except _lib.MagnifyB200Error:
                 pass
+
+
+def test_write_tiff_round_trip(tmp_path):
+    """reader.write_tiff -> the native reader, the struct-level oracle and libtiff all read the same pages."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(9)
+    for dtype in (np.uint8, np.uint16, np.int16, np.float32, np.float64):
+        pages = (rng.random((3, 45, 67)) * 200).astype(dtype)
+        for big, desc in ((False, None), (True, "stitched image, channel egfp"), (None, "x")):
+            path = reader.write_tiff(os.path.join(tmp_path, "w.tif"), pages, description=desc, bigtiff=big, threads=3)
+            with reader.TiffFile(path) as tif:
+                assert tif.num_pages == 3 and bool(tif.page_info(0).bigtiff) == bool(big)
+                np.testing.assert_array_equal(tif.read_pages([0, 1, 2]), pages)
+                assert tif.description(0) == (desc.encode() if desc else b"")
+            for k in range(3):
+                np.testing.assert_array_equal(ot.read_page(path, k), pages[k])
+            if dtype != np.float64 and dtype != np.int16:
+                ok, decoded = cv2.imreadmulti(path, flags=cv2.IMREAD_UNCHANGED)
+                assert ok and len(decoded) == 3 and np.array_equal(np.stack(decoded), pages)
+    single = reader.write_tiff(os.path.join(tmp_path, "s.tif"), pages[0])
+    with reader.TiffFile(single) as tif:
+        assert tif.num_pages == 1
+    with pytest.raises(ValueError):
+        reader.write_tiff(os.path.join(tmp_path, "bad.tif"), np.zeros((2, 2, 2, 2), np.uint8))
+    with pytest.raises(_lib.MagnifyB200Error):
+        reader.write_tiff(os.path.join(tmp_path, "no_such_dir", "x.tif"), pages)
