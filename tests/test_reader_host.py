@@ -343,3 +343,14 @@ def test_write_tiff_round_trip(tmp_path):
         reader.write_tiff(os.path.join(tmp_path, "bad.tif"), np.zeros((2, 2, 2, 2), np.uint8))
     with pytest.raises(_lib.MagnifyB200Error):
         reader.write_tiff(os.path.join(tmp_path, "no_such_dir", "x.tif"), pages)
+
+
+def test_written_tiles_read_back_through_the_pattern_reader(tmp_path):
+    """reader.write_tiff + reader.Reader: a tile stack saved page by page comes back as the same
+    lazy (channel, time, tile_row, tile_col, tile_y, tile_x) array."""
+    rng = np.random.default_rng(10)
+    tiles = rng.integers(0, 65535, (2, 2, 2, 3, 20, 28), dtype=np.uint16)
+    for idx in np.ndindex(2, 2, 2, 3):
+        reader.write_tiff(os.path.join(tmp_path, f"w_c{idx[0]}_2024010{idx[1] + 1}-000000_{idx[2]}_{idx[3]}.tif"), tiles[idx])
+    (xp,) = list(reader.Reader(threads=2)(os.path.join(tmp_path, "w_(channel)_(time)_(row)_(col).tif")))
+    np.testing.assert_array_equal(np.asarray(xp["tile"]), tiles)
