@@ -3,7 +3,6 @@ declares; host-side logic (argument errors, copy-forward map, disc table, fast-p
 import os
 import re
 import subprocess
-import sys
 
 import numpy as np
 import pytest

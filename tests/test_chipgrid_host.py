@@ -53,7 +53,7 @@ def test_grid_centers_matches_reference_find_centers_tail(monkeypatch):
     """ButtonFinder.find_centers with its circle finder pinned to given points
     (find.py:205-306 executed in place) == chipgrid.merge_channel_points + grid_centers."""
     ref = reference_find()
-    from oracle._refload import LabelledArray, LabelledAssay
+    from oracle._refload import LabelledArray
 
     rng = np.random.default_rng(3)
     rows, cols, row_dist, col_dist = 6, 4, 50.0, 80.0

@@ -4,7 +4,6 @@ gather kernel itself through peer (symmetric) memory vs the NCCL all-gather."""
 import os
 import socket
 
-import numpy as np
 import pytest
 import torch
 

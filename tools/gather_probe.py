@@ -2,7 +2,7 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from magnify_b200 import _lib, ops, pipeline, synth
+from magnify_b200 import _lib, ops
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 dev = torch.device("cuda:0")
 lib = _lib.load()

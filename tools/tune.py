@@ -1,5 +1,5 @@
 """Kernel tuning probe (run on the GPU box): times the flat-field+stitch variants and the gather."""
-import sys, os, json
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from magnify_b200 import _lib, ops, pipeline, synth
