@@ -265,7 +265,7 @@ def run_b200_arm(args, cfg):
 
     image_out = _ops.alloc_image(plan.image_shape, torch.uint16, dev)
     roi_out = torch.empty((m, c, t, length, length), dtype=torch.uint16, device=dev)
-    stats_out = torch.empty((m, c, t, 6), dtype=torch.float64, device=dev)
+    stats_out = torch.empty((m, c, t, 8), dtype=torch.float64, device=dev)
     gathered = torch.empty((world,) + tuple(stats_out.shape), dtype=torch.float64, device=dev) if world > 1 else None
     symm = None
     if world > 1 and not args.no_fused_gather:

@@ -1,7 +1,9 @@
 """End-to-end demo on synthetic data: writes a small chip experiment as TIFF tiles
-(`chip_<channel>_<time>_<row>_<col>.tif`), then runs the chip pipeline the way `mg.microfluidic_chip`
-would -- read, flat-field + stitch, button finding (GPU), crops / masks / summaries, expression
-filter -- and prints what it found and how long each part took.
+(`chip_<channel>_<time>_<row>_<col>.tif`), then chains the GPU components by hand in the order
+`mg.microfluidic_chip_pipe` uses (registry.py:243-269) -- read, stitch, button finding, crops /
+masks / summaries, expression filter -- and prints what it found and how long each part took.
+With magnify installed the same components run inside its own pipeline after
+`magnify_b200.install()`.
 
     python examples/chip_demo.py [workdir]
 """
@@ -15,8 +17,8 @@ sys.path.insert(0, ROOT)
 
 import numpy as np
 
-from magnify_b200 import api
-from magnify_b200.components import filter_expression, quantify
+from magnify_b200 import reader
+from magnify_b200.components import ButtonFinder, Stitcher, filter_expression, quantify
 from magnify_b200.reader import write_tiff
 
 
@@ -65,28 +67,24 @@ def main():
     for b in blanks:
         tags[b] = ""
     t0 = time.perf_counter()
-    xp = api.microfluidic_chip(os.path.join(workdir, "chip_(channel)_(time)_(row)_(col).tif"), tags=tags, overlap=overlap,
-                               row_dist=126, col_dist=233, min_button_diameter=16, max_button_diameter=34,
-                               search_channel="egfp", num_iter=200000)
+    (xp,) = [reader.standardize_format(x) for x in
+             reader.Reader()(os.path.join(workdir, "chip_(channel)_(time)_(row)_(col).tif"))]
+    xp = xp.assign_coords(tag=(("mark_row", "mark_col"), tags),                      # identify_buttons, identify.py:36-45
+                          valid=(("mark_row", "mark_col", "time"), np.ones(tags.shape + (xp.sizes["time"],), bool)))
+    xp = Stitcher(overlap=overlap)(xp)
+    xp = ButtonFinder(row_dist=126, col_dist=233, min_button_diameter=16, max_button_diameter=34, chamber_diameter=60,
+                      search_channel="egfp", num_iter=200000)(xp)
     t1 = time.perf_counter()
     print(f"read + stitch + find buttons + crops/masks: {t1 - t0:.2f} s; roi {xp.roi.shape} {xp.roi.dtype}")
-    err = max(np.abs(xp.x.values[..., 0] - (np.arange(cols)[None, :] + 1) * 233).max(),
-              np.abs(xp.y.values[..., 0] - (np.arange(rows)[:, None] + 1) * 126).max())
+    x0, y0 = xp.x.values[:, 0].reshape(rows, cols), xp.y.values[:, 0].reshape(rows, cols)
+    err = max(np.abs(x0 - (np.arange(cols)[None, :] + 1) * 233).max(), np.abs(y0 - (np.arange(rows)[:, None] + 1) * 126).max())
     print(f"largest centre offset from the nominal grid: {err:.1f} px (the discs are jittered by +-2 px)")
 
-    # summaries and the expression filter work on the stacked (mark, ...) layout
-    from magnify_b200.dataset import Assay
-
-    m = rows * cols
-    stacked = Assay({"roi": (("mark", "channel", "time", "roi_y", "roi_x"), xp.roi.values.reshape((m,) + xp.roi.shape[2:]))},
-                    coords={"channel": (("channel",), xp.channel.values),
-                            "fg": (("mark", "time", "roi_y", "roi_x"), xp.fg.values.reshape((m,) + xp.fg.shape[2:])),
-                            "bg": (("mark", "time", "roi_y", "roi_x"), xp.bg.values.reshape((m,) + xp.bg.shape[2:])),
-                            "valid": (("mark", "time"), xp.valid.values.reshape(m, -1))})
-    stacked = filter_expression(quantify(stacked), search_channel="egfp")
-    expressed = stacked.valid.values[:, 0].reshape(rows, cols)
-    print(f"expressed chambers: {int(expressed.sum())} of {m} ({len(blanks)} were left empty)")
-    print("mean fg intensity (egfp, t=0) of the first row:", np.round(stacked.fg_mean.values[:cols, 1, 0]).astype(int).tolist())
+    # summaries (already computed by the gather) and the expression filter
+    xp = filter_expression(quantify(xp), search_channel="egfp")
+    expressed = xp.valid.values[:, 0].reshape(rows, cols)
+    print(f"expressed chambers: {int(expressed.sum())} of {rows * cols} ({len(blanks)} were left empty)")
+    print("mean fg intensity (egfp, t=0) of the first row:", np.round(xp.fg_mean.values[:cols, 1, 0]).astype(int).tolist())
 
 
 if __name__ == "__main__":

@@ -22,7 +22,7 @@
  *   boxes  (M, T, 2) int32       (top, left) of every marker's ROI at every timepoint
  *   roi    (M, C, T, L, L)       find.py:533 / find.py:89-92 after the stack at :182
  *   fg,bg  (M, Tm, L, L) uint8   0/1 masks; Tm = number of distinct mask timesteps
- *   stats  (M, C, T, 6) float64  n_fg, n_bg, sum_fg, sum_bg, mean_fg, mean_bg
+ *   stats  (M, C, T, 8) float64  n_fg, n_bg, sum_fg, sum_bg, mean_fg, mean_bg, median_fg, median_bg
  */
 #ifndef MAGNIFY_B200_H
 #define MAGNIFY_B200_H
@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MGB_ABI_VERSION 11
+#define MGB_ABI_VERSION 12
 
 #define MGB_OK 0
 #define MGB_EINVAL (-1)      /* bad argument (null pointer, negative size, bad itemsize ...) */
@@ -149,34 +149,53 @@ int mgb_roi_gather(const void* image, int64_t image_pitch, int64_t C, int64_t T,
                    int itemsize, const int32_t* boxes, const int32_t* order, int64_t M, int L, void* roi,
                    void* stream);
 /* Gather fused with the masked reductions the consumers run (identify.py:76-80,
- * filter.py:21-22,51, README.md:21-22): uint16 only.  mask_t (T) int32 maps each timepoint to
+ * filter.py:21-22,51,74,82, README.md:21-22): uint16 only.  mask_t (T) int32 maps each timepoint to
  * its mask timestep in fg/bg (M, Tm, L, L) (beads: all 0, find.py:585-586; chip: the source
- * search timestep, find.py:151,172-173).  roi may be NULL (summaries only).  stats (M,C,T,6)
- * float64: exact integer sums, mean = sum / count (NaN for an empty mask, like nanmean). */
+ * search timestep, find.py:151,172-173); any non-zero mask byte counts as set.  roi may be NULL
+ * (summaries only).  stats (M,C,T,8) float64: counts, exact integer sums, mean = sum / count (NaN
+ * for an empty mask, like nanmean), and the exact masked medians (mean of the two middle values
+ * for even counts, NaN for an empty mask, like nanmedian).
+ *
+ * fg_count_max / bg_count_max: upper bounds of the number of set pixels in any fg / bg mask (from
+ * mgb_mask_count_max, or -1 = unknown).  With bounds of at most 1024 / 2560 pixels the kernel
+ * compacts each marker's masks into offset lists once and takes sums AND medians from the staged
+ * window in the same pass (want_median != 0).  Otherwise (unknown or larger masks, unaligned
+ * images, L > 256) the sums come from the dp2a / plain kernels and the two median columns are
+ * left NaN: *host_median_done (host pointer, nullable) tells the caller which happened so that it
+ * can run mgb_roi_median_u16 on the crops. */
 int mgb_roi_gather_stats_u16(const uint16_t* image, int64_t image_pitch, int64_t C, int64_t T, int64_t H,
                              int64_t W, const int32_t* boxes, const int32_t* order, const int32_t* mask_t,
                              int64_t Tm, const uint8_t* fg, const uint8_t* bg, int64_t M, int L,
-                             uint16_t* roi, double* stats, void* stream);
+                             uint16_t* roi, double* stats, int want_median, int fg_count_max,
+                             int bg_count_max, int* host_median_done, void* stream);
+/* counts[0] = max over the n_masks fg masks of their non-zero bytes, counts[1] likewise for bg
+ * (device int32[2]; mask_len = L*L bytes per mask). */
+int mgb_mask_count_max(const uint8_t* fg, const uint8_t* bg, int64_t n_masks, int64_t mask_len,
+                       int32_t* counts, void* stream);
 /* Multi-GPU variant: the summaries are written by the kernel itself into the gathered buffer of
  * EVERY rank over NVLink peer memory (no separate all-gather).  host_peer_stats[j] (host array of
- * n_peers <= 8 device addresses) points at THIS rank's (M,C,T,6) block inside rank j's gathered
- * (ranks,M,C,T,6) buffer (peer-mapped, e.g. torch symmetric memory); the caller synchronises the
+ * n_peers <= 8 device addresses) points at THIS rank's (M,C,T,8) block inside rank j's gathered
+ * (ranks,M,C,T,8) buffer (peer-mapped, e.g. torch symmetric memory); the caller synchronises the
  * ranks afterwards.  Needs the staged kernels (else MGB_EUNSUPPORTED). */
 int mgb_roi_gather_stats_peers_u16(const uint16_t* image, int64_t image_pitch, int64_t C, int64_t T,
                                    int64_t H, int64_t W, const int32_t* boxes, const int32_t* order, const int32_t* mask_t,
                                    int64_t Tm, const uint8_t* fg, const uint8_t* bg, int64_t M, int L,
                                    uint16_t* roi, const uint64_t* host_peer_stats, int n_peers,
-                                   void* stream);
+                                   int want_median, int fg_count_max, int bg_count_max,
+                                   int* host_median_done, void* stream);
 /* The same summaries from an roi that already exists (the `quantify` component on a dataset
- * produced elsewhere): roi (M,C,T,L,L) uint16 -> stats (M,C,T,6). */
+ * produced elsewhere): roi (M,C,T,L,L) uint16 -> stats (M,C,T,8), median columns NaN. */
 int mgb_roi_stats_u16(const uint16_t* roi, int64_t M, int64_t C, int64_t T, int L,
                       const int32_t* mask_t, int64_t Tm, const uint8_t* fg, const uint8_t* bg,
                       double* stats, void* stream);
 /* Exact masked median per (m,c,t) of a uint16 roi (M,C,T,L,L) (identify.py:79, filter.py:21-22):
- * mean of the two middle values for even counts, NaN for an empty mask, as np.nanmedian. */
+ * mean of the two middle values for even counts, NaN for an empty mask, as np.nanmedian.  Any L
+ * (keys in registers up to L = 160, re-read per bisection step above).  The result for ROI n goes
+ * to median[n * median_stride] (1 = dense (M,C,T); 8 with median = stats + 6 / + 7 fills the
+ * median columns of a stats buffer). */
 int mgb_roi_median_u16(const uint16_t* roi, int64_t M, int64_t C, int64_t T, int L,
                        const int32_t* mask_t, int64_t Tm, const uint8_t* mask, double* median,
-                       void* stream);
+                       int64_t median_stride, void* stream);
 
 /* The same two reductions for a float32 roi (the reference accepts float images, tests/test_chip.py:76-96):
  * float64 accumulation in a fixed order, NaN pixels skipped (nanmean / nanmedian); the median is the
@@ -184,7 +203,7 @@ int mgb_roi_median_u16(const uint16_t* roi, int64_t M, int64_t C, int64_t T, int
 int mgb_roi_stats_f32(const float* roi, int64_t M, int64_t C, int64_t T, int L, const int32_t* mask_t, int64_t Tm,
                       const uint8_t* fg, const uint8_t* bg, double* stats, void* stream);
 int mgb_roi_median_f32(const float* roi, int64_t M, int64_t C, int64_t T, int L, const int32_t* mask_t, int64_t Tm,
-                       const uint8_t* mask, double* median, void* stream);
+                       const uint8_t* mask, double* median, int64_t median_stride, void* stream);
 
 /* ---- F8: chip masks, reference utils.py:30-52 through find.py:380-400 ----------------------
  * fg[m] = disc(radius r_fg[m]), bg[m] = annulus(r_inner < d <= r_outer) centred on rel[m] =

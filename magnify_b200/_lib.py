@@ -43,13 +43,15 @@ SIGNATURES = {
     "mgb_copy2d_async": [_P, _I64, _P, _I64, _I64, _I64, c_int, _P],
     "mgb_bounding_boxes": [_P, _P, _I64, c_int, _I64, _I64, _P, _P, _P],
     "mgb_roi_gather": [_P, _I64, _I64, _I64, _I64, _I64, c_int, _P, _P, _I64, c_int, _P, _P],
-    "mgb_roi_gather_stats_u16": [_P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _I64, _P, _P, _I64, c_int, _P, _P, _P],
+    "mgb_roi_gather_stats_u16": [_P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _I64, _P, _P, _I64, c_int, _P, _P,
+                                 c_int, c_int, c_int, POINTER(c_int), _P],
+    "mgb_mask_count_max": [_P, _P, _I64, _I64, _P, _P],
     "mgb_roi_gather_stats_peers_u16": [_P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _I64, _P, _P, _I64, c_int, _P,
-                                       POINTER(ctypes.c_uint64), c_int, _P],
+                                       POINTER(ctypes.c_uint64), c_int, c_int, c_int, c_int, POINTER(c_int), _P],
     "mgb_roi_stats_u16": [_P, _I64, _I64, _I64, c_int, _P, _I64, _P, _P, _P, _P],
-    "mgb_roi_median_u16": [_P, _I64, _I64, _I64, c_int, _P, _I64, _P, _P, _P],
+    "mgb_roi_median_u16": [_P, _I64, _I64, _I64, c_int, _P, _I64, _P, _P, _I64, _P],
     "mgb_roi_stats_f32": [_P, _I64, _I64, _I64, c_int, _P, _I64, _P, _P, _P, _P],
-    "mgb_roi_median_f32": [_P, _I64, _I64, _I64, c_int, _P, _I64, _P, _P, _P],
+    "mgb_roi_median_f32": [_P, _I64, _I64, _I64, c_int, _P, _I64, _P, _P, _I64, _P],
     "mgb_chip_masks": [_P, _P, c_int, c_int, _I64, c_int, _P, _P, _P, _P],
     "mgb_disc_halfwidths": [c_int, POINTER(ctypes.c_int32)],
     "mgb_bead_labels": [_P, _I64, _I64, _I64, _P, c_int, _P, _P],
@@ -93,12 +95,14 @@ def load() -> ctypes.CDLL:
             f"{LIB_PATH} is missing. magnify_b200 has no CPU fallback: build the CUDA library with "
             "`python -m magnify_b200.build` (needs nvcc)."
         )
+    import torch  # noqa: F401  (loads the CUDA runtime the library links against dynamically)
+
     lib = ctypes.CDLL(LIB_PATH)
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.argtypes = argtypes
         fn.restype = _SPECIAL_RESTYPE.get(name, c_int)
-    if lib.mgb_abi_version() != 11:
+    if lib.mgb_abi_version() != 12:
         raise ImportError("libmagnify_b200.so ABI version mismatch; rebuild with `python -m magnify_b200.build --force`")
     _lib = lib
     return lib

@@ -1,7 +1,10 @@
 """Build recipe for libmagnify_b200.so (nvcc, sm_100a only, in-tree).
 
-`python -m magnify_b200.build` or `__graft_entry__.build()`.  The library is rebuilt when any
-source or header is newer than the .so.  nvcc cross-compiles without a GPU.
+`python -m magnify_b200.build [--force] [-v]` or `__graft_entry__.build()`.  Every source is
+compiled to an object file under magnify_b200/build/ (in parallel, only when it or a header is
+newer than its object) and the objects are linked into the shared library.  nvcc cross-compiles
+without a GPU.  The CUDA runtime is linked dynamically (`-cudart shared`): the process already
+has torch's libcudart, and the shipped library then carries no runtime of its own.
 """
 from __future__ import annotations
 
@@ -9,16 +12,19 @@ import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
+OBJ_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libmagnify_b200.so")
-SOURCES = ("flatfield_stitch.cu", "roi.cu", "roi_tma.cu", "masks.cu", "circles.cu", "circles_sample.cu", "circles_host.cpp", "tiff_pages.cpp")
+SOURCES = ("flatfield_stitch.cu", "roi.cu", "roi_tma.cu", "roi_lists.cu", "masks.cu", "circles.cu",
+           "circles_sample.cu", "circles_host.cpp", "tiff_pages.cpp")
 NVCC_FLAGS = (
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-O3", "-lineinfo", "-std=c++17", "-cudart", "shared",
+    "-Xcompiler", "-fPIC",
 )
 
 
@@ -29,31 +35,57 @@ def find_nvcc() -> str:
     raise RuntimeError("nvcc not found; magnify_b200 has no CPU fallback and cannot be built without it")
 
 
-def _inputs():
-    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".cpp"))]
+def _headers():
+    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     files += [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE) if f.endswith(".h")]
     return files
+
+
+def _obj(src: str) -> str:
+    return os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
+
+
+def _stale(src: str) -> bool:
+    obj = _obj(src)
+    if not os.path.exists(obj):
+        return True
+    built = os.path.getmtime(obj)
+    return any(os.path.getmtime(f) > built for f in [os.path.join(CSRC, src)] + _headers())
 
 
 def needs_build() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     built = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(f) > built for f in _inputs())
+    inputs = [os.path.join(CSRC, s) for s in SOURCES] + _headers()
+    return any(os.path.getmtime(f) > built for f in inputs)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return LIB_PATH
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-I", INCLUDE]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-lz", "-o", LIB_PATH]   # zlib: Deflate-compressed TIFF pages
+def _run(cmd, verbose: bool) -> None:
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed building libmagnify_b200.so:\n" + proc.stderr[-4000:])
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = find_nvcc()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    todo = [s for s in SOURCES if force or _stale(s)]
+
+    def compile_one(src):
+        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", _obj(src)]
+        if verbose:
+            cmd += ["-Xptxas", "-v"]
+        _run(cmd, verbose)
+
+    with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 1) or 1) as pool:
+        list(pool.map(compile_one, todo))
+    # zlib: Deflate-compressed TIFF pages
+    _run([nvcc, *NVCC_FLAGS, "-shared", *[_obj(s) for s in SOURCES], "-lz", "-o", LIB_PATH], verbose)
     return LIB_PATH
 
 

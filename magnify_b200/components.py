@@ -2,11 +2,20 @@
 magnify's own (`src/magnify/preprocess.py:62-88`, `stitch.py:6-50`, `find.py:13-629`), with the
 pixel work done on the GPU through `magnify_b200.ops`.
 
-A component is a callable `Dataset -> Dataset`.  "Dataset" is an `xarray.Dataset` when xarray
-is installed, or `magnify_b200.dataset.Assay` (a minimal stand-in with the same accessors).
-`install()` registers the factories in `magnify.registry.components` under the reference's own
-names so that `mg.mrbles`, `mg.beads` and `mg.microfluidic_chip` pick them up unchanged
-(INTEGRATION.md).
+A component is a callable `Dataset -> Dataset` written against the xarray API: it takes and
+returns `xarray.Dataset` when xarray is installed and `magnify_b200.dataset.Dataset` (the same
+API, SURVEY.md section 8b "Caveat") when it is not.  `install()` registers the factories in
+`magnify.registry.components` under the reference's own names, so `mg.mrbles`, `mg.beads`,
+`mg.microfluidic_chip` and their `*_pipe` builders run them unchanged (INTEGRATION.md;
+tests/test_dropin_reference.py executes exactly that against the reference's own package).
+
+Hand-off between components stays on the device: what a component stores in the dataset is a
+`devarray.DeviceArray` -- the next GPU component takes the tensor from it, the host copy is made
+once (pinned memory, copy stream, started in the background) when somebody reads the values.
+`flatfield_correct` is lazy like the reference's (there it is a dask graph that executes inside
+`stitch`'s cache call): followed by `stitch` it runs as ONE fused
+flat-field + stitch kernel over tiles that are uploaded once, with the maxima pass overlapping
+the upload.
 
 Centre finding (`utils.find_circles`, a random search the reference cannot reproduce from run to
 run) runs on the GPU with a seeded sampler (`magnify_b200.circles`,
@@ -22,16 +31,21 @@ from typing import Callable, Optional
 import numpy as np
 import torch
 
-from . import chipgrid, circles, ops, pipeline
-from .dataset import Assay  # noqa: F401  (re-exported: the stand-in Dataset type of this module)
+from . import circles, devarray, ops, pipeline
+from .devarray import DeviceArray, LazyArray
 
 TILE_DIMS = ("channel", "time", "tile_row", "tile_col", "tile_y", "tile_x")
 IMAGE_DIMS = ("channel", "time", "im_y", "im_x")
 
 
 # ---------------------------------------------------------------------------------------------
-# dataset adapters (xarray.Dataset or Assay)
+# dataset adapters
 # ---------------------------------------------------------------------------------------------
+def _raw(var):
+    """The array object behind a DataArray WITHOUT converting it (NumPy, dask, DeviceArray ...)."""
+    return var.data if hasattr(var, "dims") else var
+
+
 def _to_numpy(var) -> np.ndarray:
     return var.to_numpy() if hasattr(var, "to_numpy") else np.asarray(var)
 
@@ -42,61 +56,136 @@ def _device(device) -> torch.device:
     return torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
 
 
-def _image_to_device(assay, dev) -> torch.Tensor:
-    """Upload assay["image"] into an x-padded device image (aligned rows for the staged gather)."""
-    arr = np.ascontiguousarray(_to_numpy(assay["image"]))
-    host = torch.from_numpy(arr)
-    image = ops.alloc_image(host.shape, host.dtype, dev)
-    image.copy_(host)
-    return image
+def _emit(tensor: torch.Tensor, as_bool: bool = False, extras=None, prefetch: bool = True) -> DeviceArray:
+    arr = DeviceArray(tensor, as_bool=as_bool, extras=extras)
+    return arr.prefetch() if (prefetch and devarray.PREFETCH) else arr
 
 
-def _tiles_to_device(assay, dev) -> torch.Tensor:
-    tile = assay["tile"]
-    if tuple(tile.dims) != TILE_DIMS:
-        raise ValueError(f"tile must have dims {TILE_DIMS} (run standardize_format first), got {tuple(tile.dims)}")
-    values = getattr(tile, "values", None)
-    if hasattr(values, "blocks"):
-        # lazily read TIFF tiles (reader.TiffTiles): pages land in a pinned buffer, then HBM
-        host = torch.empty(tuple(values.shape), dtype=getattr(torch, str(values.dtype)), pin_memory=True)
-        values.read((), host.numpy())
-        return host.to(dev, non_blocking=True)
-    return torch.from_numpy(np.ascontiguousarray(_to_numpy(tile))).to(dev)
+def _torch_dtype(np_dtype) -> torch.dtype:
+    return torch.from_numpy(np.empty(0, dtype=np.dtype(np_dtype))).dtype
 
 
-def _roi_to_device(roi: np.ndarray, dev) -> torch.Tensor:
-    """Upload a roi for the reductions: uint16 as is; any other dtype the reference accepts
-    (float images, tests/test_chip.py:76-96; 8-bit) as float32, which represents uint8 / int16 /
-    float32 values exactly."""
-    roi = np.ascontiguousarray(roi)
-    if roi.dtype == np.uint16:
-        return torch.from_numpy(roi).to(dev)
-    if roi.dtype in (np.float32, np.uint8, np.int8, np.int16):
-        return torch.from_numpy(roi.astype(np.float32)).to(dev)
-    raise TypeError(f"roi dtype {roi.dtype} is not supported by the GPU reductions (uint16, float32, 8/16-bit integers)")
+def _is_pinned(arr: np.ndarray) -> bool:
+    return arr.size > 0 and arr.flags.c_contiguous and torch.from_numpy(arr.reshape(-1)[:1]).is_pinned()
+
+
+def _image_on_device(assay, dev) -> torch.Tensor:
+    """assay["image"] as a device tensor with 16-byte aligned rows: the tensor `stitch` left there
+    (no copy at all), or an upload of host values into an x-padded buffer."""
+    data = _raw(assay["image"])
+    if isinstance(data, DeviceArray) and data.tensor.device == dev:
+        t = data.tensor
+        try:
+            ops.image_pitch(t)
+            return t
+        except ValueError:
+            out = ops.alloc_image(t.shape, t.dtype, dev)
+            out.copy_(t)
+            return out
+    host = np.ascontiguousarray(_to_numpy(assay["image"]))
+    out = ops.alloc_image(host.shape, _torch_dtype(host.dtype), dev)
+    src = torch.from_numpy(host)
+    out.copy_(src, non_blocking=_is_pinned(host))
+    return out
+
+
+class PendingFlatfield(LazyArray):
+    """`flatfield_correct(tile)` not yet evaluated: the raw tile stack plus the flat / dark
+    fields.  `stitch` consumes it with the fused kernel; reading it (`np.asarray`) evaluates the
+    correction alone on the GPU."""
+
+    def __init__(self, raw, flat, dark, device):
+        self.raw, self.flat, self.dark, self.device = raw, flat, dark, device
+        self._host = None
+
+    shape = property(lambda self: tuple(self.raw.shape))
+    dtype = property(lambda self: np.dtype(self.raw.dtype))
+
+    def numpy(self) -> np.ndarray:
+        if self._host is None:
+            dev = _device(self.device)
+            tiles = _stage_tiles(self.raw, dev, None)
+            self._host = ops.flatfield_correct(tiles, self.flat, self.dark).cpu().numpy()
+        return self._host
+
+
+def _stage_tiles(src, dev, ff: Optional[ops.FlatFieldPlan]) -> torch.Tensor:
+    """Tile stack (C,T,R,Cc,H,W) -> device tensor, block by (channel, time) block on the copy
+    stream, with flat-field pass 1 (`ff`, optional) running on the compute stream as the blocks
+    land.  src: DeviceArray (already there), a pinned or pageable NumPy array, a lazily read
+    stack with `blocks()` (reader.TiffTiles) or a dask array."""
+    maxima = ff is not None and not ff.identity
+    if isinstance(src, DeviceArray):
+        tiles = src.tensor.contiguous()
+        if maxima:
+            ops.flatfield_maxima(tiles, ff)
+        return tiles
+    shape = tuple(int(s) for s in src.shape)
+    if len(shape) != 6:
+        raise ValueError(f"tile must have 6 dims {TILE_DIMS}, got shape {shape}")
+    dtype = _torch_dtype(src.dtype)
+    tiles = torch.empty(shape, dtype=dtype, device=dev)
+    if tiles.numel() == 0:
+        return tiles
+    compute = torch.cuda.current_stream(dev)
+    streams = devarray.Streams.of(dev)
+    streams.h2d.wait_stream(compute)
+    if maxima:
+        ff.maxima.zero_()
+
+    def landed(ci, ti, ev):
+        compute.wait_event(ev)
+        if maxima:
+            ops.flatfield_maxima_accumulate(tiles[ci, ti], ff, ci)
+
+    if isinstance(src, np.ndarray) and _is_pinned(src):
+        host = torch.from_numpy(src)
+        for ti in range(shape[1]):
+            for ci in range(shape[0]):
+                with torch.cuda.stream(streams.h2d):
+                    tiles[ci, ti].copy_(host[ci, ti], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(streams.h2d)
+                landed(ci, ti, ev)
+    else:
+        # pageable memory, dask chunks, TIFF pages: through a ring of pinned slots
+        blocks = src.blocks() if callable(getattr(src, "blocks", None)) else pipeline.iter_blocks(src)
+        ring = pipeline.PinnedRing(shape[2:], dtype)
+        try:
+            for (ci, ti), block in blocks:
+                landed(ci, ti, ring.send(block, tiles[ci, ti], streams.h2d))
+        finally:
+            ring.close()
+    tiles.record_stream(streams.h2d)
+    return tiles
 
 
 def _read_tiff(path) -> np.ndarray:
     """Flat-field / dark-field image file (preprocess.py:75-81 reads it with tifffile): first page,
-    through the native uncompressed-TIFF reader."""
+    through the native TIFF reader."""
     from . import reader
 
     with reader.TiffFile(os.fspath(path)) as tif:
         return tif.asarray(0)
 
 
+def _field(value):
+    return _read_tiff(os.path.expanduser(value)) if isinstance(value, (str, os.PathLike)) else value
+
+
+def _check_tile(assay):
+    tile = assay["tile"]
+    if tuple(tile.dims) != TILE_DIMS:
+        raise ValueError(f"tile must have dims {TILE_DIMS} (run standardize_format first), got {tuple(tile.dims)}")
+    return tile
+
+
 # ---------------------------------------------------------------------------------------------
 # flatfield_correct  (preprocess.py:62-88)
 # ---------------------------------------------------------------------------------------------
 def flatfield_correct(xp, flatfield=1.0, darkfield=0.0, device=None):
-    if isinstance(flatfield, (str, os.PathLike)):
-        flatfield = _read_tiff(os.path.expanduser(flatfield))
-    if isinstance(darkfield, (str, os.PathLike)):
-        darkfield = _read_tiff(os.path.expanduser(darkfield))
-    dev = _device(device)
-    tiles = _tiles_to_device(xp, dev)
-    out = ops.flatfield_correct(tiles, flatfield, darkfield)
-    xp["tile"] = (TILE_DIMS, out.cpu().numpy())
+    tile = _check_tile(xp)
+    xp["tile"] = (TILE_DIMS, PendingFlatfield(_raw(tile), _field(flatfield), _field(darkfield), device))
     return xp
 
 
@@ -119,9 +208,18 @@ class Stitcher:
             raise AttributeError("Dataset must contain 'tile' data variable.")  # stitch.py:13-14
         sizes = assay.sizes
         ops.check_overlap(self.overlap, sizes["tile_y"], sizes["tile_x"])  # stitch.py:16-20
+        tile = _check_tile(assay)
         dev = _device(self.device)
-        image = ops.stitch(_tiles_to_device(assay, dev), self.overlap)
-        assay["image"] = (IMAGE_DIMS, ops.to_host_dense(image, non_blocking=False).numpy())
+        src = _raw(tile)
+        if isinstance(src, PendingFlatfield) and src._host is None:
+            # flatfield_correct + stitch: one upload, the maxima pass under it, one fused kernel
+            ff = ops.FlatFieldPlan(src.shape, src.flat, src.dark, device=dev)
+            tiles = _stage_tiles(src.raw, dev, ff)
+            image = ops.flatfield_stitch(tiles, overlap=self.overlap, plan=ff, maxima=None if ff.identity else ff.maxima)
+        else:
+            tiles = _stage_tiles(src.numpy() if isinstance(src, PendingFlatfield) else src, dev, None)
+            image = ops.stitch(tiles, self.overlap)
+        assay["image"] = (IMAGE_DIMS, _emit(image))
         return assay
 
 
@@ -130,34 +228,49 @@ def make_stitch(overlap: int = 102, device=None):
 
 
 class FlatfieldStitcher:
-    """flatfield_correct + stitch in one pass over the tiles (fused kernel); equivalent to the
-    two reference components back to back, minus the corrected `tile` variable (which the
-    predefined pipelines drop anyway, postprocess.py:6-17)."""
+    """flatfield_correct + stitch as one component (what the two registered components do when
+    they follow each other), for pipelines assembled by hand."""
 
     def __init__(self, flatfield=1.0, darkfield=0.0, overlap: int = 102, device=None):
         if overlap < 0:
             raise ValueError("Overlap must be non-negative.")
-        self.flatfield, self.darkfield, self.overlap, self.device = flatfield, darkfield, overlap, device
+        self.flatfield, self.darkfield = flatfield, darkfield
+        self.stitcher = Stitcher(overlap, device)
 
     def __call__(self, assay):
         if "tile" not in assay:
             raise AttributeError("Dataset must contain 'tile' data variable.")
-        sizes = assay.sizes
-        ops.check_overlap(self.overlap, sizes["tile_y"], sizes["tile_x"])
-        flat, dark = self.flatfield, self.darkfield
-        if isinstance(flat, (str, os.PathLike)):
-            flat = _read_tiff(os.path.expanduser(flat))
-        if isinstance(dark, (str, os.PathLike)):
-            dark = _read_tiff(os.path.expanduser(dark))
-        dev = _device(self.device)
-        image = ops.flatfield_stitch(_tiles_to_device(assay, dev), flat, dark, overlap=self.overlap)
-        assay["image"] = (IMAGE_DIMS, ops.to_host_dense(image, non_blocking=False).numpy())
-        return assay
+        raw = assay["tile"]
+        out = self.stitcher(flatfield_correct(assay, self.flatfield, self.darkfield, self.stitcher.device))
+        out["tile"] = raw          # left as it was (the pipelines drop it, postprocess.py:6-17)
+        return out
 
 
 # ---------------------------------------------------------------------------------------------
 # find_beads  (find.py:445-629)
 # ---------------------------------------------------------------------------------------------
+def _channel_names(assay, n_channels: int):
+    return list(_to_numpy(assay["channel"])) if "channel" in assay else list(range(n_channels))
+
+
+def _gather(image, boxes, fg, bg, mask_t, length):
+    """Crops of every marker, plus the summaries when the image dtype has the fused kernel."""
+    if image.dtype == torch.uint16 and boxes.shape[0] > 0:
+        return ops.roi_gather_stats(image, boxes, fg, bg, length, mask_t=mask_t, medians=True)
+    return ops.roi_gather(image, boxes, length), None
+
+
+def _emit_markers(roi_d, stats, fg_d, bg_d, mask_t: np.ndarray, mask_t_d):
+    """DeviceArrays of the crops and of the (M,T,L,L) masks.  The masks live on the device as their
+    distinct timesteps (M,Tm,L,L) and expand lazily; later components find the compact tensors
+    and the summaries the gather computed in `extras`."""
+    extras = {"stats": stats, "fg": fg_d, "bg": bg_d, "mask_t": mask_t_d}
+    roi = _emit(roi_d, extras=extras)
+    fg = _emit(fg_d, as_bool=True, extras=extras, prefetch=False).take(mask_t, 1)
+    bg = _emit(bg_d, as_bool=True, extras=extras, prefetch=False).take(mask_t, 1)
+    return roi, fg, bg
+
+
 class BeadFinder:
     """ROI/mask half of the reference BeadFinder on the GPU (find.py:503-605).
 
@@ -193,8 +306,8 @@ class BeadFinder:
 
         dev = _device(self.device)
         if image is None:
-            image = _image_to_device(assay, dev)
-        names = list(_to_numpy(assay["channel"])) if "channel" in assay else list(range(image.shape[0]))
+            image = _image_on_device(assay, dev)
+        names = _channel_names(assay, image.shape[0])
         channels = self.search_channels or names
         beads = np.empty((0, 3))
         for k, ch in enumerate(channels):
@@ -210,7 +323,7 @@ class BeadFinder:
 
     def __call__(self, assay):
         dev = _device(self.device)
-        image = _image_to_device(assay, dev)
+        image = _image_on_device(assay, dev)
         beads = self.find_centers(assay, image)
         c, t, him, wim = image.shape
         length = self.roi_length
@@ -219,19 +332,18 @@ class BeadFinder:
         y = np.repeat(beads[:, 0:1], t, axis=1)
         valid = np.ones((m, t), dtype=bool)  # find.py:551-554
         if m == 0:  # find.py:557-558
-            roi = np.empty((0, c, t, length, length), dtype=_to_numpy(assay["image"]).dtype)
+            roi = np.empty((0, c, t, length, length), dtype=np.dtype(assay["image"].dtype))
             fg = np.empty((0, t, length, length), dtype=bool)
             bg = fg.copy()
         else:
-            xd = torch.from_numpy(x).to(dev).contiguous()
-            yd = torch.from_numpy(y).to(dev).contiguous()
-            boxes = ops.bounding_boxes(xd, yd, length, wim, him)
+            boxes = ops.bounding_boxes(torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev), length, wim, him)
             labels = ops.bead_labels(torch.from_numpy(beads.astype(np.int64).astype(np.int32)).to(dev), him, wim)
             fg_d, bg_d = ops.bead_masks(labels, boxes[:, 0].contiguous(), length)
-            roi = ops.roi_gather(image, boxes, length).cpu().numpy()
-            # masks are time invariant (find.py:585-586): broadcast views, not copies
-            fg = np.broadcast_to(fg_d.cpu().numpy().astype(bool)[:, None], (m, t, length, length))
-            bg = np.broadcast_to(bg_d.cpu().numpy().astype(bool)[:, None], (m, t, length, length))
+            # masks are time invariant (find.py:585-586): one timestep on the device, broadcast on the host
+            fg_d, bg_d = fg_d[:, None].contiguous(), bg_d[:, None].contiguous()
+            mask_t_d = torch.zeros(t, dtype=torch.int32, device=dev)
+            roi_d, stats = _gather(image, boxes, fg_d, bg_d, mask_t_d, length)
+            roi, fg, bg = _emit_markers(roi_d, stats, fg_d, bg_d, np.zeros(t, dtype=np.int64), mask_t_d)
         assay["roi"] = (("mark", "channel", "time", "roi_y", "roi_x"), roi)
         return assay.assign_coords(
             fg=(("mark", "time", "roi_y", "roi_x"), fg), bg=(("mark", "time", "roi_y", "roi_x"), bg),
@@ -256,8 +368,8 @@ class ButtonFinder:
     centers: callable `(assay, t) -> (x, y, fg_radius)` giving, for a search timestep t, the final
     button centres in image coordinates (rows x cols float64 each) and the foreground radii
     (rows x cols int; max_button_radius where refinement found nothing, find.py:363,378).  When
-    omitted, centres are found here: full-image circle finding on the GPU, the reference's grid
-    clustering on the host (`chipgrid`), and the per-chamber refinement as one GPU batch
+    omitted, centres are found here: full-image circle finding on the GPU, the chip-grid fit on
+    the host (`gridfit`), and the per-chamber refinement as one GPU batch
     (find.py:205-306, 336-378; seeded, unlike the reference)."""
 
     def __init__(self, row_dist: float, col_dist: float, min_button_diameter: int, max_button_diameter: int,
@@ -285,7 +397,7 @@ class ButtonFinder:
         self.seed = seed
 
     def _search_channel_indexes(self, assay, n_channels: int):
-        names = list(_to_numpy(assay["channel"])) if "channel" in assay else list(range(n_channels))
+        names = _channel_names(assay, n_channels)
         wanted = self.kwargs["search_channel"]
         if wanted is None:
             return list(range(n_channels))
@@ -294,7 +406,9 @@ class ButtonFinder:
 
     def find_centers(self, assay, image: torch.Tensor, t: int):
         """find.py:205-306: circles of every search channel's full image at time t (GPU), merged
-        across channels, clustered into the chip grid and intersected (host) -> (mark_x, mark_y)."""
+        across channels, fitted to the chip grid (host) -> (mark_x, mark_y)."""
+        from . import gridfit
+
         kw = self.kwargs
         tag = _to_numpy(assay["tag"])
         points = np.empty((0, 2))
@@ -303,9 +417,9 @@ class ButtonFinder:
             found = circles.find_circles(img, kw["low_edge_quantile"], kw["high_edge_quantile"], 20, kw["num_iter"],
                                          self.min_button_radius, self.max_button_radius, kw["min_roundness"],
                                          self.chamber_radius, seed=self.seed + 1000 * t + k)[0]
-            points = chipgrid.merge_channel_points(points, found[:, :2].astype(np.float64), self.chamber_radius)
-        return chipgrid.grid_centers(points, tag, tuple(image.shape[-2:]), self.row_dist, self.col_dist,
-                                     self.chamber_radius, kw["top_chamber"], kw["left_chamber"], kw["cluster_penalty"])
+            points = gridfit.merge_channel_points(points, found[:, :2].astype(np.float64), self.chamber_radius)
+        return gridfit.grid_centers(points, tag, tuple(image.shape[-2:]), self.row_dist, self.col_dist,
+                                    self.chamber_radius, kw["top_chamber"], kw["left_chamber"], kw["cluster_penalty"])
 
     def refine(self, assay, image: torch.Tensor, t: int, x: np.ndarray, y: np.ndarray):
         """find.py:324-378: crop every chamber at its grid position, look for the best circle in
@@ -353,7 +467,7 @@ class ButtonFinder:
 
     def __call__(self, assay):
         dev = _device(self.device)
-        image = _image_to_device(assay, dev)
+        image = _image_on_device(assay, dev)
         c, t, him, wim = image.shape
         rows, cols = assay["tag"].shape
         m = rows * cols
@@ -375,43 +489,24 @@ class ButtonFinder:
         for k, ts in enumerate(search):
             f, b = ops.chip_masks(rel[:, ts].contiguous(), torch.from_numpy(radius[:, k].copy()).to(dev),
                                   self.max_button_radius, self.chamber_radius, length)
-            fgs.append(f.cpu().numpy().astype(bool))
-            bgs.append(b.cpu().numpy().astype(bool))
+            fgs.append(f)
+            bgs.append(b)
+        fg_d, bg_d = torch.stack(fgs, 1).contiguous(), torch.stack(bgs, 1).contiguous()   # (M, Ts, L, L)
         index = {ts: k for k, ts in enumerate(search)}
-        mask_t = np.array([index[int(s)] for s in src])
-        fg = np.stack(fgs, 1)[:, mask_t]  # find.py:172-173
-        bg = np.stack(bgs, 1)[:, mask_t]
-        roi = ops.roi_gather(image, boxes, length).cpu().numpy()
+        mask_t = np.array([index[int(s)] for s in src], dtype=np.int64)                   # find.py:172-173
+        mask_t_d = torch.from_numpy(mask_t.astype(np.int32)).to(dev)
+        roi_d, stats = _gather(image, boxes, fg_d, bg_d, mask_t_d, length)
         valid = _to_numpy(assay["valid"]) if "valid" in assay else np.ones((rows, cols, t), dtype=bool)
         valid = valid[:, :, src] if valid.ndim == 3 else valid
-        return self._emit(assay, roi, fg, bg, x, y, valid, rows, cols, t, length)
-
-    @staticmethod
-    def _emit(assay, roi, fg, bg, x, y, valid, rows, cols, t, length):
-        c = roi.shape[1]
-        try:
-            import xarray as xr
-        except Exception:
-            xr = None
-        if xr is not None and isinstance(assay, xr.Dataset):
-            assay["roi"] = (("mark_row", "mark_col", "channel", "time", "roi_y", "roi_x"),
-                            roi.reshape(rows, cols, c, t, length, length))
-            assay = assay.assign_coords(
-                fg=(("mark_row", "mark_col", "time", "roi_y", "roi_x"), fg.reshape(rows, cols, t, length, length)),
-                bg=(("mark_row", "mark_col", "time", "roi_y", "roi_x"), bg.reshape(rows, cols, t, length, length)),
-                x=(("mark_row", "mark_col", "time"), x), y=(("mark_row", "mark_col", "time"), y),
-                valid=(("mark_row", "mark_col", "time"), valid.reshape(rows, cols, t)))
-            return assay.stack(mark=("mark_row", "mark_col"), create_index=True).transpose("mark", ...)  # find.py:182
-        # Assay stand-in: the stacked `mark` dimension directly, row-major like xarray's stack
-        mr, mc = np.divmod(np.arange(rows * cols), cols)
-        assay = assay.drop_vars(["tag", "valid"], errors="ignore").assign_coords(
-            mark_row=(("mark",), mr), mark_col=(("mark",), mc),
-            tag=(("mark",), _to_numpy(assay["tag"]).reshape(-1)) if "tag" in assay else (("mark",), np.full(rows * cols, "default")),
-            fg=(("mark", "time", "roi_y", "roi_x"), fg), bg=(("mark", "time", "roi_y", "roi_x"), bg),
-            x=(("mark", "time"), x.reshape(rows * cols, t)), y=(("mark", "time"), y.reshape(rows * cols, t)),
-            valid=(("mark", "time"), np.asarray(valid).reshape(rows * cols, t)))
-        assay["roi"] = (("mark", "channel", "time", "roi_y", "roi_x"), roi)
-        return assay
+        roi, fg, bg = _emit_markers(roi_d, stats, fg_d, bg_d, mask_t, mask_t_d)
+        grid = ("mark_row", "mark_col")
+        # the reference's layout before its stack (find.py:89-116), then its own stack + transpose (find.py:182)
+        assay["roi"] = (grid + ("channel", "time", "roi_y", "roi_x"), roi.reshape(rows, cols, c, t, length, length))
+        assay = assay.assign_coords(
+            fg=(grid + ("time", "roi_y", "roi_x"), fg.reshape(rows, cols, t, length, length)),
+            bg=(grid + ("time", "roi_y", "roi_x"), bg.reshape(rows, cols, t, length, length)),
+            x=(grid + ("time",), x), y=(grid + ("time",), y), valid=(grid + ("time",), valid.reshape(rows, cols, t)))
+        return assay.stack(mark=grid, create_index=True).transpose("mark", ...)
 
 
 def make_find_buttons(row_dist, col_dist, min_button_diameter, max_button_diameter, chamber_diameter, top_chamber,
@@ -427,41 +522,97 @@ def make_find_buttons(row_dist, col_dist, min_button_diameter, max_button_diamet
 # quantify: the per-marker summaries the reference's consumers compute with xarray expressions
 # (identify.py:76-80, filter.py:21-22,51,74,82, README.md:21-22)
 # ---------------------------------------------------------------------------------------------
-def quantify(assay, median: bool = True, device=None):
-    """Adds fg_count/bg_count (mark,time) and fg_sum, bg_sum, fg_mean, bg_mean[, fg_median,
-    bg_median] (mark,channel,time) computed from roi/fg/bg: `roi.where(fg).mean(["roi_x","roi_y"])`
-    etc.  uint16 roi only."""
-    dev = _device(device)
-    roi = _roi_to_device(_to_numpy(assay["roi"]), dev)
-    m, c, t, length, _ = roi.shape
+def _extras(assay) -> dict:
+    data = _raw(assay["roi"])
+    return data.extras if isinstance(data, DeviceArray) else {}
+
+
+def _cached_stats(assay) -> Optional[torch.Tensor]:
+    """The summaries the fused gather produced when this package's finder made `roi`."""
+    stats = _extras(assay).get("stats")
+    if stats is not None and tuple(assay["roi"].dims) == ("mark", "channel", "time", "roi_y", "roi_x") and \
+            tuple(stats.shape[:3]) == tuple(assay["roi"].shape[:3]):
+        return stats
+    return None
+
+
+def _roi_on_device(assay, dev) -> torch.Tensor:
+    """roi for the reductions: uint16 as is; any other dtype the reference accepts (float images,
+    tests/test_chip.py:76-96; 8-bit) as float32, which represents uint8 / int16 / float32 exactly."""
+    data = _raw(assay["roi"])
+    if isinstance(data, DeviceArray) and data.tensor.device == dev:
+        t = data.tensor
+        if t.dtype not in (torch.uint16, torch.float32):
+            t = t.to(torch.float32)
+        return t.contiguous()
+    host = np.ascontiguousarray(_to_numpy(assay["roi"]))
+    if host.dtype not in (np.uint16, np.float32, np.uint8, np.int8, np.int16):
+        raise TypeError(f"roi dtype {host.dtype} is not supported by the GPU reductions "
+                        "(uint16, float32, 8/16-bit integers)")
+    return torch.from_numpy(host if host.dtype in (np.uint16, np.float32) else host.astype(np.float32)).to(dev)
+
+
+def _masks_on_device(assay, dev):
+    """(fg, bg, mask_t): uint8 (M,Tm,L,L) device tensors + the (T,) int32 map of timepoints to them."""
+    ex = _extras(assay)
+    if all(k in ex and ex[k] is not None for k in ("fg", "bg", "mask_t")) and ex["fg"].device == dev and \
+            ex["fg"].shape[0] == assay["roi"].shape[0]:
+        return ex["fg"], ex["bg"], ex["mask_t"]
     fg = torch.from_numpy(np.ascontiguousarray(_to_numpy(assay["fg"])).view(np.uint8)).to(dev)
     bg = torch.from_numpy(np.ascontiguousarray(_to_numpy(assay["bg"])).view(np.uint8)).to(dev)
+    return fg, bg, torch.arange(fg.shape[1], dtype=torch.int32, device=dev)
+
+
+def summaries(assay, median: bool = True, device=None) -> torch.Tensor:
+    """(M, C, T, 8) float64 summaries (ops.STATS order) of a dataset with roi / fg / bg on the
+    stacked `mark` dimension: the ones the gather already produced when `find_buttons` /
+    `find_beads` of this package made the roi, else computed from the arrays."""
+    dev = _device(device)
+    if tuple(assay["roi"].dims) != ("mark", "channel", "time", "roi_y", "roi_x"):
+        raise ValueError("quantify needs the stacked schema: roi (mark, channel, time, roi_y, roi_x)")
+    cached = _cached_stats(assay)
+    if cached is not None:
+        return cached
+    roi = _roi_on_device(assay, dev)
+    if roi.shape[0] == 0:
+        return torch.empty(tuple(roi.shape[:3]) + (ops.NSTATS,), dtype=torch.float64, device=dev)
+    fg, bg, mask_t = _masks_on_device(assay, dev)
+    return ops.roi_stats(roi, fg, bg, mask_t=mask_t, medians=median)
+
+
+def quantify(assay, median: bool = True, device=None):
+    """Adds fg_count/bg_count (mark,time) and fg_sum, bg_sum, fg_mean, bg_mean[, fg_median,
+    bg_median] (mark,channel,time): `roi.where(fg).mean(["roi_x","roi_y"])` etc."""
+    s = summaries(assay, median, device).cpu().numpy()
     dims = ("mark", "channel", "time")
-    if m == 0:
-        empty = np.empty((0, c, t))
-        for name in ("fg_sum", "bg_sum", "fg_mean", "bg_mean") + (("fg_median", "bg_median") if median else ()):
-            assay[name] = (dims, empty.copy())
-        return assay
-    stats = ops.roi_stats(roi, fg, bg)
-    s = stats.cpu().numpy()
     assay["fg_sum"], assay["bg_sum"] = (dims, s[..., 2]), (dims, s[..., 3])
     assay["fg_mean"], assay["bg_mean"] = (dims, s[..., 4]), (dims, s[..., 5])
     assay["fg_count"], assay["bg_count"] = (("mark", "time"), s[:, 0, :, 0]), (("mark", "time"), s[:, 0, :, 1])
     if median:
-        assay["fg_median"] = (dims, ops.roi_median(roi, fg).cpu().numpy())
-        assay["bg_median"] = (dims, ops.roi_median(roi, bg).cpu().numpy())
+        assay["fg_median"], assay["bg_median"] = (dims, s[..., 6]), (dims, s[..., 7])
     return assay
 
 
 def _time0_medians(assay, channel_index: int, dev):
     """GPU medians of fg and bg at time 0 for one channel -> two (M,) float64 arrays."""
+    cached = _cached_stats(assay)
+    if cached is not None:
+        s = cached[:, channel_index, 0].cpu().numpy()
+        return s[:, 6], s[:, 7]
     roi = np.ascontiguousarray(_to_numpy(assay["roi"])[:, channel_index : channel_index + 1, :1])
     fg = np.ascontiguousarray(_to_numpy(assay["fg"])[:, :1]).view(np.uint8)
     bg = np.ascontiguousarray(_to_numpy(assay["bg"])[:, :1]).view(np.uint8)
-    roi_d = _roi_to_device(roi, dev)
+    roi_d = torch.from_numpy(roi if roi.dtype in (np.uint16, np.float32) else roi.astype(np.float32)).to(dev)
     fgm = ops.roi_median(roi_d, torch.from_numpy(fg).to(dev)).cpu().numpy()[:, 0, 0]
     bgm = ops.roi_median(roi_d, torch.from_numpy(bg).to(dev)).cpu().numpy()[:, 0, 0]
     return fgm, bgm
+
+
+def _wanted_channels(assay, search_channel):
+    channels = _channel_names(assay, assay["roi"].shape[1])
+    wanted = channels if search_channel is None else ([search_channel] if isinstance(search_channel, str)
+                                                      or np.isscalar(search_channel) else list(search_channel))
+    return channels, wanted
 
 
 def filter_expression(assay, search_channel=None, min_contrast=None, device=None):
@@ -469,9 +620,7 @@ def filter_expression(assay, search_channel=None, min_contrast=None, device=None
     the GPU.  The pairwise-difference statistic is the reference's
     own expression (O(M^2) on the host, like the reference)."""
     dev = _device(device)
-    channels = list(_to_numpy(assay["channel"])) if "channel" in assay else list(range(assay["roi"].shape[1]))
-    wanted = channels if search_channel is None else ([search_channel] if isinstance(search_channel, str)
-                                                      or np.isscalar(search_channel) else list(search_channel))
+    channels, wanted = _wanted_channels(assay, search_channel)
     valid = _to_numpy(assay["valid"]).astype(bool)
     expressed = np.zeros_like(valid)
     for ch in wanted:
@@ -492,9 +641,7 @@ def filter_leaky(assay, search_channel=None, device=None):
     GPU: tagged markers whose blank neighbour (previous / next mark in stacked order) is not
     "empty" are invalidated.  Needs the stacked chip schema (`tag`, `mark_row` per mark)."""
     dev = _device(device)
-    channels = list(_to_numpy(assay["channel"])) if "channel" in assay else list(range(assay["roi"].shape[1]))
-    wanted = channels if search_channel is None else ([search_channel] if isinstance(search_channel, str)
-                                                      or np.isscalar(search_channel) else list(search_channel))
+    channels, wanted = _wanted_channels(assay, search_channel)
     tag = _to_numpy(assay["tag"])
     rows = _to_numpy(assay["mark_row"])
     valid = _to_numpy(assay["valid"]).astype(bool).copy()
@@ -536,15 +683,10 @@ def filter_nonround(assay, min_roundness: float = 0.75, search_channel=None, dev
 def mrbles_intensities(assay, channels=None, device=None) -> np.ndarray:
     """The per-bead intensities `identify_mrbles` starts from (identify.py:76-80): mean of the
     foreground minus median of the background at time 0, (mark, channel)."""
-    dev = _device(device)
-    names = list(_to_numpy(assay["channel"])) if "channel" in assay else list(range(assay["roi"].shape[1]))
+    names = _channel_names(assay, assay["roi"].shape[1])
     idx = list(range(len(names))) if channels is None else [names.index(c) for c in channels]
-    roi = _roi_to_device(_to_numpy(assay["roi"])[:, idx, :1], dev)
-    fg = torch.from_numpy(np.ascontiguousarray(_to_numpy(assay["fg"])[:, :1]).view(np.uint8)).to(dev)
-    bg = torch.from_numpy(np.ascontiguousarray(_to_numpy(assay["bg"])[:, :1]).view(np.uint8)).to(dev)
-    mean_fg = ops.roi_stats(roi, fg, bg)[:, :, 0, 4]
-    med_bg = ops.roi_median(roi, bg)[:, :, 0]
-    return (mean_fg - med_bg).cpu().numpy()
+    s = summaries(assay, True, device)[:, :, 0].cpu().numpy()
+    return (s[..., 4] - s[..., 7])[:, idx]
 
 
 def make_quantify(median: bool = True, device=None):
@@ -576,19 +718,23 @@ EXTRA_FACTORIES = {
 }
 
 
-def install(override: bool = True):
-    """Register the GPU components in magnify's registry (registry.py:12-13).  With override the
-    reference's own names are replaced, so the predefined pipelines use them unchanged; the
-    `<name>_b200` aliases and "quantify" are always added."""
-    try:
-        import magnify.registry as registry
-    except Exception as e:
-        raise ImportError("magnify (and its dependencies xarray, dask, catalogue) must be importable to "
-                          "install the magnify_b200 components into its registry") from e
+def install(override: bool = True, registry=None):
+    """Register the GPU components in magnify's component registry (registry.py:12-13).  With
+    override the reference's own names are replaced, so the predefined pipelines
+    (registry.py:243-269, 431-449, 593-610) use them unchanged; the `<name>_b200` aliases and
+    "quantify" are always added.  registry: a catalogue registry (anything with `register(name)`),
+    default `magnify.registry.components`."""
+    if registry is None:
+        try:
+            import magnify.registry as mg_registry
+        except Exception as e:
+            raise ImportError("magnify (and its dependencies xarray, dask, catalogue) must be importable to "
+                              "install the magnify_b200 components into its registry") from e
+        registry = mg_registry.components
     for name, factory in FACTORIES.items():
-        registry.components.register(name + "_b200")(factory)
+        registry.register(name + "_b200")(factory)
         if override:
-            registry.components.register(name)(factory)
+            registry.register(name)(factory)
     for name, factory in EXTRA_FACTORIES.items():
-        registry.components.register(name)(factory)
+        registry.register(name)(factory)
     return sorted(list(FACTORIES) + [n + "_b200" for n in FACTORIES] + list(EXTRA_FACTORIES))

@@ -58,8 +58,11 @@ struct GatherParams {
   double* stats;
 };
 
-__device__ __forceinline__ uint64_t block_sum_u32(uint32_t v, uint32_t* smem) {
-  v = __reduce_add_sync(0xffffffffu, v);
+constexpr int kRec = 8;   // doubles per summary record: n_fg n_bg sum_fg sum_bg mean_fg mean_bg median_fg median_bg
+
+__device__ __forceinline__ uint64_t block_sum_u64(uint64_t v, uint64_t* smem) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   if (l == 0) smem[w] = v;
   __syncthreads();
@@ -69,10 +72,23 @@ __device__ __forceinline__ uint64_t block_sum_u32(uint32_t v, uint32_t* smem) {
   return s;
 }
 
+// The median columns are left NaN: the caller fills them (roi_median kernels) when it wants them.
+__device__ __forceinline__ void write_record(double* o, uint64_t na, uint64_t nb, uint64_t a, uint64_t b) {
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  o[0] = (double)na;
+  o[1] = (double)nb;
+  o[2] = (double)a;
+  o[3] = (double)b;
+  o[4] = (double)a / (double)na;   // 0/0 -> NaN, like nanmean over an empty mask
+  o[5] = (double)b / (double)nb;
+  o[6] = nan;
+  o[7] = nan;
+}
+
 // Word path: 2 x 16-bit units per thread step (Lu even).  ALIGNED: source words 4-byte aligned.
 template <bool STATS>
 __global__ void __launch_bounds__(kThreads) roi_gather_words_kernel(const GatherParams p) {
-  __shared__ uint32_t red[4][kThreads / 32];
+  __shared__ uint64_t red[4][kThreads / 32];
   const int64_t n = blockIdx.x;                 // (m*C + c)*T + t
   const int64_t t = n % p.T;
   const int64_t c = (n / p.T) % p.C;
@@ -89,7 +105,9 @@ __global__ void __launch_bounds__(kThreads) roi_gather_words_kernel(const Gather
     fgp = reinterpret_cast<const uint16_t*>(p.fg + mo);
     bgp = reinterpret_cast<const uint16_t*>(p.bg + mo);
   }
-  uint32_t s_fg = 0, s_bg = 0, n_fg = 0, n_bg = 0;
+  // per-thread sums in 64 bits: a thread sees up to L*L/256 pixel pairs of up to 2 * 65535 each
+  uint64_t s_fg = 0, s_bg = 0;
+  uint32_t n_fg = 0, n_bg = 0;
   for (uint32_t w = threadIdx.x; w < p.words; w += kThreads) {
     const uint32_t row = __umulhi(w, p.magic);
     const uint32_t col = w - row * p.half;
@@ -102,28 +120,21 @@ __global__ void __launch_bounds__(kThreads) roi_gather_words_kernel(const Gather
     }
     if (dst) dst[w] = v;
     if constexpr (STATS) {
-      const uint32_t mf = __ldg(fgp + w);
-      const uint32_t mb = __ldg(bgp + w);
-      s_fg = __dp2a_lo(v, mf, s_fg);
-      s_bg = __dp2a_lo(v, mb, s_bg);
-      n_fg = __dp2a_lo(0x00010001u, mf, n_fg);
-      n_bg = __dp2a_lo(0x00010001u, mb, n_bg);
+      // two mask bytes; any non-zero byte counts as set
+      const uint32_t mf = __vcmpne4((uint32_t)__ldg(fgp + w), 0u) & 0x0101u;
+      const uint32_t mb = __vcmpne4((uint32_t)__ldg(bgp + w), 0u) & 0x0101u;
+      s_fg += __dp2a_lo(v, mf, 0u);
+      s_bg += __dp2a_lo(v, mb, 0u);
+      n_fg += __popc(mf);
+      n_bg += __popc(mb);
     }
   }
   if constexpr (STATS) {
-    const uint64_t a = block_sum_u32(s_fg, red[0]);
-    const uint64_t b = block_sum_u32(s_bg, red[1]);
-    const uint64_t na = block_sum_u32(n_fg, red[2]);
-    const uint64_t nb = block_sum_u32(n_bg, red[3]);
-    if (threadIdx.x == 0) {
-      double* o = p.stats + n * 6;
-      o[0] = (double)na;
-      o[1] = (double)nb;
-      o[2] = (double)a;
-      o[3] = (double)b;
-      o[4] = (double)a / (double)na;   // 0/0 -> NaN, like nanmean over an empty mask
-      o[5] = (double)b / (double)nb;
-    }
+    const uint64_t a = block_sum_u64(s_fg, red[0]);
+    const uint64_t b = block_sum_u64(s_bg, red[1]);
+    const uint64_t na = block_sum_u64(n_fg, red[2]);
+    const uint64_t nb = block_sum_u64(n_bg, red[3]);
+    if (threadIdx.x == 0) write_record(p.stats + n * kRec, na, nb, a, b);
   }
 }
 
@@ -135,7 +146,7 @@ roi_gather_scalar_kernel(const U* __restrict__ image, U* __restrict__ roi, int64
                          const int32_t* __restrict__ mask_t, int64_t Tm,
                          const uint8_t* __restrict__ fg, const uint8_t* __restrict__ bg,
                          double* __restrict__ stats) {
-  __shared__ uint32_t red[4][kThreads / 32];
+  __shared__ uint64_t red[4][kThreads / 32];
   const int64_t n = blockIdx.x;
   const int64_t t = n % T;
   const int64_t c = (n / T) % C;
@@ -151,7 +162,8 @@ roi_gather_scalar_kernel(const U* __restrict__ image, U* __restrict__ roi, int64
     fgp = fg + mo;
     bgp = bg + mo;
   }
-  uint32_t s_fg = 0, s_bg = 0, n_fg = 0, n_bg = 0;
+  uint64_t s_fg = 0, s_bg = 0;
+  uint32_t n_fg = 0, n_bg = 0;
   const int total = L * L;
   for (int i = threadIdx.x; i < total; i += kThreads) {
     const int row = i / L, col = i - row * L;
@@ -159,22 +171,18 @@ roi_gather_scalar_kernel(const U* __restrict__ image, U* __restrict__ roi, int64
     if (dst) dst[i] = v;
     if constexpr (STATS) {
       const uint32_t f = fgp[i], b = bgp[i];
-      s_fg += f ? (uint32_t)v : 0u;
-      s_bg += b ? (uint32_t)v : 0u;
+      s_fg += f ? (uint64_t)v : 0u;
+      s_bg += b ? (uint64_t)v : 0u;
       n_fg += f ? 1u : 0u;
       n_bg += b ? 1u : 0u;
     }
   }
   if constexpr (STATS) {
-    const uint64_t a = block_sum_u32(s_fg, red[0]);
-    const uint64_t b = block_sum_u32(s_bg, red[1]);
-    const uint64_t na = block_sum_u32(n_fg, red[2]);
-    const uint64_t nb = block_sum_u32(n_bg, red[3]);
-    if (threadIdx.x == 0) {
-      double* o = stats + n * 6;
-      o[0] = (double)na; o[1] = (double)nb; o[2] = (double)a; o[3] = (double)b;
-      o[4] = (double)a / (double)na; o[5] = (double)b / (double)nb;
-    }
+    const uint64_t a = block_sum_u64(s_fg, red[0]);
+    const uint64_t b = block_sum_u64(s_bg, red[1]);
+    const uint64_t na = block_sum_u64(n_fg, red[2]);
+    const uint64_t nb = block_sum_u64(n_bg, red[3]);
+    if (threadIdx.x == 0) write_record(stats + n * kRec, na, nb, a, b);
   }
 }
 
@@ -200,7 +208,7 @@ template <int NPT, typename TPix>
 __global__ void __launch_bounds__(kThreads)
 roi_median_kernel(const TPix* __restrict__ roi, int64_t C, int64_t T, int L,
                       const int32_t* __restrict__ mask_t, int64_t Tm,
-                      const uint8_t* __restrict__ mask, double* __restrict__ median) {
+                      const uint8_t* __restrict__ mask, double* __restrict__ median, int64_t stride) {
   __shared__ uint32_t red[2][kThreads / 32];
   const int64_t n = blockIdx.x;
   const int64_t t = n % T;
@@ -232,7 +240,7 @@ roi_median_kernel(const TPix* __restrict__ roi, int64_t C, int64_t T, int L,
   };
   const uint32_t nvalid = block_count(cnt);
   if (nvalid == 0) {
-    if (threadIdx.x == 0) median[n] = __longlong_as_double(0x7ff8000000000000LL);
+    if (threadIdx.x == 0) median[n * stride] = __longlong_as_double(0x7ff8000000000000LL);
     return;
   }
   const uint32_t k1 = (nvalid - 1) >> 1;  // lower middle (0-based)
@@ -282,7 +290,64 @@ roi_median_kernel(const TPix* __restrict__ roi, int64_t C, int64_t T, int L,
     for (int i = 0; i < kThreads / 32; ++i) g = min(g, red[buf][i]);
     if (tot < k1 + 2) v2 = g;
   }
-  if (threadIdx.x == 0) median[n] = 0.5 * (median_value<TPix>(v1) + median_value<TPix>(v2));
+  if (threadIdx.x == 0) median[n * stride] = 0.5 * (median_value<TPix>(v1) + median_value<TPix>(v2));
+}
+
+// Any L: the keys do not fit in registers, so every bisection step re-reads the window (it stays
+// in L2: at most 16 + 3 passes for uint16, 32 + 3 for float32).  One CTA per ROI.
+template <typename TPix>
+__global__ void __launch_bounds__(kThreads)
+roi_median_big_kernel(const TPix* __restrict__ roi, int64_t C, int64_t T, int L, const int32_t* __restrict__ mask_t,
+                      int64_t Tm, const uint8_t* __restrict__ mask, double* __restrict__ median, int64_t stride) {
+  __shared__ uint32_t red[3][kThreads / 32];
+  const int64_t n = blockIdx.x;
+  const int64_t t = n % T;
+  const int64_t m = n / (T * C);
+  const int total = L * L;
+  const TPix* src = roi + n * (int64_t)total;
+  const uint8_t* mk = mask + (m * Tm + mask_t[t]) * (int64_t)total;
+  // one block-wide pass: count of keys <= bound, smallest key > bound, and (first == true) min / max
+  auto sweep = [&](uint32_t bound, uint32_t* count, uint32_t* above, uint32_t* lowest) {
+    uint32_t c = 0, a = 0xffffffffu, lo = 0xffffffffu;
+    for (int i = threadIdx.x; i < total; i += kThreads) {
+      if (!mk[i]) continue;
+      const uint32_t k = median_key(src[i]);
+      if (k == 0xffffffffu) continue;
+      c += (k <= bound) ? 1u : 0u;
+      if (k > bound) a = min(a, k);
+      lo = min(lo, k);
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    a = __reduce_min_sync(0xffffffffu, a);
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    __syncthreads();   // the previous sweep's readers are done with `red`
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = c; red[1][threadIdx.x >> 5] = a; red[2][threadIdx.x >> 5] = lo; }
+    __syncthreads();
+    uint32_t sc = 0, sa = 0xffffffffu, sl = 0xffffffffu;
+#pragma unroll
+    for (int i = 0; i < kThreads / 32; ++i) { sc += red[0][i]; sa = min(sa, red[1][i]); sl = min(sl, red[2][i]); }
+    *count = sc; *above = sa; *lowest = sl;
+  };
+  uint32_t nvalid, above, lo;
+  sweep(0xfffffffeu, &nvalid, &above, &lo);     // every valid key is <= 0xfffffffe
+  if (nvalid == 0) {
+    if (threadIdx.x == 0) median[n * stride] = __longlong_as_double(0x7ff8000000000000LL);
+    return;
+  }
+  const uint32_t k1 = (nvalid - 1) >> 1;
+  uint32_t hi = 0xfffffffeu, cnt, dummy;
+  if (sizeof(TPix) == 2) hi = 0xffffu;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    sweep(mid, &cnt, &above, &dummy);
+    if (cnt >= k1 + 1) hi = mid; else lo = mid + 1;
+  }
+  uint32_t v2 = lo;
+  if ((nvalid & 1u) == 0) {
+    sweep(lo, &cnt, &above, &dummy);
+    if (cnt < k1 + 2) v2 = above;
+  }
+  if (threadIdx.x == 0) median[n * stride] = 0.5 * (median_value<TPix>(lo) + median_value<TPix>(v2));
 }
 
 // Masked sums of a float32 roi: one CTA per (m, c, t), float64 accumulation in a fixed order
@@ -316,10 +381,11 @@ roi_stats_f32_kernel(const float* __restrict__ roi, int64_t C, int64_t T, int L,
     double s[4] = {0.0, 0.0, 0.0, 0.0};
     for (int w = 0; w < kThreads / 32; ++w)
       for (int k = 0; k < 4; ++k) s[k] += red[k][w];
-    double* out = stats + n * 6;
+    double* out = stats + n * kRec;
     out[0] = s[0]; out[1] = s[1]; out[2] = s[2]; out[3] = s[3];
     out[4] = s[2] / s[0];   // 0 / 0 = NaN for an empty mask, like np.nanmean
     out[5] = s[3] / s[1];
+    out[6] = out[7] = __longlong_as_double(0x7ff8000000000000LL);   // medians: filled by the median kernel
   }
 }
 
@@ -330,6 +396,12 @@ int roi_gather_tma(const void* image, int64_t pitch, int64_t C, int64_t T, int64
                    const int32_t* boxes, const int32_t* order, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
                    const uint8_t* bg, int64_t M, int L, void* roi, double* stats, const uint64_t* host_peers,
                    int n_peers, cudaStream_t st);
+
+// roi_lists.cu
+int roi_gather_lists(const void* image, int64_t pitch, int64_t C, int64_t T, int64_t H, int64_t W,
+                     const int32_t* boxes, const int32_t* order, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
+                     const uint8_t* bg, int64_t M, int L, void* roi, double* stats, int want_median, int nf_max,
+                     int nb_max, const uint64_t* host_peers, int n_peers, cudaStream_t st);
 
 extern int g_gather_loader;
 extern int g_gather_wpm;
@@ -342,22 +414,22 @@ using namespace mgb;
 
 template <typename TPix>
 static int launch_roi_median(const TPix* roi, int64_t M, int64_t C, int64_t T, int L, const int32_t* mask_t, int64_t Tm,
-                             const uint8_t* mask, double* median, void* stream) {
-  if (M < 0 || C < 0 || T < 0 || L <= 0) return MGB_EINVAL;
+                             const uint8_t* mask, double* median, int64_t stride, void* stream) {
+  if (M < 0 || C < 0 || T < 0 || L <= 0 || stride < 1) return MGB_EINVAL;
   const int64_t n_roi = M * C * T;
   if (n_roi == 0) return MGB_OK;
   if (n_roi > INT32_MAX) return MGB_EUNSUPPORTED;
   if (!roi || !mask_t || !mask || !median || Tm <= 0) return MGB_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   const int npt = (int)ceil_div((int64_t)L * L, kThreads);
-#define MGB_MED(N) roi_median_kernel<N, TPix><<<(unsigned)n_roi, kThreads, 0, st>>>(roi, C, T, L, mask_t, Tm, mask, median)
+#define MGB_MED(N) roi_median_kernel<N, TPix><<<(unsigned)n_roi, kThreads, 0, st>>>(roi, C, T, L, mask_t, Tm, mask, median, stride)
   if (npt <= 4) MGB_MED(4);
   else if (npt <= 10) MGB_MED(10);
   else if (npt <= 21) MGB_MED(21);
   else if (npt <= 40) MGB_MED(40);
   else if (npt <= 64) MGB_MED(64);
   else if (npt <= 100) MGB_MED(100);
-  else return MGB_EUNSUPPORTED;   // L > 160
+  else roi_median_big_kernel<TPix><<<(unsigned)n_roi, kThreads, 0, st>>>(roi, C, T, L, mask_t, Tm, mask, median, stride);   // L > 160
 #undef MGB_MED
   MGB_CUDA_LAUNCH_CHECK();
   return MGB_OK;
@@ -379,7 +451,9 @@ int mgb_bounding_boxes(const double* x, const double* y, int64_t n, int L, int64
 static int gather_common(const void* image, int64_t image_pitch, int64_t C, int64_t T, int64_t H, int64_t W,
                          int itemsize, const int32_t* boxes, const int32_t* order, int64_t marker_stride, const int32_t* mask_t, int64_t Tm, const uint8_t* fg,
                          const uint8_t* bg, int64_t M, int L, void* roi, double* stats,
-                         cudaStream_t st, const uint64_t* host_peers = nullptr, int n_peers = 0) {
+                         cudaStream_t st, const uint64_t* host_peers = nullptr, int n_peers = 0,
+                         int want_median = 0, int nf_max = -1, int nb_max = -1, int* host_median_done = nullptr) {
+  if (host_median_done) *host_median_done = 0;
   const bool with_stats = stats != nullptr;
   if (M < 0 || C < 0 || T < 0 || L <= 0 || H < L || W < L) return MGB_EINVAL;
   const int64_t pitch = image_pitch > 0 ? image_pitch : W;   // row pitch in elements
@@ -391,6 +465,13 @@ static int gather_common(const void* image, int64_t image_pitch, int64_t C, int6
   if (n_roi > INT32_MAX) return MGB_EUNSUPPORTED;
   if (!image || (!boxes && marker_stride == 0) || (!roi && !with_stats)) return MGB_EINVAL;
   if (with_stats && (!mask_t || !fg || !bg || Tm <= 0 || itemsize != 2)) return MGB_EINVAL;
+  if (g_tma_enabled && marker_stride == 0 && with_stats && nf_max >= 0 && nb_max >= 0) {
+    // masked-value lists: sums, means and (optionally) medians in the gather (roi_lists.cu)
+    const int rc = roi_gather_lists(image, pitch, C, T, H, W, boxes, order, mask_t, Tm, fg, bg, M, L, roi, stats,
+                                    want_median, nf_max, nb_max, host_peers, n_peers, st);
+    if (rc == MGB_OK && want_median && host_median_done) *host_median_done = 1;
+    if (rc != MGB_EALIGN) return rc;
+  }
   if (g_tma_enabled && marker_stride == 0) {
     // TMA-staged path (roi_tma.cu); MGB_EALIGN means "not applicable here", fall through.
     const int rc = roi_gather_tma(image, pitch, C, T, H, W, itemsize, boxes, order, mask_t, Tm, fg, bg, M, L, roi, stats,
@@ -456,21 +537,26 @@ int mgb_roi_gather(const void* image, int64_t image_pitch, int64_t C, int64_t T,
 int mgb_roi_gather_stats_u16(const uint16_t* image, int64_t image_pitch, int64_t C, int64_t T, int64_t H,
                              int64_t W, const int32_t* boxes, const int32_t* order, const int32_t* mask_t, int64_t Tm,
                              const uint8_t* fg, const uint8_t* bg, int64_t M, int L,
-                             uint16_t* roi, double* stats, void* stream) {
+                             uint16_t* roi, double* stats, int want_median, int fg_count_max, int bg_count_max,
+                             int* host_median_done, void* stream) {
+  if (host_median_done) *host_median_done = 0;
   if (!stats && M * C * T > 0) return MGB_EINVAL;
   return gather_common(image, image_pitch, C, T, H, W, 2, boxes, order, 0, mask_t, Tm, fg, bg, M, L, roi, stats,
-                       (cudaStream_t)stream);
+                       (cudaStream_t)stream, nullptr, 0, want_median, fg_count_max, bg_count_max, host_median_done);
 }
 
 int mgb_roi_gather_stats_peers_u16(const uint16_t* image, int64_t image_pitch, int64_t C, int64_t T, int64_t H,
                                    int64_t W, const int32_t* boxes, const int32_t* order, const int32_t* mask_t,
                                    int64_t Tm, const uint8_t* fg, const uint8_t* bg, int64_t M, int L,
-                                   uint16_t* roi, const uint64_t* host_peer_stats, int n_peers, void* stream) {
+                                   uint16_t* roi, const uint64_t* host_peer_stats, int n_peers, int want_median,
+                                   int fg_count_max, int bg_count_max, int* host_median_done, void* stream) {
+  if (host_median_done) *host_median_done = 0;
   if (!host_peer_stats || n_peers < 1 || n_peers > 8) return MGB_EINVAL;
   if (M * C * T == 0) return MGB_OK;
   // `stats` only flags "with summaries" here; every record is written through the peer pointers
   return gather_common(image, image_pitch, C, T, H, W, 2, boxes, order, 0, mask_t, Tm, fg, bg, M, L, roi,
-                       reinterpret_cast<double*>(host_peer_stats[0]), (cudaStream_t)stream, host_peer_stats, n_peers);
+                       reinterpret_cast<double*>(host_peer_stats[0]), (cudaStream_t)stream, host_peer_stats, n_peers,
+                       want_median, fg_count_max, bg_count_max, host_median_done);
 }
 
 int mgb_roi_stats_u16(const uint16_t* roi, int64_t M, int64_t C, int64_t T, int L, const int32_t* mask_t,
@@ -483,13 +569,13 @@ int mgb_roi_stats_u16(const uint16_t* roi, int64_t M, int64_t C, int64_t T, int 
 
 int mgb_roi_median_u16(const uint16_t* roi, int64_t M, int64_t C, int64_t T, int L,
                        const int32_t* mask_t, int64_t Tm, const uint8_t* mask, double* median,
-                       void* stream) {
-  return launch_roi_median<uint16_t>(roi, M, C, T, L, mask_t, Tm, mask, median, stream);
+                       int64_t median_stride, void* stream) {
+  return launch_roi_median<uint16_t>(roi, M, C, T, L, mask_t, Tm, mask, median, median_stride, stream);
 }
 
 int mgb_roi_median_f32(const float* roi, int64_t M, int64_t C, int64_t T, int L, const int32_t* mask_t, int64_t Tm,
-                       const uint8_t* mask, double* median, void* stream) {
-  return launch_roi_median<float>(roi, M, C, T, L, mask_t, Tm, mask, median, stream);
+                       const uint8_t* mask, double* median, int64_t median_stride, void* stream) {
+  return launch_roi_median<float>(roi, M, C, T, L, mask_t, Tm, mask, median, median_stride, stream);
 }
 
 int mgb_roi_stats_f32(const float* roi, int64_t M, int64_t C, int64_t T, int L, const int32_t* mask_t, int64_t Tm,

@@ -7,7 +7,7 @@ built library the calls raise.
 
 Layouts follow the reference:
   tiles (C,T,R,Cc,H,W) -> image (C,T,Him,Wim) -> roi (M,C,T,L,L), fg/bg (M,Tm,L,L),
-  stats (M,C,T,6) = n_fg, n_bg, sum_fg, sum_bg, mean_fg, mean_bg.
+  stats (M,C,T,8) = n_fg, n_bg, sum_fg, sum_bg, mean_fg, mean_bg, median_fg, median_bg.
 """
 from __future__ import annotations
 
@@ -19,7 +19,8 @@ import torch
 
 from . import _lib
 
-STATS = ("n_fg", "n_bg", "sum_fg", "sum_bg", "mean_fg", "mean_bg")
+STATS = ("n_fg", "n_bg", "sum_fg", "sum_bg", "mean_fg", "mean_bg", "median_fg", "median_bg")
+NSTATS = len(STATS)
 
 _DTYPE_CODE = {
     torch.uint8: _lib.MGB_U8,
@@ -404,6 +405,50 @@ def roi_gather(image: torch.Tensor, boxes: torch.Tensor, roi_length: int, out: O
     return out
 
 
+def _masks_u8(fg, bg, m, roi_length):
+    fg = fg.view(torch.uint8) if fg.dtype == torch.bool else fg
+    bg = bg.view(torch.uint8) if bg.dtype == torch.bool else bg
+    _check(fg, "fg", dtype=torch.uint8, ndim=4)
+    _check(bg, "bg", dtype=torch.uint8, ndim=4)
+    tm = fg.shape[1]
+    if tuple(fg.shape) != (m, tm, roi_length, roi_length) or fg.shape != bg.shape:
+        raise ValueError(f"fg/bg must have shape ({m}, Tm, {roi_length}, {roi_length})")
+    return fg, bg, tm
+
+
+def _default_mask_t(mask_t, tm, t, device, what="fg/bg"):
+    if mask_t is None:
+        if tm == 1:
+            mask_t = torch.zeros(t, dtype=torch.int32, device=device)
+        elif tm == t:
+            mask_t = torch.arange(t, dtype=torch.int32, device=device)
+        else:
+            raise ValueError(f"mask_t is required when {what} hold neither 1 nor T timesteps")
+    _check(mask_t, "mask_t", dtype=torch.int32, ndim=1)
+    if mask_t.numel() != t:
+        raise ValueError("mask_t must have one entry per timepoint")
+    return mask_t
+
+
+def mask_count_max(fg: torch.Tensor, bg: torch.Tensor):
+    """(largest fg pixel count, largest bg pixel count) over all masks of (M,Tm,L,L) stacks, as
+    Python ints (one small kernel + a 8-byte read-back).  The fused gather sizes its per-marker
+    value lists from these bounds; callers that reuse masks (a `QuantifyPlan`) compute them once."""
+    fg = fg.view(torch.uint8) if fg.dtype == torch.bool else fg
+    bg = bg.view(torch.uint8) if bg.dtype == torch.bool else bg
+    _check(fg, "fg", dtype=torch.uint8)
+    _check(bg, "bg", dtype=torch.uint8)
+    if fg.shape != bg.shape or fg.dim() < 2:
+        raise ValueError("fg and bg must have the same shape (..., L, L)")
+    length = fg.shape[-1] * fg.shape[-2]
+    n = fg.numel() // length if length else 0
+    counts = torch.empty(2, dtype=torch.int32, device=fg.device)
+    with torch.cuda.device(fg.device):
+        _lib.call("mgb_mask_count_max", _ptr(fg), _ptr(bg), n, length, _ptr(counts), _stream())
+    c = counts.cpu()
+    return int(c[0]), int(c[1])
+
+
 def roi_gather_stats(
     image: torch.Tensor,
     boxes: torch.Tensor,
@@ -416,41 +461,38 @@ def roi_gather_stats(
     out_stats: Optional[torch.Tensor] = None,
     order: Optional[torch.Tensor] = None,
     peer_stats: Optional[Sequence[int]] = None,
+    medians: bool = True,
+    mask_counts: Optional[Sequence[int]] = None,
 ):
-    """Gather fused with per-(marker, channel, time) masked sums / counts / means.
+    """Gather fused with per-(marker, channel, time) masked counts / sums / means / medians.
 
-    fg, bg: (M, Tm, L, L) uint8 (0/1) or bool; mask_t (T,) int32 maps timepoints to mask
-    timesteps (default: all 0 when Tm == 1, identity when Tm == T).  Returns (roi | None, stats)
-    with stats (M,C,T,6) float64 in `STATS` order."""
+    fg, bg: (M, Tm, L, L) uint8 (any non-zero byte = set) or bool; mask_t (T,) int32 maps
+    timepoints to mask timesteps (default: all 0 when Tm == 1, identity when Tm == T).  Returns
+    (roi | None, stats) with stats (M,C,T,8) float64 in `STATS` order; with medians=False the two
+    median columns are NaN.
+
+    mask_counts: `mask_count_max(fg, bg)` when the caller already has it (otherwise it is computed
+    here, which costs a device->host read of 8 bytes).  Masks of at most 1024 fg / 2560 bg pixels
+    per marker get sums and medians from the staged window in one pass; larger masks take the
+    dp2a sums and a separate exact-median pass over the crops (peer_stats: medians stay NaN)."""
     if image.dtype != torch.uint16:
         raise TypeError(f"image must have dtype torch.uint16, got {image.dtype}")
     pitch = image_pitch(image)
     c, t, h, w = image.shape
     m = boxes.shape[0]
     _check_boxes(boxes, m, t)
-    fg = fg.view(torch.uint8) if fg.dtype == torch.bool else fg
-    bg = bg.view(torch.uint8) if bg.dtype == torch.bool else bg
-    _check(fg, "fg", dtype=torch.uint8, ndim=4)
-    _check(bg, "bg", dtype=torch.uint8, ndim=4)
-    tm = fg.shape[1]
-    if tuple(fg.shape) != (m, tm, roi_length, roi_length) or fg.shape != bg.shape:
-        raise ValueError(f"fg/bg must have shape ({m}, Tm, {roi_length}, {roi_length})")
-    if mask_t is None:
-        if tm == 1:
-            mask_t = torch.zeros(t, dtype=torch.int32, device=image.device)
-        elif tm == t:
-            mask_t = torch.arange(t, dtype=torch.int32, device=image.device)
-        else:
-            raise ValueError("mask_t is required when fg/bg hold neither 1 nor T timesteps")
-    _check(mask_t, "mask_t", dtype=torch.int32, ndim=1)
-    if mask_t.numel() != t:
-        raise ValueError("mask_t must have one entry per timepoint")
+    fg, bg, tm = _masks_u8(fg, bg, m, roi_length)
+    mask_t = _default_mask_t(mask_t, tm, t, image.device)
     roi = None
+    shape = (m, c, t, roi_length, roi_length)
     if want_roi:
-        shape = (m, c, t, roi_length, roi_length)
         roi = out_roi if out_roi is not None else torch.empty(shape, dtype=image.dtype, device=image.device)
         if tuple(roi.shape) != shape or roi.dtype != image.dtype:
             raise ValueError(f"out_roi must have shape {shape} and dtype {image.dtype}")
+    if mask_counts is None:
+        mask_counts = mask_count_max(fg, bg) if m * tm > 0 else (0, 0)
+    nf_max, nb_max = int(mask_counts[0]), int(mask_counts[1])
+    done = ctypes.c_int(0)
     if peer_stats is not None:
         # Multi-GPU: the kernel writes every summary record into this rank's block of each rank's
         # gathered buffer (peer-mapped addresses, see magnify_b200.dist.SymmetricSummaries).
@@ -459,49 +501,57 @@ def roi_gather_stats(
         with torch.cuda.device(image.device):
             _lib.call("mgb_roi_gather_stats_peers_u16", _ptr(image), pitch, c, t, h, w, _ptr(boxes),
                       _ptr(_check_order(order, m)), _ptr(mask_t), tm, _ptr(fg), _ptr(bg), m, int(roi_length),
-                      _ptr(roi), arr, n_peers, _stream())
+                      _ptr(roi), arr, n_peers, int(bool(medians)), nf_max, nb_max, ctypes.byref(done), _stream())
         return roi, None
-    stats = out_stats if out_stats is not None else torch.empty((m, c, t, 6), dtype=torch.float64, device=image.device)
-    if tuple(stats.shape) != (m, c, t, 6) or stats.dtype != torch.float64:
-        raise ValueError("out_stats must be float64 with shape (M, C, T, 6)")
+    stats = out_stats if out_stats is not None else torch.empty((m, c, t, NSTATS), dtype=torch.float64,
+                                                                device=image.device)
+    if tuple(stats.shape) != (m, c, t, NSTATS) or stats.dtype != torch.float64 or not stats.is_contiguous():
+        raise ValueError(f"out_stats must be contiguous float64 with shape (M, C, T, {NSTATS})")
     with torch.cuda.device(image.device):
         _lib.call("mgb_roi_gather_stats_u16", _ptr(image), pitch, c, t, h, w, _ptr(boxes), _ptr(_check_order(order, m)),
-                  _ptr(mask_t), tm, _ptr(fg), _ptr(bg), m, int(roi_length), _ptr(roi), _ptr(stats), _stream())
+                  _ptr(mask_t), tm, _ptr(fg), _ptr(bg), m, int(roi_length), _ptr(roi), _ptr(stats),
+                  int(bool(medians)), nf_max, nb_max, ctypes.byref(done), _stream())
+    if medians and not done.value and m * c * t > 0:
+        # masks too large for the in-kernel lists (or an image the staged kernels do not take):
+        # exact medians from the crops in a second pass
+        crops = roi if roi is not None else roi_gather(image, boxes, roi_length, order=order)
+        _median_into(crops, fg, mask_t, tm, stats, 6)
+        _median_into(crops, bg, mask_t, tm, stats, 7)
     return roi, stats
 
 
-def roi_stats(roi: torch.Tensor, fg: torch.Tensor, bg: torch.Tensor, mask_t: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Masked sums / counts / means of an existing roi (M,C,T,L,L) uint16 or float32 -> (M,C,T,6)
-    float64 (float32: float64 accumulation, NaN pixels skipped)."""
+def _median_into(roi, mask, mask_t, tm, stats, column: int) -> None:
+    m, c, t, length, _ = roi.shape
+    out = stats.view(-1)[column:]
+    with torch.cuda.device(roi.device):
+        _lib.call("mgb_roi_median_u16" if roi.dtype == torch.uint16 else "mgb_roi_median_f32", _ptr(roi), m, c, t,
+                  int(length), _ptr(mask_t), tm, _ptr(mask), _ptr(out), NSTATS, _stream())
+
+
+def roi_stats(roi: torch.Tensor, fg: torch.Tensor, bg: torch.Tensor, mask_t: Optional[torch.Tensor] = None,
+              medians: bool = True) -> torch.Tensor:
+    """Masked counts / sums / means / medians of an existing roi (M,C,T,L,L) uint16 or float32 ->
+    (M,C,T,8) float64 (float32: float64 accumulation, NaN pixels skipped)."""
     if roi.dtype not in (torch.uint16, torch.float32):
         raise TypeError(f"roi must be uint16 or float32, got {roi.dtype}")
     _check(roi, "roi", ndim=5)
     m, c, t, length, _ = roi.shape
-    fg = fg.view(torch.uint8) if fg.dtype == torch.bool else fg
-    bg = bg.view(torch.uint8) if bg.dtype == torch.bool else bg
-    _check(fg, "fg", dtype=torch.uint8, ndim=4)
-    _check(bg, "bg", dtype=torch.uint8, ndim=4)
-    tm = fg.shape[1]
-    if tuple(fg.shape) != (m, tm, length, length) or fg.shape != bg.shape:
-        raise ValueError(f"fg/bg must have shape ({m}, Tm, {length}, {length})")
-    if mask_t is None:
-        if tm == 1:
-            mask_t = torch.zeros(t, dtype=torch.int32, device=roi.device)
-        elif tm == t:
-            mask_t = torch.arange(t, dtype=torch.int32, device=roi.device)
-        else:
-            raise ValueError("mask_t is required when fg/bg hold neither 1 nor T timesteps")
-    stats = torch.empty((m, c, t, 6), dtype=torch.float64, device=roi.device)
+    fg, bg, tm = _masks_u8(fg, bg, m, length)
+    mask_t = _default_mask_t(mask_t, tm, t, roi.device)
+    stats = torch.empty((m, c, t, NSTATS), dtype=torch.float64, device=roi.device)
     with torch.cuda.device(roi.device):
         _lib.call("mgb_roi_stats_u16" if roi.dtype == torch.uint16 else "mgb_roi_stats_f32", _ptr(roi), m, c, t,
                   int(length), _ptr(mask_t), tm, _ptr(fg), _ptr(bg), _ptr(stats), _stream())
+    if medians and m * c * t > 0:
+        _median_into(roi, fg, mask_t, tm, stats, 6)
+        _median_into(roi, bg, mask_t, tm, stats, 7)
     return stats
 
 
 def roi_median(roi: torch.Tensor, mask: torch.Tensor, mask_t: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Exact masked median per (m,c,t) -> (M,C,T) float64, NaN for an empty mask
     (`roi.where(mask).median(dim=["roi_x","roi_y"])`, identify.py:79, filter.py:21-22); uint16 or
-    float32 roi (NaN pixels skipped)."""
+    float32 roi (NaN pixels skipped), any roi_length."""
     if roi.dtype not in (torch.uint16, torch.float32):
         raise TypeError(f"roi must be uint16 or float32, got {roi.dtype}")
     _check(roi, "roi", ndim=5)
@@ -511,17 +561,11 @@ def roi_median(roi: torch.Tensor, mask: torch.Tensor, mask_t: Optional[torch.Ten
     tm = mask.shape[1]
     if tuple(mask.shape) != (m, tm, length, length):
         raise ValueError(f"mask must have shape ({m}, Tm, {length}, {length})")
-    if mask_t is None:
-        if tm == 1:
-            mask_t = torch.zeros(t, dtype=torch.int32, device=roi.device)
-        elif tm == t:
-            mask_t = torch.arange(t, dtype=torch.int32, device=roi.device)
-        else:
-            raise ValueError("mask_t is required when mask holds neither 1 nor T timesteps")
+    mask_t = _default_mask_t(mask_t, tm, t, roi.device, "mask")
     out = torch.empty((m, c, t), dtype=torch.float64, device=roi.device)
     with torch.cuda.device(roi.device):
         _lib.call("mgb_roi_median_u16" if roi.dtype == torch.uint16 else "mgb_roi_median_f32", _ptr(roi), m, c, t,
-                  int(length), _ptr(mask_t), tm, _ptr(mask), _ptr(out), _stream())
+                  int(length), _ptr(mask_t), tm, _ptr(mask), _ptr(out), 1, _stream())
     return out
 
 

@@ -51,7 +51,7 @@ class QuantifyResult:
     bg: torch.Tensor                   # (M,Tm,L,L) uint8
     mask_t: torch.Tensor               # (T,) int32 index into Tm
     boxes: torch.Tensor                # (M,T,2) int32
-    stats: torch.Tensor                # (M,C,T,6) float64
+    stats: torch.Tensor                # (M,C,T,8) float64 in ops.STATS order (medians included)
     maxima: Optional[torch.Tensor] = None
     timings: dict = field(default_factory=dict)
 
@@ -73,6 +73,8 @@ class QuantifyPlan:
         self.boxes = None
         self.order = None
         self.fg = self.bg = self.mask_t = None
+        self.mask_counts = None      # (largest fg count, largest bg count): sizes the gather's value lists
+        self.medians = True          # per-marker medians are part of the summaries (identify.py:79, filter.py:21-22)
 
     # -- markers ------------------------------------------------------------------------------
     def set_chip_markers(self, x, y, fg_radius, chamber_radius: int, max_button_radius: int,
@@ -107,6 +109,7 @@ class QuantifyPlan:
         index = {ts: k for k, ts in enumerate(search)}
         self.mask_t = torch.tensor([index[int(s)] for s in src], dtype=torch.int32, device=dev)
         self.order = ops.spatial_order(self.boxes)
+        self.mask_counts = ops.mask_count_max(self.fg, self.bg) if m else (0, 0)
         self.x, self.y = x, y
         return self
 
@@ -128,6 +131,7 @@ class QuantifyPlan:
         self.fg, self.bg = fg[:, None].contiguous(), bg[:, None].contiguous()
         self.mask_t = torch.zeros(t, dtype=torch.int32, device=dev)
         self.order = ops.spatial_order(self.boxes) if t > 0 else None
+        self.mask_counts = ops.mask_count_max(self.fg, self.bg) if m else (0, 0)
         self.x, self.y = x, y
         return self
 
@@ -152,12 +156,12 @@ class QuantifyPlan:
         finder + host grid fit + batched refinement, find.py:205-378) at its search timesteps,
         copied forward to the others (find.py:143-157), then `set_chip_markers`.  No image bytes
         leave the GPU.  tag: (rows, cols) array of chamber names ("" = blank)."""
-        from .dataset import Assay
+        from .dataset import Dataset
 
         c, t = self.tile_shape[:2]
         tag = np.asarray(tag)
         names = np.asarray(channels if channels is not None else [f"c{k}" for k in range(c)])
-        assay = Assay(coords={"tag": (("mark_row", "mark_col"), tag), "channel": (("channel",), names)})
+        assay = Dataset(coords={"tag": (("mark_row", "mark_col"), tag), "channel": (("channel",), names)})
         rows, cols = tag.shape
         src = copy_forward_sources(t, finder.search_timesteps)
         search = sorted(set(src.tolist()))
@@ -175,10 +179,10 @@ class QuantifyPlan:
     def locate_bead_markers(self, image: torch.Tensor, finder, channels=None):
         """Bead centres found on the device image by a `components.BeadFinder` (find.py:476-501),
         then `set_bead_markers`."""
-        from .dataset import Assay
+        from .dataset import Dataset
 
         names = np.asarray(channels if channels is not None else [f"c{k}" for k in range(self.tile_shape[0])])
-        beads = finder.find_centers(Assay(coords={"channel": (("channel",), names)}), image)
+        beads = finder.find_centers(Dataset(coords={"channel": (("channel",), names)}), image)
         return self.set_bead_markers(beads)
 
     def run_device(self, tiles: torch.Tensor, want_roi: bool = True, image_out=None, roi_out=None,
@@ -222,7 +226,8 @@ class QuantifyPlan:
             raise ValueError(f"image has shape {tuple(image.shape)}, plan expects {tuple(self.image_shape)}")
         roi, stats = stage("roi_gather_stats", lambda: ops.roi_gather_stats(
             image, self.boxes, self.fg, self.bg, self.roi_length, mask_t=self.mask_t, want_roi=want_roi,
-            out_roi=roi_out, out_stats=stats_out, order=self.order, peer_stats=peer_stats))
+            out_roi=roi_out, out_stats=stats_out, order=self.order, peer_stats=peer_stats, medians=self.medians,
+            mask_counts=self.mask_counts))
         return QuantifyResult(image, roi, self.fg, self.bg, self.mask_t, self.boxes, stats, maxima)
 
 
@@ -245,7 +250,7 @@ class HostStagedRunner:
         m = plan.boxes.shape[0]
         length = plan.roi_length
         self.roi_dev = torch.empty((m, c, t, length, length), dtype=torch.uint16, device=dev) if want_roi else None
-        self.stats_dev = torch.empty((m, c, t, 6), dtype=torch.float64, device=dev)
+        self.stats_dev = torch.empty((m, c, t, ops.NSTATS), dtype=torch.float64, device=dev)
         self.h2d = torch.cuda.Stream(device=dev)
         self.d2h = torch.cuda.Stream(device=dev)
         self.h2d_bytes = self.tiles_dev.numel() * 2
@@ -314,7 +319,7 @@ class HostStagedRunner:
                 ops.to_host_dense(image, out=image_host)   # one pitched copy, also for a padded image
         roi, stats = ops.roi_gather_stats(image, plan.boxes, plan.fg, plan.bg, plan.roi_length, mask_t=plan.mask_t,
                                           want_roi=self.want_roi, out_roi=self.roi_dev, out_stats=self.stats_dev,
-                                          order=plan.order)
+                                          order=plan.order, medians=plan.medians, mask_counts=plan.mask_counts)
         done_roi = torch.cuda.Event()
         done_roi.record(compute)
         with torch.cuda.stream(self.d2h):
@@ -329,6 +334,62 @@ class HostStagedRunner:
         torch.cuda.current_stream(self.plan.device).synchronize()
 
 
+class PinnedRing:
+    """`depth` pinned host slots of one block shape: the hop between memory the copy engine cannot
+    read asynchronously (pageable arrays, dask chunks, TIFF pages) and HBM.
+
+    `send(block, dst, stream)` waits until the next slot's previous upload has left it, fills it
+    -- `block` is an ndarray (copied by a small thread pool: NumPy copies release the GIL, so the
+    pageable->pinned memcpy of block k+1 overlaps the PCIe copy of block k) or a callable
+    `fill(slot_array)` that writes the block itself (reader.TiffTiles.blocks: native page reads
+    land in the slot, no pageable intermediate) -- and queues the upload into `dst` on `stream`.
+    Returns the event recorded after that upload."""
+
+    def __init__(self, block_shape, dtype=torch.uint16, depth: int = 4, threads: int = 4):
+        from concurrent.futures import ThreadPoolExecutor
+
+        self.block_shape = tuple(int(s) for s in block_shape)
+        self.slots = [torch.empty(self.block_shape, dtype=dtype, pin_memory=True) for _ in range(depth)]
+        self.free = [None] * depth
+        self.pool = ThreadPoolExecutor(max_workers=threads)
+        self.threads = threads
+        self.sent = 0
+
+    def _fill(self, slot: int, block) -> None:
+        dst = self.slots[slot].numpy()
+        if callable(block):
+            block(dst)
+            return
+        src = np.asarray(block)
+        if src.shape != dst.shape:
+            raise ValueError(f"chunk has shape {src.shape}, expected {dst.shape}")
+        if src.dtype != dst.dtype:
+            raise TypeError(f"chunk has dtype {src.dtype}, expected {dst.dtype}")
+        rows = max(1, dst.shape[0] * (dst.shape[1] if dst.ndim > 1 else 1))
+        d2, s2 = dst.reshape((rows, -1)), src.reshape((rows, -1))
+        parts = [idx for idx in np.array_split(np.arange(rows), self.threads) if len(idx)]
+        list(self.pool.map(lambda idx: np.copyto(d2[idx[0]:idx[-1] + 1], s2[idx[0]:idx[-1] + 1]), parts))
+
+    def send(self, block, dst: torch.Tensor, stream) -> "torch.cuda.Event":
+        slot = self.sent % len(self.slots)
+        if self.free[slot] is not None:
+            self.free[slot].synchronize()
+        self._fill(slot, block)
+        with torch.cuda.stream(stream):
+            dst.copy_(self.slots[slot], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        self.free[slot] = ev
+        self.sent += 1
+        return ev
+
+    def close(self) -> None:
+        for ev in self.free:
+            if ev is not None:
+                ev.synchronize()
+        self.pool.shutdown(wait=True)
+
+
 class ChunkStager:
     """Chunk provider -> pinned ring -> HBM: the staging loop for tiles that are NOT already in
     pinned memory (the reference's per-page dask chunks, reader.py:265-292, or any iterable of
@@ -336,41 +397,14 @@ class ChunkStager:
 
     `chunks` yields `((channel, time), block)` with block an ndarray shaped (R, Cc, H, W) -- one
     (channel, timepoint) block of the tile stack, in any order -- or a callable `fill(dst)` that
-    writes the block into the pinned slot itself (`reader.TiffTiles.blocks()`).  Each block is copied into one of
-    `depth` pinned staging buffers by a small thread pool (NumPy copies release the GIL, so the
-    pageable->pinned memcpy of block k+1 overlaps the PCIe copy of block k) and then sent to its
-    slot of the device tile stack on the copy stream; flat-field pass 1 runs on the compute stream
-    as blocks land.  After `feed()` the runner's `finish()` does pass 2 + gather + drain.
-    """
+    writes the block into the pinned slot itself (`reader.TiffTiles.blocks()`).  Flat-field pass 1
+    runs on the compute stream as blocks land.  After `feed()` the runner's `finish()` does
+    pass 2 + gather + drain."""
 
     def __init__(self, runner: HostStagedRunner, depth: int = 4, threads: int = 4):
-        from concurrent.futures import ThreadPoolExecutor
-
         self.runner = runner
         c, t, r, cc, h, w = runner.plan.tile_shape
-        self.block_shape = (r, cc, h, w)
-        self.staging = [torch.empty(self.block_shape, dtype=torch.uint16, pin_memory=True) for _ in range(depth)]
-        self.free_events = [None] * depth
-        self.pool = ThreadPoolExecutor(max_workers=threads)
-        self.threads = threads
-
-    def _fill(self, slot: int, block) -> None:
-        dst = self.staging[slot].numpy()
-        if callable(block):
-            # a reader that writes the block itself (reader.TiffTiles.blocks: native page reads
-            # land in the pinned slot, no pageable intermediate)
-            block(dst)
-            return
-        src = np.asarray(block)
-        if src.shape != dst.shape:
-            raise ValueError(f"chunk has shape {src.shape}, expected {dst.shape}")
-        if src.dtype != np.uint16:
-            raise TypeError(f"chunk has dtype {src.dtype}, expected uint16")
-        # split the copy over the pool's threads (row blocks of the first axis)
-        parts = np.array_split(np.arange(dst.shape[0] * dst.shape[1]), self.threads)
-        d2, s2 = dst.reshape((-1,) + dst.shape[2:]), src.reshape((-1,) + src.shape[2:])
-        list(self.pool.map(lambda idx: np.copyto(d2[idx[0]:idx[-1] + 1], s2[idx[0]:idx[-1] + 1]) if len(idx) else None,
-                           parts))
+        self.ring = PinnedRing((r, cc, h, w), torch.uint16, depth, threads)
 
     def feed(self, chunks) -> int:
         """Stage every chunk and run flat-field pass 1 on it.  Returns the number of blocks."""
@@ -382,15 +416,7 @@ class ChunkStager:
             ff.maxima.zero_()
         n = 0
         for (ci, ti), block in chunks:
-            slot = n % len(self.staging)
-            if self.free_events[slot] is not None:
-                self.free_events[slot].synchronize()      # the slot's previous H2D has left it
-            self._fill(slot, block)
-            with torch.cuda.stream(runner.h2d):
-                runner.tiles_dev[ci, ti].copy_(self.staging[slot], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(runner.h2d)
-            self.free_events[slot] = ev
+            ev = self.ring.send(block, runner.tiles_dev[ci, ti], runner.h2d)
             compute.wait_event(ev)
             if not ff.identity:
                 ops.flatfield_maxima_accumulate(runner.tiles_dev[ci, ti], ff, ci)
@@ -398,7 +424,7 @@ class ChunkStager:
         return n
 
     def close(self):
-        self.pool.shutdown(wait=True)
+        self.ring.close()
 
 
 def iter_blocks(tiles):
@@ -429,7 +455,7 @@ class StreamingRunner:
     (c, t) -- e.g. `lambda c, t, dst: tiles.read((c, t), dst)` for a `reader.TiffTiles`.
     sink(t, image, roi, stats): called once per timepoint, in order, with NumPy views of pinned
     buffers that are only valid during the call: image (C, Him, Wim) or None, roi (M, C, L, L) or
-    None, stats (M, C, 6)."""
+    None, stats (M, C, 8)."""
 
     def __init__(self, plan: QuantifyPlan, depth: int = 2, want_image: bool = True, want_roi: bool = True,
                  threads: int = 4):
@@ -451,12 +477,12 @@ class StreamingRunner:
         self.image_dev = [ops.alloc_image((c, 1, him, wim), torch.uint16, dev) for _ in range(depth)]
         self.roi_dev = [torch.empty((m, c, 1, length, length), dtype=torch.uint16, device=dev) if want_roi else None
                         for _ in range(depth)]
-        self.stats_dev = [torch.empty((m, c, 1, 6), dtype=torch.float64, device=dev) for _ in range(depth)]
+        self.stats_dev = [torch.empty((m, c, 1, ops.NSTATS), dtype=torch.float64, device=dev) for _ in range(depth)]
         self.image_pin = [torch.empty((c, 1, him, wim), dtype=torch.uint16, **pin) if want_image else None
                           for _ in range(depth)]
         self.roi_pin = [torch.empty((m, c, 1, length, length), dtype=torch.uint16, **pin) if want_roi else None
                         for _ in range(depth)]
-        self.stats_pin = [torch.empty((m, c, 1, 6), dtype=torch.float64, **pin) for _ in range(depth)]
+        self.stats_pin = [torch.empty((m, c, 1, ops.NSTATS), dtype=torch.float64, **pin) for _ in range(depth)]
         self.h2d = torch.cuda.Stream(device=dev)
         self.d2h = torch.cuda.Stream(device=dev)
         self.boxes_t = [plan.boxes[:, ti:ti + 1].contiguous() for ti in range(t)]
@@ -519,7 +545,8 @@ class StreamingRunner:
                                          maxima=None if ff.identity else ff.maxima, out=self.image_dev[slot])
             roi, stats = ops.roi_gather_stats(image, self.boxes_t[ti], plan.fg, plan.bg, plan.roi_length,
                                               mask_t=self.mask_t[ti], want_roi=self.want_roi,
-                                              out_roi=self.roi_dev[slot], out_stats=self.stats_dev[slot], order=plan.order)
+                                              out_roi=self.roi_dev[slot], out_stats=self.stats_dev[slot], order=plan.order,
+                                              medians=plan.medians, mask_counts=plan.mask_counts)
             done = torch.cuda.Event()
             done.record(compute)
             consumed[slot] = done

@@ -35,7 +35,7 @@ from typing import Callable, Dict, Iterator, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from .dataset import Assay, Var
+from .dataset import DataArray, Dataset
 
 TILE_ORDER = ("channel", "time", "tile_row", "tile_col", "tile_y", "tile_x")
 LETTER_TO_DIM = {"C": "channel", "T": "time", "Z": "depth", "Y": "tile_y", "X": "tile_x", "R": "tile_pos"}
@@ -385,6 +385,14 @@ class TiffTiles:
     def to_numpy(self) -> np.ndarray:
         return self.read(())
 
+    def __array_function__(self, func, types, args, kwargs):
+        # duck array: a Dataset keeps the lazy stack as it is; NumPy functions read it
+        conv = lambda o: o.read(()) if isinstance(o, TiffTiles) else o   # noqa: E731
+        return func(*[conv(a) for a in args], **{k: conv(v) for k, v in kwargs.items()})
+
+    def __getitem__(self, key):
+        return self.read(())[key]
+
     def blocks(self) -> Iterator[Tuple[Tuple[int, int], Callable[[np.ndarray], None]]]:
         """((channel, time), fill) for every block of a canonical 6-d stack: `fill(dst)` reads the
         block's pages straight into `dst` -- the chunk protocol of pipeline.ChunkStager.feed."""
@@ -401,7 +409,7 @@ class TiffTiles:
 # ---------------------------------------------------------------------------------------------
 # read_tiffs  (reader.py:163-326)
 # ---------------------------------------------------------------------------------------------
-def read_tiffs(xp_dict: Dict[tuple, str], name: str, meta_dict, threads: int = 8) -> Assay:
+def read_tiffs(xp_dict: Dict[tuple, str], name: str, meta_dict, threads: int = 8) -> Dataset:
     channel_idxs, time_idxs, row_idxs, col_idxs = (sorted(set(idx)) for idx in zip(*xp_dict.keys()))
     dims_in_path, outer_shape = [], ()
     for idxs, dim in ((channel_idxs, "channel"), (time_idxs, "time"), (row_idxs, "tile_row"), (col_idxs, "tile_col")):
@@ -450,54 +458,36 @@ def read_tiffs(xp_dict: Dict[tuple, str], name: str, meta_dict, threads: int = 8
     ordered = tuple(d for d in TILE_ORDER if d in dims) + tuple(d for d in dims if d not in TILE_ORDER)
     tiles = tiles.transpose(ordered)
 
-    xp = Assay(attrs={"name": name})
-    xp.data_vars["tile"] = LazyVar(ordered, tiles)
+    coords = {}
     if channels is not None:
-        xp.coords["channel"] = Var(("channel",), np.asarray(channels))
+        coords["channel"] = (("channel",), np.asarray(channels))
     if times is not None:
-        xp.coords["time"] = Var(("time",), np.asarray([int(t.timestamp()) for t in times]))
+        coords["time"] = (("time",), np.asarray([int(t.timestamp()) for t in times]))
     for (meta_name, dim), values in meta_dict.items():
         if dim == "time":
-            dim_idxs = [datetime.datetime.fromtimestamp(int(i)) for i in xp.coords[dim].values]
+            dim_idxs = [datetime.datetime.fromtimestamp(int(i)) for i in coords[dim][1]]
         else:
-            dim_idxs = list(xp.coords[dim].values)
-        xp.coords[meta_name] = Var((dim,), np.asarray([values[i] for i in dim_idxs]))
-    return xp
+            dim_idxs = list(coords[dim][1])
+        coords[meta_name] = ((dim,), np.asarray([values[i] for i in dim_idxs]))
+    return Dataset({"tile": (ordered, tiles)}, coords=coords, attrs={"name": name})
 
 
-class LazyVar(Var):
-    """A Var whose values are a TiffTiles (nothing is read until asked)."""
-
-    def __init__(self, dims, tiles: TiffTiles):
-        self.dims = tuple(dims)
-        self.values = tiles
-        if tiles.ndim != len(self.dims):
-            raise ValueError(f"{tiles.ndim}-d tiles given {len(self.dims)} dimension names")
-
-    def to_numpy(self) -> np.ndarray:
-        return self.values.to_numpy()
-
-    def __array__(self, dtype=None, copy=None):
-        return self.values.__array__(dtype)
-
-    def __getitem__(self, key):
-        return self.to_numpy()[key]
-
-
-def standardize_format(xp: Assay) -> Assay:
+def standardize_format(xp: Dataset) -> Dataset:
     """`standardize_format` (preprocess.py:11-42) for a lazily read tile stack: remember the
     original dims, add the missing canonical dims as length-1 and order them
-    (channel, time, tile_row, tile_col, tile_y, tile_x).  Extra (non-canonical) dims, which the
-    reference stacks into `time`, are not produced by `read_tiffs` and are rejected."""
+    (channel, time, tile_row, tile_col, tile_y, tile_x) without reading a page.  Extra
+    (non-canonical) dims, which the reference stacks into `time`, are not produced by `read_tiffs`
+    and are rejected."""
     tile = xp["tile"]
-    if not isinstance(tile, LazyVar):
-        raise TypeError("standardize_format here handles the lazy TIFF tile stack; use an in-memory Assay directly")
+    tiles = tile.data
+    if not isinstance(tiles, TiffTiles):
+        raise TypeError("standardize_format here handles the lazy TIFF tile stack of read_tiffs")
     extra = [d for d in tile.dims if d not in TILE_ORDER]
     if extra:
         raise ValueError(f"unexpected tile dims {extra}")
     new = xp.copy()
     new.attrs = dict(xp.attrs, __original_tile_dims__=list(tile.dims))
-    new.data_vars["tile"] = LazyVar(TILE_ORDER, tile.values.transpose(TILE_ORDER))
+    new["tile"] = (TILE_ORDER, tiles.transpose(TILE_ORDER))
     return new
 
 
@@ -507,10 +497,10 @@ class Reader:
     def __init__(self, threads: int = 8):
         self.threads = threads
 
-    def __call__(self, data) -> Iterator[Assay]:
-        items = [data] if isinstance(data, (str, os.PathLike, Assay)) else list(data)
+    def __call__(self, data) -> Iterator[Dataset]:
+        items = [data] if isinstance(data, (str, os.PathLike, Dataset, DataArray)) else list(data)
         for d in items:
-            if isinstance(d, Assay):
+            if isinstance(d, (Dataset, DataArray)):
                 yield d
                 continue
             path_dict, meta_dict = extract_paths(d, assay="str", channel="str", time="time", row="int", col="int")

@@ -963,3 +963,117 @@ def reference_identify_buttons(num_times, shape=None, pinlist=None, blank=None):
     assay = LabelledAssay({"image": (("channel", "time", "im_y", "im_x"), np.zeros((1, num_times, 2, 2), np.uint8))}, {})
     out = mod.identify_buttons(assay, shape=shape, pinlist=pinlist, blank=blank)
     return out._vars["tag"][1], out._vars["valid"][1]
+
+
+# ---------------------------------------------------------------------------------------------
+# The WHOLE reference package, unmodified, imported in place: `magnify` is created as a package
+# whose __path__ is /root/reference/src/magnify, so every submodule (registry.py, pipeline.py,
+# preprocess.py, stitch.py, find.py, identify.py, postprocess.py, reader.py ...) is executed from
+# the reference's own files by the normal import system.  Only the third-party packages that
+# are not installed here are stood in for:
+#   xarray        -> magnify_b200.dataset (the subset of the xarray API the pipeline uses)
+#   dask.array    -> NumPy (`empty`, `empty_like`; nothing is lazy)
+#   catalogue     -> a 20-line registry (create / register / get / get_all)
+#   tifffile, bs4 -> empty modules (only the TIFF reader needs them)
+#   napari, magnify.plot -> empty modules (GUI)
+# This is how the drop-in claim is exercised: `magnify_b200.components.install()` registers the
+# GPU components in the reference's own registry, and the reference's own `*_pipe` builders and
+# `Pipeline.__call__` (pipeline.py:14-29) run them.
+# ---------------------------------------------------------------------------------------------
+class CatalogueRegistry:
+    """catalogue.Registry: `register(name)` is a decorator (or `register(name, func=f)`), `get`
+    raises for unknown names, re-registering a name replaces it."""
+
+    def __init__(self, namespace):
+        self.namespace = tuple(namespace)
+        self._items = {}
+
+    def register(self, name, *, func=None):
+        def do(f):
+            self._items[name] = f
+            return f
+
+        return do(func) if func is not None else do
+
+    def get(self, name):
+        if name not in self._items:
+            raise KeyError(f"Cant't find '{name}' in registry {' -> '.join(self.namespace)}. "
+                           f"Available names: {', '.join(sorted(self._items)) or 'none'}")
+        return self._items[name]
+
+    def get_all(self):
+        return dict(self._items)
+
+    def __contains__(self, name):
+        return name in self._items
+
+
+_cached_pkg = None
+
+
+def load_reference_package():
+    """Import the reference package in place (see above).  Returns the `magnify` module, or None
+    when /root/reference is absent.  The stand-in modules stay in sys.modules afterwards (the
+    reference's functions look `xr`, `da` ... up at call time through their module globals,
+    which are bound at import, so this is only for later `import magnify.x` statements)."""
+    global _cached_pkg
+    if _cached_pkg is not None:
+        return _cached_pkg
+    root = os.path.join(REFERENCE_ROOT, "src", "magnify")
+    if not os.path.isdir(root):
+        return None
+    try:
+        import cv2  # noqa: F401
+        import numba  # noqa: F401
+        import pandas  # noqa: F401
+        import scipy  # noqa: F401
+        import tqdm  # noqa: F401
+    except Exception:
+        return None
+    import numpy as np
+
+    from magnify_b200 import dataset as xr_standin
+
+    mods = {}
+    mods["xarray"] = xr_standin
+    dask = types.ModuleType("dask")
+    da = types.ModuleType("dask.array")
+    da.Array = type("Array", (), {})
+    da.empty = lambda shape, dtype=float, chunks=None: np.empty(shape, dtype=dtype)
+    da.empty_like = lambda a, dtype=None, chunks=None: np.empty_like(np.asarray(a), dtype=dtype)
+    dask.array = da
+    mods["dask"], mods["dask.array"] = dask, da
+    catalogue = types.ModuleType("catalogue")
+    catalogue.create = lambda *namespace, entry_points=False: CatalogueRegistry(namespace)
+    mods["catalogue"] = catalogue
+    mods["tifffile"] = types.ModuleType("tifffile")
+    mods["bs4"] = types.ModuleType("bs4")
+    napari = types.ModuleType("napari")
+    napari_types = types.ModuleType("napari.types")
+    napari_types.LayerDataTuple = tuple
+    napari.types = napari_types
+    mods["napari"], mods["napari.types"] = napari, napari_types
+    plot = types.ModuleType("magnify.plot")
+    plot.__path__ = []
+    vis = types.ModuleType("magnify.plot.vis")
+    vis.InteractiveUI = type("InteractiveUI", (), {})
+    plot.vis = vis
+    mods["magnify.plot"], mods["magnify.plot.vis"] = plot, vis
+    for k, v in mods.items():
+        sys.modules.setdefault(k, v)
+    if sys.modules["xarray"] is not xr_standin:
+        return None       # a real xarray is installed: import magnify normally instead
+    spec = importlib.util.spec_from_file_location("magnify", os.path.join(root, "__init__.py"),
+                                                  submodule_search_locations=[root])
+    pkg = importlib.util.module_from_spec(spec)
+    sys.modules["magnify"] = pkg
+    pkg.plot = plot
+    try:
+        spec.loader.exec_module(pkg)
+    except Exception:
+        sys.modules.pop("magnify", None)
+        for k in [k for k in sys.modules if k.startswith("magnify.")]:
+            sys.modules.pop(k, None)
+        raise
+    _cached_pkg = pkg
+    return pkg

@@ -13,11 +13,11 @@ import warnings
 
 import numpy as np
 
-STATS = ("n_fg", "n_bg", "sum_fg", "sum_bg", "mean_fg", "mean_bg")
+STATS = ("n_fg", "n_bg", "sum_fg", "sum_bg", "mean_fg", "mean_bg", "median_fg", "median_bg")
 
 
 def masked_stats(roi: np.ndarray, fg: np.ndarray, bg: np.ndarray) -> np.ndarray:
-    """roi (M, C, T, L, L), fg/bg (M, T, L, L) bool -> (M, C, T, 6) float64 in STATS order."""
+    """roi (M, C, T, L, L), fg/bg (M, T, L, L) bool -> (M, C, T, 8) float64 in STATS order."""
     m, c, t = roi.shape[:3]
     out = np.empty((m, c, t, len(STATS)), dtype=np.float64)
     r = roi.astype(np.float64)
@@ -29,6 +29,7 @@ def masked_stats(roi: np.ndarray, fg: np.ndarray, bg: np.ndarray) -> np.ndarray:
             out[..., 0 + k] = np.broadcast_to(mask.sum(axis=(-2, -1))[:, None], (m, c, t))
             out[..., 2 + k] = np.nansum(vals, axis=(-2, -1))
             out[..., 4 + k] = np.nanmean(vals, axis=(-2, -1))
+            out[..., 6 + k] = np.nanmedian(vals.reshape(vals.shape[:3] + (-1,)), axis=-1)
     return out
 
 

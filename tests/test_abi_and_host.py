@@ -28,7 +28,7 @@ def test_library_exports_header_symbols(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mgb_abi_version() == 11
+    assert lib.mgb_abi_version() == 12
     assert lib.mgb_error_string(-2).decode().startswith("pointer")
 
 
@@ -38,6 +38,11 @@ def test_sass_is_sm100a():
     if out.returncode != 0:
         pytest.skip("cuobjdump unavailable")
     assert "sm_100a" in out.stdout
+    # the staged gather really is TMA + mbarrier code, the masked sums really are dot-product
+    # instructions (profiles/r02_sass_summary.md holds the per-kernel counts)
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    for mnemonic in ("UTMALDG", "SYNCS", "LDGSTS", "IDP.2A", "REDUX"):
+        assert mnemonic in sass, mnemonic
 
 
 def test_disc_halfwidths_host_entry_point(lib, golden):

@@ -1,13 +1,13 @@
-"""CPU-side behaviour of the component layer: the Assay stand-in, argument errors that must be
-raised before anything touches a GPU, and the registry installer's failure mode."""
+"""CPU-side behaviour of the component layer: the Dataset container used when xarray is absent,
+argument errors that must be raised before anything touches a GPU, the registry installer."""
 import numpy as np
 import pytest
 
 
-def test_assay_container():
-    from magnify_b200.dataset import Assay
+def test_dataset_container():
+    from magnify_b200.dataset import Dataset
 
-    a = Assay({"tile": (("channel", "y", "x"), np.zeros((2, 4, 5)))}, coords={"channel": (("channel",), np.array(["a", "b"]))})
+    a = Dataset({"tile": (("channel", "y", "x"), np.zeros((2, 4, 5)))}, coords={"channel": (("channel",), np.array(["a", "b"]))})
     assert "tile" in a and "image" not in a and a.sizes == {"channel": 2, "y": 4, "x": 5}
     assert a.tile.dims == ("channel", "y", "x") and a["tile"].shape == (2, 4, 5)
     with pytest.raises(AttributeError):
@@ -18,6 +18,32 @@ def test_assay_container():
     assert "valid" in b and "valid" not in a
     assert b.drop_vars(["tile"]).sizes == {"channel": 2}
     assert a.tile.isel(channel=0).dims == ("y", "x")
+    assert a.tile.sel(channel="b").dims == ("y", "x") and list(a.channel.values) == ["a", "b"]
+
+
+def test_dataset_stack_unstack_like_xarray():
+    """stack puts the merged dimension last and broadcasts variables that hold only some of the
+    dims; unstack puts the level dims last (xarray's orders, which find.py:182 and
+    postprocess.py:22 rely on); write-through views (find.py:127-137 assigns into `assay.x[..., t]`)."""
+    from magnify_b200.dataset import Dataset
+
+    ds = Dataset({"roi": (("r", "c", "t"), np.arange(24).reshape(2, 3, 4))},
+                 coords={"tag": (("r", "c"), np.array([["a", "b", "c"], ["d", "e", "f"]])), "rowinfo": (("r",), [10, 20])})
+    st = ds.stack(mark=("r", "c"))
+    assert st.roi.dims == ("t", "mark") and st.tag.dims == ("mark",) and st.rowinfo.dims == ("mark",)
+    assert list(st.rowinfo.values) == [10, 10, 10, 20, 20, 20] and list(st.r.values) == [0, 0, 0, 1, 1, 1]
+    np.testing.assert_array_equal(st.transpose("mark", ...).roi.values, np.arange(24).reshape(6, 4))
+    un = st.unstack()
+    assert un.roi.dims == ("t", "r", "c")
+    np.testing.assert_array_equal(un.roi.transpose("r", "c", "t").values, ds.roi.values)
+    ds.roi[:, 1, 2] = -1
+    assert (ds["roi"].values[:, 1, 2] == -1).all()
+    ds.roi[..., 0] = ds.roi[..., 3]
+    np.testing.assert_array_equal(ds.roi.values[..., 0], ds.roi.values[..., 3])
+    masked = ds.roi.where(ds.roi > 5)
+    assert masked.dtype == np.float64 and np.isnan(masked.values[0, 0, 1])
+    assert ds.roi.astype(np.uint16).where(ds.roi > 5).dtype == np.float32          # xarray's maybe_promote
+    assert float(masked.median(dim=["r", "c"]).values[1]) == np.nanmedian(masked.values[:, :, 1])
 
 
 def test_constructor_errors_match_reference():
@@ -38,80 +64,28 @@ def test_constructor_errors_match_reference():
 def test_install_needs_magnify():
     from magnify_b200 import components
 
-    try:
-        import magnify  # noqa: F401
-    except Exception:
-        with pytest.raises(ImportError):
-            components.install()
-    else:
-        names = components.install()
-        assert "stitch" in names and "quantify" in names
+    import sys
 
+    if "magnify" not in sys.modules:
+        try:
+            import magnify  # noqa: F401
+        except Exception:
+            with pytest.raises(ImportError):
+                components.install()
+            from magnify_b200 import api
 
-def test_api_standardize_and_restore_shapes():
-    """api._standardized / _restore: the dims bookkeeping of standardize_format / restore_format
-    (preprocess.py:11-42, postprocess.py:20-49) without touching the GPU."""
-    from magnify_b200 import api
-    from magnify_b200.dataset import Var
+            with pytest.raises(ImportError):
+                api.beads(None)
 
-    arr = np.arange(2 * 3 * 4 * 5, dtype=np.uint16).reshape(3, 2, 4, 5)            # (time, channel, y, x)
-    (xp,) = api._standardized(arr, ("time", "channel", "y", "x"), {"channel": ["a", "b"]})
-    assert xp["tile"].dims == ("channel", "time", "tile_row", "tile_col", "tile_y", "tile_x")
-    assert xp["tile"].values.shape == (2, 3, 1, 1, 4, 5)
-    np.testing.assert_array_equal(xp["tile"].values[1, 2, 0, 0], arr[2, 1])
-    assert xp.attrs["__original_tile_dims__"] == ["time", "channel", "tile_y", "tile_x"]
-    with pytest.raises(ValueError):
-        api._standardized(arr, None, None)
+    class Registry(dict):                       # anything with catalogue's `register(name)` works
+        def register(self, name):
+            return lambda f: self.__setitem__(name, f) or f
 
-    class Labelled:                                   # the duck type of xarray.DataArray
-        dims = ("channel", "y", "x")
-        values = arr[0]
-        coords = {"channel": Var(("channel",), np.array(["bf", "gfp"]))}
-
-    (lab,) = api._standardized(Labelled(), None, None)
-    assert lab["tile"].values.shape == (2, 1, 1, 1, 4, 5) and list(lab.coords["channel"].values) == ["bf", "gfp"]
-    with pytest.raises(NotImplementedError):
-        api._standardized(arr, ("time", "depth", "y", "x"), None)
-    # restore: un-stack marks, squeeze the added channel axis, keep the original time axis
-    (xp,) = api._standardized(arr[:, 0], ("time", "y", "x"), None)
-    xp.data_vars["roi"] = Var(("mark", "channel", "time", "roi_y", "roi_x"), np.zeros((6, 1, 3, 8, 8), np.uint16))
-    xp.coords["x"] = Var(("mark", "time"), np.zeros((6, 3)))
-    xp.coords["mark_row"] = Var(("mark",), np.repeat(np.arange(2), 3))
-    out = api._restore(xp, (2, 3))
-    assert out.roi.dims == ("mark_row", "mark_col", "time", "roi_y", "roi_x") and out.roi.shape == (2, 3, 3, 8, 8)
-    assert out.x.dims == ("mark_row", "mark_col", "time") and "tile" not in out and "mark_row" not in out
-    assert "__original_tile_dims__" not in out.attrs
-    only = api._restore(xp, (2, 3), roi_only=True)
-    assert only.dims == out.roi.dims and only.shape == out.roi.shape
-    kept = api._restore(xp, (2, 3), drop_tiles=False)
-    assert kept.tile.dims == ("time", "tile_y", "tile_x") and kept.tile.shape == (3, 4, 5)
-
-
-def test_pinlist_matches_reference_identify_buttons(tmp_path):
-    """api.read_pinlist == the tag array of the reference's identify_buttons (identify.py:13-45, pandas)
-    run in place, for names, listed blanks, missing names and a custom blank list."""
-    import os
-
-    from magnify_b200 import api
-    from oracle._refload import reference_identify_buttons
-
-    path = os.path.join(tmp_path, "pins.csv")
-    with open(path, "w") as f:
-        f.write("Indices,MutantID,Other\n")
-        names = {(1, 1): "wt", (2, 1): "blank", (3, 1): "mutA", (1, 2): "", (2, 2): "BLANK", (3, 2): "a_longer_name_17",
-                 (1, 3): "x", (2, 3): "EMPTY", (3, 3): "y"}
-        for (col, row), name in names.items():
-            f.write(f'"({col},{row})",{name},7\n')
-    for blank in (None, ["EMPTY", "x"]):
-        mine = api.read_pinlist(path, blank)
-        assert mine.shape == (3, 3)
-        ref = reference_identify_buttons(4, pinlist=path, blank=blank)
-        if ref is None:
-            pytest.skip("/root/reference not available (GPU box)")
-        np.testing.assert_array_equal(mine, ref[0].astype(mine.dtype))
-        assert ref[1].shape == (3, 3, 4) and ref[1].all()
-    tag, valid = reference_identify_buttons(2, shape=(2, 5))
-    assert tag.shape == (2, 5) and (tag == "default").all() and tag.dtype == np.dtype("<U200")
+    reg = Registry()
+    names = components.install(registry=reg)
+    assert "stitch" in names and "quantify" in names and reg["stitch"] is components.make_stitch
+    assert reg["find_buttons_b200"] is reg["find_buttons"]
+    assert "stitch" not in Registry() and components.install(False, Registry()) == names
 
 
 def test_factories_cover_the_reference_names():

@@ -38,7 +38,7 @@ def test_chip_pipeline_from_tiff_tiles(cuda_device, tmp_path):
                            rows_per_strip=50)
     (xp,) = list(reader.Reader()(os.path.join(tmp_path, "chip_(channel)_(time)_(row)_(col).tif")))
     xp = reader.standardize_format(xp)
-    assert xp["tile"].values.shape == (1, t, 2, 2, 350 + overlap, 250 + overlap)
+    assert xp["tile"].shape == (1, t, 2, 2, 350 + overlap, 250 + overlap)
     tag = np.full(shape, "default", dtype="<U200")                                          # identify.py:30-32
     tag[1, 2] = ""
     xp = xp.assign_coords(tag=(("mark_row", "mark_col"), tag),

@@ -23,7 +23,7 @@ def dev(a, device):
 @pytest.fixture(params=["staged_cpasync", "staged_tma", "plain"])
 def gather_path(request, cuda_device):
     """Run the ROI-gather tests through every implementation: windows staged in shared memory by
-    cp.async chunks (default) or by TMA tensor copies, and the plain load/store kernels."""
+    TMA tensor copies (the default) or by cp.async chunks, and the plain load/store kernels."""
     from magnify_b200 import _lib
 
     lib = _lib.load()
@@ -283,7 +283,7 @@ def test_beads_zero_markers(cuda_device, gather_path):
     assert tuple(roi.shape) == (0, 2, 1, 20, 20)
     fg, bg = ops.bead_masks(labels, boxes[:, 0].contiguous(), 20)
     roi, stats = ops.roi_gather_stats(image, boxes, fg[:, None].contiguous(), bg[:, None].contiguous(), 20)
-    assert tuple(stats.shape) == (0, 2, 1, 6)
+    assert tuple(stats.shape) == (0, 2, 1, 8)
 
 
 # -------------------------------------------------------------------------------- chip golden
@@ -642,10 +642,120 @@ def test_float32_roi_stats_and_median(cuda_device):
                     np.testing.assert_allclose(stats[mi, ci, ti, :4], want, rtol=1e-12)
                     with np.errstate(invalid="ignore", divide="ignore"):
                         means = [np.float64(want[2]) / want[0], np.float64(want[3]) / want[1]]
-                    np.testing.assert_allclose(stats[mi, ci, ti, 4:], means, rtol=1e-12, equal_nan=True)
+                    np.testing.assert_allclose(stats[mi, ci, ti, 4:6], means, rtol=1e-12, equal_nan=True)
                     vals = np.sort(px[f & ok])
                     if len(vals) == 0:
-                        assert np.isnan(med[mi, ci, ti])
+                        assert np.isnan(med[mi, ci, ti]) and np.isnan(stats[mi, ci, ti, 6])
                     else:
                         lo, hi = vals[(len(vals) - 1) // 2], vals[len(vals) // 2]
                         assert med[mi, ci, ti] == 0.5 * (lo + hi), (length, mi, ci, ti)
+                        assert stats[mi, ci, ti, 6] == med[mi, ci, ti]
+
+
+# ------------------------------------------------------- fused medians, hardened reductions
+def _disc_masks(rng, m, tm, length, r_fg, r_in, r_out):
+    yy, xx = np.mgrid[0:length, 0:length]
+    fg = np.zeros((m, tm, length, length), dtype=bool)
+    bg = np.zeros_like(fg)
+    for i in range(m):
+        for k in range(tm):
+            cy, cx = rng.integers(length // 2 - 3, length // 2 + 4, 2)
+            d2 = (yy - cy) ** 2 + (xx - cx) ** 2
+            r = rng.integers(max(1, r_fg - 4), r_fg + 1)
+            fg[i, k] = d2 <= r * r
+            bg[i, k] = (d2 > r_in * r_in) & (d2 <= r_out * r_out)
+    return fg, bg
+
+
+@pytest.mark.parametrize("layout", ["cta", "warp"])
+@pytest.mark.parametrize("length,r_fg,r_in,r_out", [(72, 15, 15, 30), (50, 10, 12, 24), (64, 14, 0, 26), (33, 6, 7, 15),
+                                                      (100, 17, 20, 28)])
+def test_gather_fused_medians(cuda_device, monkeypatch, layout, length, r_fg, r_in, r_out):
+    """Masks small enough for the in-kernel value lists (chip discs / annuli, bead-sized masks):
+    counts, sums, means and both medians come out of the gather itself, in both work layouts
+    (one CTA per marker, one warp per marker) and with or without the crops; they equal the
+    oracle's nanmean / nanmedian (identify.py:76-80, filter.py:21-22) exactly."""
+    from magnify_b200 import ops
+
+    monkeypatch.setenv("MGB_GATHER_LAYOUT", "1" if layout == "warp" else "0")
+    rng = np.random.default_rng(length)
+    c, t, h, w, m = 3, 4, 300, 512, 37
+    image = np.clip(rng.normal(600, 40, (c, t, h, w)), 0, 65535).astype(np.uint16)
+    image[0, 0, :40] = 65535                      # saturated band
+    image[1] //= 64                               # few distinct values: many ties around the median
+    x = rng.uniform(-5, w + 5, (m, t))
+    y = rng.uniform(-5, h + 5, (m, t))
+    mask_t = np.array([0, 1, 1, 0], dtype=np.int32)
+    fg, bg = _disc_masks(rng, m, 2, length, r_fg, r_in, r_out)
+    fg[3] = False                                 # empty masks -> NaN mean and median
+    bg[4, 1] = False
+    fg[5, 0] = False
+    fg[5, 0, 10, 10] = True                       # single pixel
+    fg[6, 0] = False
+    fg[6, 0, 10, 10:12] = True                    # two pixels: mean of both
+    want_roi = o_rois.gather_rois(image, x, y, length)
+    want = o_red.masked_stats(want_roi, fg[:, mask_t], bg[:, mask_t])
+    boxes = ops.bounding_boxes(dev(x, cuda_device), dev(y, cuda_device), length, w, h)
+    fg_d, bg_d = dev(fg.view(np.uint8) * 255, cuda_device), dev(bg.view(np.uint8), cuda_device)   # 0/255 and 0/1 bytes
+    counts = ops.mask_count_max(fg_d, bg_d)
+    assert counts == (int(fg.sum((-1, -2)).max()), int(bg.sum((-1, -2)).max()))
+    for want_roi_flag in (True, False):
+        roi, stats = ops.roi_gather_stats(dev(image, cuda_device), boxes, fg_d, bg_d, length,
+                                          mask_t=dev(mask_t, cuda_device), want_roi=want_roi_flag, mask_counts=counts)
+        if want_roi_flag:
+            np.testing.assert_array_equal(roi.cpu().numpy(), want_roi)
+        got = stats.cpu().numpy()
+        np.testing.assert_array_equal(got[..., :4], want[..., :4])
+        np.testing.assert_allclose(got[..., 4:6], want[..., 4:6], rtol=1e-12, equal_nan=True)
+        np.testing.assert_array_equal(got[..., 6:], want[..., 6:])
+    _, no_med = ops.roi_gather_stats(dev(image, cuda_device), boxes, fg_d, bg_d, length, mask_t=dev(mask_t, cuda_device),
+                                     medians=False, mask_counts=counts)
+    no_med = no_med.cpu().numpy()
+    np.testing.assert_array_equal(no_med[..., :6], got[..., :6])
+    assert np.isnan(no_med[..., 6:]).all()
+
+
+@pytest.mark.parametrize("length", [256, 300, 1024])
+def test_saturated_sums_do_not_wrap(cuda_device, gather_path, length):
+    """A 65535-valued image under full masks: the per-ROI sums (L^2 * 65535, above 2^32 from
+    L = 257) must be exact in every gather kernel, also with 255-valued mask bytes."""
+    from magnify_b200 import ops
+
+    c, t, h, w, m = 1, 2, length + 8, length + 16, 3
+    image = torch.full((c, t, h, w), 65535, dtype=torch.uint16, device=cuda_device)
+    x = torch.tensor([[length / 2, length / 2 + 3.0]] * m, dtype=torch.float64, device=cuda_device)
+    y = torch.tensor([[length / 2 + 1.0, length / 2]] * m, dtype=torch.float64, device=cuda_device)
+    boxes = ops.bounding_boxes(x, y, length, w, h)
+    fg = torch.full((m, 1, length, length), 255, dtype=torch.uint8, device=cuda_device)
+    bg = torch.ones((m, 1, length, length), dtype=torch.uint8, device=cuda_device)
+    bg[1, 0, ::2] = 0
+    roi, stats = ops.roi_gather_stats(image, boxes, fg, bg, length)
+    assert bool((roi == 65535).all())
+    s = stats.cpu().numpy()
+    n_bg = bg.sum((-1, -2, -3)).cpu().numpy().astype(np.float64)
+    np.testing.assert_array_equal(s[..., 0], float(length * length))
+    np.testing.assert_array_equal(s[..., 2], float(length * length) * 65535.0)
+    np.testing.assert_array_equal(s[..., 1], np.broadcast_to(n_bg[:, None, None], s[..., 1].shape))
+    np.testing.assert_array_equal(s[..., 3], np.broadcast_to(n_bg[:, None, None] * 65535.0, s[..., 3].shape))
+    np.testing.assert_array_equal(s[..., 4:], 65535.0)
+    stats2 = ops.roi_stats(roi, fg, bg).cpu().numpy()
+    np.testing.assert_array_equal(stats2, s)
+
+
+@pytest.mark.parametrize("length", [161, 200, 333])
+def test_median_large_roi(cuda_device, length):
+    """roi_length above 160 (max_bead_diameter > 80 gives L = 2 d; chamber_diameter > 133 gives
+    L = 1.2 d): the median re-reads the window per bisection step instead of refusing."""
+    from magnify_b200 import ops
+
+    rng = np.random.default_rng(length)
+    m, c, t = 3, 2, 2
+    roi = rng.integers(0, 65535, (m, c, t, length, length), dtype=np.uint16, endpoint=True)
+    roi[1] //= 4096
+    mask = rng.random((m, t, length, length)) < 0.5
+    mask[2, 1] = False
+    got = ops.roi_median(dev(roi, cuda_device), dev(mask.view(np.uint8), cuda_device)).cpu().numpy()
+    np.testing.assert_array_equal(got, o_red.masked_median(roi, mask))
+    f32 = (rng.standard_normal((m, c, t, length, length)) * 100).astype(np.float32)
+    got = ops.roi_median(dev(f32, cuda_device), dev(mask.view(np.uint8), cuda_device)).cpu().numpy()
+    np.testing.assert_array_equal(got, o_red.masked_median(f32, mask))

@@ -157,7 +157,7 @@ def test_tiff_tiles_staged_through_pinned_ring(cuda_device, tmp_path):
         write_tiff(os.path.join(tmp_path, f"chip_ch{idx[0]}_2024010{idx[1] + 1}-000000_{idx[2]}_{idx[3]}.tif"),
                    [tiles_np[idx]], rows_per_strip=[None, 64, 100][idx[3] % 3], big=bool(idx[2] % 2))
     (xp,) = list(reader.Reader(threads=4)(os.path.join(tmp_path, "chip_(channel)_(time)_(row)_(col).tif")))
-    tiles = xp["tile"].values
+    tiles = xp["tile"].data
     assert tiles.shape == tiles_np.shape
 
     plan = pipeline.QuantifyPlan(case.tiles.shape, case.overlap, case.roi_length, case.flat, case.dark,
@@ -270,7 +270,7 @@ def test_streaming_runner_two_passes(cuda_device, tmp_path, identity):
         for idx in np.ndindex(*tiles_np.shape[:4]):
             write_tiff(os.path.join(tmp_path, f"s_ch{idx[0]}_2024010{idx[1] + 1}-000000_{idx[2]}_{idx[3]}.tif"), [tiles_np[idx]])
         (xp,) = list(reader.Reader(threads=4)(os.path.join(tmp_path, "s_(channel)_(time)_(row)_(col).tif")))
-        lazy = xp["tile"].values
+        lazy = xp["tile"].data
         check(lambda ci, ti, dst: lazy.read((ci, ti), dst), depth=2)
     with pytest.raises(ValueError):
         pipeline.StreamingRunner(plan, depth=1)

@@ -1,9 +1,10 @@
-"""magnify_b200/chipgrid.py against the reference's own clustering helpers (find.py:630-757)
-loaded in place, and against the tail of ButtonFinder.find_centers (find.py:233-306)."""
+"""magnify_b200/gridfit.py (all comb offsets evaluated at once, closed-form line fits) side by side
+with the reference's own helpers (find.py:630-757) loaded in place, and with the tail of
+ButtonFinder.find_centers (find.py:233-306): identical labels, fits equal to rounding."""
 import numpy as np
 import pytest
 
-from magnify_b200 import chipgrid
+from magnify_b200 import gridfit
 
 
 def reference_find():
@@ -35,23 +36,23 @@ def test_helpers_match_reference_functions():
         pts = jittered_grid(rng, rows, cols, row_dist, col_dist, top, left)
         shape = (int(top + rows * row_dist + 80), int(left + cols * col_dist + 80))
         ideal_r, ideal_c = np.full(rows, cols), np.full(cols, rows)
-        a = chipgrid.cluster_1d(pts[:, 0], shape[0], rows, row_dist, ideal_r, 10)
+        a = gridfit.comb_labels(pts[:, 0], shape[0], rows, row_dist, ideal_r, 10)
         np.testing.assert_array_equal(a, ref.cluster_1d(pts[:, 0], shape[0], rows, row_dist, ideal_r, 10))
-        b = chipgrid.label_clusters(pts[:, 1], left - 20, cols, 40, col_dist - 40)
+        b = gridfit.spaced_labels(pts[:, 1], left - 20, cols, 40, col_dist - 40)
         np.testing.assert_array_equal(b, ref.label_clusters(pts[:, 1], left - 20, cols, 40, col_dist - 40))
         keep = (a >= 0) & (b >= 0)
-        got = chipgrid.regress_clusters(pts[keep, 1], pts[keep, 0], a[keep], rows, ideal_r)
+        got = gridfit.fit_lines(pts[keep, 1], pts[keep, 0], a[keep], rows, ideal_r)
         want = ref.regress_clusters(pts[keep, 1], pts[keep, 0], a[keep], rows, ideal_r)
-        assert got[0] == want[0]
-        np.testing.assert_array_equal(got[1], want[1])
-    one = chipgrid.regress_clusters(np.array([1.0, 2.0, 4.0]), np.array([2.0, 4.1, 8.2]), np.zeros(3, int), 1, np.array([3]))
+        np.testing.assert_allclose(got[0], want[0], rtol=1e-10)
+        np.testing.assert_allclose(got[1], want[1], rtol=1e-10, atol=1e-9)
+    one = gridfit.fit_lines(np.array([1.0, 2.0, 4.0]), np.array([2.0, 4.1, 8.2]), np.zeros(3, int), 1, np.array([3]))
     ref_one = ref.regress_clusters(np.array([1.0, 2.0, 4.0]), np.array([2.0, 4.1, 8.2]), np.zeros(3, int), 1, np.array([3]))
-    assert tuple(one) == tuple(ref_one)
+    np.testing.assert_allclose(one, ref_one, rtol=1e-12)
 
 
 def test_grid_centers_matches_reference_find_centers_tail(monkeypatch):
     """ButtonFinder.find_centers with its circle finder pinned to given points
-    (find.py:205-306 executed in place) == chipgrid.merge_channel_points + grid_centers."""
+    (find.py:205-306 executed in place) == gridfit.merge_channel_points + grid_centers."""
     ref = reference_find()
     from oracle._refload import LabelledArray
 
@@ -90,7 +91,7 @@ def test_grid_centers_matches_reference_find_centers_tail(monkeypatch):
         want_x, want_y = finder.find_centers(images, assay)
         pts = np.empty((0, 2))
         for new in per_channel:
-            pts = chipgrid.merge_channel_points(pts, new, finder.chamber_radius)
-        got_x, got_y = chipgrid.grid_centers(pts, tag, shape, row_dist, col_dist, finder.chamber_radius, top, left, 10)
-        np.testing.assert_array_equal(got_x, want_x)
-        np.testing.assert_array_equal(got_y, want_y)
+            pts = gridfit.merge_channel_points(pts, new, finder.chamber_radius)
+        got_x, got_y = gridfit.grid_centers(pts, tag, shape, row_dist, col_dist, finder.chamber_radius, top, left, 10)
+        np.testing.assert_allclose(got_x, want_x, rtol=1e-10, atol=1e-8)
+        np.testing.assert_allclose(got_y, want_y, rtol=1e-10, atol=1e-8)

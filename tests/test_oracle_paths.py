@@ -231,13 +231,15 @@ def test_masked_stats_and_median():
     bg = ~fg
     fg[1] = False
     s = red.masked_stats(roi, fg, bg)
-    assert s.shape == (3, 2, 2, 6)
-    assert np.isnan(s[1, :, :, 4]).all() and (s[1, :, :, 0] == 0).all()
+    assert s.shape == (3, 2, 2, 8)
+    assert np.isnan(s[1, :, :, 4]).all() and (s[1, :, :, 0] == 0).all() and np.isnan(s[1, :, :, 6]).all()
     m, c, t = 2, 1, 0
     vals = roi[m, c, t][fg[m, t]]
     assert s[m, c, t, 0] == vals.size and s[m, c, t, 2] == vals.sum() and s[m, c, t, 4] == vals.mean()
     med = red.masked_median(roi, fg)
     assert med[m, c, t] == np.median(vals) and np.isnan(med[1]).all()
+    np.testing.assert_array_equal(s[..., 6], med)
+    np.testing.assert_array_equal(s[..., 7], red.masked_median(roi, bg))
 
 
 def filter_cases(g):

@@ -171,12 +171,12 @@ def test_read_tiffs_file_per_index(tmp_path):
         write_tiff(os.path.join(tmp_path, f"xp_{chs[idx[0]]}_{stamps[idx[1]]}_{idx[2]}_{idx[3]}.tif"), [tiles[idx]],
                    rows_per_strip=7)
     (xp,) = list(reader.Reader(threads=3)(os.path.join(tmp_path, "xp_(channel)_(time)_(row)_(col).tif")))
-    assert xp["tile"].dims == reader.TILE_ORDER and xp["tile"].values.shape == tiles.shape
+    assert xp["tile"].dims == reader.TILE_ORDER and xp["tile"].shape == tiles.shape
     np.testing.assert_array_equal(np.asarray(xp["tile"]), tiles)
-    np.testing.assert_array_equal(xp["tile"].values.read((1, 2)), tiles[1, 2])
+    np.testing.assert_array_equal(xp["tile"].data.read((1, 2)), tiles[1, 2])
     assert list(xp.coords["channel"].values) == chs
     assert np.diff(xp.coords["time"].values).tolist() == [60, 60]
-    blocks = dict(xp["tile"].values.blocks())
+    blocks = dict(xp["tile"].data.blocks())
     dst = np.empty((r, cc, h, w), np.uint16)
     blocks[(0, 1)](dst)
     np.testing.assert_array_equal(dst, tiles[0, 1])
@@ -184,7 +184,7 @@ def test_read_tiffs_file_per_index(tmp_path):
     (xp2,) = list(reader.Reader()(os.path.join(tmp_path, "xp_cy5_20240101-120000_(row)_(col).tif")))
     assert xp2["tile"].dims == ("tile_row", "tile_col", "tile_y", "tile_x")
     std = reader.standardize_format(xp2)
-    assert std["tile"].dims == reader.TILE_ORDER and std["tile"].values.shape == (1, 1, r, cc, h, w)
+    assert std["tile"].dims == reader.TILE_ORDER and std["tile"].shape == (1, 1, r, cc, h, w)
     assert std.attrs["__original_tile_dims__"] == ["tile_row", "tile_col", "tile_y", "tile_x"]
     np.testing.assert_array_equal(np.asarray(std["tile"])[0, 0], tiles[0, 0])
     with pytest.raises(FileNotFoundError):
@@ -210,7 +210,7 @@ def test_read_tiffs_ome_series_with_micromanager_summary(tmp_path):
     assert list(xp.coords["channel"].values) == ["a", "b"]
     assert np.diff(xp.coords["time"].values).tolist() == [2, 2]      # DeltaT of every c-th plane
     std = reader.standardize_format(xp)
-    np.testing.assert_array_equal(std["tile"].values.read((1, 2)), arr[1, 2][:, None])
+    np.testing.assert_array_equal(std["tile"].data.read((1, 2)), arr[1, 2][:, None])
     # a multi-page file without OME-XML has the series axis "I": unmappable, like reader.py:208
     write_tiff(os.path.join(tmp_path, "plain_0.tif"), [planes[0, 0], planes[0, 1]])
     with pytest.raises(KeyError):

@@ -21,7 +21,7 @@ rad = torch.full((rows * cols,), 14, dtype=torch.int32, device=dev)
 fg, bg = ops.chip_masks(rel[:, 0].contiguous(), rad, 15, 30, 72)
 fg, bg = fg[:, None].contiguous(), bg[:, None].contiguous()
 roi = torch.empty((rows * cols, 4, T, 72, 72), dtype=torch.uint16, device=dev)
-stats = torch.empty((rows * cols, 4, T, 6), dtype=torch.float64, device=dev)
+stats = torch.empty((rows * cols, 4, T, 8), dtype=torch.float64, device=dev)
 for gran in (None,):
     for name, tma, loader in (("cpasync", 1, 1), ("tma", 1, 0), ("plain", 0, 1)):
         lib.mgb_set_tma_enabled(tma); lib.mgb_set_gather_loader(loader)

@@ -35,7 +35,7 @@ try:
     out["files"] = c * t * r * cc
     out["write_s"] = time.perf_counter() - t0
     (xp,) = list(reader.Reader(threads=16)(os.path.join(root, "chip_(channel)_(time)_(row)_(col).tif")))
-    tiles = xp["tile"].values
+    tiles = xp["tile"].data
     paths = tiles.filenames
     nbytes = tiles.nbytes
     pinned = torch.empty(tiles.shape, dtype=torch.uint16, pin_memory=True)

@@ -70,7 +70,7 @@ if "--tiff" in sys.argv:
             write_tiff(os.path.join(root, f"s_ch{idx[0]}_2024{idx[1] // 28 + 1:02d}{idx[1] % 28 + 1:02d}-000000_{idx[2]}_{idx[3]}.tif"),
                        [tiles_np[idx]], rows_per_strip=64)
         (xp,) = list(reader.Reader(threads=16)(os.path.join(root, "s_(channel)_(time)_(row)_(col).tif")))
-        lazy = xp["tile"].values
+        lazy = xp["tile"].data
         lazy.threads = 8
         runner = pipeline.StreamingRunner(plan, depth=3, threads=4)
         checks = []

@@ -37,7 +37,7 @@ for v in (0, 1, 2):
     print(f"plain stitch variant {v}: {ms:.3f} ms  {(4 * phi) * px / ms / 1e6:.0f} GB/s")
 m, c, t, L = plan.boxes.shape[0], 4, T, case.roi_length
 roi = torch.empty((m, c, t, L, L), dtype=torch.uint16, device=dev)
-stats = torch.empty((m, c, t, 6), dtype=torch.float64, device=dev)
+stats = torch.empty((m, c, t, 8), dtype=torch.float64, device=dev)
 for gran in (0,):
   for name, tma, loader in (("staged cp.async", 1, 1), ("staged TMA", 1, 0), ("plain LSU", 0, 1)):
       lib.mgb_set_tma_enabled(tma)
