@@ -56,9 +56,9 @@ def _device(device) -> torch.device:
     return torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
 
 
-def _emit(tensor: torch.Tensor, as_bool: bool = False, extras=None, prefetch: bool = True) -> DeviceArray:
+def _emit(tensor: torch.Tensor, as_bool: bool = False, extras=None, prefetch: bool = True, name: str = "") -> DeviceArray:
     arr = DeviceArray(tensor, as_bool=as_bool, extras=extras)
-    return arr.prefetch() if (prefetch and devarray.PREFETCH) else arr
+    return arr.prefetch() if (prefetch and devarray.PREFETCH and name not in devarray.PREFETCH_SKIP) else arr
 
 
 def _torch_dtype(np_dtype) -> torch.dtype:
@@ -202,6 +202,13 @@ class Stitcher:
             raise ValueError("Overlap must be non-negative.")  # stitch.py:8-9
         self.overlap = overlap
         self.device = device
+        self._ff = None            # (key, FlatFieldPlan): the device tables of the last flat / dark fields
+
+    def _plan(self, src: "PendingFlatfield", dev) -> ops.FlatFieldPlan:
+        key = (id(src.flat), id(src.dark), tuple(src.shape), str(dev))
+        if self._ff is None or self._ff[0] != key:
+            self._ff = (key, ops.FlatFieldPlan(src.shape, src.flat, src.dark, device=dev), src.flat, src.dark)
+        return self._ff[1]
 
     def __call__(self, assay):
         if "tile" not in assay:
@@ -213,13 +220,13 @@ class Stitcher:
         src = _raw(tile)
         if isinstance(src, PendingFlatfield) and src._host is None:
             # flatfield_correct + stitch: one upload, the maxima pass under it, one fused kernel
-            ff = ops.FlatFieldPlan(src.shape, src.flat, src.dark, device=dev)
+            ff = self._plan(src, dev)
             tiles = _stage_tiles(src.raw, dev, ff)
             image = ops.flatfield_stitch(tiles, overlap=self.overlap, plan=ff, maxima=None if ff.identity else ff.maxima)
         else:
             tiles = _stage_tiles(src.numpy() if isinstance(src, PendingFlatfield) else src, dev, None)
             image = ops.stitch(tiles, self.overlap)
-        assay["image"] = (IMAGE_DIMS, _emit(image))
+        assay["image"] = (IMAGE_DIMS, _emit(image, name="image"))
         return assay
 
 
@@ -265,7 +272,7 @@ def _emit_markers(roi_d, stats, fg_d, bg_d, mask_t: np.ndarray, mask_t_d):
     distinct timesteps (M,Tm,L,L) and expand lazily; later components find the compact tensors
     and the summaries the gather computed in `extras`."""
     extras = {"stats": stats, "fg": fg_d, "bg": bg_d, "mask_t": mask_t_d}
-    roi = _emit(roi_d, extras=extras)
+    roi = _emit(roi_d, extras=extras, name="roi")
     fg = _emit(fg_d, as_bool=True, extras=extras, prefetch=False).take(mask_t, 1)
     bg = _emit(bg_d, as_bool=True, extras=extras, prefetch=False).take(mask_t, 1)
     return roi, fg, bg

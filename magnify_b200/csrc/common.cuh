@@ -32,23 +32,30 @@ __host__ __device__ inline bool aligned16(const void* p) {
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // Stream-ordered scratch for the few entry points whose temporary sizes are only known inside the
-// call (CUB temp storage, the unique-circle list).  The device's default memory pool is told once
-// to keep freed blocks instead of returning them to the driver at every synchronisation, so
-// repeated calls do not pay an allocation from the OS each time.
+// call (CUB temp storage, the unique-circle list, large-mask workspaces).  The blocks come from a
+// PRIVATE memory pool per device, created on first use, that keeps at most 1 GiB of freed blocks
+// cached: repeated calls do not pay an allocation from the driver each time, and the process-wide
+// default pool (which the caller's framework may rely on) is left exactly as it was.
 inline cudaError_t scratch_alloc(void** ptr, size_t bytes, cudaStream_t stream) {
-  static thread_local int tuned_device = -1;
+  static cudaMemPool_t pools[64] = {};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  if (tuned_device != dev) {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    tuned_device = dev;
+  if (dev < 0 || dev >= 64) return cudaMallocAsync(ptr, bytes, stream);
+  if (!pools[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool = nullptr;
+    e = cudaMemPoolCreate(&pool, &props);
+    if (e != cudaSuccess) return e;
+    unsigned long long keep = 1ull << 30;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    pools[dev] = pool;
   }
-  return cudaMallocAsync(ptr, bytes, stream);
+  return cudaMallocFromPoolAsync(ptr, bytes, pools[dev], stream);
 }
 
 // Streaming 128-bit global accesses: every tile / image / roi byte is touched once per pass,

@@ -1,6 +1,8 @@
 // F5-F8: per-ROI foreground / background masks, hand-written for sm_100a.
 // Reference: src/magnify/utils.py:30-52 (circle, annulus), 380-465 (circle_labels,
 // filled_circle_points, circle_points); call sites find.py:380-400 (chip), 561-586 (beads).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace mgb {
@@ -229,20 +231,18 @@ const char* mgb_error_string(int code) {
 // ---------------------------------------------------------------------------------------------
 namespace mgb {
 
-__global__ void __launch_bounds__(32) mask_perimeter_kernel(const uint8_t* __restrict__ masks, int L,
-                                                            double* __restrict__ perimeter) {
-  extern __shared__ int16_t sm[];
+// LT = label type: int16 in shared memory (L <= 160: at most L*L + 1 < 32768 borders), int32 in a
+// global workspace for larger masks.  f: P*P labels, parent: one per border, is_hole: one byte per border.
+template <typename LT>
+__device__ __forceinline__ double trace_mask(LT* f, LT* parent, uint8_t* is_hole, const uint8_t* __restrict__ mask,
+                                             int L) {
   const int P = L + 2;                       // framed side
-  int16_t* f = sm;                           // P * P labels
-  int16_t* parent = sm + P * P;              // per border
-  uint8_t* is_hole = reinterpret_cast<uint8_t*>(parent + (L * L + 4));   // every pixel starts at most one border
-  const uint8_t* mask = masks + (int64_t)blockIdx.x * L * L;
   for (int i = threadIdx.x; i < P * P; i += 32) {
     const int y = i / P - 1, x = i % P - 1;
     f[i] = (y >= 0 && y < L && x >= 0 && x < L && mask[y * L + x]) ? 1 : 0;
   }
   __syncwarp();
-  if (threadIdx.x != 0) return;
+  if (threadIdx.x != 0) return 0.0;
   const int di[8] = {0, -1, -1, -1, 0, 1, 1, 1};      // counter-clockwise from east (rows grow downwards)
   const int dj[8] = {1, 1, 0, -1, -1, -1, 0, 1};
   int nbd = 1;
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(32) mask_perimeter_kernel(const uint8_t* __res
           }
         }
         if (first < 0) {
-          f[i * P + j] = (int16_t)(-nbd);             // isolated pixel: a one-point contour of length 0
+          f[i * P + j] = (LT)(-nbd);             // isolated pixel: a one-point contour of length 0
         } else {
           const int i1 = i + di[first], j1 = j + dj[first];
           int i2 = i1, j2 = j1, i3 = i, j3 = j;
@@ -300,8 +300,8 @@ __global__ void __launch_bounds__(32) mask_perimeter_kernel(const uint8_t* __res
             }
             const int i4 = i3 + di[d4], j4 = j3 + dj[d4];
             // (3.4)
-            if (east_zero) f[i3 * P + j3] = (int16_t)(-nbd);
-            else if (f[i3 * P + j3] == 1) f[i3 * P + j3] = (int16_t)nbd;
+            if (east_zero) f[i3 * P + j3] = (LT)(-nbd);
+            else if (f[i3 * P + j3] == 1) f[i3 * P + j3] = (LT)nbd;
             length += (d4 & 1) ? 1.4142135623730951 : 1.0;
             // (3.5)
             if (i4 == i && j4 == j && i3 == i1 && j3 == j1) break;
@@ -315,21 +315,62 @@ __global__ void __launch_bounds__(32) mask_perimeter_kernel(const uint8_t* __res
       if (now != 1) lnbd = now < 0 ? -now : now;
     }
   }
-  perimeter[blockIdx.x] = total;
+  return total;
 }
+
+__global__ void __launch_bounds__(32) mask_perimeter_kernel(const uint8_t* __restrict__ masks, int L,
+                                                            double* __restrict__ perimeter) {
+  extern __shared__ int16_t sm[];
+  const int P = L + 2;
+  int16_t* parent = sm + P * P;
+  uint8_t* is_hole = reinterpret_cast<uint8_t*>(parent + (L * L + 4));   // every pixel starts at most one border
+  const double total = trace_mask<int16_t>(sm, parent, is_hole, masks + (int64_t)blockIdx.x * L * L, L);
+  if (threadIdx.x == 0) perimeter[blockIdx.x] = total;
+}
+
+// The same walk with int32 labels in global memory (one workspace slice per mask of the batch).
+__global__ void __launch_bounds__(32) mask_perimeter_big_kernel(const uint8_t* __restrict__ masks, int L,
+                                                                int32_t* __restrict__ work, int64_t slice_words,
+                                                                double* __restrict__ perimeter) {
+  const int P = L + 2, borders = L * L + 4;
+  int32_t* f = work + (int64_t)blockIdx.x * slice_words;
+  int32_t* parent = f + P * P;
+  uint8_t* is_hole = reinterpret_cast<uint8_t*>(parent + borders);
+  const double total = trace_mask<int32_t>(f, parent, is_hole, masks + (int64_t)blockIdx.x * L * L, L);
+  if (threadIdx.x == 0) perimeter[blockIdx.x] = total;
+}
+
 
 }  // namespace mgb
 
 extern "C" int mgb_mask_perimeters(const uint8_t* masks, int64_t M, int L, double* perimeter, void* stream) {
-  if (M < 0 || L <= 0 || L > 160) return MGB_EINVAL;   // labels are int16 and the tables must fit shared memory
+  if (M < 0 || L <= 0 || L > 4096) return MGB_EINVAL;
   if (M == 0) return MGB_OK;
   if (!masks || !perimeter) return MGB_EINVAL;
   if (M > INT32_MAX) return MGB_EUNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
   const int P = L + 2, borders = L * L + 4;
-  const size_t bytes = (size_t)P * P * 2 + (size_t)borders * 2 + (size_t)borders + 16;
-  if (bytes > 48 * 1024)
-    MGB_CUDA_TRY(cudaFuncSetAttribute(mgb::mask_perimeter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  mgb::mask_perimeter_kernel<<<(unsigned)M, 32, bytes, (cudaStream_t)stream>>>(masks, L, perimeter);
-  MGB_CUDA_LAUNCH_CHECK();
-  return MGB_OK;
+  if (L <= 160) {   // int16 labels and the tables fit shared memory
+    const size_t bytes = (size_t)P * P * 2 + (size_t)borders * 2 + (size_t)borders + 16;
+    if (bytes > 48 * 1024)
+      MGB_CUDA_TRY(cudaFuncSetAttribute(mgb::mask_perimeter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    mgb::mask_perimeter_kernel<<<(unsigned)M, 32, bytes, st>>>(masks, L, perimeter);
+    MGB_CUDA_LAUNCH_CHECK();
+    return MGB_OK;
+  }
+  // larger masks (max_bead_diameter > 80, chamber_diameter > 133): int32 labels in a stream-ordered
+  // workspace of at most 256 MB, the masks in batches
+  const int64_t slice_words = (int64_t)P * P + borders + (borders + 3) / 4 + 4;
+  const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(M, (256ll << 20) / (slice_words * 4)));
+  void* work = nullptr;
+  MGB_CUDA_TRY(mgb::scratch_alloc(&work, (size_t)(batch * slice_words * 4), st));
+  for (int64_t first = 0; first < M; first += batch) {
+    const int64_t n = std::min(batch, M - first);
+    mgb::mask_perimeter_big_kernel<<<(unsigned)n, 32, 0, st>>>(masks + first * (int64_t)L * L, L, (int32_t*)work,
+                                                               slice_words, perimeter + first);
+    mgb_count_launch_();
+  }
+  const cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(work, st);
+  return e == cudaSuccess ? MGB_OK : (int)e;
 }

@@ -303,20 +303,16 @@ roi_gather_lists_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGathe
 
   Cursor ahead{0, 0, 0}, cur{0, 0, 0};
   if (nt > 0) { advance(ahead, first); advance(cur, first); }
-  for (int s = 0; s < p.n_stages - 1; ++s) {
+  // every stage holds a window in flight; a stage is refilled as soon as its window has been copied
+  // out and its masked pixels sit in registers, i.e. BEFORE the medians of that window are worked
+  // out -- so even a single stage per warp overlaps its next load with half of the work
+  for (int s = 0; s < p.n_stages; ++s) {
     if (ahead.i < n_items) issue_tma(ahead, s);
     if (nt > 0) advance(ahead, step);
   }
   int s = 0;
   uint32_t parity = 0;
   for (; cur.i < n_items; advance(cur, step)) {
-    {
-      // keep n_stages - 1 windows in flight behind the one being consumed (a single stage: load, then consume)
-      int rs = s + p.n_stages - 1;
-      if (rs >= p.n_stages) rs -= p.n_stages;
-      if (ahead.i < n_items) issue_tma(ahead, rs);
-      advance(ahead, step);
-    }
     const int64_t c = cur.c, t = tlist[cur.k];
     const int shift = p.boxes[(m * p.T + t) * 2 + 1] & 7;
     const int64_t n = (m * p.C + c) * p.T + t;
@@ -360,12 +356,18 @@ roi_gather_lists_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGathe
     }
 
     double dsf = nan_f64(), dsb = nan_f64(), mf = nan_f64(), mb = nan_f64();
-    if (!overflow) {
+    if (overflow) {
+      __syncwarp();
+      if (ahead.i < n_items) issue_tma(ahead, s);
+      advance(ahead, step);
+    } else {
       // ---- 2. + 3. the masked pixels of this window through the lists (every slot is a valid
       // pixel: the slots beyond the mask repeat the mask's first pixel)
       const uint16_t* s16 = reinterpret_cast<const uint16_t*>(buf) + shift;
-      const uint16_t* flg = fl + 8 * lane;
-      const uint16_t* blg = bl + 8 * lane;
+      // slot k of group g reads entry 256 g + 32 k + lane: the 32 lanes read consecutive list
+      // entries (one 64-byte wavefront) which are mostly consecutive pixels of a mask row
+      const uint16_t* flg = fl + lane;
+      const uint16_t* blg = bl + lane;
       uint32_t vf[kNFL], vb[kNBL];
       uint32_t sf = 0, sb = 0;
 #pragma unroll
@@ -373,7 +375,7 @@ roi_gather_lists_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGathe
         if (gi >= GF) break;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          vf[8 * gi + k] = s16[flg[256 * gi + k]];
+          vf[8 * gi + k] = s16[flg[256 * gi + 32 * k]];
           sf += vf[8 * gi + k];
         }
       }
@@ -382,11 +384,14 @@ roi_gather_lists_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGathe
         if (gi >= GB) break;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          vb[8 * gi + k] = s16[blg[256 * gi + k]];
+          vb[8 * gi + k] = s16[blg[256 * gi + 32 * k]];
           sb += vb[8 * gi + k];
         }
       }
       const uint32_t v0f = s16[fl[0]], v0b = s16[bl[0]];     // the pixel the padding repeats
+      __syncwarp();                                          // every lane is done with the staged window
+      if (ahead.i < n_items) issue_tma(ahead, s);
+      advance(ahead, step);
       sf = __reduce_add_sync(0xffffffffu, sf) - pad_f * v0f;
       sb = __reduce_add_sync(0xffffffffu, sb) - pad_b * v0b;
       dsf = (double)sf;

@@ -24,6 +24,8 @@ _NP_OF = {torch.uint8: np.uint8, torch.uint16: np.uint16, torch.int16: np.int16,
           torch.int64: np.int64, torch.float32: np.float32, torch.float64: np.float64, torch.bool: np.bool_}
 
 PREFETCH = True      # start the device->host copy of emitted results in the background
+PREFETCH_SKIP = ()   # names of dataset variables that are NOT copied in the background (e.g. ("image",) when the
+#                      caller only wants the crops: the reference's drop(roi_only=True), postprocess.py:6-17)
 
 
 class Streams:
@@ -41,6 +43,63 @@ class Streams:
         if idx not in cls._by_device:
             cls._by_device[idx] = Streams(torch.device("cuda", idx))
         return cls._by_device[idx]
+
+
+class _PinnedBlock:
+    """One pinned host buffer on loan from the pool.  NumPy arrays made from it (`np.asarray(block)`,
+    through `__array_interface__`) keep it alive as their base object; when the last of them -- and
+    the DeviceArray that filled it -- is gone, the buffer goes back to the pool.  So a host view a
+    caller still holds is never overwritten by a later result."""
+
+    def __init__(self, pool: "PinnedPool", raw: torch.Tensor, shape, dtype: torch.dtype):
+        self._pool, self._raw = pool, raw
+        self.tensor = raw[: int(np.prod(shape, dtype=np.int64)) * torch.empty(0, dtype=dtype).element_size()].view(dtype).view(tuple(shape))
+        self.last_copy = None                        # event after the last device->host copy into the buffer
+        npdt = np.dtype(_NP_OF[dtype])
+        self.__array_interface__ = {"shape": tuple(int(s) for s in shape), "typestr": npdt.str,
+                                    "data": (self.tensor.data_ptr(), False), "version": 3}
+
+    def __del__(self):
+        pool, raw = self.__dict__.get("_pool"), self.__dict__.get("_raw")
+        if pool is not None and raw is not None:
+            pool._give_back(raw, self.last_copy)
+
+
+class PinnedPool:
+    """Pinned host buffers, recycled by size.  Page-locking memory costs about half a second per
+    GB (measured: 1.7-2.2 s for the 3.9 GB image of an 8-timepoint chip stack, every time), far
+    more than copying into it, so the result buffers of one assay are reused by the next."""
+
+    def __init__(self, max_cached_bytes: int = 96 << 30):
+        self.max_cached_bytes = max_cached_bytes
+        self.free = {}                                # nbytes -> [(raw uint8 tensor, last-copy event)]
+        self.cached = 0
+
+    def acquire(self, shape, dtype: torch.dtype, stream=None) -> _PinnedBlock:
+        nbytes = max(1, int(np.prod(shape, dtype=np.int64)) * torch.empty(0, dtype=dtype).element_size())
+        nbytes = -(-nbytes // 4096) * 4096
+        bucket = self.free.get(nbytes)
+        if bucket:
+            raw, last = bucket.pop()
+            self.cached -= nbytes
+            if last is not None and stream is not None:
+                stream.wait_event(last)               # a copy into the buffer may still be in flight
+        else:
+            raw = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        return _PinnedBlock(self, raw, shape, dtype)
+
+    def _give_back(self, raw: torch.Tensor, last_copy) -> None:
+        n = raw.numel()
+        if self.cached + n <= self.max_cached_bytes:
+            self.free.setdefault(n, []).append((raw, last_copy))
+            self.cached += n
+
+    def clear(self) -> None:
+        self.free.clear()
+        self.cached = 0
+
+
+PINNED = PinnedPool()
 
 
 class LazyArray:
@@ -103,7 +162,7 @@ class DeviceArray(LazyArray):
                  _root: Optional["DeviceArray"] = None, _ops: tuple = (), _meta: Optional[torch.Tensor] = None):
         self.as_bool = as_bool
         self.extras = extras if extras is not None else {}
-        self.root = _root if _root is not None else self
+        self._root = _root                         # None for a root (no self-reference: arrays must die by refcount)
         self._ops = _ops
         self._tensor = tensor                      # None for a view until somebody asks for it
         self._meta = _meta if _meta is not None else torch.empty(tuple(tensor.shape), dtype=tensor.dtype, device="meta")
@@ -112,6 +171,7 @@ class DeviceArray(LazyArray):
 
     shape = property(lambda self: tuple(self._meta.shape))
     dtype = property(lambda self: np.dtype(np.bool_ if self.as_bool else _NP_OF[self._meta.dtype]))
+    root = property(lambda self: self if self._root is None else self._root)
 
     @property
     def tensor(self) -> torch.Tensor:
@@ -135,14 +195,15 @@ class DeviceArray(LazyArray):
         streams = Streams.of(t.device)
         produced = torch.cuda.Event()
         produced.record(torch.cuda.current_stream(t.device))
-        host = torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
+        block = PINNED.acquire(tuple(t.shape), t.dtype, streams.d2h)
         with torch.cuda.stream(streams.d2h):
             streams.d2h.wait_event(produced)
-            _copy_to_host(t, host)
+            _copy_to_host(t, block.tensor)
             done = torch.cuda.Event()
             done.record(streams.d2h)
+        block.last_copy = done
         t.record_stream(streams.d2h)
-        root._pending = (host, done)
+        root._pending = (block, done)
         return self
 
     def _root_numpy(self) -> np.ndarray:
@@ -152,10 +213,10 @@ class DeviceArray(LazyArray):
             if t.is_cuda and t.numel() > 0:
                 if root._pending is None:
                     root.prefetch()
-                host, done = root._pending
+                block, done = root._pending
                 done.synchronize()
                 root._pending = None
-                root._host = host.numpy()
+                root._host = np.asarray(block)       # the array keeps the pinned block alive (and out of the pool)
             else:
                 root._host = t.contiguous().cpu().numpy() if t.is_cuda else t.contiguous().numpy()
         return root._host

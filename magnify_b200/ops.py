@@ -30,6 +30,9 @@ _DTYPE_CODE = {
 }
 
 
+_UNSIGNED = (torch.uint8, torch.uint16)
+
+
 def _stream() -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -283,8 +286,9 @@ def flatfield_stitch(
     check_overlap(overlap, h, w)
     if plan is None:
         plan = FlatFieldPlan(tiles.shape, flatfield, darkfield, device=tiles.device)
-    if plan.identity:
-        # (x * M) / M == x exactly for integers below 2^53: the defaults are the identity.
+    if plan.identity and tiles.dtype in _UNSIGNED:
+        # (x * M) / M == x exactly for non-negative integers below 2^53: the defaults are the identity.
+        # Float tiles still go through the arithmetic (clip(min=0) zeroes negatives, preprocess.py:83).
         return stitch(tiles, overlap, out=out)
     out = _image_out(out, stitched_shape(tiles.shape, overlap), tiles.dtype, tiles.device)
     if tiles.numel() == 0:
@@ -327,7 +331,7 @@ def flatfield_correct(tiles: torch.Tensor, flatfield=1.0, darkfield=0.0, plan=No
     c, t, r, cc, h, w = tiles.shape
     if plan is None:
         plan = FlatFieldPlan(tiles.shape, flatfield, darkfield, device=tiles.device)
-    if plan.identity:
+    if plan.identity and tiles.dtype in _UNSIGNED:
         return tiles.clone()
     # Every tile is its own 1x1 "image": same kernel, overlap 0.
     as_images = tiles.view(c, t * r * cc, 1, 1, h, w)

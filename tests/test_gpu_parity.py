@@ -759,3 +759,21 @@ def test_median_large_roi(cuda_device, length):
     f32 = (rng.standard_normal((m, c, t, length, length)) * 100).astype(np.float32)
     got = ops.roi_median(dev(f32, cuda_device), dev(mask.view(np.uint8), cuda_device)).cpu().numpy()
     np.testing.assert_array_equal(got, o_red.masked_median(f32, mask))
+
+
+def test_identity_flatfield_on_float_tiles_still_clips(cuda_device):
+    """flat = 1, dark = 0 is only the identity for unsigned integers: the reference still runs
+    clip(min=0) and (x * M) / M on float tiles (preprocess.py:83-87), which zeroes negative pixels."""
+    from magnify_b200 import ops
+
+    rng = np.random.default_rng(5)
+    for dtype in (np.float32, np.float64):
+        tiles = (rng.standard_normal((2, 1, 2, 2, 24, 32)) * 100).astype(dtype)
+        want_tiles = o_ff.flatfield_correct(tiles, 1.0, 0.0)
+        assert (want_tiles >= 0).all() and (tiles < 0).any()
+        got = ops.flatfield_correct(dev(tiles, cuda_device), 1.0, 0.0).cpu().numpy()
+        np.testing.assert_array_equal(got, want_tiles)
+        got = ops.flatfield_stitch(dev(tiles, cuda_device), 1.0, 0.0, overlap=4).cpu().numpy()
+        np.testing.assert_array_equal(got, o_st.stitch(want_tiles, 4))
+    u16 = rng.integers(0, 65535, (1, 1, 2, 2, 16, 16), dtype=np.uint16, endpoint=True)
+    np.testing.assert_array_equal(ops.flatfield_correct(dev(u16, cuda_device), 1.0, 0.0).cpu().numpy(), u16)
