@@ -56,6 +56,11 @@ int mgb_sm_count(void);
 /* Kernels launched by this library in this process so far (bench.py's gpu_launches). */
 int64_t mgb_launch_count(void);
 
+/* Experiment knob (tools/l2_reuse_probe.py): make [base, base+bytes) a persisting-L2 access-policy window of
+ * `stream` (hit_ratio of its lines are kept, the rest stream through); base == NULL resets the stream's window
+ * and hands the persisting lines back.  Results never depend on it. */
+int mgb_l2_persist(void* stream, const void* base, int64_t bytes, float hit_ratio);
+
 /* Tuning knob of the vectorised stitch / flat-field+stitch kernel: prefetch-ring depth x CTAs per
  * SM (0: 6x2 default, 1: 11x2, 2: 8x3).  Returns the previous value.  Results do not depend on it. */
 int mgb_set_stitch_variant(int variant);

@@ -30,6 +30,7 @@ SIGNATURES = {
     "mgb_error_string": [c_int],
     "mgb_sm_count": [],
     "mgb_launch_count": [],
+    "mgb_l2_persist": [_P, _P, _I64, ctypes.c_float],
     "mgb_set_tma_enabled": [c_int],
     "mgb_set_stitch_variant": [c_int],
     "mgb_set_gather_loader": [c_int],

@@ -198,6 +198,32 @@ int mgb_copy2d_async(void* dst, int64_t dst_pitch_bytes, const void* src, int64_
 
 int mgb_abi_version(void) { return MGB_ABI_VERSION; }
 
+int mgb_l2_persist(void* stream, const void* base, int64_t bytes, float hit_ratio) {
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaStreamAttrValue attr = {};
+  if (!base || bytes <= 0) {           // reset: no window, persisting lines handed back
+    attr.accessPolicyWindow.num_bytes = 0;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    MGB_CUDA_TRY(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+    MGB_CUDA_TRY(cudaCtxResetPersistingL2Cache());
+    return MGB_OK;
+  }
+  int dev = 0, max_persist = 0, max_window = 0;
+  MGB_CUDA_TRY(cudaGetDevice(&dev));
+  MGB_CUDA_TRY(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+  MGB_CUDA_TRY(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+  if (max_persist <= 0 || max_window <= 0) return MGB_EUNSUPPORTED;
+  MGB_CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist));
+  attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+  attr.accessPolicyWindow.num_bytes = (size_t)(bytes < max_window ? bytes : max_window);
+  attr.accessPolicyWindow.hitRatio = hit_ratio;
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  MGB_CUDA_TRY(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+  return MGB_OK;
+}
+
 static unsigned long long g_launches = 0;
 void mgb_count_launch_(void) { __atomic_add_fetch(&g_launches, 1ULL, __ATOMIC_RELAXED); }
 int64_t mgb_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }

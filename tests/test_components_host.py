@@ -101,3 +101,67 @@ def test_factories_cover_the_reference_names():
     assert callable(comp.FACTORIES["filter_expression"](min_contrast=40))
     with pytest.raises(ValueError):
         comp.FACTORIES["stitch"](overlap=-1)                                         # stitch.py:8-9
+
+
+def test_device_array_views_and_pool_on_cpu_tensors():
+    """DeviceArray is a duck array: a Dataset keeps it un-materialised through stack / transpose /
+    unstack / squeeze / basic indexing (lazy views that replay on the root's single host copy),
+    boolean masks expand lazily from their distinct timesteps, nothing holds a reference cycle
+    (pinned buffers go back to the pool by refcount), and a host view outlives its DeviceArray."""
+    import gc
+    import weakref
+
+    import torch
+
+    from magnify_b200.dataset import Dataset
+    from magnify_b200.devarray import PINNED, DeviceArray
+
+    t = torch.arange(2 * 3 * 4 * 5, dtype=torch.int32).reshape(2, 3, 4, 5)
+    root = DeviceArray(t, extras={"stats": "by-product"})
+    ds = Dataset({"roi": (("mark_row", "mark_col", "c", "y"), root)})
+    st = ds.stack(mark=("mark_row", "mark_col"), create_index=True).transpose("mark", ...)
+    lazy = st.roi.data
+    assert isinstance(lazy, DeviceArray) and not lazy.materialised and lazy.extras["stats"] == "by-product"
+    assert lazy.tensor.data_ptr() == t.data_ptr() and lazy.tensor.is_contiguous()       # stack + transpose = no copy
+    np.testing.assert_array_equal(st.roi.values, t.numpy().reshape(6, 4, 5))
+    assert root.materialised                                                            # one host copy, at the root
+    un = st.unstack()
+    assert un.roi.data.root is root
+    np.testing.assert_array_equal(un.roi.transpose("mark_row", "mark_col", ...).values, t.numpy())
+    sq = Dataset({"im": (("c", "t", "y", "x"), DeviceArray(t[:1, :1]))}).squeeze("c").squeeze("t")
+    assert isinstance(sq.im.data, DeviceArray) and sq.im.shape == (4, 5)
+    np.testing.assert_array_equal(sq.im.values, t.numpy()[0, 0])
+    masks = DeviceArray(torch.tensor([[[1, 0], [0, 1]], [[1, 1], [0, 0]]], dtype=torch.uint8)[:, None], as_bool=True)
+    full = masks.take([0, 0, 0], 1)
+    assert full.shape == (2, 3, 2, 2) and full.dtype == np.bool_ and full.numpy().strides[1] == 0   # broadcast, not copied
+    assert full.tensor.shape == (2, 3, 2, 2)                                            # and a real tensor for a GPU consumer
+    np.testing.assert_array_equal(np.asarray(full)[:, 2], masks.numpy()[:, 0])
+    gc.disable()
+    try:
+        a = DeviceArray(torch.zeros(3, 4))
+        w = weakref.ref(a)
+        b = a.transpose(1, 0)
+        del a
+        assert w() is not None
+        del b
+        assert w() is None                                                              # freed by refcount alone
+    finally:
+        gc.enable()
+    real_empty = torch.empty
+    try:                                                                                # pin_memory needs a CUDA runtime
+        torch.empty = lambda *a, **k: real_empty(*a, **{kk: v for kk, v in k.items() if kk != "pin_memory"})
+        PINNED.clear()
+        block = PINNED.acquire((3, 4), torch.uint16)
+        block.tensor.fill_(7)
+        view = np.asarray(block)[1:]
+        ptr = block.tensor.data_ptr()
+        del block
+        assert PINNED.cached == 0 and (view == 7).all()                                 # the view keeps the buffer out of the pool
+        del view
+        assert PINNED.cached == 4096
+        again = PINNED.acquire((3, 4), torch.uint16)
+        assert again.tensor.data_ptr() == ptr and PINNED.cached == 0
+        del again
+    finally:
+        torch.empty = real_empty
+        PINNED.clear()
