@@ -810,6 +810,7 @@ def measure_e2e(args, cfg, hc, tiles_dev, dev, world, group, barrier, max_over_r
         del prev, cur
         barrier()
         units = (m * c * t_e2e * length * length) if m else (c * t_e2e * cfg["r"] * cfg["cc"] * cfg["h"] * cfg["w"])
+        mem = torch.cuda.memory_stats(dev)
         h2d = tiles_host.numel() * 2
         gbps = (h2d + d2h) * steps / sec / 1e9
         entry = {
@@ -818,6 +819,8 @@ def measure_e2e(args, cfg, hc, tiles_dev, dev, world, group, barrier, max_over_r
             "h2d_plus_d2h_GBps_per_gpu": gbps,
             "path": "registered components (" + " -> ".join(n for n, _ in pipe) + ") chained like Pipeline.__call__",
             "outputs_copied_back": ("stitched image + " if want_image else "") + ("roi + summaries" if m else "image"),
+            "device_allocator": {"alloc_retries": int(mem.get("num_alloc_retries", 0)),
+                                 "peak_reserved_GB": mem.get("reserved_bytes.all.peak", 0) / 1e9},
         }
         if pcie and "bidirectional_GBps_per_gpu_each_way" in pcie:
             # the link-bound time of a step that moves h2d and d2h bytes concurrently: no direction faster than

@@ -260,10 +260,21 @@ def _channel_names(assay, n_channels: int):
     return list(_to_numpy(assay["channel"])) if "channel" in assay else list(range(n_channels))
 
 
-def _gather(image, boxes, fg, bg, mask_t, length):
-    """Crops of every marker, plus the summaries when the image dtype has the fused kernel."""
+def _disc_pixels(radius: int) -> int:
+    """Pixels of {dx^2 + dy^2 <= r^2}: an upper bound of any disc mask of that radius inside a window."""
+    r = int(radius)
+    d = np.arange(-r, r + 1)
+    return int((d[:, None] ** 2 + d[None, :] ** 2 <= r * r).sum())
+
+
+def _gather(image, boxes, fg, bg, mask_t, length, mask_counts):
+    """Crops of every marker, plus the summaries when the image dtype has the fused kernel.
+    mask_counts: host-side upper bounds of the fg / bg pixel counts (they size the kernel's value
+    lists).  Computed from the radii instead of read back from the device: a device->host read
+    here would queue behind the stitched image already on its way to the host and stall the
+    whole pipeline for the length of that transfer."""
     if image.dtype == torch.uint16 and boxes.shape[0] > 0:
-        return ops.roi_gather_stats(image, boxes, fg, bg, length, mask_t=mask_t, medians=True)
+        return ops.roi_gather_stats(image, boxes, fg, bg, length, mask_t=mask_t, medians=True, mask_counts=mask_counts)
     return ops.roi_gather(image, boxes, length), None
 
 
@@ -349,7 +360,10 @@ class BeadFinder:
             # masks are time invariant (find.py:585-586): one timestep on the device, broadcast on the host
             fg_d, bg_d = fg_d[:, None].contiguous(), bg_d[:, None].contiguous()
             mask_t_d = torch.zeros(t, dtype=torch.int32, device=dev)
-            roi_d, stats = _gather(image, boxes, fg_d, bg_d, mask_t_d, length)
+            # a bead's fg is at most its own disc (utils.py:398-430), its bg at most the whole window
+            hw = ops.disc_halfwidth_table(max(int(beads[:, 2].max()), 1))[max(int(beads[:, 2].max()), 1)]
+            counts = (int((2 * hw + 1).sum() * 2 - (2 * hw[0] + 1)), length * length)
+            roi_d, stats = _gather(image, boxes, fg_d, bg_d, mask_t_d, length, counts)
             roi, fg, bg = _emit_markers(roi_d, stats, fg_d, bg_d, np.zeros(t, dtype=np.int64), mask_t_d)
         assay["roi"] = (("mark", "channel", "time", "roi_y", "roi_x"), roi)
         return assay.assign_coords(
@@ -502,7 +516,8 @@ class ButtonFinder:
         index = {ts: k for k, ts in enumerate(search)}
         mask_t = np.array([index[int(s)] for s in src], dtype=np.int64)                   # find.py:172-173
         mask_t_d = torch.from_numpy(mask_t.astype(np.int32)).to(dev)
-        roi_d, stats = _gather(image, boxes, fg_d, bg_d, mask_t_d, length)
+        counts = (_disc_pixels(int(radius.max())), max(0, _disc_pixels(self.chamber_radius) - _disc_pixels(self.max_button_radius)))
+        roi_d, stats = _gather(image, boxes, fg_d, bg_d, mask_t_d, length, counts)
         valid = _to_numpy(assay["valid"]) if "valid" in assay else np.ones((rows, cols, t), dtype=bool)
         valid = valid[:, :, src] if valid.ndim == 3 else valid
         roi, fg, bg = _emit_markers(roi_d, stats, fg_d, bg_d, mask_t, mask_t_d)
@@ -590,7 +605,10 @@ def summaries(assay, median: bool = True, device=None) -> torch.Tensor:
 def quantify(assay, median: bool = True, device=None):
     """Adds fg_count/bg_count (mark,time) and fg_sum, bg_sum, fg_mean, bg_mean[, fg_median,
     bg_median] (mark,channel,time): `roi.where(fg).mean(["roi_x","roi_y"])` etc."""
-    s = summaries(assay, median, device).cpu().numpy()
+    # the (M,C,T,8) records go to the host once, in the background, BEHIND the crops on the copy stream (a
+    # blocking read here would wait for the whole image / roi transfer queued before it on the copy engine and
+    # stall the next assay's upload); the variables are lazy column views of that one array
+    s = _emit(summaries(assay, median, device), name="summaries")
     dims = ("mark", "channel", "time")
     assay["fg_sum"], assay["bg_sum"] = (dims, s[..., 2]), (dims, s[..., 3])
     assay["fg_mean"], assay["bg_mean"] = (dims, s[..., 4]), (dims, s[..., 5])

@@ -120,6 +120,13 @@ def chip_masks(rel, fg_radius, inner_radius, outer_radius, roi_length, want_coun
     return _t(fg), _t(bg)
 
 
+def disc_halfwidth_table(rmax):
+    table = np.zeros((int(rmax) + 1, int(rmax) + 1), dtype=np.int32)
+    for r in range(1, int(rmax) + 1):
+        table[r, : r + 1] = o_geo.disc_halfwidths(r)
+    return table
+
+
 def bead_labels(beads, im_y, im_x):
     return _t(o_geo.circle_labels(_np(beads).astype(np.int64), im_y, im_x).astype(np.int32))
 
