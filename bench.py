@@ -206,7 +206,7 @@ def cpu_hot_path(cfg, s, threads):
         else:
             beads = s["beads"]
             x, y = beads[:, 1:2], beads[:, 0:1]
-            fg, bg = o_rois.bead_masks(beads, image.shape[-2], image.shape[-1], length)
+            _, fg, bg = o_rois.bead_masks(beads, image.shape[-2], image.shape[-1], length)
         roi = o_rois.gather_rois(image, x, y, length)
         fgt, bgt = np.repeat(fg[:, None], t, 1), np.repeat(bg[:, None], t, 1)
         parts = [p for p in np.array_split(np.arange(roi.shape[0]), max(1, threads)) if len(p)]
@@ -451,7 +451,7 @@ def run_b200_arm(args, name, cfg):
     if not args.no_parity:
         try:
             got_stats = None if not has_markers else (symm.gathered[rank] if symm is not None else stats_out)
-            parity = sampled_parity(case, plan, image_out, roi_out, got_stats)
+            parity = sampled_parity(case, plan, image_out, roi_out, got_stats, group)
         except Exception as exc:
             parity = {"ok": False, "error": repr(exc)[:300]}
 
@@ -509,7 +509,7 @@ def run_b200_arm(args, name, cfg):
     return line
 
 
-def sampled_parity(case, plan, image, roi, stats):
+def sampled_parity(case, plan, image, roi, stats, group=None):
     """Timepoints {0, T/2, T-1} of the full-size result against torch float64 eager arithmetic
     (flat-field: the reference's operation order; IEEE float64 on the GPU is bit-identical to
     NumPy's), plain slicing (stitch, crops) and torch sorts / sums (summaries of 64 sampled markers)."""
@@ -531,6 +531,12 @@ def sampled_parity(case, plan, image, roi, stats):
                 x = (case.tiles[ci, ti].to(torch.float64) - dark[k]).clamp_(min=0)
                 m1 = torch.maximum(m1, x.max())
                 m2 = torch.maximum(m2, (x / flat[k]).max())
+        if group is not None:          # both maxima are global over every rank's tiles (preprocess.py:84,86)
+            import torch.distributed as dist
+
+            both = torch.stack([m1, m2])
+            dist.all_reduce(both, op=dist.ReduceOp.MAX, group=group)
+            m1, m2 = both[0], both[1]
         if not torch.equal(torch.stack([m1, m2]), plan.ff.maxima):
             return {"ok": False, "what": "flat-field maxima differ from torch float64"}
     for ti in times:
@@ -780,7 +786,7 @@ def measure_e2e(args, cfg, hc, tiles_dev, dev, world, group, barrier, max_over_r
             n += sum(np.asarray(assay[k].values).nbytes for k in ("fg_mean", "bg_mean", "fg_median", "bg_median", "fg_sum", "bg_sum"))
         return n
 
-    steps = 4 if not args.e2e_timepoints else max(1, min(args.steps, 6))   # assays back to back
+    steps = 6 if not args.e2e_timepoints else max(1, min(args.steps, 6))   # assays back to back
     results = []
     for want_image in ((True, False) if m else (True,)):
         devarray.PREFETCH_SKIP = () if want_image else ("image",)
