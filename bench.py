@@ -457,7 +457,7 @@ def run_b200_arm(args, name, cfg):
 
     host_case = dict(x=getattr(case, "x", None), y=getattr(case, "y", None), fg_radius=getattr(case, "fg_radius", None),
                      beads=getattr(case, "beads", None), flat=case.flat, dark=case.dark)
-    tiles_dev = case.tiles
+    tiles_dev = [case.tiles]                # handed over (and released) inside measure_e2e
     del image_out, roi_out, stats_out, gathered, plan, case
     torch.cuda.empty_cache()
 
@@ -471,7 +471,7 @@ def run_b200_arm(args, name, cfg):
         e2e, e2e_roi = measure_e2e(args, cfg, host_case, tiles_dev, dev, world, group, barrier, max_over_ranks, pcie)
     except Exception as exc:  # keep the device numbers even if the host leg cannot allocate
         e2e = {"value": None, "unit": unit, "error": repr(exc)[:300]}
-    del tiles_dev
+    tiles_dev.clear()
     torch.cuda.empty_cache()
 
     # ---- strong scaling on the named shapes (this run's N)
@@ -725,16 +725,24 @@ def measure_e2e(args, cfg, hc, tiles_dev, dev, world, group, barrier, max_over_r
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     # pinned: the input stack once, the outputs of two assays in flight (rounded up by the allocator)
     t_e2e = int(min(t, max(1, (0.6 * avail / local_world) // (per_t_in + 3 * per_t_out))))
+    # device: tiles + outputs of two assays in flight must fit without allocator retries (a retry frees
+    # cached blocks with a device synchronise, which breaks the upload/download overlap)
+    hbm = torch.cuda.get_device_properties(dev).total_memory
+    t_e2e = int(min(t_e2e, max(1, (0.8 * hbm) // (2 * (per_t_in + per_t_out)))))
     if args.e2e_timepoints:
         t_e2e = min(t, args.e2e_timepoints)
     if world > 1:  # every rank must agree on the shape of the problem
         tt = torch.tensor([t_e2e], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MIN, group=group)
         t_e2e = int(tt.item())
-    shape = (c, t_e2e) + tuple(tiles_dev.shape[2:])
+    shape = (c, t_e2e) + tuple(tiles_dev[0].shape[2:])
     tiles_host = torch.empty(shape, dtype=torch.uint16, pin_memory=True)
-    tiles_host.copy_(tiles_dev[:, :t_e2e])
+    tiles_host.copy_(tiles_dev[0][:, :t_e2e])
     torch.cuda.synchronize(dev)
+    tiles_dev.clear()                       # the resident stack of the device-timed leg is not needed any more
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats(dev)
+    retries0 = int(torch.cuda.memory_stats(dev).get("num_alloc_retries", 0))
     tiles_np = tiles_host.numpy()
 
     # the registry `install()` fills, and the chain the reference's builder assembles from it
@@ -803,16 +811,41 @@ def measure_e2e(args, cfg, hc, tiles_dev, dev, world, group, barrier, max_over_r
         barrier()
         # Wall clock around fully synchronised ends: the region holds every H2D copy, kernel and D2H
         # copy of `steps` assays; the D2H of assay k (copy stream) overlaps the H2D of assay k+1.
+        timeline = [] if os.environ.get("MGB_E2E_TIMELINE") else None   # diagnostic: where each stream is per assay
+        if timeline is not None:
+            streams = devarray.Streams.of(dev)
+            watched = (streams.h2d, torch.cuda.current_stream(dev), streams.d2h)
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record(watched[1])
+            devarray.TRACE = []
         t0 = time.perf_counter()
         prev = None
         for _ in range(steps):
             cur = run_pipe()
+            if timeline is not None:
+                t_ret = time.perf_counter() - t0
+                evs = [torch.cuda.Event(enable_timing=True) for _ in watched]
+                for e, st in zip(evs, watched):
+                    e.record(st)
             if prev is not None:
                 read_back(prev, want_image)
+            if timeline is not None:
+                timeline.append((t_ret, time.perf_counter() - t0, evs))
             prev = cur
         read_back(prev, want_image)
         torch.cuda.synchronize(dev)
         sec = max_over_ranks((time.perf_counter() - t0) * 1e3) / 1e3
+        if timeline is not None:
+            for k, (t_ret, t_read, evs) in enumerate(timeline):
+                print(f"[e2e timeline image={want_image}] assay {k}: run_pipe returned {1e3 * t_ret:8.1f} ms, previous read "
+                      f"{1e3 * t_read:8.1f} ms | h2d done {ev0.elapsed_time(evs[0]):8.1f}  compute done "
+                      f"{ev0.elapsed_time(evs[1]):8.1f}  d2h done {ev0.elapsed_time(evs[2]):8.1f} ms", file=sys.stderr)
+            for shape, nbytes, began, done in devarray.TRACE:
+                if nbytes >= (64 << 20):
+                    print(f"[e2e timeline image={want_image}] download {nbytes / 1e9:6.2f} GB {shape}: "
+                          f"{ev0.elapsed_time(began):8.1f} -> {ev0.elapsed_time(done):8.1f} ms", file=sys.stderr)
+            devarray.TRACE = None
+            print(f"[e2e timeline image={want_image}] total {1e3 * sec:.1f} ms", file=sys.stderr)
         del prev, cur
         barrier()
         units = (m * c * t_e2e * length * length) if m else (c * t_e2e * cfg["r"] * cfg["cc"] * cfg["h"] * cfg["w"])
@@ -825,7 +858,7 @@ def measure_e2e(args, cfg, hc, tiles_dev, dev, world, group, barrier, max_over_r
             "h2d_plus_d2h_GBps_per_gpu": gbps,
             "path": "registered components (" + " -> ".join(n for n, _ in pipe) + ") chained like Pipeline.__call__",
             "outputs_copied_back": ("stitched image + " if want_image else "") + ("roi + summaries" if m else "image"),
-            "device_allocator": {"alloc_retries": int(mem.get("num_alloc_retries", 0)),
+            "device_allocator": {"alloc_retries": int(mem.get("num_alloc_retries", 0)) - retries0,
                                  "peak_reserved_GB": mem.get("reserved_bytes.all.peak", 0) / 1e9},
         }
         if pcie and "bidirectional_GBps_per_gpu_each_way" in pcie:

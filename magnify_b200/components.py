@@ -267,6 +267,16 @@ def _disc_pixels(radius: int) -> int:
     return int((d[:, None] ** 2 + d[None, :] ** 2 <= r * r).sum())
 
 
+def _upload(values: np.ndarray, dev) -> torch.Tensor:
+    """Small host array -> device on the current stream WITHOUT blocking the host: a pageable copy
+    waits for everything queued on the stream (the tile upload and the stitch of this assay), which
+    would keep the next assay's upload from being queued behind this one's."""
+    host = torch.from_numpy(np.ascontiguousarray(values))
+    if dev.type != "cuda":
+        return host
+    return host.pin_memory().to(dev, non_blocking=True)   # torch's caching host allocator holds the block until the copy ran
+
+
 def _gather(image, boxes, fg, bg, mask_t, length, mask_counts):
     """Crops of every marker, plus the summaries when the image dtype has the fused kernel.
     mask_counts: host-side upper bounds of the fg / bg pixel counts (they size the kernel's value
@@ -354,8 +364,8 @@ class BeadFinder:
             fg = np.empty((0, t, length, length), dtype=bool)
             bg = fg.copy()
         else:
-            boxes = ops.bounding_boxes(torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev), length, wim, him)
-            labels = ops.bead_labels(torch.from_numpy(beads.astype(np.int64).astype(np.int32)).to(dev), him, wim)
+            boxes = ops.bounding_boxes(_upload(x, dev), _upload(y, dev), length, wim, him)
+            labels = ops.bead_labels(beads.astype(np.int64).astype(np.int32), him, wim, device=dev)
             fg_d, bg_d = ops.bead_masks(labels, boxes[:, 0].contiguous(), length)
             # masks are time invariant (find.py:585-586): one timestep on the device, broadcast on the host
             fg_d, bg_d = fg_d[:, None].contiguous(), bg_d[:, None].contiguous()
@@ -457,8 +467,7 @@ class ButtonFinder:
         planes = ops.alloc_image((len(chans), 1, him, wim), image.dtype, dev)
         for k, ch in enumerate(chans):
             planes[k, 0].copy_(image[ch, t])
-        xd = torch.from_numpy(np.ascontiguousarray(x.reshape(m, 1))).to(dev)
-        yd = torch.from_numpy(np.ascontiguousarray(y.reshape(m, 1))).to(dev)
+        xd, yd = _upload(x.reshape(m, 1), dev), _upload(y.reshape(m, 1), dev)
         boxes = ops.bounding_boxes(xd, yd, length, wim, him)
         crops = ops.roi_gather(planes, boxes, length)                           # (m, channels, 1, L, L)
         batch = circles.to_uint8(crops.reshape(m * len(chans), length, length), batched=True)   # find.py:343
@@ -503,19 +512,18 @@ class ButtonFinder:
             x[..., ts], y[..., ts], radius[:, k] = xs, ys, np.asarray(rs).reshape(m)
         for ti in range(t):  # copy-forward of the centres, find.py:156-157,174-175
             x[..., ti], y[..., ti] = x[..., src[ti]], y[..., src[ti]]
-        xd = torch.from_numpy(np.ascontiguousarray(x.reshape(m, t))).to(dev)
-        yd = torch.from_numpy(np.ascontiguousarray(y.reshape(m, t))).to(dev)
+        xd, yd = _upload(x.reshape(m, t), dev), _upload(y.reshape(m, t), dev)
         boxes, rel = ops.bounding_boxes(xd, yd, length, wim, him, want_rel=True)
         fgs, bgs = [], []
         for k, ts in enumerate(search):
-            f, b = ops.chip_masks(rel[:, ts].contiguous(), torch.from_numpy(radius[:, k].copy()).to(dev),
+            f, b = ops.chip_masks(rel[:, ts].contiguous(), _upload(radius[:, k], dev),
                                   self.max_button_radius, self.chamber_radius, length)
             fgs.append(f)
             bgs.append(b)
         fg_d, bg_d = torch.stack(fgs, 1).contiguous(), torch.stack(bgs, 1).contiguous()   # (M, Ts, L, L)
         index = {ts: k for k, ts in enumerate(search)}
         mask_t = np.array([index[int(s)] for s in src], dtype=np.int64)                   # find.py:172-173
-        mask_t_d = torch.from_numpy(mask_t.astype(np.int32)).to(dev)
+        mask_t_d = _upload(mask_t.astype(np.int32), dev)
         counts = (_disc_pixels(int(radius.max())), max(0, _disc_pixels(self.chamber_radius) - _disc_pixels(self.max_button_radius)))
         roi_d, stats = _gather(image, boxes, fg_d, bg_d, mask_t_d, length, counts)
         valid = _to_numpy(assay["valid"]) if "valid" in assay else np.ones((rows, cols, t), dtype=bool)

@@ -24,6 +24,7 @@ _NP_OF = {torch.uint8: np.uint8, torch.uint16: np.uint16, torch.int16: np.int16,
           torch.int64: np.int64, torch.float32: np.float32, torch.float64: np.float64, torch.bool: np.bool_}
 
 PREFETCH = True      # start the device->host copy of emitted results in the background
+TRACE = None         # diagnostic (bench.py MGB_E2E_TIMELINE): a list collecting (shape, bytes, start, end events) per download
 PREFETCH_SKIP = ()   # names of dataset variables that are NOT copied in the background (e.g. ("image",) when the
 #                      caller only wants the crops: the reference's drop(roi_only=True), postprocess.py:6-17)
 
@@ -198,9 +199,14 @@ class DeviceArray(LazyArray):
         block = PINNED.acquire(tuple(t.shape), t.dtype, streams.d2h)
         with torch.cuda.stream(streams.d2h):
             streams.d2h.wait_event(produced)
+            if TRACE is not None:
+                began = torch.cuda.Event(enable_timing=True)
+                began.record(streams.d2h)
             _copy_to_host(t, block.tensor)
-            done = torch.cuda.Event()
+            done = torch.cuda.Event(enable_timing=TRACE is not None)
             done.record(streams.d2h)
+            if TRACE is not None:
+                TRACE.append((tuple(t.shape), t.numel() * t.element_size(), began, done))
         block.last_copy = done
         t.record_stream(streams.d2h)
         root._pending = (block, done)

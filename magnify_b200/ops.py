@@ -614,18 +614,38 @@ def disc_halfwidth_table(rmax: int) -> np.ndarray:
     return table
 
 
-def bead_labels(beads: torch.Tensor, im_y: int, im_x: int) -> torch.Tensor:
+def _upload_async(values: np.ndarray, device) -> torch.Tensor:
+    """Host array -> device on the current stream without blocking the host (pinned staging from
+    torch's caching host allocator, which keeps the block until the copy has run)."""
+    return torch.from_numpy(np.ascontiguousarray(values)).pin_memory().to(device, non_blocking=True)
+
+
+def bead_labels(beads, im_y: int, im_x: int, device=None) -> torch.Tensor:
     """Label raster of utils.circle_labels (utils.py:380-395): beads (M,3) int32 rows
-    (row, col, radius >= 1) -> (im_y, im_x) int32 with -1 none / i sole owner / -2 shared."""
-    _check(beads, "beads", dtype=torch.int32, ndim=2)
-    m = beads.shape[0]
-    if m and beads.shape[1] != 3:
-        raise ValueError("beads must be (M,3)")
-    labels = torch.empty((im_y, im_x), dtype=torch.int32, device=beads.device)
-    rmax = int(beads[:, 2].max().item()) if m else 0
-    if m and int(beads[:, 2].min().item()) < 1:
+    (row, col, radius >= 1) -> (im_y, im_x) int32 with -1 none / i sole owner / -2 shared.
+
+    beads: a device tensor, or a HOST array together with `device` -- then the radius range is
+    taken on the host and nothing is read back from the device (a read would wait behind whatever
+    download is in flight on the copy engine)."""
+    if isinstance(beads, np.ndarray):
+        if device is None:
+            raise ValueError("device is required with host beads")
+        host = np.ascontiguousarray(beads, dtype=np.int32)
+        if host.ndim != 2 or (host.shape[0] and host.shape[1] != 3):
+            raise ValueError("beads must be (M,3)")
+        m = host.shape[0]
+        rmin, rmax = (int(host[:, 2].min()), int(host[:, 2].max())) if m else (1, 0)
+        beads = _upload_async(host, torch.device(device))
+    else:
+        _check(beads, "beads", dtype=torch.int32, ndim=2)
+        m = beads.shape[0]
+        if m and beads.shape[1] != 3:
+            raise ValueError("beads must be (M,3)")
+        rmin, rmax = (int(beads[:, 2].min().item()), int(beads[:, 2].max().item())) if m else (1, 0)
+    if m and rmin < 1:
         raise ValueError("bead radii must be >= 1 (filled_circle_points(0) raises in the reference)")
-    hw = torch.from_numpy(disc_halfwidth_table(max(rmax, 1))).to(beads.device)
+    labels = torch.empty((im_y, im_x), dtype=torch.int32, device=beads.device)
+    hw = _upload_async(disc_halfwidth_table(max(rmax, 1)), beads.device)
     with torch.cuda.device(beads.device):
         _lib.call("mgb_bead_labels", _ptr(beads), m, int(im_y), int(im_x), _ptr(hw), max(rmax, 1), _ptr(labels),
                   _stream())

@@ -127,7 +127,7 @@ def disc_halfwidth_table(rmax):
     return table
 
 
-def bead_labels(beads, im_y, im_x):
+def bead_labels(beads, im_y, im_x, device=None):
     return _t(o_geo.circle_labels(_np(beads).astype(np.int64), im_y, im_x).astype(np.int32))
 
 

@@ -248,6 +248,11 @@ def test_beads_golden(cuda_device, golden, make_pattern_image, gather_path):
     beads_i = dev(beads.astype(np.int32), cuda_device)
     labels = ops.bead_labels(beads_i, h, w)
     np.testing.assert_array_equal(labels.cpu().numpy(), g["labels"])
+    # beads handed over from the host (the component path: no device read of the radius range)
+    labels_h = ops.bead_labels(beads.astype(np.int32), h, w, device=cuda_device)
+    np.testing.assert_array_equal(labels_h.cpu().numpy(), g["labels"])
+    with pytest.raises(ValueError):
+        ops.bead_labels(np.array([[5, 5, 0]], dtype=np.int32), h, w, device=cuda_device)
     x = dev(np.repeat(beads[:, 1:2], t, axis=1), cuda_device)
     y = dev(np.repeat(beads[:, 0:1], t, axis=1), cuda_device)
     boxes = ops.bounding_boxes(x, y, length, w, h)
