@@ -107,7 +107,7 @@ __device__ __forceinline__ void hist_locate(const uint32_t* hist, int lane, uint
 // Mean of the two middles for an even count, NaN for n == 0 (np.nanmedian).
 template <int N>
 __device__ __forceinline__ double warp_median_radix(const uint32_t (&v)[N], int G, uint32_t n, uint32_t pad,
-                                                    uint32_t v0, uint32_t* hist, int lane) {
+                                                    uint32_t v0, uint32_t* hist, int lane, uint32_t spill) {
   if (n == 0) return nan_f64();
   uint32_t lo = v[0], hi = v[0];
 #pragma unroll
@@ -154,8 +154,8 @@ __device__ __forceinline__ double warp_median_radix(const uint32_t (&v)[N], int 
     b = __reduce_min_sync(0xffffffffu, b);
     return 0.5 * ((double)a + (double)b);
   }
-  // both middles in one coarse bin: bin its 2^s values exactly (everything else goes to bin 256 + ...,
-  // outside the 256 bins that are read back)
+  // both middles in one coarse bin: bin its 2^s values exactly (everything else goes to the lane's own
+  // slot behind the 256 bins that are read back)
   const uint32_t base = lo + (bin1 << s), width = 1u << s;
   __syncwarp();
   h4[2 * lane] = make_uint4(0, 0, 0, 0);
@@ -167,7 +167,7 @@ __device__ __forceinline__ double warp_median_radix(const uint32_t (&v)[N], int 
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const uint32_t d = v[8 * g + k] - base;
-      atomicAdd(hist + min(d, 256u), 1u);      // slot 256 = "not in this bin"
+      atomicAdd(hist + (d < 256u ? d : spill), 1u);      // slots 256.. = "not in this bin", one per lane (no conflicts)
     }
   }
   __syncwarp();
@@ -178,14 +178,14 @@ __device__ __forceinline__ double warp_median_radix(const uint32_t (&v)[N], int 
   return 0.5 * ((double)(base + f1) + (double)(base + f2));
 }
 
-constexpr int kHistWords = 256 + 8;   // 256 bins + the overflow slot (kept 32-byte aligned)
+constexpr int kHistWords = 256 + 32;   // 256 bins + one overflow slot per lane
 
 // VPL > 0: rows are whole 16-byte vectors, the copy loop is unrolled (VPL vectors per lane).
 // QPL > 0: rows of an even number of pixels copied as 8-byte quads (QPL quads per lane).
 // both 0 : run-time loops (vector rows of any size, word rows, odd rows).
 // WPM    : one warp per marker instead of one CTA per marker.   NW: warps per CTA (launch bound).
 template <int VPL, int QPL, bool WPM, int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
+__global__ void __launch_bounds__(NW * 32, NW == 6 ? 2 : 1)
 roi_gather_lists_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGatherParams p, int64_t M,
                         uint32_t magic_l) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -398,9 +398,10 @@ roi_gather_lists_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGathe
       dsb = (double)sb;
       // ---- 4. medians
       if (p.want_median) {
-        mf = warp_median_radix(vf, GF, nf, pad_f, v0f, my_hist, lane);
+        const uint32_t spill = 256u + (uint32_t)lane;   // this lane's slot for "not in the bin" (no conflicts)
+        mf = warp_median_radix(vf, GF, nf, pad_f, v0f, my_hist, lane, spill);
         __syncwarp();
-        mb = warp_median_radix(vb, GB, nb, pad_b, v0b, my_hist, lane);
+        mb = warp_median_radix(vb, GB, nb, pad_b, v0b, my_hist, lane, spill);
       }
     }
     write_stats(p, lane, n, cnt_fg, cnt_bg, dsf, dsb, mf, mb);
@@ -491,25 +492,38 @@ int roi_gather_lists(const void* image, int64_t pitch, int64_t C, int64_t T, int
   MGB_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   MGB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   // (a warp per marker needs many more markers than warp slots, else the last wave runs half empty:
-  // 1792 markers on 148 x 12 slots took 2.25 ms in that layout against 1.15 ms with a CTA per marker)
+  // 1792 markers on 148 x 12 slots took 2.25 ms in that layout against 1.15 ms with a CTA per marker.
+  // Handing every warp an equal run of the flattened (marker, window) space instead was tried and
+  // is slower still -- 3.9 ms against 2.0 ms at config 3, 14.1 against 10.3 ms at config 5 T = 4:
+  // 1776 warps then write crops into 1776 regions megabytes apart at once.)
   bool wpm = g_gather_wpm && items < 128 && M * Tm >= (int64_t)sms * 12 * 8;
   if (const char* e = getenv("MGB_GATHER_LAYOUT")) wpm = atoi(e) == 1 ? true : atoi(e) == 0 ? false : wpm;   // tuning only
 
   const size_t list_bytes = (size_t)(p.cap_f + p.cap_b) * sizeof(uint16_t);
+  int sm_smem = 0;
+  MGB_CUDA_TRY(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
   int nw = 0, ns = 0;
   size_t smem_bytes = 0;
   // warps per CTA x stages per warp: more warps hide the latency of the per-window reductions,
-  // more stages that of the window loads; 12 x 1 ... 8 x 2 ... 4 x 2 in order of preference
+  // more stages that of the window loads; 12 x 1 ... 8 x 2 ... 4 x 2 in order of preference.
+  // With a CTA per marker and fewer than 128 windows per marker, two CTAs of 6 warps share an SM
+  // instead: the list building of one overlaps the windows of the other and fewer warps idle in
+  // a marker's last round (config 3: 0.46 against 0.54 ms at T = 7, 1.12 against 1.17 ms at
+  // T = 25, 2.06 against 2.03 ms at T = 50).
   int want_nw = 0;
   if (const char* e = getenv("MGB_GATHER_WARPS")) want_nw = atoi(e);   // tuning only
   for (int pass = 0; pass < 2 && !nw; ++pass) {
-    for (int cand : {12, 8, 4}) {
-      if (want_nw && cand != want_nw) continue;
+    const bool pair = !wpm && items < 128;
+    for (int cand : {6, 12, 8, 4}) {
+      if (want_nw ? cand != want_nw : (cand == 6 && !pair)) continue;
       const size_t fixed = (wpm ? cand : 1) * list_bytes + (size_t)cand * kHistWords * sizeof(uint32_t) +
                            (size_t)cand * 4 * sizeof(uint64_t) + (size_t)T * sizeof(int32_t) + 128;
-      if ((size_t)max_smem < fixed + 1024) continue;
-      const int n = (int)std::min<size_t>(cand == 12 ? 1 : 4, ((size_t)max_smem - fixed - 1024) / ((size_t)cand * p.stage_bytes));
-      if (n >= (cand == 12 ? 1 : 2)) { nw = cand; ns = n; smem_bytes = (size_t)cand * n * p.stage_bytes + fixed; break; }
+      // 6 warps: two CTAs share an SM (half of its shared memory each, 1 KB reserved per CTA)
+      const size_t room = cand == 6 ? (size_t)(sm_smem / 2 - 1024) : (size_t)max_smem;
+      if (room < fixed + 1024) continue;
+      const bool one = cand == 12 || cand == 6;
+      const int n = (int)std::min<size_t>(one ? 1 : 4, (room - fixed - 1024) / ((size_t)cand * p.stage_bytes));
+      if (n >= (one ? 1 : 2)) { nw = cand; ns = n; smem_bytes = (size_t)cand * n * p.stage_bytes + fixed; break; }
     }
     if (!nw && wpm) wpm = false;   // per-warp lists do not fit: share one marker per CTA instead
   }
@@ -540,6 +554,7 @@ int roi_gather_lists(const void* image, int64_t pitch, int64_t C, int64_t T, int
 #define MGB_LAUNCH_NW(VP, QP, WP)                       \
   do {                                                  \
     if (nw == 12) MGB_LAUNCH_L(VP, QP, WP, 12);         \
+    else if (nw == 6) MGB_LAUNCH_L(VP, QP, WP, 6);      \
     else MGB_LAUNCH_L(VP, QP, WP, 8);                   \
   } while (0)
 #define MGB_LAUNCH_CP(WP)                        \

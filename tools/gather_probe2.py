@@ -1,5 +1,5 @@
 """Gather + reductions variants on a config-3 shaped stack (run on the GPU box):
-    python tools/gather_probe2.py [T] [--c5]
+    python tools/gather_probe2.py [T] [--c5] [--variants=cta:12,cta:6,...]
 Times, with CUDA events on the launching stream, the fused gather with and without medians, in
 both work layouts (CTA per marker / warp per marker), with and without the crops, against the
 round-1 arrangement (dp2a sums in the gather + two stand-alone median passes).  One JSON line
@@ -55,7 +55,11 @@ def gather(medians=True, want_roi=True, counts=plan.mask_counts):
 
 ref = None
 alg = 4.0 * roi.numel()
-for layout, algo in (("auto", "auto"), ("cta", "8"), ("cta", "12"), ("warp", "8"), ("warp", "12")):
+variants = (("auto", "auto"), ("cta", "8"), ("cta", "12"), ("warp", "8"), ("warp", "12"))
+for arg in sys.argv:
+    if arg.startswith("--variants="):           # e.g. --variants=cta:12,cta:6
+        variants = tuple(tuple(v.split(":")) for v in arg.split("=", 1)[1].split(","))
+for layout, algo in variants:
     if layout == "auto":
         os.environ.pop("MGB_GATHER_LAYOUT", None)
     else:
