@@ -28,6 +28,30 @@ namespace mgb {
 constexpr int kNFL = 32;   // fg values per lane
 constexpr int kNBL = 80;   // bg values per lane
 
+// One (L x L) byte mask, global -> shared memory, with asynchronous copies (all in flight at once;
+// the compaction below then reads shared memory instead of paying a DRAM round trip per 32 bytes:
+// with one warp per marker that loop was 63 us of the 183 us a config-5 marker took at T = 4).
+// Called by `nth` threads (`tid` among them); the caller waits (cp_async_wait_all + barrier).
+__device__ __forceinline__ void stage_mask(const uint8_t* __restrict__ g, int n, uint8_t* s, int tid, int nth) {
+  const uint32_t sa = smem_u32(s);
+  if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
+    const int nv = n >> 4;
+    for (int i = tid; i < nv; i += nth)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa + 16u * i), "l"(g + 16 * i) : "memory");
+    for (int i = (nv << 4) + tid; i < n; i += nth) s[i] = g[i];
+  } else if ((reinterpret_cast<uintptr_t>(g) & 3u) == 0) {
+    const int nv = n >> 2;
+    for (int i = tid; i < nv; i += nth)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa + 4u * i), "l"(g + 4 * i) : "memory");
+    for (int i = (nv << 2) + tid; i < n; i += nth) s[i] = g[i];
+  } else {
+    for (int i = tid; i < n; i += nth) s[i] = g[i];
+  }
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// generic-proxy accesses to shared memory before this, async-proxy (TMA) writes to it after
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // Compact the non-zero bytes of one (L x L) mask into window offsets row * wpu + col.
 // Called by `nwarps` warps (`wi` = this warp's index among them); `cnt` is a shared counter the
 // warps advance with one atomic per 32 bytes (nwarps == 1: the count stays in a register).
@@ -226,12 +250,24 @@ roi_gather_lists_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGathe
   uint16_t* fl = lists + (size_t)g * (p.cap_f + p.cap_b);
   uint16_t* bl = fl + p.cap_f;
   uint32_t nf = 0, nb = 0;
+  // the two masks go through the (still unused) window stages: the warp's own in the warp layout,
+  // the start of the stage area in the CTA layout (a stage holds rows x wpu x 2 >= 2 x rows^2 bytes)
+  const int mask_len = p.rows * p.rows, mask_room = (mask_len + 15) & ~15;
+  uint8_t* mstage = stages + (WPM ? (size_t)warp * p.n_stages * p.stage_bytes : 0);
   if (active) {
-    const uint8_t* f = p.fg + (m * p.Tm + tm) * (int64_t)p.rows * p.rows;
-    const uint8_t* b = p.bg + (m * p.Tm + tm) * (int64_t)p.rows * p.rows;
-    nf = build_list(f, p.rows, p.wpu, magic_l, fl, p.cap_f, lane, WPM ? 0 : warp, WPM ? 1 : nw, &s_cnt[0]);
-    nb = build_list(b, p.rows, p.wpu, magic_l, bl, p.cap_b, lane, WPM ? 0 : warp, WPM ? 1 : nw, &s_cnt[1]);
+    const uint8_t* f = p.fg + (m * p.Tm + tm) * (int64_t)mask_len;
+    const uint8_t* b = p.bg + (m * p.Tm + tm) * (int64_t)mask_len;
+    stage_mask(f, mask_len, mstage, WPM ? lane : (int)threadIdx.x, WPM ? 32 : (int)blockDim.x);
+    stage_mask(b, mask_len, mstage + mask_room, WPM ? lane : (int)threadIdx.x, WPM ? 32 : (int)blockDim.x);
   }
+  cp_async_wait_all();
+  __syncthreads();
+  if (active) {
+    nf = build_list(mstage, p.rows, p.wpu, magic_l, fl, p.cap_f, lane, WPM ? 0 : warp, WPM ? 1 : nw, &s_cnt[0]);
+    nb = build_list(mstage + mask_room, p.rows, p.wpu, magic_l, bl, p.cap_b, lane, WPM ? 0 : warp, WPM ? 1 : nw,
+                    &s_cnt[1]);
+  }
+  fence_proxy_async_smem();
   __syncthreads();
   if (!WPM) { nf = s_cnt[0]; nb = s_cnt[1]; }
   // a mask larger than the lists cannot happen when the caller sized them from the masks
@@ -364,28 +400,33 @@ roi_gather_lists_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGathe
       // ---- 2. + 3. the masked pixels of this window through the lists (every slot is a valid
       // pixel: the slots beyond the mask repeat the mask's first pixel)
       const uint16_t* s16 = reinterpret_cast<const uint16_t*>(buf) + shift;
-      // slot k of group g reads entry 256 g + 32 k + lane: the 32 lanes read consecutive list
-      // entries (one 64-byte wavefront) which are mostly consecutive pixels of a mask row
-      const uint16_t* flg = fl + lane;
-      const uint16_t* blg = bl + lane;
+      // slots 2q, 2q+1 of group g read entries 256 g + 64 q + 2 lane (+1): one 4-byte load brings two
+      // offsets per lane (a full 128-byte wavefront for the warp), and the 32 lanes then read every
+      // second entry -- mostly every second pixel of a mask row, one bank each
+      const uint32_t* flg = reinterpret_cast<const uint32_t*>(fl) + lane;
+      const uint32_t* blg = reinterpret_cast<const uint32_t*>(bl) + lane;
       uint32_t vf[kNFL], vb[kNBL];
       uint32_t sf = 0, sb = 0;
 #pragma unroll
       for (int gi = 0; gi < kNFL / 8; ++gi) {
         if (gi >= GF) break;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          vf[8 * gi + k] = s16[flg[256 * gi + 32 * k]];
-          sf += vf[8 * gi + k];
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t o2 = flg[128 * gi + 32 * q];
+          vf[8 * gi + 2 * q] = s16[o2 & 0xffffu];
+          vf[8 * gi + 2 * q + 1] = s16[o2 >> 16];
+          sf += vf[8 * gi + 2 * q] + vf[8 * gi + 2 * q + 1];
         }
       }
 #pragma unroll
       for (int gi = 0; gi < kNBL / 8; ++gi) {
         if (gi >= GB) break;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          vb[8 * gi + k] = s16[blg[256 * gi + 32 * k]];
-          sb += vb[8 * gi + k];
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t o2 = blg[128 * gi + 32 * q];
+          vb[8 * gi + 2 * q] = s16[o2 & 0xffffu];
+          vb[8 * gi + 2 * q + 1] = s16[o2 >> 16];
+          sb += vb[8 * gi + 2 * q] + vb[8 * gi + 2 * q + 1];
         }
       }
       const uint32_t v0f = s16[fl[0]], v0b = s16[bl[0]];     // the pixel the padding repeats
