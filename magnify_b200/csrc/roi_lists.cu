@@ -244,7 +244,17 @@ roi_gather_lists_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGathe
   }
   __syncthreads();
 
-  const int64_t mi = WPM ? (int64_t)blockIdx.x * nw + warp : (int64_t)blockIdx.x;
+  // CTA layout: CTA b < split_from works on all the windows of marker b; the markers from
+  // split_from on (the ones that would run as a nearly empty last wave) are shared by split_parts
+  // CTAs each, which deal the marker's rounds of nw windows among themselves.
+  int64_t mi = WPM ? (int64_t)blockIdx.x * nw + warp : (int64_t)blockIdx.x;
+  int part = 0, nparts = 1;
+  if (!WPM && mi >= p.split_from) {
+    const int64_t r = mi - p.split_from;
+    mi = p.split_from + r / p.split_parts;
+    part = (int)(r % p.split_parts);
+    nparts = p.split_parts;
+  }
   const bool active = mi < M;
   const int64_t m = active ? (p.order ? p.order[mi] : mi) : 0;
   uint16_t* fl = lists + (size_t)g * (p.cap_f + p.cap_b);
@@ -317,7 +327,7 @@ roi_gather_lists_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGathe
   const uint32_t my_bar0 = smem_u32(&bars[warp * 4]);
   uint32_t* my_hist = hists + (size_t)warp * kHistWords;
   const uint32_t tx_bytes = (uint32_t)(p.rows * p.wpu * 2);
-  const int first = WPM ? 0 : warp, step = WPM ? 1 : nw;
+  const int first = WPM ? 0 : part * nw + warp, step = WPM ? 1 : nparts * nw;
 
   // (channel, index into tlist) of an item, advanced without divisions
   struct Cursor { int i, c, k; };
@@ -569,6 +579,8 @@ int roi_gather_lists(const void* image, int64_t pitch, int64_t C, int64_t T, int
     if (!nw && wpm) wpm = false;   // per-warp lists do not fit: share one marker per CTA instead
   }
   if (!nw) return MGB_EALIGN;
+  bool split_tail = true;
+  if (const char* e = getenv("MGB_GATHER_SPLIT")) split_tail = atoi(e) != 0;   // tuning / tests only
   p.n_stages = ns;
 
   CUtensorMap tmap;
@@ -585,12 +597,29 @@ int roi_gather_lists(const void* image, int64_t pitch, int64_t C, int64_t T, int
   p.Wu = pitch;
 
   const uint32_t magic_l = magic_u32_((uint32_t)L);
-  const dim3 grid(wpm ? (unsigned)((M + nw - 1) / nw) : (unsigned)M, (unsigned)Tm);
+  // CTA layout: with M markers on `slots` resident CTAs the last M % slots markers would run as a
+  // wave that leaves most SMs idle for a whole marker's duration (config 3: 1792 = 12 x 148 + 16).
+  // Those markers are split over up to 8 CTAs each, so that the last wave is short.
 #define MGB_LAUNCH_L(VP, QP, WP, NWARPS)                                                                   \
   do {                                                                                                    \
-    MGB_CUDA_TRY(cudaFuncSetAttribute(roi_gather_lists_kernel<VP, QP, WP, NWARPS>,                        \
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));     \
-    roi_gather_lists_kernel<VP, QP, WP, NWARPS><<<grid, nw * 32, smem_bytes, st>>>(tmap, p, M, magic_l);  \
+    auto kern = roi_gather_lists_kernel<VP, QP, WP, NWARPS>;                                              \
+    MGB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); \
+    dim3 grid(WP ? (unsigned)((M + nw - 1) / nw) : (unsigned)M, (unsigned)Tm);                            \
+    p.split_from = M;                                                                                     \
+    p.split_parts = 1;                                                                                    \
+    if (!WP && split_tail) {                                                                          \
+      int resident = 1;                                                                                   \
+      MGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, nw * 32, smem_bytes));  \
+      const int64_t slots = (int64_t)std::max(resident, 1) * sms, tail = (M * Tm) % slots;                \
+      const int64_t rounds = (items + nw - 1) / nw;                                                       \
+      const int parts = (int)std::min<int64_t>({8, tail ? slots / tail : 1, rounds});                     \
+      if (Tm == 1 && M > slots && parts >= 2) {                                                           \
+        p.split_from = M - tail;                                                                          \
+        p.split_parts = parts;                                                                            \
+        grid.x = (unsigned)(p.split_from + tail * parts);                                                 \
+      }                                                                                                   \
+    }                                                                                                     \
+    kern<<<grid, nw * 32, smem_bytes, st>>>(tmap, p, M, magic_l);                                         \
   } while (0)
 #define MGB_LAUNCH_NW(VP, QP, WP)                       \
   do {                                                  \

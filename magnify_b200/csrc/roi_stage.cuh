@@ -42,6 +42,8 @@ struct TmaGatherParams {
   int cap_f, cap_b;         // list capacities (entries), multiples of 32
   int want_median;          // 0: sums / means only
   int store;                // 0: summaries only (roi == null)
+  int split_parts;          // CTA layout: CTAs sharing each marker from split_from on (1: none)
+  int64_t split_from;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

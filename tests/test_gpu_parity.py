@@ -720,6 +720,40 @@ def test_gather_fused_medians(cuda_device, monkeypatch, layout, length, r_fg, r_
     assert np.isnan(no_med[..., 6:]).all()
 
 
+@pytest.mark.parametrize("c,t", [(3, 10), (4, 33)])
+def test_gather_split_last_wave(cuda_device, monkeypatch, c, t):
+    """A few more markers than a multiple of the resident CTAs: the markers of the last, nearly
+    empty wave are shared by several CTAs each (roi_lists.cu).  Same crops and summaries as the
+    oracle and as the unsplit launch, with few windows per marker (two 6-warp CTAs per SM) and
+    with many (one 12-warp CTA)."""
+    from magnify_b200 import ops
+
+    sms = torch.cuda.get_device_properties(cuda_device).multi_processor_count
+    m, length, h, w = 2 * sms + 9, 33, 200, 320
+    rng = np.random.default_rng(c * 100 + t)
+    image = np.clip(rng.normal(700, 60, (c, t, h, w)), 0, 65535).astype(np.uint16)
+    x = rng.uniform(0, w, (m, t))
+    y = rng.uniform(0, h, (m, t))
+    fg, bg = _disc_masks(rng, m, 1, length, 6, 7, 15)
+    want_roi = o_rois.gather_rois(image, x, y, length)
+    want = o_red.masked_stats(want_roi, np.repeat(fg, t, 1), np.repeat(bg, t, 1))
+    boxes = ops.bounding_boxes(dev(x, cuda_device), dev(y, cuda_device), length, w, h)
+    fg_d, bg_d = dev(fg.view(np.uint8), cuda_device), dev(bg.view(np.uint8), cuda_device)
+    counts = ops.mask_count_max(fg_d, bg_d)
+    monkeypatch.setenv("MGB_GATHER_LAYOUT", "0")
+    results = []
+    for split in ("1", "0"):
+        monkeypatch.setenv("MGB_GATHER_SPLIT", split)
+        roi, stats = ops.roi_gather_stats(dev(image, cuda_device), boxes, fg_d, bg_d, length, mask_counts=counts)
+        np.testing.assert_array_equal(roi.cpu().numpy(), want_roi)
+        got = stats.cpu().numpy()
+        np.testing.assert_array_equal(got[..., :4], want[..., :4])
+        np.testing.assert_allclose(got[..., 4:6], want[..., 4:6], rtol=1e-12, equal_nan=True)
+        np.testing.assert_array_equal(got[..., 6:], want[..., 6:])
+        results.append(got)
+    np.testing.assert_array_equal(results[0], results[1])
+
+
 @pytest.mark.parametrize("length", [256, 300, 1024])
 def test_saturated_sums_do_not_wrap(cuda_device, gather_path, length):
     """A 65535-valued image under full masks: the per-ROI sums (L^2 * 65535, above 2^32 from
