@@ -453,6 +453,9 @@ def mask_count_max(fg: torch.Tensor, bg: torch.Tensor):
     return int(c[0]), int(c[1])
 
 
+last_gather_fused = True   # diagnostic: did the last roi_gather_stats call get its medians from the fused kernel?
+
+
 def roi_gather_stats(
     image: torch.Tensor,
     boxes: torch.Tensor,
@@ -506,6 +509,9 @@ def roi_gather_stats(
             _lib.call("mgb_roi_gather_stats_peers_u16", _ptr(image), pitch, c, t, h, w, _ptr(boxes),
                       _ptr(_check_order(order, m)), _ptr(mask_t), tm, _ptr(fg), _ptr(bg), m, int(roi_length),
                       _ptr(roi), arr, n_peers, int(bool(medians)), nf_max, nb_max, ctypes.byref(done), _stream())
+        if medians and not done.value and m * c * t > 0:
+            raise RuntimeError("peer_stats needs the fused gather (masks of at most 1024 fg / 2560 bg pixels per marker, "
+                               "uint16 image); gather locally and all_gather the summaries instead")
         return roi, None
     stats = out_stats if out_stats is not None else torch.empty((m, c, t, NSTATS), dtype=torch.float64,
                                                                 device=image.device)
@@ -515,6 +521,8 @@ def roi_gather_stats(
         _lib.call("mgb_roi_gather_stats_u16", _ptr(image), pitch, c, t, h, w, _ptr(boxes), _ptr(_check_order(order, m)),
                   _ptr(mask_t), tm, _ptr(fg), _ptr(bg), m, int(roi_length), _ptr(roi), _ptr(stats),
                   int(bool(medians)), nf_max, nb_max, ctypes.byref(done), _stream())
+    global last_gather_fused
+    last_gather_fused = bool(done.value) or not medians
     if medians and not done.value and m * c * t > 0:
         # masks too large for the in-kernel lists (or an image the staged kernels do not take):
         # exact medians from the crops in a second pass
