@@ -1,5 +1,5 @@
 """ncu target: a few launches of the fused gather (lists + medians) on a config-3 shaped stack.
-    python tools/gather_ncu.py [T] [--no-medians]"""
+    python tools/gather_ncu.py [T] [--no-medians] [--c5]"""
 import os
 import sys
 
@@ -10,9 +10,15 @@ from magnify_b200 import ops, pipeline, synth  # noqa: E402
 
 T = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 8
 dev = torch.device("cuda:0")
-case = synth.chip_case(c=4, t=T, seed=0, device=dev)
-plan = pipeline.QuantifyPlan(case.tiles.shape, case.overlap, case.roi_length, case.flat, case.dark, device=dev)
-plan.set_chip_markers(case.x, case.y, case.fg_radius, case.chamber_radius, case.max_button_radius)
+if "--c5" in sys.argv:
+    case = synth.bead_case(c=4, t=T, r=10, cc=10, h=2048, w=2048, overlap=0, n_beads=100000, min_radius=4,
+                           max_radius=12, roi_length=50, seed=0, device=dev)
+    plan = pipeline.QuantifyPlan(case.tiles.shape, case.overlap, case.roi_length, case.flat, case.dark, device=dev)
+    plan.set_bead_markers(case.beads)
+else:
+    case = synth.chip_case(c=4, t=T, seed=0, device=dev)
+    plan = pipeline.QuantifyPlan(case.tiles.shape, case.overlap, case.roi_length, case.flat, case.dark, device=dev)
+    plan.set_chip_markers(case.x, case.y, case.fg_radius, case.chamber_radius, case.max_button_radius)
 image = plan.stitched(case.tiles)
 m, L = plan.boxes.shape[0], plan.roi_length
 roi = torch.empty((m, 4, T, L, L), dtype=torch.uint16, device=dev)
