@@ -120,26 +120,28 @@ __device__ __forceinline__ void hist_locate(const uint32_t* hist, int lane, uint
   *bin2 = __shfl_sync(0xffffffffu, b2, o2);
 }
 
-// Exact median of the n values a warp holds in v[] (G groups of 8 slots per lane; the slots
-// beyond n hold `pad` extra copies of the value v0) by radix selection on a per-warp
-// shared-memory histogram of 256 bins: the values are binned by (v - min) >> s with s chosen so
-// that the maximum lands in the last bins, and a warp scan of the bin counts locates the bins of
-// the two middle ranks.  With a range below 256 the bins are single values and one pass is the
-// answer (typical background: a few dozen grey levels); otherwise the bin of the lower middle is
-// binned again at full resolution (2^s <= 256 values), or -- when the two middles fall into
-// different bins -- they are the largest value of the one and the smallest of the other.
-// Mean of the two middles for an even count, NaN for n == 0 (np.nanmedian).
+// Exact median of the n values a warp holds in v[]: two 16-bit values per register, G groups of
+// 4 registers (8 slots) per lane; the slots beyond n hold `pad` extra copies of the value v0.
+// Radix selection on a per-warp shared-memory histogram of 256 bins: the values are binned by
+// (v - min) >> s with s chosen so that the maximum lands in the last bins, and a warp scan of the
+// bin counts locates the bins of the two middle ranks.  With a range below 256 the bins are
+// single values and one pass is the answer (typical background: a few dozen grey levels);
+// otherwise the bin of the lower middle is binned again at full resolution (2^s <= 256 values),
+// or -- when the two middles fall into different bins -- they are the largest value of the one
+// and the smallest of the other.  Mean of the two middles for an even count, NaN for n == 0
+// (np.nanmedian).
 template <int N>
 __device__ __forceinline__ double warp_median_radix(const uint32_t (&v)[N], int G, uint32_t n, uint32_t pad,
                                                     uint32_t v0, uint32_t* hist, int lane, uint32_t spill) {
   if (n == 0) return nan_f64();
-  uint32_t lo = v[0], hi = v[0];
+  uint32_t lo2 = v[0], hi2 = v[0];
 #pragma unroll
-  for (int g = 0; g < N / 8; ++g) {
+  for (int g = 0; g < N / 4; ++g) {
     if (g >= G) break;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { lo = min(lo, v[8 * g + k]); hi = max(hi, v[8 * g + k]); }
+    for (int k = 0; k < 4; ++k) { lo2 = __vminu2(lo2, v[4 * g + k]); hi2 = __vmaxu2(hi2, v[4 * g + k]); }
   }
+  uint32_t lo = min(lo2 & 0xffffu, lo2 >> 16), hi = max(hi2 & 0xffffu, hi2 >> 16);
   lo = __reduce_min_sync(0xffffffffu, lo);
   hi = __reduce_max_sync(0xffffffffu, hi);
   if (lo == hi) return (double)lo;
@@ -151,10 +153,14 @@ __device__ __forceinline__ double warp_median_radix(const uint32_t (&v)[N], int 
   h4[2 * lane + 1] = make_uint4(0, 0, 0, 0);
   __syncwarp();
 #pragma unroll
-  for (int g = 0; g < N / 8; ++g) {
+  for (int g = 0; g < N / 4; ++g) {
     if (g >= G) break;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(hist + ((v[8 * g + k] - lo) >> s), 1u);
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t w = v[4 * g + k];
+      atomicAdd(hist + (((w & 0xffffu) - lo) >> s), 1u);
+      atomicAdd(hist + (((w >> 16) - lo) >> s), 1u);
+    }
   }
   __syncwarp();
   if (lane == 0 && pad) hist[(v0 - lo) >> s] -= pad;
@@ -165,13 +171,17 @@ __device__ __forceinline__ double warp_median_radix(const uint32_t (&v)[N], int 
   if (bin1 != bin2) {
     uint32_t a = 0, b = 0xffffffffu;
 #pragma unroll
-    for (int g = 0; g < N / 8; ++g) {
+    for (int g = 0; g < N / 4; ++g) {
       if (g >= G) break;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint32_t x = v[8 * g + k], bin = (x - lo) >> s;
-        a = max(a, bin == bin1 ? x : 0u);
-        b = min(b, bin == bin2 ? x : 0xffffffffu);
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t w = v[4 * g + k];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t x = h ? (w >> 16) : (w & 0xffffu), bin = (x - lo) >> s;
+          a = max(a, bin == bin1 ? x : 0u);
+          b = min(b, bin == bin2 ? x : 0xffffffffu);
+        }
       }
     }
     a = __reduce_max_sync(0xffffffffu, a);
@@ -186,12 +196,14 @@ __device__ __forceinline__ double warp_median_radix(const uint32_t (&v)[N], int 
   h4[2 * lane + 1] = make_uint4(0, 0, 0, 0);
   __syncwarp();
 #pragma unroll
-  for (int g = 0; g < N / 8; ++g) {
+  for (int g = 0; g < N / 4; ++g) {
     if (g >= G) break;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const uint32_t d = v[8 * g + k] - base;
-      atomicAdd(hist + (d < 256u ? d : spill), 1u);      // slots 256.. = "not in this bin", one per lane (no conflicts)
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t w = v[4 * g + k];
+      const uint32_t d0 = (w & 0xffffu) - base, d1 = (w >> 16) - base;
+      atomicAdd(hist + (d0 < 256u ? d0 : spill), 1u);      // slots 256.. = "not in this bin", one per lane (no conflicts)
+      atomicAdd(hist + (d1 < 256u ? d1 : spill), 1u);
     }
   }
   __syncwarp();
@@ -296,31 +308,11 @@ roi_gather_lists_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGathe
   const int nt = s_nt;
   const int n_items = nt * (int)p.C;           // item i -> (c = i / nt, t = tlist[i % nt])
 
-  // window-independent per-lane state of the copy loop
+  // The per-lane shared-memory offsets of the copy loop do not depend on the window, but keeping
+  // them in registers across the medians (21 to 48 of them) costs more than recomputing them per
+  // window with a multiply-high; `opaque` keeps the compiler from hoisting them out of the loop.
   constexpr int kV = VPL > 0 ? VPL : 1;
-  constexpr int kQ = QPL > 0 ? QPL : 1;
-  uint32_t svo[kV];
-  uint32_t offa[kQ], offb[kQ];
   const int nquads = (p.rows * p.wu) >> 2;
-  if constexpr (VPL > 0) {
-    const uint32_t nvec = p.rows * p.vpr, pitch = p.wpu >> 3;
-#pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-      const uint32_t v = lane + 32 * k;
-      const uint32_t vv = v < nvec ? v : 0;
-      const uint32_t row = __umulhi(vv, p.magic_vpr);
-      svo[k] = row * pitch + (vv - row * p.vpr);
-    }
-  } else if constexpr (QPL > 0) {
-#pragma unroll
-    for (int k = 0; k < QPL; ++k) {
-      const int q = lane + 32 * k;
-      const int u = q < nquads ? 4 * q : 0;
-      const int row = u / p.wu, col = u - row * p.wu;
-      offa[k] = row * p.wpu + col;
-      offb[k] = (col + 2 < p.wu) ? offa[k] + 2 : (row + 1) * p.wpu;     // second pair wraps to the next row
-    }
-  }
 
   uint8_t* my_stages = stages + (size_t)warp * p.n_stages * p.stage_bytes;
   const uint32_t my_stage0 = smem_u32(my_stages);
@@ -368,6 +360,8 @@ roi_gather_lists_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGathe
     // ---- 1. the crop
     if (p.store) {
       uint16_t* dst = p.roi + n * (int64_t)p.rows * p.wu;
+      uint32_t opaque = 0;
+      asm volatile("" : "+r"(opaque));
       if constexpr (QPL > 0) {
         uint2* d2 = reinterpret_cast<uint2*>(dst);
         const uint32_t* s32 = reinterpret_cast<const uint32_t*>(buf);
@@ -377,8 +371,12 @@ roi_gather_lists_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGathe
           for (int k = 0; k < QPL; ++k) {
             const int q = lane + 32 * k;
             if (q < nquads) {
-              const uint32_t lo = load_pair<PAR>(s32, offa[k] + shift);
-              const uint32_t hi = load_pair<PAR>(s32, offb[k] + shift);
+              const uint32_t u = 4u * q + opaque;
+              const uint32_t row = __umulhi(u, p.magic_wu), col = u - row * p.wu;
+              const uint32_t oa = row * p.wpu + col + shift;
+              const uint32_t ob = (col + 2 < (uint32_t)p.wu) ? oa + 2 : (row + 1) * p.wpu + shift;   // second pair wraps to the next row
+              const uint32_t lo = load_pair<PAR>(s32, oa);
+              const uint32_t hi = load_pair<PAR>(s32, ob);
               asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(d2 + q), "r"(lo), "r"(hi) : "memory");
             }
           }
@@ -388,6 +386,17 @@ roi_gather_lists_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGathe
       } else {
         uint32_t dummy_f, dummy_b;
         if (p.vpr) {
+          uint32_t svo[kV];
+          if constexpr (VPL > 0) {
+            const uint32_t nvec = p.rows * p.vpr, pitch = p.wpu >> 3;
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+              const uint32_t v = lane + 32 * k;
+              const uint32_t vv = (v < nvec ? v : 0) + opaque;
+              const uint32_t row = __umulhi(vv, p.magic_vpr);
+              svo[k] = row * pitch + (vv - row * p.vpr);
+            }
+          }
           switch (shift) {
 #define MGB_COPY(SS) \
   case SS: consume_vec<false, true, SS, VPL>(p, buf, dst, nullptr, nullptr, lane, nullptr, nullptr, svo, &dummy_f, &dummy_b); break;
@@ -415,7 +424,7 @@ roi_gather_lists_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGathe
       // second entry -- mostly every second pixel of a mask row, one bank each
       const uint32_t* flg = reinterpret_cast<const uint32_t*>(fl) + lane;
       const uint32_t* blg = reinterpret_cast<const uint32_t*>(bl) + lane;
-      uint32_t vf[kNFL], vb[kNBL];
+      uint32_t vf[kNFL / 2], vb[kNBL / 2];                  // two 16-bit values per register
       uint32_t sf = 0, sb = 0;
 #pragma unroll
       for (int gi = 0; gi < kNFL / 8; ++gi) {
@@ -423,9 +432,9 @@ roi_gather_lists_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGathe
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint32_t o2 = flg[128 * gi + 32 * q];
-          vf[8 * gi + 2 * q] = s16[o2 & 0xffffu];
-          vf[8 * gi + 2 * q + 1] = s16[o2 >> 16];
-          sf += vf[8 * gi + 2 * q] + vf[8 * gi + 2 * q + 1];
+          const uint32_t w = (uint32_t)s16[o2 & 0xffffu] | ((uint32_t)s16[o2 >> 16] << 16);
+          vf[4 * gi + q] = w;
+          sf = __dp2a_lo(w, 0x0101u, sf);                    // both halves added (exact: <= 112 x 65535 per lane)
         }
       }
 #pragma unroll
@@ -434,9 +443,9 @@ roi_gather_lists_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGathe
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint32_t o2 = blg[128 * gi + 32 * q];
-          vb[8 * gi + 2 * q] = s16[o2 & 0xffffu];
-          vb[8 * gi + 2 * q + 1] = s16[o2 >> 16];
-          sb += vb[8 * gi + 2 * q] + vb[8 * gi + 2 * q + 1];
+          const uint32_t w = (uint32_t)s16[o2 & 0xffffu] | ((uint32_t)s16[o2 >> 16] << 16);
+          vb[4 * gi + q] = w;
+          sb = __dp2a_lo(w, 0x0101u, sb);
         }
       }
       const uint32_t v0f = s16[fl[0]], v0b = s16[bl[0]];     // the pixel the padding repeats
@@ -557,6 +566,9 @@ int roi_gather_lists(const void* image, int64_t pitch, int64_t C, int64_t T, int
   size_t smem_bytes = 0;
   // warps per CTA x stages per warp: more warps hide the latency of the per-window reductions,
   // more stages that of the window loads; 12 x 1 ... 8 x 2 ... 4 x 2 in order of preference.
+  // The warp layout (small windows, dense masks: latency-bound) takes 16 warps at 128 registers when
+  // they fit (config 5: 13.2 against 14.9 ms); the CTA layout at config 3 is memory-bound and loses
+  // with 16 (1.98 against 1.80 ms: the spills of the 128-register build cost more than the warps gain).
   // With a CTA per marker and fewer than 128 windows per marker, two CTAs of 6 warps share an SM
   // instead: the list building of one overlaps the windows of the other and fewer warps idle in
   // a marker's last round (config 3: 0.46 against 0.54 ms at T = 7, 1.12 against 1.17 ms at
@@ -565,14 +577,14 @@ int roi_gather_lists(const void* image, int64_t pitch, int64_t C, int64_t T, int
   if (const char* e = getenv("MGB_GATHER_WARPS")) want_nw = atoi(e);   // tuning only
   for (int pass = 0; pass < 2 && !nw; ++pass) {
     const bool pair = !wpm && items < 128;
-    for (int cand : {6, 12, 8, 4}) {
-      if (want_nw ? cand != want_nw : (cand == 6 && !pair)) continue;
+    for (int cand : {6, 16, 12, 8, 4}) {
+      if (want_nw ? cand != want_nw : ((cand == 6 && !pair) || (cand == 16 && !wpm))) continue;
       const size_t fixed = (wpm ? cand : 1) * list_bytes + (size_t)cand * kHistWords * sizeof(uint32_t) +
                            (size_t)cand * 4 * sizeof(uint64_t) + (size_t)T * sizeof(int32_t) + 128;
       // 6 warps: two CTAs share an SM (half of its shared memory each, 1 KB reserved per CTA)
       const size_t room = cand == 6 ? (size_t)(sm_smem / 2 - 1024) : (size_t)max_smem;
       if (room < fixed + 1024) continue;
-      const bool one = cand == 12 || cand == 6;
+      const bool one = cand >= 12 || cand == 6;
       const int n = (int)std::min<size_t>(one ? 1 : 4, (room - fixed - 1024) / ((size_t)cand * p.stage_bytes));
       if (n >= (one ? 1 : 2)) { nw = cand; ns = n; smem_bytes = (size_t)cand * n * p.stage_bytes + fixed; break; }
     }
@@ -582,6 +594,7 @@ int roi_gather_lists(const void* image, int64_t pitch, int64_t C, int64_t T, int
   bool split_tail = true;
   if (const char* e = getenv("MGB_GATHER_SPLIT")) split_tail = atoi(e) != 0;   // tuning / tests only
   p.n_stages = ns;
+  p.magic_wu = magic_u32_((uint32_t)wu);
 
   CUtensorMap tmap;
   const cuuint64_t gdim[3] = {(cuuint64_t)pitch, (cuuint64_t)H, (cuuint64_t)(C * T)};
@@ -623,7 +636,8 @@ int roi_gather_lists(const void* image, int64_t pitch, int64_t C, int64_t T, int
   } while (0)
 #define MGB_LAUNCH_NW(VP, QP, WP)                       \
   do {                                                  \
-    if (nw == 12) MGB_LAUNCH_L(VP, QP, WP, 12);         \
+    if (nw == 16) MGB_LAUNCH_L(VP, QP, WP, 16);         \
+    else if (nw == 12) MGB_LAUNCH_L(VP, QP, WP, 12);    \
     else if (nw == 6) MGB_LAUNCH_L(VP, QP, WP, 6);      \
     else MGB_LAUNCH_L(VP, QP, WP, 8);                   \
   } while (0)

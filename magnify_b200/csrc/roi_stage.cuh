@@ -38,6 +38,7 @@ struct TmaGatherParams {
   uint32_t magic_vpr;       // ceil(2^32 / vpr)
   uint32_t half;            // wu / 2 words per row when the word path applies, else 0
   uint32_t magic_half;
+  uint32_t magic_wu;        // ceil(2^32 / wu)
   // masked-value lists (roi_lists.cu)
   int cap_f, cap_b;         // list capacities (entries), multiples of 32
   int want_median;          // 0: sums / means only
