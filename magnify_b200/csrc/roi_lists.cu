@@ -52,6 +52,15 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // generic-proxy accesses to shared memory before this, async-proxy (TMA) writes to it after
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Where the i-th masked pixel (in raster order) sits in the list: within every run of 64, pixel
+// 32 h + l goes to position 2 l + h.  A lane's 4-byte load of positions 2 l, 2 l + 1 then brings the
+// offsets of pixels l and 32 + l, so each of the two pixel loads that follow reads 32 CONSECUTIVE
+// masked pixels across the warp (one row segment, conflict-free) instead of every second one of 64
+// (two rows, which collide when the staged row pitch is a multiple of 128 bytes).
+__device__ __forceinline__ uint32_t list_slot(uint32_t i) {
+  return (i & ~63u) | ((i & 31u) << 1) | ((i >> 5) & 1u);
+}
+
 // Compact the non-zero bytes of one (L x L) mask into window offsets row * wpu + col.
 // Called by `nwarps` warps (`wi` = this warp's index among them); `cnt` is a shared counter the
 // warps advance with one atomic per 32 bytes (nwarps == 1: the count stays in a register).
@@ -76,7 +85,7 @@ __device__ __forceinline__ uint32_t build_list(const uint8_t* __restrict__ mask,
     if (on) {
       const uint32_t pos = start + __popc(bal & ((1u << lane) - 1u));
       const uint32_t row = __umulhi((uint32_t)e, magic_l);
-      if (pos < (uint32_t)cap) list[pos] = (uint16_t)(row * wpu + (e - row * L));
+      if (pos < (uint32_t)cap) list[list_slot(pos)] = (uint16_t)(row * wpu + (e - row * L));
     }
     mine += __popc(bal);
   }
@@ -88,7 +97,7 @@ __device__ __forceinline__ uint32_t build_list(const uint8_t* __restrict__ mask,
 // copies of that pixel are taken out again arithmetically (sum) or from its histogram bin (median).
 __device__ __forceinline__ void pad_list(uint16_t* list, uint32_t n, int cap, int tid, int nthreads) {
   const uint16_t fill = n ? list[0] : (uint16_t)0;
-  for (int i = (int)n + tid; i < cap; i += nthreads) list[i] = fill;
+  for (int i = (int)n + tid; i < cap; i += nthreads) list[list_slot((uint32_t)i)] = fill;
 }
 
 // Bins of the two middle ranks r1 <= r2 in a 256-bin histogram, by a warp scan: lane l owns bins
@@ -419,9 +428,9 @@ roi_gather_lists_kernel(const __grid_constant__ CUtensorMap tmap, const TmaGathe
       // ---- 2. + 3. the masked pixels of this window through the lists (every slot is a valid
       // pixel: the slots beyond the mask repeat the mask's first pixel)
       const uint16_t* s16 = reinterpret_cast<const uint16_t*>(buf) + shift;
-      // slots 2q, 2q+1 of group g read entries 256 g + 64 q + 2 lane (+1): one 4-byte load brings two
-      // offsets per lane (a full 128-byte wavefront for the warp), and the 32 lanes then read every
-      // second entry -- mostly every second pixel of a mask row, one bank each
+      // slots 2q, 2q+1 of group g read list positions 256 g + 64 q + 2 lane (+1): one 4-byte load brings
+      // two offsets per lane (a full 128-byte wavefront for the warp); by list_slot() they are masked
+      // pixels 64 q' + lane and 64 q' + 32 + lane, so each pixel load covers 32 consecutive masked pixels
       const uint32_t* flg = reinterpret_cast<const uint32_t*>(fl) + lane;
       const uint32_t* blg = reinterpret_cast<const uint32_t*>(bl) + lane;
       uint32_t vf[kNFL / 2], vb[kNBL / 2];                  // two 16-bit values per register
