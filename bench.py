@@ -804,7 +804,8 @@ def measure_e2e(args, cfg, hc, tiles_dev, dev, world, group, barrier, max_over_r
             n += sum(np.asarray(assay[k].values).nbytes for k in ("fg_mean", "bg_mean", "fg_median", "bg_median", "fg_sum", "bg_sum"))
         return n
 
-    steps = 6 if not args.e2e_timepoints else max(1, min(args.steps, 6))   # assays back to back
+    steps = 8 if not args.e2e_timepoints else max(1, min(args.steps, 8))   # assays back to back (the first upload and
+    #                                                  the last download overlap with nothing: amortised over the chain)
     results = []
     for want_image in ((True, False) if m else (True,)):
         devarray.PREFETCH_SKIP = () if want_image else ("image",)
