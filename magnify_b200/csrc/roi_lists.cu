@@ -8,12 +8,12 @@
 // shared memory).  For every window the warp that owns it
 //
 //   1. re-aligns and stores the crop (no mask work in that loop),
-//   2. loads its share of the masked pixels through the lists into registers
-//      (<= 32 fg + 80 bg values per lane, i.e. fg <= 1024 and bg <= 2560 pixels per marker),
+//   2. loads its share of the masked pixels through the lists into registers, two 16-bit values
+//      per register (<= 32 fg + 80 bg values per lane, i.e. fg <= 1024 and bg <= 2560 pixels per
+//      marker), and refills its stage with the next window right away,
 //   3. sums them (exact integers) and
-//   4. finds both exact medians by bisection on the value between the masked minimum and
-//      maximum: one compare+add per value and one warp reduction per step, fg and bg in
-//      lockstep, no block-level synchronisation and no second pass over the crops.
+//   4. finds both exact medians by radix selection on a per-warp shared-memory histogram
+//      (warp_median_radix): no block-level synchronisation and no second pass over the crops.
 //
 // Two work layouts share the code: one CTA per marker with the windows dealt to its warps
 // (many windows per marker: chip time series), or one WARP per marker (many markers with few
@@ -25,8 +25,8 @@
 
 namespace mgb {
 
-constexpr int kNFL = 32;   // fg values per lane
-constexpr int kNBL = 80;   // bg values per lane
+constexpr int kNFL = 32;   // fg values per lane (16 registers)
+constexpr int kNBL = 80;   // bg values per lane (40 registers)
 
 // One (L x L) byte mask, global -> shared memory, with asynchronous copies (all in flight at once;
 // the compaction below then reads shared memory instead of paying a DRAM round trip per 32 bytes:
