@@ -200,6 +200,48 @@ def bead_input(case):
     raise KeyError(case)
 
 
+def mrbles_input(tmpdir):
+    """(DataArray, kwargs of mg.mrbles): 24 beads carrying three lanthanide codes (dy / eu volume
+    ratio 0, 0.5, 1) seen through three channels, with the spectra and codes tables of
+    identify_mrbles (identify.py:52-80) written as CSV files."""
+    import xarray as xr
+
+    channels = ["c435", "c546", "c620"]
+    spectra = {"eu": [0.1, 0.2, 1.0], "dy": [0.9, 0.5, 0.1]}                  # rows: lanthanide, columns: channel
+    ratios = {"code_a": 0.0, "code_b": 0.5, "code_c": 1.0}
+    spectra_path, codes_path = os.path.join(tmpdir, "spectra.csv"), os.path.join(tmpdir, "codes.csv")
+    with open(spectra_path, "w") as f:
+        f.write("name," + ",".join(channels) + "\n")
+        for ln in ("dy", "eu"):                                               # reference lanthanide deliberately not first
+            f.write(ln + "," + ",".join(str(v) for v in spectra[ln]) + "\n")
+    with open(codes_path, "w") as f:
+        f.write("name,eu,dy\n")
+        for name, r in ratios.items():
+            f.write(f"{name},1.0,{r}\n")
+    rng = np.random.default_rng(11)
+    beads, values = [], []
+    names = list(ratios)
+    for i in range(4):
+        for j in range(6):
+            row, col, r = 45 + 70 * i + int(rng.integers(-5, 6)), 45 + 70 * j + int(rng.integers(-5, 6)), int(rng.integers(7, 12))
+            beads.append((row, col, r))
+            code = names[(i * 6 + j) % 3]
+            vol_eu = 900.0 * (1 + 0.05 * rng.standard_normal())
+            vol_dy = vol_eu * ratios[code] * (1 + 0.03 * rng.standard_normal())
+            values.append([vol_eu * spectra["eu"][k] + vol_dy * spectra["dy"][k] for k in range(3)])
+    frames = []
+    for k in range(3):
+        img = np.zeros((330, 470), dtype=np.float64)
+        for (row, col, r), v in zip(beads, values):
+            pts = _disc(r)
+            img[pts[:, 0] + row, pts[:, 1] + col] = v[k]
+        frames.append(img + 100 + _noise((330, 470), 20 + k, scale=10))
+    data = xr.DataArray(data=np.asarray(frames).astype(np.uint16), dims=("channel", "y", "x"), coords={"channel": channels})
+    kwargs = dict(spectra=spectra_path, codes=codes_path, min_bead_diameter=10, max_bead_diameter=30, num_iter=1000, overlap=0,
+                  search_channel="c620", reference="eu")
+    return data, kwargs
+
+
 # ---------------------------------------------------------------------------------------------
 # comparison
 # ---------------------------------------------------------------------------------------------

@@ -2,7 +2,8 @@
 preprocess.py, stitch.py, find.py, identify.py, postprocess.py, reader.py ...) is imported in
 place (oracle/_refload.py::load_reference_package), `magnify_b200.components.install()` replaces
 its hot-path components in its own registry, and the reference's own builders
-(`microfluidic_chip_pipe`, `beads_pipe`, `mg.microfluidic_chip`, `mg.beads`; registry.py:32-612)
+(`microfluidic_chip_pipe`, `beads_pipe`, `mrbles_pipe`, `mg.microfluidic_chip`, `mg.beads`, `mg.mrbles`;
+registry.py:32-612)
 run `Pipeline.__call__` (pipeline.py:14-29) over them.  The resulting dataset must be IDENTICAL
 (variables, dims, dtypes, coordinates, attrs, values) to the one the reference's own components
 produce through the same pipe on the same input.
@@ -19,7 +20,7 @@ import numpy as np
 import pytest
 
 from dropin_cases import (assert_same_dataset, bead_input, chip_input, deterministic_find_circles, installed, load_mg,
-                          pin_circle_finders)
+                          mrbles_input, pin_circle_finders)
 
 
 @pytest.fixture()
@@ -80,6 +81,25 @@ def test_beads_pipeline_identical_to_reference(mg, monkeypatch, case):
     with installed(mg, monkeypatch):
         got = mg.beads(data, **kwargs)
     assert_same_dataset(got, want)
+
+
+def test_mrbles_pipeline_identical_to_reference(mg, monkeypatch, tmp_path):
+    """`mg.mrbles` (registry.py:272-449): flatfield_correct -> stitch -> find_beads from this package,
+    then the reference's OWN identify_mrbles (identify.py:49-232: `where(fg).mean - where(bg).median`
+    intensities, lanthanide volumes by least squares, code assignment by the mixture model) consumes
+    their output.  Volumes, ratios and the code of every bead must come out as through the
+    reference's own components."""
+    data, kwargs = mrbles_input(str(tmp_path))
+    want = mg.mrbles(data, **kwargs)
+    with installed(mg, monkeypatch):
+        pipe = mg.mrbles_pipe(**{k: v for k, v in kwargs.items()})
+        assert [n for n, _ in pipe.components] == ["standardize_format", "flatfield_correct", "stitch", "find_beads",
+                                                   "identify_mrbles", "drop", "restore_format"]
+        got = mg.mrbles(data, **kwargs)
+    assert_same_dataset(got, want)
+    tags = np.asarray(want["tag"].values)
+    assert len(tags) == 24 and {"code_a", "code_b", "code_c"} <= set(tags.tolist())     # the fixture really separates the codes
+    assert np.isfinite(np.asarray(want["ln_ratio"].values)).all()
 
 
 def test_chip_pipe_with_flatfield_and_quantify(mg, monkeypatch):
