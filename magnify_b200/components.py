@@ -701,7 +701,7 @@ def filter_nonround(assay, min_roundness: float = 0.75, search_channel=None, dev
     reference repeats the same test once per search channel although `fg` has no channel axis; the
     outcome is that of a single pass."""
     dev = _device(device)
-    fg0 = np.ascontiguousarray(_to_numpy(assay["fg"])[:, 0])
+    fg0 = np.array(_to_numpy(assay["fg"])[:, 0], order="C")     # a copy: masks broadcast over time are read-only views
     valid = _to_numpy(assay["valid"]).astype(bool).copy()
     if fg0.shape[0]:
         perimeter = ops.mask_perimeters(torch.from_numpy(fg0.view(np.uint8)).to(dev)).cpu().numpy()

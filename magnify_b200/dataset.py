@@ -149,14 +149,34 @@ class DataArray:
 
     # -- basic properties -----------------------------------------------------------------------
     dims = property(lambda self: self.variable.dims)
-    data = property(lambda self: self.variable.data)
+    @property
+    def data(self):
+        return self.variable.data
+
+    @data.setter
+    def data(self, value):
+        """xarray's `da.data = array`: the array behind the variable is replaced in place, so a
+        DataArray taken out of a Dataset writes through to it (filter.py:60, 92 rely on that)."""
+        value = _as_data(value)
+        if tuple(value.shape) != self.variable.shape:
+            raise ValueError(f"replacement data must match the Variable's shape. replacement data has shape "
+                             f"{tuple(value.shape)}; Variable has shape {self.variable.shape}")
+        self.variable.data = value
+
     shape = property(lambda self: self.variable.shape)
     dtype = property(lambda self: self.variable.dtype)
     ndim = property(lambda self: self.variable.ndim)
     sizes = property(lambda self: self.variable.sizes)
     size = property(lambda self: int(np.prod(self.variable.shape, dtype=np.int64)))
     attrs = property(lambda self: self.variable.attrs)
-    values = property(lambda self: np.asarray(self.variable.data))
+    @property
+    def values(self):
+        return np.asarray(self.variable.data)
+
+    @values.setter
+    def values(self, value):
+        self.data = np.asarray(value)
+
     coords = property(lambda self: {k: DataArray(v, name=k) for k, v in self._coords.items()})
 
     def _new(self, variable: Variable, coords=None, name="__same__") -> "DataArray":

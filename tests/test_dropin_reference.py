@@ -102,6 +102,33 @@ def test_mrbles_pipeline_identical_to_reference(mg, monkeypatch, tmp_path):
     assert np.isfinite(np.asarray(want["ln_ratio"].values)).all()
 
 
+@pytest.mark.parametrize("case", ["chip_series", "chip_blank_float"])
+def test_chip_pipe_with_filters(mg, monkeypatch, case):
+    """The consumers of the crops, through the registry: filter_expression, filter_nonround and
+    filter_leaky (filter.py:11-94) added to the chip pipe with add_pipe.  install() replaces all
+    three (medians and contour perimeters from the kernels); `valid` and everything else must come
+    out as from the reference's own filters, on a time series and on a chip with a blank chamber."""
+    data, kwargs = chip_input(case)
+
+    def build():
+        pipe = mg.microfluidic_chip_pipe(**kwargs)
+        pipe.add_pipe("filter_expression", after="find_buttons")
+        pipe.add_pipe("filter_nonround", after="filter_expression", min_roundness=0.6)
+        pipe.add_pipe("filter_leaky", after="filter_nonround")
+        return pipe
+
+    want = build()(data)
+    with installed(mg, monkeypatch):
+        from magnify_b200 import components
+
+        pipe = build()
+        for name in ("filter_expression", "filter_nonround", "filter_leaky"):     # really this package's
+            assert dict(pipe.components)[name].__module__ == components.__name__
+        got = pipe(data)
+    assert_same_dataset(got, want)
+    assert np.asarray(want["valid"].values).any()
+
+
 def test_chip_pipe_with_flatfield_and_quantify(mg, monkeypatch):
     """BASELINE config 3's pipe: the chip pipe has no flat-field step (registry.py:243-269), it is
     inserted with add_pipe (pipeline.py:31-78).  The lazy
