@@ -632,9 +632,10 @@ def _time0_medians(assay, channel_index: int, dev):
     if cached is not None:
         s = cached[:, channel_index, 0].cpu().numpy()
         return s[:, 6], s[:, 7]
-    roi = np.ascontiguousarray(_to_numpy(assay["roi"])[:, channel_index : channel_index + 1, :1])
-    fg = np.ascontiguousarray(_to_numpy(assay["fg"])[:, :1]).view(np.uint8)
-    bg = np.ascontiguousarray(_to_numpy(assay["bg"])[:, :1]).view(np.uint8)
+    # copies: host views of pooled / broadcast arrays can be read-only, which torch.from_numpy warns about
+    roi = np.array(_to_numpy(assay["roi"])[:, channel_index : channel_index + 1, :1], order="C")
+    fg = np.array(_to_numpy(assay["fg"])[:, :1], order="C").view(np.uint8)
+    bg = np.array(_to_numpy(assay["bg"])[:, :1], order="C").view(np.uint8)
     roi_d = torch.from_numpy(roi if roi.dtype in (np.uint16, np.float32) else roi.astype(np.float32)).to(dev)
     fgm = ops.roi_median(roi_d, torch.from_numpy(fg).to(dev)).cpu().numpy()[:, 0, 0]
     bgm = ops.roi_median(roi_d, torch.from_numpy(bg).to(dev)).cpu().numpy()[:, 0, 0]

@@ -11,6 +11,10 @@ is run component by component and two states are saved:
   * `out__*` -- the dataset leaving the last hot-path component (`find_buttons` / `find_beads`),
                 before the reference's `drop` / `restore_format`: image, roi, fg, bg, x, y, valid;
 
+  * `valid_after__<filter>` (chip cases) -- `valid` after the reference's own filter_expression,
+                filter_nonround(min_roundness=0.6) and filter_leaky applied in that order to the
+                `out__` state;
+
 plus the marker centres (and fg radii) the reference arrived at, so that the GPU side can pin
 them (`centers=` hook) -- the reference's own centre search is random and unseeded.
 tests/test_gpu_dropin.py replays the hot-path components of `magnify_b200.components` with the
@@ -41,7 +45,7 @@ def pack(prefix, ds, out, skip=()):
     for name, var in ds.variables.items():
         if name in skip:
             continue
-        values = np.asarray(var.values)
+        values = np.array(var.values, copy=True)       # a snapshot: later components write into `valid` in place
         if values.dtype.kind in "OU":
             values = values.astype(str)
         out[f"{prefix}__{name}"] = values
@@ -83,6 +87,13 @@ def run_case(mg, kind, case):
                 break
             ds = comp(ds)
         pack("out", ds, out, skip=("tile",))      # the tile stack is the input, already saved
+        if kind == "chip":
+            # the reference's own consumers of the crops, one after the other on that state
+            # (filter.py:11-94); only `valid` changes
+            reg = mg.registry.components
+            for name, fkw in (("filter_expression", {}), ("filter_nonround", {"min_roundness": 0.6}), ("filter_leaky", {})):
+                ds = reg.get(name)(**fkw)(ds)
+                out[f"valid_after__{name}"] = np.asarray(ds["valid"].values).copy()
     finally:
         mg.utils.circle = real_circle
         mg.utils.circle_labels = real_labels

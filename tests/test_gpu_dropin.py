@@ -6,7 +6,8 @@ entering the first hot-path component (`in__*`) and the one leaving the last (`o
 GPU components registered by `components.install()` (the same factories, the same kwargs the
 reference's builder passes, the same order: [flatfield_correct,] stitch, find_buttons / find_beads)
 run on the `in__` state the way `Pipeline.__call__` runs them (pipeline.py:19-22) and must
-reproduce the `out__` state exactly -- values, dims, dtypes, coordinates.  /root/reference is not
+reproduce the `out__` state exactly -- values, dims, dtypes, coordinates -- and, for the chip cases,
+the `valid` flags the reference's own three filters leave on that state.  /root/reference is not
 needed (and does not exist) on the GPU box; centres are pinned to the ones the reference found.
 tests/test_dropin_reference.py is the other half: the same layer inside the reference's real
 Pipeline, on the CPU stand-in for the kernels.
@@ -94,6 +95,11 @@ def test_chip_components_reproduce_reference_pipeline(cuda_device, case):
         sel = want["roi"].where(want["fg"])
         np.testing.assert_array_equal(got["fg_median"].values, sel.median(dim=["roi_x", "roi_y"]).values)
         np.testing.assert_allclose(got["fg_mean"].values, sel.mean(dim=["roi_x", "roi_y"]).values, rtol=1e-6)
+    # the consumers of the crops, in the order the golden generator ran the reference's own
+    # (filter.py:11-94): medians and contour perimeters from the kernels, `valid` must follow exactly
+    for name, fkw in (("filter_expression", {}), ("filter_nonround", {"min_roundness": 0.6}), ("filter_leaky", {})):
+        got = reg.get(name)(**fkw)(got)
+        np.testing.assert_array_equal(np.asarray(got["valid"].values), g[f"valid_after__{name}"], err_msg=name)
 
 
 @pytest.mark.parametrize("case", ["beads_single", "beads_flatfield_tiles", "beads_none"])
