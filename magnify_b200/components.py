@@ -272,8 +272,6 @@ def _upload(values: np.ndarray, dev) -> torch.Tensor:
     waits for everything queued on the stream (the tile upload and the stitch of this assay), which
     would keep the next assay's upload from being queued behind this one's."""
     host = torch.from_numpy(np.ascontiguousarray(values))
-    if dev.type != "cuda":
-        return host
     return host.pin_memory().to(dev, non_blocking=True)   # torch's caching host allocator holds the block until the copy ran
 
 

@@ -212,3 +212,4 @@ def patch_components(monkeypatch):
     monkeypatch.setattr(components, "ops", this)
     monkeypatch.setattr(components, "_device", lambda device: torch.device("cpu"))
     monkeypatch.setattr(components, "_stage_tiles", _stage_tiles)
+    monkeypatch.setattr(components, "_upload", lambda values, dev: torch.from_numpy(np.ascontiguousarray(values)))
